@@ -1,0 +1,143 @@
+"""Generate tests/golden/*.npz by running the REFERENCE'S OWN Python.  TEST INFRASTRUCTURE.
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+Every vector below is an output of the unmodified reference modules imported from
+/root/reference under oracle/stubs.py (PyG ops = oracle/pyg_ops.py, T5 = oracle/fake_t5.py),
+on seeded synthetic inputs with the seeded synthetic weights of text2loc_b200/synth.py.
+
+  cells_small.npz   CellRetrievalNetwork.encode_objects on ragged cells (1..30 objects, one
+                    cell beyond object_size=28, duplicate-point objects, two NormalizeScale'd
+                    cells whose ball queries do not hit the 32-neighbour cap)
+  text_small.npz    CellRetrievalNetwork.encode_text on 8 six-sentence descriptions
+  eval_e2e.npz      training.coarse.eval_epoch(return_encodings=True) + evaluation.coarse.run_coarse
+                    on a 24-cell / 40-pose synthetic dataset
+  search_small.npz  the training/coarse.py:119-125 loop on random unit rows
+"""
+from __future__ import annotations
+
+import contextlib
+import hashlib
+import io
+import os
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader
+
+from text2loc_b200 import dataio, synth
+
+from . import fake_t5, reference_run, restate
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+WEIGHT_SEED = 0
+FAKE_T5_SEED = 0
+
+
+def digest(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def cells_case():
+    """Ragged cells; returns raw objects + per-cell point batches (FixedPoints applied once)."""
+    counts = [1, 3, 8, 2, 30, 16, 5, 4]
+    cells = synth.make_cell_objects(11, len(counts), counts, max_raw=700)
+    # degenerate objects: a single raw point (all 256 samples identical) and a padding-like blob
+    rng = np.random.default_rng(99)
+    cells[1][0] = synth.SynthObject(0, np.array([[0.3, 0.4, 0.05]]), np.array([[0.2, 0.5, 0.7]]))
+    cells[2][3] = synth.SynthObject(3, rng.random((8, 3)) * 0.001, np.zeros((8, 3)))
+    np.random.seed(2024)
+    fixed = dataio.FixedPoints(256)
+    both = dataio.Compose([dataio.FixedPoints(256), dataio.NormalizeScale()])
+    batches = [dataio.batch_object_points(objs, both if i >= 6 else fixed) for i, objs in enumerate(cells)]
+    return cells, batches
+
+
+def text_case():
+    rng = np.random.default_rng(5)
+    out = []
+    for _ in range(8):
+        out.append(" ".join(
+            f"The pose is {synth.DIRECTIONS[rng.integers(5)]} of a {synth.COLOR_WORDS[rng.integers(8)]} {synth.CLASS_WORDS[rng.integers(22)]}."
+            for _ in range(6)))
+    return out
+
+
+def e2e_dataset():
+    counts = [int(c) for c in np.random.default_rng(8).integers(1, 13, 24)]
+    counts[5] = 31
+    return synth.SynthCoarseDataset(seed=3, n_cells=24, n_poses=40, n_obj=counts, max_raw=400)
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    sd = synth.make_state_dict(WEIGHT_SEED)
+    model = reference_run.build_model(sd, fake_seed=FAKE_T5_SEED)
+    ref = reference_run.load()
+    args = reference_run.default_args()
+
+    # ---- cells
+    cells, batches = cells_case()
+    with torch.no_grad():
+        cell_emb = model.encode_objects(cells, batches).numpy()
+    pts, meta, cell_ptr = dataio.pack_cells(cells, batches)
+    out, aux = restate.encode_cells(sd, pts, meta, cell_ptr, return_aux=True)
+    print("cells: restatement vs reference max abs diff", np.abs(out.numpy() - cell_emb).max())
+    np.savez_compressed(
+        os.path.join(GOLDEN_DIR, "cells_small.npz"),
+        pts=pts.numpy(), meta=meta.numpy(), cell_ptr=cell_ptr.numpy(), cell_emb=cell_emb,
+        fps1=aux["fps1"].numpy().astype(np.int16), fps2=aux["fps2"].numpy().astype(np.int16),
+        fps3=aux["fps3"].numpy().astype(np.int16),
+        nbr_digest=np.array([digest(aux[f"nbr{i}"].numpy().astype(np.int16)) for i in (1, 2, 3)]),
+        nbr_count=np.array([(aux[f"nbr{i}"] >= 0).sum().item() for i in (1, 2, 3)]),
+        features2=aux["features2"].numpy(), object_emb=aux["object_emb"].numpy(),
+        weight_seed=WEIGHT_SEED,
+    )
+
+    # ---- text
+    texts = text_case()
+    with torch.no_grad():
+        text_emb = model.encode_text(texts).numpy()
+    feat, n_sent = fake_t5.FakeFrontend(FAKE_T5_SEED)(texts)
+    out = restate.encode_text(sd, feat, n_sent)
+    print("text: restatement vs reference max abs diff", np.abs(out.numpy() - text_emb).max())
+    np.savez_compressed(
+        os.path.join(GOLDEN_DIR, "text_small.npz"),
+        texts=np.array(texts), text_emb=text_emb, t5_shape=np.array(feat.shape), t5_digest=digest(feat.numpy()),
+        n_sent=n_sent, weight_seed=WEIGHT_SEED, fake_t5_seed=FAKE_T5_SEED,
+    )
+
+    # ---- end to end through eval_epoch / run_coarse
+    ds = e2e_dataset()
+    args.batch_size = 4
+    loader = DataLoader(ds, batch_size=args.batch_size, collate_fn=dataio.collate_fn, shuffle=False)
+    np.random.seed(123)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        acc, acc_close, retr, cell_enc, text_enc = ref["eval_epoch"](model, loader, args, return_encodings=True)
+    np.random.seed(123)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        retrievals, accuracies = ref["run_coarse"](model, loader, args)
+    assert all((retrievals[i] == retr[i]).all() for i in range(len(ds)))
+    np.savez_compressed(
+        os.path.join(GOLDEN_DIR, "eval_e2e.npz"),
+        retrievals=np.stack([retr[i] for i in range(len(ds))]),
+        acc=np.array([acc[k] for k in args.top_k]), acc_close=np.array([acc_close[k] for k in args.top_k]),
+        run_coarse_acc=np.array([[accuracies[k][t] for t in args.threshs] for k in args.top_k]),
+        cell_enc=cell_enc, text_enc=text_enc, top_k=np.array(args.top_k), threshs=np.array(args.threshs),
+        np_seed=123, batch_size=args.batch_size, weight_seed=WEIGHT_SEED, fake_t5_seed=FAKE_T5_SEED,
+    )
+    print("e2e: acc", acc, "close", acc_close)
+
+    # ---- search loop alone
+    D = synth.make_unit_rows(21, 3000)
+    Q = synth.make_unit_rows(22, 64)
+    idx_ref = restate.search_topk_reference_loop(D.astype(np.float64), Q.astype(np.float64), 10)
+    idx, sc = restate.search_topk(D, Q, 10)
+    assert (idx == idx_ref).all(), "stable-order oracle differs from the reference loop on tie-free data"
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "search_small.npz"), d_seed=21, q_seed=22, n=3000, nq=64, idx=idx_ref, score=sc)
+    for f in sorted(os.listdir(GOLDEN_DIR)):
+        print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,149 @@
+"""Pin the CPU oracle: restatement vs the golden vectors produced by the reference's own
+Python (oracle/make_golden.py), plus hand-checkable micro-cases for the pinned PyG choices."""
+import argparse
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+from torch.utils.data import DataLoader
+
+from oracle import fake_t5, pyg_ops, reference_run, restate
+from text2loc_b200 import dataio, synth
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def test_cells_golden(state_dict, golden):
+    g = golden("cells_small.npz")
+    out, aux = restate.encode_cells(state_dict, g["pts"], g["meta"], g["cell_ptr"], return_aux=True)
+    assert np.abs(out.numpy() - g["cell_emb"]).max() < 2e-6  # reference's own encode_objects
+    for i in (1, 2, 3):
+        assert (aux[f"fps{i}"].numpy() == g[f"fps{i}"]).all()
+        assert digest(aux[f"nbr{i}"].numpy().astype(np.int16)) == str(g["nbr_digest"][i - 1])
+    assert np.abs(aux["features2"].numpy() - g["features2"]).max() < 1e-5
+    # the two NormalizeScale'd cells must exercise the below-cap branch of the ball query
+    n_obj = int(g["cell_ptr"][-1])
+    assert int(g["nbr_count"][0]) < n_obj * 128 * 32
+
+
+def test_text_golden(state_dict, golden):
+    g = golden("text_small.npz")
+    feat, n_sent = fake_t5.FakeFrontend(int(g["fake_t5_seed"]))([str(t) for t in g["texts"]])
+    assert digest(feat.numpy()) == str(g["t5_digest"]) and n_sent == int(g["n_sent"])
+    out = restate.encode_text(state_dict, feat, n_sent)
+    assert np.abs(out.numpy() - g["text_emb"]).max() < 2e-6
+
+
+def test_search_golden(golden):
+    g = golden("search_small.npz")
+    D = synth.make_unit_rows(int(g["d_seed"]), int(g["n"]))
+    Q = synth.make_unit_rows(int(g["q_seed"]), int(g["nq"]))
+    idx, sc = restate.search_topk(D, Q, 10)
+    assert (idx == g["idx"]).all()
+    assert np.array_equal(sc, g["score"])
+
+
+def test_eval_epoch_golden(state_dict, golden):
+    from oracle.make_golden import e2e_dataset
+
+    g = golden("eval_e2e.npz")
+    args = argparse.Namespace(top_k=[int(k) for k in g["top_k"]], batch_size=int(g["batch_size"]), ranking_loss="pairwise")
+    ds = e2e_dataset()
+    loader = DataLoader(ds, batch_size=args.batch_size, collate_fn=dataio.collate_fn, shuffle=False)
+    np.random.seed(int(g["np_seed"]))
+    acc, acc_close, retr, cell_enc, text_enc = restate.eval_epoch(
+        state_dict, loader, args, fake_t5.FakeFrontend(int(g["fake_t5_seed"])), return_encodings=True)
+    assert np.abs(cell_enc - g["cell_enc"]).max() < 2e-6
+    assert np.abs(text_enc - g["text_enc"]).max() < 2e-6
+    got = np.stack([retr[i] for i in range(len(ds))])
+    # identical except where the reference's own k/k+1 score gap is below the 2e-6 encoding noise
+    same = (got == g["retrievals"]).all(axis=1)
+    assert same.mean() > 0.95
+    assert np.allclose([acc[k] for k in args.top_k], g["acc"], atol=0.03)
+
+
+# ---- micro-cases for the pinned third-party behaviour --------------------------------------
+
+def test_fps_three_points_and_ties():
+    pos = torch.tensor([[0.0, 0, 0], [1.0, 0, 0], [0.4, 0, 0], [1.0, 0, 0]])
+    # start 0; farthest is index 1 (tie with 3 -> lowest index); then 2 (0.16 vs 0.36 -> min 0.16) vs 3 (0)
+    assert pyg_ops.fps(pos, None, 0.75).tolist() == [0, 1, 2]
+    dense = restate.fps_dense(pos[None], 3)
+    assert dense[0].tolist() == [0, 1, 2]
+
+
+def test_fps_all_duplicates_returns_zero():
+    pos = torch.ones(8, 3) * 0.3
+    assert pyg_ops.fps(pos, None, 0.5).tolist() == [0, 0, 0, 0]
+
+
+def test_radius_cap_first_32_ascending_and_strict():
+    x = torch.zeros(40, 3)
+    x[:, 0] = torch.arange(40) * 1e-3
+    y = torch.zeros(1, 3)
+    e = pyg_ops.radius(x, y, 0.2)
+    assert e.shape[1] == 32 and e[1].tolist() == list(range(32))
+    # strict inequality: a point at distance exactly r (in fp32 arithmetic) is excluded
+    r = 0.5
+    x2 = torch.tensor([[0.5, 0, 0], [0.25, 0, 0]])
+    assert pyg_ops.radius(x2, y, r)[1].tolist() == [1]
+    nbr = restate.ball_query_dense(x[None], y[None], 0.2)
+    assert nbr[0, 0].tolist() == list(range(32))
+
+
+def test_pointconv_self_loop_quirk_two_objects():
+    """Centroid i always receives the dense point with the same per-cell global index i,
+    which for object 1 is a point of object 0."""
+    torch.manual_seed(0)
+    nn = torch.nn.Linear(3 + 3, 4)
+    conv = pyg_ops.PointConv(local_nn=nn)
+    pos = torch.rand(8, 3)  # two objects of 4 points
+    x = torch.rand(8, 3)
+    sub = torch.tensor([0, 2, 4, 6])  # centroids: 2 per object
+    # no radius edges at all: the output must be exactly the self-loop messages
+    out = conv(x, (pos, pos[sub]), torch.zeros(2, 0, dtype=torch.long))
+    want = nn(torch.cat([x[:4], pos[:4] - pos[sub]], dim=1))  # dense points 0..3, all of object 0
+    assert torch.allclose(out, want)
+
+
+def test_search_ties_resolve_by_index():
+    D = synth.make_unit_rows(1, 50)
+    D[7] = D[3]
+    D[20] = D[3]
+    Q = D[3:4].copy()
+    idx, sc = restate.search_topk(D, Q, 5)
+    assert idx[0, :3].tolist() == [3, 7, 20] and sc[0, 0] == sc[0, 1] == sc[0, 2]
+
+
+def test_search_k_larger_than_db():
+    D = synth.make_unit_rows(1, 4)
+    idx, _ = restate.search_topk(D, D[:2], 10)
+    assert idx.shape == (2, 4)
+
+
+def test_cell_with_more_than_28_objects_ignores_the_tail(state_dict):
+    """Objects beyond object_size are encoded then dropped (cell_retrieval.py:94-98)."""
+    cells = synth.make_cell_objects(5, 1, [30], max_raw=300)
+    pts, meta, ptr = synth.pack_cells(cells, 5)
+    f2 = restate.pointnet2_features2(state_dict, torch.from_numpy(pts), ptr)
+    emb = restate.object_embeddings(state_dict, f2, torch.from_numpy(meta))
+    full = restate.aggregate_cells(state_dict, emb, ptr)
+    cut = restate.aggregate_cells(state_dict, emb[:28], np.array([0, 28]))
+    assert torch.equal(full, cut)
+
+
+@pytest.mark.skipif(not reference_run.available(), reason="reference tree not present (GPU box)")
+def test_restatement_matches_reference_modules_other_seed():
+    sd = synth.make_state_dict(7)
+    model = reference_run.build_model(sd)
+    cells = synth.make_cell_objects(3, 3, [2, 5, 1], max_raw=300)
+    np.random.seed(1)
+    batches = [dataio.batch_object_points(o, dataio.FixedPoints(256)) for o in cells]
+    with torch.no_grad():
+        want = model.encode_objects(cells, batches)
+    pts, meta, ptr = dataio.pack_cells(cells, batches)
+    got = restate.encode_cells(sd, pts, meta, ptr)
+    assert (got - want).abs().max() < 2e-6

@@ -1,0 +1,119 @@
+"""Host-side containers and packing for the coarse path's inputs.
+
+Mirrors the part of the reference's data plumbing whose OUTPUT LAYOUT is the hot path's
+input contract:
+
+  dataloading/kitti360pose/utils.py:134-146   batch_object_points -> one point batch per cell
+  evaluation/coarse.py:95-98                  T.FixedPoints(256) [+ T.NormalizeScale()]
+  models/object_encoder.py:122-145            per-object mean rgb, centre, raw point count
+  dataloading/kitti360pose/base.py:83-87      dict-of-lists collate
+
+The reference uses PyG's Data/Batch; the engine only needs `.x` (rgb), `.pos` (xyz) and equal
+256-point objects, so any object exposing those (a real PyG Batch included) is accepted.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+NUM_POINTS = 256
+
+
+class PointsBatch:
+    """x = rgb [n*P, 3], pos = xyz [n*P, 3], batch = object id per point (PyG Batch surface)."""
+
+    def __init__(self, x: torch.Tensor, pos: torch.Tensor, batch: torch.Tensor = None, num_graphs: int = None):
+        self.x = x
+        self.pos = pos
+        self.batch = batch
+        self.num_graphs = num_graphs
+
+    @property
+    def num_nodes(self):
+        return self.pos.shape[0]
+
+    def to(self, device):
+        return self
+
+    @classmethod
+    def from_data_list(cls, data_list: Sequence["PointsBatch"]):
+        x = torch.cat([d.x for d in data_list])
+        pos = torch.cat([d.pos for d in data_list])
+        batch = torch.cat([torch.full((d.num_nodes,), i, dtype=torch.long) for i, d in enumerate(data_list)])
+        return cls(x, pos, batch, len(data_list))
+
+
+class FixedPoints:
+    """T.FixedPoints(num): `num` indices with replacement from the global numpy RNG."""
+
+    def __init__(self, num: int = NUM_POINTS):
+        self.num = num
+
+    def __call__(self, data: PointsBatch) -> PointsBatch:
+        choice = torch.from_numpy(np.random.choice(data.num_nodes, self.num, replace=True)).long()
+        return PointsBatch(data.x[choice], data.pos[choice])
+
+
+class NormalizeScale:
+    """T.NormalizeScale(): centre on the mean and scale into (-1, 1)."""
+
+    def __call__(self, data: PointsBatch) -> PointsBatch:
+        pos = data.pos - data.pos.mean(dim=-2, keepdim=True)
+        pos = pos * ((1 / pos.abs().max()) * 0.999999)
+        return PointsBatch(data.x, pos)
+
+
+class Compose:
+    def __init__(self, transforms):
+        self.transforms = transforms
+
+    def __call__(self, data):
+        for t in self.transforms:
+            data = t(data)
+        return data
+
+
+def batch_object_points(objects, transform) -> PointsBatch:
+    """One point batch for the objects of a single cell (utils.py:134-146, default branch)."""
+    data_list = [
+        transform(PointsBatch(torch.tensor(obj.rgb, dtype=torch.float), torch.tensor(obj.xyz, dtype=torch.float)))
+        for obj in objects
+    ]
+    assert len(data_list) >= 1
+    return PointsBatch.from_data_list(data_list)
+
+
+def collate_fn(data):
+    """Kitti360BaseDataset.collate_fn (base.py:83-87): dict of lists."""
+    return {key: [d[key] for d in data] for key in data[0].keys()}
+
+
+def pack_cells(objects: List[list], object_points: Sequence) -> tuple:
+    """Flatten (objects, object_points) of a batch of cells into the engine layout:
+
+      pts      f32 [n_total, 256, 6]   xyz ‖ rgb
+      meta     f32 [n_total, 7]        mean rgb ‖ centre ‖ raw count  (object_encoder.py:122-145;
+                                       float64 numpy means narrowed to f32 as torch.tensor(..., dtype=float) does)
+      cell_ptr i32 [B+1]
+    """
+    assert len(objects) == len(object_points)
+    pts, meta, ptr = [], [], [0]
+    for objs, pb in zip(objects, object_points):
+        n = len(objs)
+        pos, x = torch.as_tensor(pb.pos), torch.as_tensor(pb.x)
+        if pos.shape[0] != n * NUM_POINTS:
+            raise ValueError(
+                f"cell has {n} objects but {pos.shape[0]} points; the engine requires exactly "
+                f"{NUM_POINTS} points per object (pointnet_numpoints, evaluation/args.py:58)"
+            )
+        pts.append(torch.cat([pos.float(), x.float()], dim=1).reshape(n, NUM_POINTS, 6))
+        for obj in objs:
+            meta.append(np.concatenate([obj.get_color_rgb(), obj.get_center(), [len(obj.xyz)]]))
+        ptr.append(ptr[-1] + n)
+    return (
+        torch.cat(pts).contiguous(),
+        torch.from_numpy(np.asarray(meta, dtype=np.float64).astype(np.float32)),
+        torch.tensor(ptr, dtype=torch.int32),
+    )
