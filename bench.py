@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Headline benchmark: coarse-retrieval queries/sec over an N-cell database (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload)
+  N=1   BASELINE configs[1]: 10 000 cells x 4 096 queries, 8 objects/cell x 256 points, d=256, k=10
+  N>1   weak scaling towards configs[2]: 12 500 cells and 4 096 queries PER GPU (N=8: 100 000 x 32 768),
+        database row-sharded, one all-gather of per-shard top-k.
+
+A "step"  is the query path over one batch: text head on the T5 features ->
+(all-gather of query embeddings) -> tensor-core candidate search + fp64 re-rank over the local shard
+-> (all-gather + merge of per-shard top-k).  The database is encoded once before the timed region;
+that encode is timed on its own (db_encode_cells_per_s) and folded into cold_db_qps.
+`value` times the step with inputs resident in HBM; `e2e` times the same call chain through the
+public drop-in objects with HOST buffers: pinned-host T5 features copied H2D and the top-k copied
+D2H inside the timed region, every step.
+
+--impl reference times the reference's own CPU implementation of the same path (the oracle port
+of its Python: torch CPU text head + numpy float64 GEMV/argsort loop) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+K_TOP = 10
+N_SENT, N_TOK = 6, 12
+OBJ_PER_CELL = 8
+METRIC = "coarse-retrieval queries/sec over N-cell DB; top-k index match"
+
+
+def workload(n_gpus: int):
+    if n_gpus == 1:
+        return dict(cells_per_gpu=10000, queries_per_gpu=4096, name="configs[1]: 10k cells x 4k queries, 8 obj/cell x 256 pts, d=256, k=10, 1xB200")
+    return dict(cells_per_gpu=12500, queries_per_gpu=4096,
+                name=f"weak-scaled configs[2]: {12500 * n_gpus} cells x {4096 * n_gpus} queries, DB row-sharded over {n_gpus}xB200 "
+                     f"(12.5k cells + 4k queries per GPU), all-gather of per-shard top-k")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.stop, self.t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU side: the oracle port of the reference's own path, timed on the host cores
+# ---------------------------------------------------------------------------------------------
+
+def cpu_reference_sample(sd, n_db: int, n_queries_total: int, text_q: int, search_q: int, encode_cells: int, seed: int = 0):
+    """Bounded sample of the workload through the oracle (reference semantics):
+    text head on `text_q` queries, the float64 GEMV + argsort loop for `search_q` queries over an
+    n_db-row database, PointNet++/attention encode of `encode_cells` cells.  Returns per-unit times."""
+    import torch
+
+    from oracle import restate
+    from text2loc_b200 import synth
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    t5 = synth.make_t5_features(seed + 100, text_q, N_SENT, N_TOK)
+    t0 = time.perf_counter()
+    q_emb = restate.encode_text(sd, t5, N_SENT).numpy()
+    t_text = (time.perf_counter() - t0) / text_q
+    D64 = synth.make_unit_rows(seed + 101, n_db).astype(np.float64)  # cell_encodings is a float64 buffer (training/coarse.py:81)
+    Q64 = np.resize(q_emb, (search_q, 256)).astype(np.float64)
+    t0 = time.perf_counter()
+    restate.search_topk_reference_loop(D64, Q64, K_TOP)
+    t_search = (time.perf_counter() - t0) / search_q
+    t_cell = None
+    if encode_cells:
+        pts, meta, ptr = synth.make_packed_cells(seed + 102, encode_cells, OBJ_PER_CELL)
+        t0 = time.perf_counter()
+        restate.encode_cells(sd, pts, meta, ptr)
+        t_cell = (time.perf_counter() - t0) / encode_cells
+    return dict(t_text=t_text, t_search=t_search, t_cell=t_cell, threads=threads)
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU path (oracle port) on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from text2loc_b200 import synth
+
+    wl = workload(args.gpus)
+    n_db, nq = wl["cells_per_gpu"] * args.gpus, wl["queries_per_gpu"] * args.gpus
+    sd = synth.make_state_dict(0)
+    text_q, search_q = 48, 96
+    times = []
+    for step in range(args.warmup + args.steps):
+        r = cpu_reference_sample(sd, n_db, nq, text_q, search_q, 0, seed=step)
+        if step >= args.warmup:
+            times.append(r)
+    t_text = float(np.mean([r["t_text"] for r in times]))
+    t_search = float(np.mean([r["t_search"] for r in times]))
+    per_query = t_text + t_search
+    value = 1.0 / per_query
+    cores = times[0]["threads"]
+    sample = (f"per step: text head on {text_q} queries (6 sentences x 12 tokens of T5 features) + float64 GEMV/argsort loop for "
+              f"{search_q} queries over the full {n_db}-row database; queries/s = 1 / (t_text + t_search) per query, DB pre-encoded "
+              f"as on the engine arm")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * per_query * nq, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 encoders / f64 scoring", "data": "synthetic",
+        "config": {"workload": wl["name"], "n_cells": n_db, "n_queries": nq, "k": K_TOP, "timed_region": "text head + search, DB pre-encoded"},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample,
+                         "ms_text_head_per_query": 1e3 * t_text, "ms_search_per_query": 1e3 * t_search},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# engine arm
+# ---------------------------------------------------------------------------------------------
+
+def run_engine_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from text2loc_b200 import CellRetrievalNetwork, synth
+    from text2loc_b200 import distributed as t2ld
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run --nproc-per-node N")
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wl = workload(world)
+    n_cells_local, nq_local = wl["cells_per_gpu"], wl["queries_per_gpu"]
+    n_db, nq = n_cells_local * world, nq_local * world
+    row_lo = rank * n_cells_local
+
+    sd = synth.make_state_dict(0)
+    ns = argparse.Namespace(coarse_embed_dim=256, pointnet_layers=3, pointnet_variation=0, pointnet_numpoints=256, pointnet_features=2,
+                            object_size=28, object_inter_module_num_heads=4, object_inter_module_num_layers=2, inter_module_num_heads=4,
+                            inter_module_num_layers=1, intra_module_num_heads=4, intra_module_num_layers=1, class_embed=False,
+                            color_embed=False, use_features=["class", "color", "position", "num"], hungging_model="t5-large")
+    def no_frontend(descriptions):
+        raise RuntimeError("bench.py feeds T5 features directly (encode_text_features)")
+
+    model = CellRetrievalNetwork([], [], ns, text_frontend=no_frontend, device=dev)
+    model.load_state_dict({k: torch.as_tensor(np.asarray(v)) for k, v in sd.items()}, strict=False)
+    eng = model.engine
+
+    # ---- inputs (synthetic, seeded per rank), host-pinned + device-resident copies
+    pts_h, meta_h, ptr = synth.make_packed_cells(1000 + rank, n_cells_local, OBJ_PER_CELL)
+    t5_h = torch.from_numpy(synth.make_t5_features(2000 + rank, nq_local, N_SENT, N_TOK)).pin_memory()
+    pts_hp, meta_hp = torch.from_numpy(pts_h).pin_memory(), torch.from_numpy(meta_h).pin_memory()
+    t5_d = t5_h.to(dev, non_blocking=True)
+    pts_d, meta_d = pts_hp.to(dev, non_blocking=True), meta_hp.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    # ---- database encode (before the timed region; timed on its own, twice: cold then warm)
+    enc_ms = []
+    for _ in range(2):
+        barrier()
+        a, b = ev(), ev()
+        a.record()
+        D_local = model.encode_cells_packed(pts_d, meta_d, ptr)
+        b.record()
+        torch.cuda.synchronize()
+        enc_ms.append(a.elapsed_time(b))
+    enc_ms_max = max_over_ranks(enc_ms[-1])
+    eng.db_build(D_local, row_offset=row_lo)
+
+    # ---- the step
+    def step_resident():
+        q_local = model.encode_text_features(t5_d, N_SENT)
+        return t2ld.sharded_search(eng, q_local, K_TOP, queries_are_sharded=world > 1)
+
+    def step_e2e():
+        t5 = t5_h.to(dev, non_blocking=True)
+        q_local = model.encode_text_features(t5, N_SENT)
+        idx, score, nfb = t2ld.sharded_search(eng, q_local, K_TOP, queries_are_sharded=world > 1)
+        return idx.to("cpu", non_blocking=True), score.to("cpu", non_blocking=True), nfb
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        l0 = eng.launch_count
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(steps):
+            out = fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)) / steps, (eng.launch_count - l0) // steps, out
+
+    with ClockSampler(local_rank) as clocks:
+        ms_step, launches, out = timed(step_resident, args.steps, args.warmup)
+    ms_e2e, _, out_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    idx, score, nfb = out
+
+    # stage split (resident), one extra pass with events between the stages
+    barrier()
+    e0, e1, e2 = ev(), ev(), ev()
+    e0.record()
+    q_local = model.encode_text_features(t5_d, N_SENT)
+    e1.record()
+    t2ld.sharded_search(eng, q_local, K_TOP, queries_are_sharded=world > 1)
+    e2.record()
+    torch.cuda.synchronize()
+    ms_text, ms_search = e0.elapsed_time(e1), e1.elapsed_time(e2)
+
+    # ---- parity spot check inside the bench: engine top-k == fp64 oracle on the engine's own embeddings
+    parity = None
+    if rank == 0:
+        from oracle import restate
+
+        q_all = t2ld.all_gather_rows(q_local).reshape(-1, 256) if world == 1 else None
+        if q_all is not None:
+            nchk = 64
+            oidx, _ = restate.search_topk(D_local.cpu().numpy(), q_all[:nchk].cpu().numpy(), K_TOP)
+            parity = bool((idx[:nchk].cpu().numpy() == oidx + row_lo).all())
+
+    # ---- roofline of the dominant kernel: the text head's tf32 tcgen05 GEMM (FFN up-projection
+    # shape: M = tokens of one chunk, N = 4096, K = 1024), timed alone with CUDA events
+    pk = peaks()
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        M, N, K = 32768 // (N_SENT * N_TOK) * (N_SENT * N_TOK), 4096, 1024
+        A = torch.randn(M, K, device=dev)
+        Wt = torch.randn(N, K, device=dev) / 32
+        bias = torch.zeros(N, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            eng.debug_linear(A, Wt, bias, act=1, path=1)
+        durs = []
+        for _ in range(10):
+            flush.zero_()  # L2 flush between timed launches
+            a, b = ev(), ev()
+            a.record()
+            eng.debug_linear(A, Wt, bias, act=1, path=1)
+            b.record()
+            torch.cuda.synchronize()
+            durs.append(a.elapsed_time(b))
+        dur = float(np.mean(durs))
+        achieved = 2.0 * M * N * K / (dur * 1e-3) / 1e12
+        # cuBLAS tf32 on the same shape, same timing: the tf32 counterpart of MEASURED_PEAKS' bf16 figure
+        torch.backends.cuda.matmul.allow_tf32 = True
+        for _ in range(3):
+            torch.matmul(A, Wt.T)
+        cb = []
+        for _ in range(10):
+            flush.zero_()
+            a, b = ev(), ev()
+            a.record()
+            torch.matmul(A, Wt.T)
+            b.record()
+            torch.cuda.synchronize()
+            cb.append(a.elapsed_time(b))
+        cublas_tf32 = 2.0 * M * N * K / (float(np.mean(cb)) * 1e-3) / 1e12
+        peak_tf32 = pk["bf16"] / 2.0  # tf32 issues at half the bf16 rate on the same tensor pipe
+        roof = {"bound": "tensor", "kernel": "umma_gemm_kernel<GemmCfg<256,tf32>,StoreEpi> (text-head FFN1 shape %dx%dx%d)" % (M, N, K),
+                "achieved": achieved, "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32, "traffic": None,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({pk['source']}) / 2 for kind::tf32", "ms_per_launch": dur,
+                "cublas_tf32_same_shape_tflops": cublas_tf32, "frac_of_cublas_tf32": achieved / cublas_tf32,
+                "step_share_text_head": ms_text / (ms_text + ms_search)}
+        del A, Wt, flush
+
+        # ---- CPU baseline beside it (oracle port on the host cores; N=1 only)
+        if world == 1:
+            r = cpu_reference_sample(sd, n_db, nq, text_q=256, search_q=512, encode_cells=24)
+            per_q = r["t_text"] + r["t_search"]
+            cpu_base = {"value": 1.0 / per_q, "unit": "queries/s", "cores": r["threads"], "kind": "port",
+                        "sample": f"oracle port of the reference path: text head on 256 queries, float64 GEMV+argsort loop for 512 queries over "
+                                  f"{n_db} rows, encode of 24 cells; warm-DB queries/s = 1/(t_text+t_search)",
+                        "ms_text_head_per_query": 1e3 * r["t_text"], "ms_search_per_query": 1e3 * r["t_search"],
+                        "ms_encode_per_cell": 1e3 * r["t_cell"],
+                        "cold_db_queries_per_s": nq / (nq * per_q + n_db * r["t_cell"])}
+
+    if rank == 0:
+        h2d = t5_h.numel() * 4 * world
+        d2h = nq * K_TOP * (8 + 8)
+        value = nq / (ms_step * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 tensor-core encoders (fp32 tails) / bf16x3 split candidates + f64 re-rank", "data": "synthetic",
+            "config": {"workload": wl["name"], "n_cells": n_db, "n_queries": nq, "k": K_TOP, "objects_per_cell": OBJ_PER_CELL,
+                       "sentences_x_tokens": [N_SENT, N_TOK], "timed_region": "text head + search (+ all-gathers, merge), DB pre-encoded",
+                       "l2": "inputs larger than L2 (1.2 GB of T5 features per GPU per step)", "parallelism": f"db-rowshard{world}"},
+            "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "cpu_baseline": cpu_base,
+            "ms_text_head": ms_text, "ms_search": ms_search, "search_fallbacks": int(nfb),
+            "db_encode_cells_per_s": n_db / (enc_ms_max * 1e-3), "db_encode_ms": enc_ms_max, "db_encode_ms_first": enc_ms[0],
+            "cold_db_qps": nq / ((ms_step + enc_ms_max) * 1e-3), "topk_matches_fp64_oracle_sample": parity,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_engine_arm(args)
+
+
+if __name__ == "__main__":
+    main()

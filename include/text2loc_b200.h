@@ -1,0 +1,111 @@
+/* text2loc_b200 -- C ABI of the B200-native coarse cell-retrieval engine.
+ *
+ * Drop-in boundary for Text2Loc's global place-recognition path.  The reference has no FFI;
+ * its seam is two Python methods and two functions.  Each entry point
+ * below names the reference code it replaces; the Python mirror in text2loc_b200/ binds these
+ * with ctypes (INTEGRATION.md shows the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; t2l_last_error() gives the text.
+ *     Nothing throws across the ABI.
+ *   - data buffers are CALLER-OWNED DEVICE memory unless a parameter says "host"; the engine
+ *     owns weights, the prepared database planes and its workspace.
+ *   - all work is enqueued on the caller's cudaStream_t (passed as void*); no hidden device
+ *     synchronisation except where documented (t2l_finalize_weights, t2l_create).
+ *   - an engine is bound to one device and is not thread-safe; distinct engines are independent.
+ *   - sm_100a only.  There is no CPU or other fallback: on a non-Blackwell device t2l_create fails.
+ */
+#ifndef TEXT2LOC_B200_H
+#define TEXT2LOC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct t2l_engine t2l_engine;
+
+#define T2L_EMBED_DIM 256    /* coarse_embed_dim, evaluation/args.py:55 */
+#define T2L_T5_DIM 1024      /* t5-large d_model, README.md:127 */
+#define T2L_NUM_POINTS 256   /* pointnet_numpoints, evaluation/args.py:58 */
+#define T2L_OBJECT_SLOTS 28  /* object_size, evaluation/args.py:68 */
+#define T2L_MAX_TOPK 12      /* fast path; the reference uses max(top_k) = 10, evaluation/args.py:20 */
+
+/* Engine for CUDA device `device`.  Replaces CellRetrievalNetwork.__init__ + .to(device)
+ * (models/cell_retrieval.py:14-54, evaluation/coarse.py:118-124). */
+int t2l_create(int device, t2l_engine** out);
+void t2l_destroy(t2l_engine* e);
+const char* t2l_last_error(const t2l_engine* e); /* e may be NULL: error of the last failed t2l_create */
+int t2l_version(void);
+
+/* Weights.  Replaces load_state_dict(strict=False) (evaluation/coarse.py:123).  `name` is one of
+ * the folded-layer names listed in text2loc_b200/weights.py (BatchNorm already folded into the
+ * preceding Linear on the host, eval-mode affine: models/language_encoder.py:28-31); `data` is a
+ * HOST fp32 row-major [rows, cols] array.  t2l_finalize_weights uploads derived copies (tf32-
+ * rounded operands) and synchronises the device once. */
+int t2l_set_weight(t2l_engine* e, const char* name, const float* data_host, int rows, int cols);
+int t2l_finalize_weights(t2l_engine* e);
+
+/* CellRetrievalNetwork.encode_objects (models/cell_retrieval.py:65-110) = PointNet2 features2
+ * (models/pointcloud/pointnet2.py:80-90) -> ObjectEncoder.forward (models/object_encoder.py:92-149)
+ * -> intra-cell attention, max over slots, L2 normalise.
+ *   pts          device f32 [n_objects, 256, 6]   xyz | rgb of each object's 256-sample
+ *   meta         device f32 [n_objects, 7]        mean rgb | centre | raw point count
+ *   cell_ptr     HOST   i32 [n_cells + 1]         object range of each cell
+ *   out          device f32 [n_cells, 256]        unit rows */
+int t2l_encode_cells(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr_host,
+                     int n_cells, float* out, void* stream);
+
+/* Intermediate of the same call, for parity tests: PointNet2.forward(...).features2 and the FPS /
+ * ball-query index sets (any pointer may be NULL).
+ *   features2 device f32 [n_objects, 256];  fps1/2/3 device u8 [n_objects, 128|64|32] local indices
+ *   nbr1/2/3  device u8 [n_objects, 128|64|32, 32] (slots >= cnt undefined);  cnt1/2/3 device u8 */
+int t2l_encode_objects_debug(t2l_engine* e, const float* pts, const int32_t* cell_ptr_host, int n_cells,
+                             float* features2, uint8_t* fps1, uint8_t* fps2, uint8_t* fps3,
+                             uint8_t* nbr1, uint8_t* nbr2, uint8_t* nbr3,
+                             uint8_t* cnt1, uint8_t* cnt2, uint8_t* cnt3, void* stream);
+
+/* CellRetrievalNetwork.encode_text after the frozen T5 (models/language_encoder.py:125-148,
+ * models/cell_retrieval.py:57-63).
+ *   t5   device f32 [n_queries * n_sent, n_tok, 1024]  T5 last_hidden_state (pads included, unmasked)
+ *   out  device f32 [n_queries, 256]                   unit rows */
+int t2l_encode_text(t2l_engine* e, const float* t5, int n_queries, int n_sent, int n_tok, float* out, void* stream);
+
+/* Database side of eval_epoch's search loop (training/coarse.py:81-84,105-113): registers this
+ * rank's shard of cell embeddings.  D device f32 [n_rows, 256]; the engine keeps a reference to D
+ * (it must stay alive and unchanged) and builds its bf16 hi/lo operand planes.  row_offset is
+ * added to returned indices (global row id of local row 0). */
+int t2l_db_build(t2l_engine* e, const float* D, int64_t n_rows, int64_t row_offset, void* stream);
+
+/* eval_epoch's per-query `scores = D @ q; argsort(-scores)[:k]` (training/coarse.py:119-125) for a
+ * whole query batch: tensor-core candidate pass, exact fp64 re-rank, margin proof, exact rescan
+ * of the queries whose proof fails.  Order: score descending, row index ascending on ties.
+ *   Q device f32 [nq, 256];  out_idx device i64 [nq, k];  out_score device f64 [nq, k]
+ *   out_n_fallback device i32 [1] (may be NULL): queries that needed the exact rescan
+ * If the shard has fewer than k rows the tail is filled with idx -1 / score -inf. */
+int t2l_search_topk(t2l_engine* e, const float* Q, int nq, int k, int64_t* out_idx, double* out_score,
+                    int32_t* out_n_fallback, void* stream);
+
+/* Exact fp64 scan only (no tensor-core pass); same contract.  Used for k > T2L_MAX_TOPK. */
+int t2l_search_topk_exact(t2l_engine* e, const float* Q, int nq, int k, int64_t* out_idx, double* out_score, void* stream);
+
+/* Merge of per-shard top-k lists after the all-gather:
+ *   idx_all device i64 [n_shards, nq, k], score_all device f64 [n_shards, nq, k] -> global top-k,
+ *   same (score desc, index asc) order, independent of the number of shards. */
+int t2l_merge_topk(t2l_engine* e, const int64_t* idx_all, const double* score_all, int n_shards, int nq, int k,
+                   int64_t* out_idx, double* out_score, void* stream);
+
+/* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
+int64_t t2l_launch_count(const t2l_engine* e);
+
+/* Test hook: C[M,N] = act(A[M,K] * W[N,K]^T + bias) through the tcgen05 tf32 GEMM (path=1) or the
+ * fp32 SIMT GEMM (path=0).  act: 0 none, 1 relu.  segmax != 0: rows are max-reduced in groups of 32
+ * after relu (C is [M/32, N]).  All pointers device. */
+int t2l_debug_linear(t2l_engine* e, int path, const float* A, int lda, const float* W, int ldw, const float* bias,
+                     float* C, int ldc, int M, int N, int K, int act, int segmax, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEXT2LOC_B200_H */

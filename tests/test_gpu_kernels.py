@@ -1,0 +1,108 @@
+"""GPU parity of the individual kernels through the C ABI: the tcgen05 tf32 GEMM and its fused
+epilogues, the fp32 SIMT GEMM, FPS / ball query index sets (bit-exact vs the oracle)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from text2loc_b200.engine import Engine
+
+    return Engine("cuda:0")
+
+
+def tf32_trunc(x):
+    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def tf32_rna(x):
+    return ((x.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (300, 256, 64), (1000, 512, 259), (4096, 1024, 1024), (96, 64, 32), (4224, 64, 32),
+                                   (2000, 3072, 1024), (777, 1024, 4096)])
+def test_umma_gemm_matches_tf32_emulation(eng, M, N, K):
+    """kind::tf32 reads fp32 operands and ignores the low 13 mantissa bits: the result must equal
+    an fp64 product of truncated operands up to fp32 accumulation error."""
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    ld = (K + 3) // 4 * 4
+    A = torch.zeros(M, ld, device="cuda")
+    W = torch.zeros(N, ld, device="cuda")
+    A[:, :K] = torch.randn(M, K, device="cuda", generator=g)
+    W[:, :K] = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    C = eng.debug_linear(A[:, :K], W[:, :K], b, act=0, path=1)
+    want_trunc = tf32_trunc(A).double() @ tf32_trunc(W).double().T + b.double()
+    want_rna = tf32_rna(A).double() @ tf32_rna(W).double().T + b.double()
+    e_trunc = (C.double() - want_trunc).abs().max().item()
+    e_rna = (C.double() - want_rna).abs().max().item()
+    exact = A.double() @ W.double().T + b.double()
+    print(f"\n[{M}x{N}x{K}] |C-trunc|={e_trunc:.3e} |C-rna|={e_rna:.3e} |C-fp64|={(C.double() - exact).abs().max().item():.3e}")
+    assert min(e_trunc, e_rna) < 2e-5 * max(1.0, K / 256) ** 0.5
+    # pre-rounded operands (what the engine feeds): result independent of the hardware's rounding of raw fp32
+    Cr = eng.debug_linear(tf32_rna(A)[:, :K], tf32_rna(W)[:, :K], b, act=1, path=1)
+    assert (Cr.double() - want_rna.clamp(min=0)).abs().max().item() < 2e-5 * max(1.0, K / 256) ** 0.5
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (4224 * 4, 64, 32), (2112 * 3, 128, 128), (1056, 256, 256), (64, 1024, 512)])
+def test_umma_segmax_epilogue(eng, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = tf32_rna(torch.randn(M, K, device="cuda", generator=g))
+    W = tf32_rna(torch.randn(N, K, device="cuda", generator=g) / K ** 0.5)
+    b = torch.randn(N, device="cuda", generator=g)
+    got = eng.debug_linear(A, W, b, act=1, segmax=True, path=1)
+    want = (A.double() @ W.double().T + b.double()).clamp(min=0).view(M // 32, 32, N).max(dim=1)[0]
+    assert got.shape == (M // 32, N)
+    assert (got.double() - want).abs().max().item() < 2e-5
+    simt = eng.debug_linear(A, W, b, act=1, segmax=True, path=0)
+    assert (simt.double() - want).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(77, 50, 3), (1000, 32, 3), (5, 64, 1), (513, 256, 64), (28 * 9, 768, 256), (300, 256, 1024)])
+def test_simt_gemm_fp32(eng, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g)
+    b = torch.randn(N, device="cuda", generator=g)
+    got = eng.debug_linear(A, W, b, act=1, path=0)
+    want = (A.double() @ W.double().T + b.double()).clamp(min=0)
+    assert (got.double() - want).abs().max().item() < 1e-5 * K ** 0.5 * 4
+
+
+def test_fps_and_ball_query_bit_exact(eng, state_dict, golden):
+    """Index sets are discrete: they must equal the oracle's exactly (golden fps*, digest of nbr*)."""
+    from oracle import restate
+
+    g = golden("cells_small.npz")
+    pts = torch.from_numpy(g["pts"])
+    d = eng.encode_objects_debug(pts, g["cell_ptr"]) if eng.has_weights else None
+    if d is None:
+        eng.load_state_dict(state_dict)
+        d = eng.encode_objects_debug(pts, g["cell_ptr"])
+    torch.cuda.synchronize()
+    for i in (1, 2, 3):
+        assert (d[f"fps{i}"].cpu().numpy().astype(np.int16) == g[f"fps{i}"]).all(), f"fps level {i}"
+    _, aux = restate.pointnet2_features2(state_dict, pts, g["cell_ptr"], return_aux=True)
+    for i in (1, 2, 3):
+        want = aux[f"nbr{i}"].numpy()
+        cnt = (want >= 0).sum(axis=2)
+        assert (d[f"cnt{i}"].cpu().numpy() == cnt).all(), f"neighbour counts level {i}"
+        got = d[f"nbr{i}"].cpu().numpy().astype(np.int64)
+        mask = want >= 0
+        assert (got[mask] == want[mask]).all(), f"neighbour lists level {i}"
+    assert int((aux["nbr1"] >= 0).sum()) == int(g["nbr_count"][0])
+
+
+def test_features2_within_tolerance(eng, state_dict, golden):
+    g = golden("cells_small.npz")
+    if not eng.has_weights:
+        eng.load_state_dict(state_dict)
+    d = eng.encode_objects_debug(torch.from_numpy(g["pts"]), g["cell_ptr"])
+    got = d["features2"].cpu().numpy()
+    want = g["features2"]
+    rel = np.abs(got - want).max() / np.abs(want).max()
+    print(f"\nfeatures2 max rel-to-max error {rel:.3e}")
+    assert rel < 1e-3

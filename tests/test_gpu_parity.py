@@ -1,0 +1,237 @@
+"""GPU parity of the path through the C ABI and the drop-in API against the golden vectors
+(outputs of the reference's own Python) and the oracle.
+
+Tolerances (north_star): top-k indices bit-exact; embeddings and similarities within 1e-3
+relative.  For unit-norm embeddings "relative" is taken as ||got - want||_2 / ||want||_2 per row.
+"""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+from torch.utils.data import DataLoader
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+EMB_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def eng(state_dict):
+    from text2loc_b200.engine import Engine
+
+    e = Engine("cuda:0")
+    e.load_state_dict(state_dict)
+    return e
+
+
+def row_rel_err(got, want):
+    return float((np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)).max())
+
+
+# ---- encoders ----------------------------------------------------------------------------------
+
+def test_encode_cells_golden(eng, golden):
+    g = golden("cells_small.npz")
+    out = eng.encode_cells(g["pts"], g["meta"], g["cell_ptr"]).cpu().numpy()
+    err = row_rel_err(out, g["cell_emb"])
+    print(f"\ncell embedding max row-relative error vs reference: {err:.3e}")
+    assert out.shape == g["cell_emb"].shape
+    assert np.allclose(np.linalg.norm(out, axis=1), 1.0, atol=1e-5)
+    assert err < EMB_TOL
+
+
+def test_encode_cells_independent_of_batching(eng, golden):
+    """Cells are independent units: encoding them one at a time or all at once is the same."""
+    g = golden("cells_small.npz")
+    cp = g["cell_ptr"]
+    full = eng.encode_cells(g["pts"], g["meta"], cp).cpu().numpy()
+    for c in (0, 4, 7):
+        o0, o1 = cp[c], cp[c + 1]
+        one = eng.encode_cells(g["pts"][o0:o1], g["meta"][o0:o1], np.array([0, o1 - o0], np.int32)).cpu().numpy()
+        assert np.abs(one[0] - full[c]).max() < 1e-6
+
+
+def test_encode_cells_rejects_bad_input(eng):
+    from text2loc_b200.engine import EngineError
+
+    with pytest.raises(EngineError):
+        eng.encode_cells(np.zeros((2, 256, 6), np.float32), np.zeros((2, 7), np.float32), np.array([0, 0, 2], np.int32))  # empty cell
+    with pytest.raises(EngineError):
+        eng.encode_cells(np.zeros((2, 100, 6), np.float32), np.zeros((2, 7), np.float32), np.array([0, 2], np.int32))  # not 256 points
+
+
+def test_encode_text_golden(eng, golden):
+    from oracle import fake_t5
+
+    g = golden("text_small.npz")
+    feat, n_sent = fake_t5.FakeFrontend(int(g["fake_t5_seed"]))([str(t) for t in g["texts"]])
+    out = eng.encode_text(feat, n_sent).cpu().numpy()
+    err = row_rel_err(out, g["text_emb"])
+    print(f"\ntext embedding max row-relative error vs reference: {err:.3e}")
+    assert err < EMB_TOL
+
+
+def test_encode_text_shapes(eng, state_dict):
+    """Different token counts / sentence counts, chunk boundary in the middle of the batch."""
+    from oracle import restate
+    from text2loc_b200 import synth
+
+    for nq, S, L in ((3, 6, 9), (5, 4, 17), (2, 1, 1), (40, 6, 12)):
+        t5 = synth.make_t5_features(nq + S + L, nq, S, L)
+        got = eng.encode_text(t5, S).cpu().numpy()
+        want = restate.encode_text(state_dict, t5, S).numpy()
+        assert row_rel_err(got, want) < EMB_TOL, (nq, S, L)
+
+
+# ---- search ----------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n,nq,k", [(3000, 64, 10), (20000, 1000, 10), (257, 130, 5), (100000, 512, 10), (1000, 1, 1), (5000, 300, 12)])
+def test_search_matches_fp64_oracle(eng, n, nq, k):
+    from oracle import restate
+    from text2loc_b200 import synth
+
+    D = synth.make_unit_rows(n, n)
+    Q = synth.make_unit_rows(nq + 1, nq)
+    eng.db_build(D)
+    idx, sc, nfb = eng.search_topk(Q, k)
+    oidx, osc = restate.search_topk(D, Q, k)
+    assert (idx.cpu().numpy() == oidx).all()
+    assert np.abs(sc.cpu().numpy() - osc).max() < 1e-12  # fp64 dots, different summation order only
+    print(f"\nN={n} nq={nq} k={k}: exact-rescan fallbacks {int(nfb)} / {nq}")
+    assert int(nfb) <= max(1, nq // 20)
+    eidx, esc, _ = eng.search_topk(Q, k, exact=True)
+    assert (eidx.cpu().numpy() == oidx).all()
+
+
+def test_search_golden_reference_loop(eng, golden):
+    from text2loc_b200 import synth
+
+    g = golden("search_small.npz")
+    eng.db_build(synth.make_unit_rows(int(g["d_seed"]), int(g["n"])))
+    idx, sc, _ = eng.search_topk(synth.make_unit_rows(int(g["q_seed"]), int(g["nq"])), 10)
+    assert (idx.cpu().numpy() == g["idx"]).all()  # the reference's own np.argsort loop
+    assert np.abs(sc.cpu().numpy() - g["score"]).max() < 1e-12
+
+
+def test_search_ties_duplicates_and_clusters(eng):
+    """Duplicate rows tie exactly -> index order; a tight cluster forces the margin proof to fail
+    and the exact rescan to take over.  Either way the result is the oracle's."""
+    from oracle import restate
+    from text2loc_b200 import synth
+
+    D = synth.make_unit_rows(5, 4000)
+    D[100] = D[7]
+    D[3999] = D[7]
+    D[2000:2040] = D[1999] + 1e-6 * np.random.default_rng(0).standard_normal((40, 256)).astype(np.float32)  # 41 near-identical rows
+    Q = np.concatenate([D[7:8], D[1999:2000], synth.make_unit_rows(6, 30)])
+    eng.db_build(D)
+    idx, sc, nfb = eng.search_topk(Q, 10)
+    oidx, osc = restate.search_topk(D, Q, 10)
+    assert (idx.cpu().numpy() == oidx).all()
+    assert idx[0, :3].tolist() == [7, 100, 3999]
+    assert int(nfb) >= 1  # the cluster query cannot be proven from 16 candidates per split
+
+
+def test_search_small_db_and_row_offset(eng):
+    from oracle import restate
+    from text2loc_b200 import synth
+
+    D = synth.make_unit_rows(9, 6)
+    Q = synth.make_unit_rows(10, 3)
+    eng.db_build(D, row_offset=1000)
+    idx, sc, _ = eng.search_topk(Q, 10)
+    oidx, osc = restate.search_topk(D, Q, 10)
+    got = idx.cpu().numpy()
+    assert (got[:, :6] == oidx + 1000).all() and (got[:, 6:] == -1).all()
+    assert np.isneginf(sc.cpu().numpy()[:, 6:]).all()
+
+
+def test_merge_topk_is_shard_count_independent(eng):
+    """Row-shard the DB 1/2/4/8 ways on one GPU, merge the per-shard lists: identical result."""
+    from oracle import restate
+    from text2loc_b200 import synth
+
+    D = synth.make_unit_rows(11, 10000)
+    D[9000] = D[10]  # a tie across shards
+    Q = np.concatenate([D[10:11], synth.make_unit_rows(12, 99)])
+    oidx, osc = restate.search_topk(D, Q, 10)
+    for G in (1, 2, 4, 8):
+        bounds = np.linspace(0, len(D), G + 1).astype(int)
+        idxs, scs = [], []
+        for gi in range(G):
+            eng.db_build(D[bounds[gi]:bounds[gi + 1]], row_offset=int(bounds[gi]))
+            i, s, _ = eng.search_topk(Q, 10)
+            idxs.append(i)
+            scs.append(s)
+        idx, sc = eng.merge_topk(torch.stack(idxs), torch.stack(scs))
+        assert (idx.cpu().numpy() == oidx).all(), G
+        assert np.abs(sc.cpu().numpy() - osc).max() < 1e-12
+
+
+# ---- drop-in API ---------------------------------------------------------------------------------------
+
+def make_model(state_dict, fake_seed=0):
+    from oracle import fake_t5, reference_run
+    from text2loc_b200 import CellRetrievalNetwork
+
+    args = reference_run.default_args()
+    model = CellRetrievalNetwork(["c"] * 22, ["k"] * 8, args, text_frontend=fake_t5.FakeFrontend(fake_seed))
+    model.load_state_dict({k: torch.as_tensor(np.asarray(v)) for k, v in state_dict.items()}, strict=False)
+    return model.eval(), args
+
+
+def test_dropin_eval_epoch_and_run_coarse_golden(state_dict, golden):
+    """The reference's own eval_epoch / run_coarse outputs on the same seeded dataset."""
+    from oracle.make_golden import e2e_dataset
+    from text2loc_b200 import dataio, eval_epoch, run_coarse
+
+    g = golden("eval_e2e.npz")
+    model, args = make_model(state_dict, int(g["fake_t5_seed"]))
+    args.batch_size = int(g["batch_size"])
+    ds = e2e_dataset()
+    loader = DataLoader(ds, batch_size=args.batch_size, collate_fn=dataio.collate_fn, shuffle=False)
+    np.random.seed(int(g["np_seed"]))
+    acc, acc_close, retr, cell_enc, text_enc = eval_epoch(model, loader, args, return_encodings=True)
+    assert cell_enc.dtype == np.float64 and text_enc.dtype == np.float64
+    ec, et = row_rel_err(cell_enc, g["cell_enc"]), row_rel_err(text_enc, g["text_enc"])
+    print(f"\ne2e embeddings vs reference: cells {ec:.3e}, text {et:.3e}")
+    assert ec < EMB_TOL and et < EMB_TOL
+    # L1 parity: the engine's top-k on ITS embeddings equals the fp64 oracle on those same embeddings
+    from oracle import restate
+
+    oidx, _ = restate.search_topk(cell_enc, text_enc, 10)
+    ids = np.array([c.id for c in ds.all_cells])
+    got = np.stack([retr[i] for i in range(len(ds))])
+    assert got.dtype.kind == "U" and got.shape == (len(ds), 10)
+    assert (got == ids[oidx]).all()
+    # L3 parity: vs the reference's retrievals; a query may differ only where the reference's own
+    # k/k+1 score gap is inside twice the embedding error
+    ref = g["retrievals"]
+    s_ref = g["text_enc"] @ g["cell_enc"].T
+    for q in np.nonzero((got != ref).any(axis=1))[0]:
+        srt = np.sort(s_ref[q])[::-1]
+        assert np.min(np.abs(np.diff(srt[:11]))) < 2 * (ec + et), f"query {q} differs with a clear score gap"
+    np.random.seed(int(g["np_seed"]))
+    retrievals, accuracies = run_coarse(model, loader, args, verbose=False)
+    assert len(retrievals) == len(ds) and all(len(r) == 10 for r in retrievals)
+    assert set(accuracies.keys()) == set(args.top_k) and set(accuracies[1].keys()) == set(args.threshs)
+    assert np.allclose([[accuracies[k][t] for t in args.threshs] for k in args.top_k], g["run_coarse_acc"], atol=0.1)
+
+
+def test_dropin_surface(state_dict):
+    from text2loc_b200.engine import EngineError
+
+    model, args = make_model(state_dict)
+    assert model.embed_dim == 256 and model.object_size == 28
+    assert model.device.type == "cuda" and model.get_device() == model.device
+    assert model.to("cuda") is model
+    with pytest.raises(Exception, match="Not implemented"):
+        model.forward()
+    with pytest.raises(EngineError):
+        model.to("cpu")
+    bad = argparse.Namespace(**{**vars(args), "coarse_embed_dim": 128})
+    from text2loc_b200 import CellRetrievalNetwork
+
+    with pytest.raises(EngineError):
+        CellRetrievalNetwork([], [], bad)

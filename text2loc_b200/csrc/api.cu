@@ -1,0 +1,527 @@
+// C ABI of the engine (include/text2loc_b200.h): handle, weights, workspace arena and the
+// orchestration of the kernels in this directory into encode_cells / encode_text / search.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/text2loc_b200.h"
+#include "ops.h"
+#include "umma_gemm.cuh"
+
+namespace t2l {
+
+static TmaApi g_tma;
+const TmaApi& tma_api() { return g_tma; }
+static std::string g_create_error;
+
+struct Weight {
+  float* dev = nullptr;
+  int rows = 0, cols = 0, ld = 0;
+};
+
+// bump allocator over one device arena, reset per chunk
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, off = 0;
+  template <class T>
+  T* get(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace t2l
+
+using namespace t2l;
+
+struct t2l_engine {
+  int device = 0;
+  std::string err;
+  std::map<std::string, Weight> w;
+  bool finalized = false;
+  Arena arena;
+  Launches lc;
+  SearchDb db;
+  SearchWork sw{};
+  size_t sw_planes_rows = 0;
+  int obj_chunk = 2048;      // objects per encode chunk (cell-aligned)
+  int tok_chunk = 32768;     // tokens per text chunk (query-aligned)
+};
+
+static int fail(t2l_engine* e, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return 1;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _c = (call);                                                                       \
+    if (_c != cudaSuccess) return fail(e, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_c), __FILE__, __LINE__); \
+  } while (0)
+
+static int ensure_arena(t2l_engine* e, size_t bytes) {
+  if (e->arena.cap >= bytes) { e->arena.off = 0; return 0; }
+  if (e->arena.base) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->arena.base)); e->arena.base = nullptr; e->arena.cap = 0; }
+  bytes += bytes / 8;
+  CU(cudaMalloc(&e->arena.base, bytes));
+  e->arena.cap = bytes;
+  e->arena.off = 0;
+  return 0;
+}
+
+extern "C" int t2l_version(void) { return 1; }
+
+extern "C" const char* t2l_last_error(const t2l_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int64_t t2l_launch_count(const t2l_engine* e) { return e ? e->lc.n : 0; }
+
+extern "C" int t2l_create(int device, t2l_engine** out) {
+  t2l_engine* e = nullptr;
+  if (!out) return fail(e, "t2l_create: out is NULL");
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+    return fail(e, "t2l_create: no CUDA device visible; this engine has no CPU path");
+  if (device < 0 || device >= n_dev) return fail(e, "t2l_create: device %d out of range (%d visible)", device, n_dev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(e, "t2l_create: device %d is sm_%d%d; the kernels are sm_100a (Blackwell B200) only", device, prop.major, prop.minor);
+  if (!g_tma.encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(e, "t2l_create: cuTensorMapEncodeTiled not available in this driver");
+    g_tma.encode = reinterpret_cast<TmaApi::EncodeTiled>(fn);
+  }
+  g_tma.num_sms = prop.multiProcessorCount;
+  e = new t2l_engine();
+  e->device = device;
+  if (cudaMalloc(&e->db.max_norm, sizeof(float)) != cudaSuccess) { delete e; return fail(nullptr, "t2l_create: cudaMalloc failed"); }
+  *out = e;
+  return 0;
+}
+
+static void free_search_work(t2l_engine* e) {
+  cudaFree(e->sw.q_planes); cudaFree(e->sw.q_norm); cudaFree(e->sw.cand_score); cudaFree(e->sw.cand_idx);
+  cudaFree(e->sw.cand_thr); cudaFree(e->sw.flags);
+  e->sw = SearchWork{};
+}
+
+extern "C" void t2l_destroy(t2l_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : e->w) cudaFree(kv.second.dev);
+  cudaFree(e->arena.base);
+  cudaFree(e->db.planes);
+  cudaFree(e->db.max_norm);
+  free_search_work(e);
+  delete e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weights
+// ---------------------------------------------------------------------------------------------
+static bool is_tf32_operand(const std::string& n) {
+  // weights consumed by the tcgen05 tf32 GEMMs: pre-rounded once (round-to-nearest) so the tensor
+  // core's own truncation of the B operand is exact
+  static const char* pre[] = {"sa1.w2", "sa2.w1x", "sa2.w2", "sa3.w1x", "sa3.w2", "ga.w1", "ga.w2", "lin1.w", "lin2.w",
+                              "mlp_pointnet.w", "merge.w", "txt_intra.in_w", "txt_intra.out_w", "txt_intra.l1_w", "txt_intra.l2_w"};
+  for (const char* p : pre) if (n == p) return true;
+  return false;
+}
+
+static float host_round_tf32(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) != 0x7f800000u) u = (u + 0x1000u) & ~0x1fffu;  // rna: add half ulp of the 10-bit mantissa, truncate
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+extern "C" int t2l_set_weight(t2l_engine* e, const char* name, const float* data, int rows, int cols) {
+  if (!e || !name || !data || rows <= 0 || cols <= 0) return fail(e, "t2l_set_weight: bad argument");
+  CU(cudaSetDevice(e->device));
+  Weight& w = e->w[name];
+  if (w.dev) { CU(cudaFree(w.dev)); w.dev = nullptr; }
+  w.rows = rows; w.cols = cols; w.ld = (cols + 3) & ~3;
+  std::vector<float> host(static_cast<size_t>(rows) * w.ld, 0.f);
+  const bool rnd = is_tf32_operand(name);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) {
+      const float v = data[static_cast<size_t>(r) * cols + c];
+      host[static_cast<size_t>(r) * w.ld + c] = rnd ? host_round_tf32(v) : v;
+    }
+  CU(cudaMalloc(&w.dev, host.size() * sizeof(float)));
+  CU(cudaMemcpy(w.dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  e->finalized = false;
+  return 0;
+}
+
+static const char* kRequired[] = {
+    "sa1.w1x", "sa1.w1p", "sa1.b1", "sa1.w2", "sa1.b2", "sa2.w1x", "sa2.w1p", "sa2.b1", "sa2.w2", "sa2.b2",
+    "sa3.w1x", "sa3.w1p", "sa3.b1", "sa3.w2", "sa3.b2", "ga.w1", "ga.b1", "ga.w2", "ga.b2",
+    "lin1.w", "lin1.b", "lin2.w", "lin2.b", "mlp_pointnet.w", "mlp_pointnet.b",
+    "color.w1", "color.b1", "color.w2", "color.b2", "pos.w1", "pos.b1", "pos.w2", "pos.b2",
+    "num.w1", "num.b1", "num.w2", "num.b2", "merge.w", "merge.b", "txt_mlp.w", "txt_mlp.b"};
+static const char* kAttn[] = {"obj_attn0", "obj_attn1", "txt_intra", "txt_inter"};
+static const char* kAttnParts[] = {"in_w", "in_b", "out_w", "out_b", "l1_w", "l1_b", "l2_w", "l2_b", "n1_w", "n1_b", "n2_w", "n2_b"};
+
+extern "C" int t2l_finalize_weights(t2l_engine* e) {
+  if (!e) return 1;
+  for (const char* n : kRequired)
+    if (!e->w.count(n)) return fail(e, "t2l_finalize_weights: missing weight '%s'", n);
+  for (const char* a : kAttn)
+    for (const char* p : kAttnParts) {
+      std::string n = std::string(a) + "." + p;
+      if (!e->w.count(n)) return fail(e, "t2l_finalize_weights: missing weight '%s'", n.c_str());
+    }
+  CU(cudaSetDevice(e->device));
+  CU(cudaDeviceSynchronize());
+  e->finalized = true;
+  return 0;
+}
+
+static const Weight& W(t2l_engine* e, const std::string& n) { return e->w.at(n); }
+
+// y = act(x W^T + b) helper
+static cudaError_t lin(t2l_engine* e, bool umma, const float* A, long lda, int M, const std::string& wname, const std::string& bname,
+                       float* C, long ldc, int act, cudaStream_t st, const float* residual = nullptr, long ldr = 0, int round_out = 0,
+                       int segmax = 0, const float* side = nullptr, long lds = 0) {
+  const Weight& w = W(e, wname);
+  Linear l;
+  l.A = A; l.lda = lda; l.W = w.dev; l.ldw = w.ld; l.bias = bname.empty() ? nullptr : W(e, bname).dev;
+  l.C = C; l.ldc = ldc; l.M = M; l.N = w.rows; l.K = w.cols; l.act = act;
+  l.residual = residual; l.ldr = ldr; l.round_out = round_out; l.segmax = segmax; l.side = side; l.lds = lds;
+  return umma ? linear_umma(l, st, &e->lc) : linear_simt(l, st, &e->lc);
+}
+
+// One post-norm nn.TransformerEncoderLayer on packed rows [n_seq * S, d] (sequence-major).
+// umma: run the four projections on the tf32 tensor-core path (text token layer only).
+static int encoder_layer(t2l_engine* e, const std::string& pfx, bool umma, const float* X, float* Xout, int n_seq, int S, int d, int ffn,
+                         cudaStream_t st) {
+  const int rows = n_seq * S;
+  Arena& a = e->arena;
+  float* qkv = a.get<float>(static_cast<size_t>(rows) * 3 * d);
+  float* att = a.get<float>(static_cast<size_t>(rows) * d);
+  float* y = a.get<float>(static_cast<size_t>(rows) * d);
+  float* x1 = a.get<float>(static_cast<size_t>(rows) * d);
+  float* h = a.get<float>(static_cast<size_t>(rows) * ffn);
+  CU(lin(e, umma, X, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st));
+  CU(mha_small(qkv, att, n_seq, S, d, 4, st, &e->lc));
+  CU(lin(e, umma, att, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, X, d));
+  CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc));
+  CU(lin(e, umma, x1, d, rows, pfx + ".l1_w", pfx + ".l1_b", h, ffn, 1, st, nullptr, 0, umma ? 1 : 0));
+  CU(lin(e, umma, h, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x1, d));
+  CU(layer_norm_rows(y, Xout, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, rows, d, st, &e->lc));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// encode_cells
+// ---------------------------------------------------------------------------------------------
+struct ObjDebug {
+  float* features2 = nullptr;
+  uint8_t *fps1 = nullptr, *fps2 = nullptr, *fps3 = nullptr, *nbr1 = nullptr, *nbr2 = nullptr, *nbr3 = nullptr, *cnt1 = nullptr,
+          *cnt2 = nullptr, *cnt3 = nullptr;
+};
+
+static size_t obj_chunk_bytes(size_t n, size_t cells) {
+  // generous upper bound of everything encode_chunk carves from the arena
+  return n * (size_t(1) << 21) + n * 700000 + cells * size_t(28) * 256 * 4 * 12 + (size_t(1) << 20);
+}
+
+static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr, int c0, int c1, float* out,
+                        const ObjDebug* dbg, cudaStream_t st) {
+  const int o0 = cell_ptr[c0], o1 = cell_ptr[c1];
+  const int n = o1 - o0, B = c1 - c0;
+  if (ensure_arena(e, obj_chunk_bytes(n, B))) return 1;
+  Arena& a = e->arena;
+  const float* p = pts + static_cast<size_t>(o0) * kPoints * 6;
+
+  // self-loop source of each object (PyG add_self_loops on per-cell indices) + local cell_ptr
+  std::vector<int32_t> host(2 * static_cast<size_t>(n) + B + 1);
+  for (int c = c0; c < c1; ++c)
+    for (int o = cell_ptr[c]; o < cell_ptr[c + 1]; ++o) {
+      const int b = o - cell_ptr[c];
+      host[o - o0] = (cell_ptr[c] - o0) + b / 2;
+      host[n + (o - o0)] = b & 1;
+    }
+  for (int c = c0; c <= c1; ++c) host[2 * static_cast<size_t>(n) + (c - c0)] = cell_ptr[c] - o0;
+  int32_t* d_host = a.get<int32_t>(host.size());
+  CU(cudaMemcpyAsync(d_host, host.data(), host.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  const int32_t* loop_src = d_host;
+  const int32_t* loop_half = d_host + n;
+  const int32_t* cell_ptr_dev = d_host + 2 * static_cast<size_t>(n);
+
+  Geometry g;
+  const size_t N = n;
+  g.fps1 = a.get<uint8_t>(N * 128); g.fps2 = a.get<uint8_t>(N * 64); g.fps3 = a.get<uint8_t>(N * 32);
+  g.cpos1 = a.get<float>(N * 128 * 3); g.cpos2 = a.get<float>(N * 64 * 3); g.cpos3 = a.get<float>(N * 32 * 3);
+  g.nbr1 = a.get<uint8_t>(N * 128 * 32); g.nbr2 = a.get<uint8_t>(N * 64 * 32); g.nbr3 = a.get<uint8_t>(N * 32 * 32);
+  g.cnt1 = a.get<uint8_t>(N * 128); g.cnt2 = a.get<uint8_t>(N * 64); g.cnt3 = a.get<uint8_t>(N * 32);
+  CU(fps_all_levels(p, n, g, st, &e->lc));
+  CU(ball_query_all_levels(p, n, g, st, &e->lc));
+
+  float* x0 = a.get<float>(N * 256 * 4);
+  float* px = a.get<float>(N * 256 * 32);      // max over levels: 256*32 = 128*128/2 ... sized below
+  float* px23 = a.get<float>(N * 128 * 128);   // Px of levels 2 and 3 (n*128*128 == n*64*256)
+  float* H = a.get<float>(N * 32 * 32 * 256);  // edge rows, largest level (1 MB / object)
+  float* Hs = a.get<float>(N * 64 * 128);      // self-loop rows (n*128*32, n*64*128, n*32*256)
+  float* S = a.get<float>(N * 64 * 128);       // second-layer output of the self-loop rows
+  float* x1 = a.get<float>(N * 128 * 64);
+  float* x2 = a.get<float>(N * 64 * 128);
+  float* x3 = a.get<float>(N * 32 * 256);
+  CU(extract_rgb(p, n, x0, st, &e->lc));
+
+  struct Level { const char* name; int C1, C2, P, M; const float* x; long ldx; const float* dense; int dstride; const float* cpos;
+                 const uint8_t* nbr; const uint8_t* cnt; float* Px; float* xout; bool px_umma; };
+  Level lv[3] = {
+      {"sa1", 32, 64, 256, 128, x0, 4, p, 6, g.cpos1, g.nbr1, g.cnt1, px, x1, false},
+      {"sa2", 128, 128, 128, 64, x1, 64, g.cpos1, 3, g.cpos2, g.nbr2, g.cnt2, px23, x2, true},
+      {"sa3", 256, 256, 64, 32, x2, 128, g.cpos2, 3, g.cpos3, g.nbr3, g.cnt3, px23, x3, true},
+  };
+  for (const Level& L : lv) {
+    const std::string nm = L.name;
+    // per-point half of the first Linear (no bias; b1 is added with the position term per edge)
+    CU(lin(e, L.px_umma, L.x, L.ldx, n * L.P, nm + ".w1x", "", L.Px, L.C1, 0, st));
+    EdgeGather eg;
+    eg.Px = L.Px; eg.C1 = L.C1; eg.dense_pos = L.dense; eg.dense_stride = L.dstride; eg.cpos = L.cpos; eg.nbr = L.nbr; eg.cnt = L.cnt;
+    eg.loop_src_obj = loop_src; eg.loop_half = loop_half; eg.Wp = W(e, nm + ".w1p").dev; eg.b1 = W(e, nm + ".b1").dev;
+    eg.n_obj = n; eg.P = L.P; eg.M = L.M; eg.H = H; eg.Hself = Hs;
+    if (W(e, nm + ".w1p").ld != 4) return fail(e, "internal: w1p pitch");
+    CU(edge_gather(eg, st, &e->lc));
+    // second Linear + ReLU; max over each centroid's 32 slots in the GEMM epilogue, joined with the self-loop row
+    CU(lin(e, true, Hs, L.C1, n * L.M, nm + ".w2", nm + ".b2", S, L.C2, 1, st));
+    CU(lin(e, true, H, L.C1, n * L.M * 32, nm + ".w2", nm + ".b2", L.xout, L.C2, 1, st, nullptr, 0, /*round_out=*/1, /*segmax=*/1, S, L.C2));
+  }
+
+  // GlobalAbstraction: mlp([x | pos]) then max over the object's 32 points (pointnet2.py:45-49)
+  float* gaA = a.get<float>(N * 32 * 260);
+  float* g1 = a.get<float>(N * 32 * 512);
+  float* f0 = a.get<float>(N * 1024);
+  float* f1 = a.get<float>(N * 512);
+  float* f2 = a.get<float>(N * 256);
+  CU(ga_concat(x3, g.cpos3, n, gaA, st, &e->lc));
+  CU(lin(e, true, gaA, 260, n * 32, "ga.w1", "ga.b1", g1, 512, 1, st, nullptr, 0, 1));
+  CU(lin(e, true, g1, 512, n * 32, "ga.w2", "ga.b2", f0, 1024, 1, st, nullptr, 0, 1, 1));
+  CU(lin(e, true, f0, 1024, n, "lin1.w", "lin1.b", f1, 512, 1, st, nullptr, 0, 1));  // relu(lin1) (:89)
+  CU(lin(e, true, f1, 512, n, "lin2.w", "lin2.b", f2, 256, 1, st, nullptr, 0, 1));   // relu(lin2) = features2 (:90)
+
+  if (dbg) {
+    if (dbg->features2) CU(cudaMemcpyAsync(dbg->features2 + static_cast<size_t>(o0) * 256, f2, N * 256 * 4, cudaMemcpyDeviceToDevice, st));
+    struct { uint8_t* dst; const uint8_t* src; size_t per; } cp[] = {
+        {dbg->fps1, g.fps1, 128}, {dbg->fps2, g.fps2, 64}, {dbg->fps3, g.fps3, 32}, {dbg->nbr1, g.nbr1, 128 * 32}, {dbg->nbr2, g.nbr2, 64 * 32},
+        {dbg->nbr3, g.nbr3, 32 * 32}, {dbg->cnt1, g.cnt1, 128}, {dbg->cnt2, g.cnt2, 64}, {dbg->cnt3, g.cnt3, 32}};
+    for (auto& c : cp)
+      if (c.dst) CU(cudaMemcpyAsync(c.dst + static_cast<size_t>(o0) * c.per, c.src, N * c.per, cudaMemcpyDeviceToDevice, st));
+    if (!out) return 0;
+  }
+
+  // ObjectEncoder.forward (object_encoder.py:98-149): four normalised 256-d features -> mlp_merge
+  float* cat = a.get<float>(N * 1024);
+  float* t256 = a.get<float>(N * 256);
+  float* t64 = a.get<float>(N * 64);
+  float* numf = a.get<float>(N);
+  float* emb = a.get<float>(N * 256);
+  const float* m = meta + static_cast<size_t>(o0) * 7;
+  CU(lin(e, true, f2, 256, n, "mlp_pointnet.w", "mlp_pointnet.b", t256, 256, 1, st));
+  CU(l2_normalize_rows(t256, 256, cat + 0, 1024, n, 256, st, &e->lc));
+  CU(lin(e, false, m + 0, 7, n, "color.w1", "color.b1", t64, 64, 1, st));
+  CU(lin(e, false, t64, 64, n, "color.w2", "color.b2", t256, 256, 1, st));
+  CU(l2_normalize_rows(t256, 256, cat + 256, 1024, n, 256, st, &e->lc));
+  CU(lin(e, false, m + 3, 7, n, "pos.w1", "pos.b1", t64, 64, 1, st));
+  CU(lin(e, false, t64, 64, n, "pos.w2", "pos.b2", t256, 256, 1, st));
+  CU(l2_normalize_rows(t256, 256, cat + 512, 1024, n, 256, st, &e->lc));
+  CU(num_feature(m, n, numf, st, &e->lc));
+  CU(lin(e, false, numf, 1, n, "num.w1", "num.b1", t64, 64, 1, st));
+  CU(lin(e, false, t64, 64, n, "num.w2", "num.b2", t256, 256, 1, st));
+  CU(l2_normalize_rows(t256, 256, cat + 768, 1024, n, 256, st, &e->lc));
+  CU(lin(e, true, cat, 1024, n, "merge.w", "merge.b", emb, 256, 1, st));
+
+  // intra-cell attention (cell_retrieval.py:85-108); fp32 throughout: these two layers amplify
+  // operand rounding the most (precision table)
+  float* X = a.get<float>(static_cast<size_t>(B) * 28 * 256);
+  float* Xb = a.get<float>(static_cast<size_t>(B) * 28 * 256);
+  float* pooled = a.get<float>(static_cast<size_t>(B) * 256);
+  CU(scatter_objects(emb, cell_ptr_dev, B, X, st, &e->lc));
+  const size_t mark = a.off;
+  if (encoder_layer(e, "obj_attn0", false, X, Xb, B, 28, 256, 512, st)) return 1;
+  a.off = mark;
+  if (encoder_layer(e, "obj_attn1", false, Xb, X, B, 28, 256, 512, st)) return 1;
+  CU(max_over_rows(X, pooled, B, 28, 256, st, &e->lc));
+  CU(l2_normalize_rows(pooled, 256, out + static_cast<size_t>(c0) * 256, 256, B, 256, st, &e->lc));
+  return 0;
+}
+
+static int encode_cells_impl(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr, int n_cells, float* out,
+                             const ObjDebug* dbg, cudaStream_t st) {
+  if (!e) return 1;
+  if (!e->finalized) return fail(e, "weights not finalized");
+  if (n_cells < 0 || !cell_ptr || cell_ptr[0] != 0) return fail(e, "encode_cells: bad cell_ptr");
+  CU(cudaSetDevice(e->device));
+  for (int c = 0; c < n_cells; ++c)
+    if (cell_ptr[c + 1] <= cell_ptr[c]) return fail(e, "encode_cells: cell %d has no objects (the reference asserts >= 1, cells.py:202)", c);
+  int c0 = 0;
+  while (c0 < n_cells) {
+    int c1 = c0 + 1;
+    while (c1 < n_cells && cell_ptr[c1 + 1] - cell_ptr[c0] <= e->obj_chunk) ++c1;
+    if (encode_chunk(e, pts, meta, cell_ptr, c0, c1, out, dbg, st)) return 1;
+    c0 = c1;
+  }
+  return 0;
+}
+
+extern "C" int t2l_encode_cells(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr_host, int n_cells, float* out,
+                                void* stream) {
+  if (!pts || !meta || !out) return fail(e, "encode_cells: NULL buffer");
+  return encode_cells_impl(e, pts, meta, cell_ptr_host, n_cells, out, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int t2l_encode_objects_debug(t2l_engine* e, const float* pts, const int32_t* cell_ptr_host, int n_cells, float* features2,
+                                        uint8_t* fps1, uint8_t* fps2, uint8_t* fps3, uint8_t* nbr1, uint8_t* nbr2, uint8_t* nbr3,
+                                        uint8_t* cnt1, uint8_t* cnt2, uint8_t* cnt3, void* stream) {
+  ObjDebug d;
+  d.features2 = features2; d.fps1 = fps1; d.fps2 = fps2; d.fps3 = fps3; d.nbr1 = nbr1; d.nbr2 = nbr2; d.nbr3 = nbr3;
+  d.cnt1 = cnt1; d.cnt2 = cnt2; d.cnt3 = cnt3;
+  return encode_cells_impl(e, pts, nullptr, cell_ptr_host, n_cells, nullptr, &d, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// encode_text
+// ---------------------------------------------------------------------------------------------
+extern "C" int t2l_encode_text(t2l_engine* e, const float* t5, int nq, int S, int L, float* out, void* stream) {
+  if (!e) return 1;
+  if (!e->finalized) return fail(e, "weights not finalized");
+  if (!t5 || !out || nq < 0 || S < 1 || S > 32 || L < 1 || L > 32) return fail(e, "encode_text: bad argument (n_sent, n_tok must be in 1..32)");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int d = T2L_T5_DIM;
+  int qc = e->tok_chunk / (S * L);
+  if (qc < 1) qc = 1;
+  for (int q0 = 0; q0 < nq; q0 += qc) {
+    const int nqc = (nq - q0 < qc) ? nq - q0 : qc;
+    const int n_seq = nqc * S;               // sentences
+    const size_t T = static_cast<size_t>(n_seq) * L;  // tokens
+    if (ensure_arena(e, T * (3 * d + 3 * d + 4 * d + d) * 4 + static_cast<size_t>(n_seq) * (d + 16 * 256) * 4 + (size_t(1) << 22))) return 1;
+    Arena& a = e->arena;
+    const float* X = t5 + static_cast<size_t>(q0) * S * L * d;
+    // intra_module: one encoder layer over the tokens of each sentence, no key-padding mask (:130-131)
+    float* X2 = a.get<float>(T * d);
+    if (encoder_layer(e, "txt_intra", true, X, X2, n_seq, L, d, 4 * d, st)) return 1;
+    // max over tokens (:133), inter_mlp = Linear + BN folded, no ReLU (:137)
+    float* pooled = a.get<float>(static_cast<size_t>(n_seq) * d);
+    float* z = a.get<float>(static_cast<size_t>(n_seq) * 256);
+    float* z2 = a.get<float>(static_cast<size_t>(n_seq) * 256);
+    float* zq = a.get<float>(static_cast<size_t>(nqc) * 256);
+    CU(max_over_rows(X2, pooled, n_seq, L, d, st, &e->lc));
+    CU(lin(e, false, pooled, d, n_seq, "txt_mlp.w", "txt_mlp.b", z, 256, 0, st));
+    // inter_module over the S sentences of each query with the extra residual `x += layer(x)` (:143-145)
+    if (encoder_layer(e, "txt_inter", false, z, z2, nqc, S, 256, 1024, st)) return 1;
+    CU(add_rows(z, z2, z2, static_cast<long>(n_seq) * 256, st, &e->lc));
+    CU(max_over_rows(z2, zq, nqc, S, 256, st, &e->lc));                       // max over sentences (:147)
+    CU(l2_normalize_rows(zq, 256, out + static_cast<size_t>(q0) * 256, 256, nqc, 256, st, &e->lc));  // cell_retrieval.py:61
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// search
+// ---------------------------------------------------------------------------------------------
+extern "C" int t2l_db_build(t2l_engine* e, const float* D, int64_t n_rows, int64_t row_offset, void* stream) {
+  if (!e) return 1;
+  if (n_rows < 0 || (n_rows > 0 && !D) || n_rows > 0x7fffff00LL) return fail(e, "db_build: bad argument");
+  CU(cudaSetDevice(e->device));
+  if (static_cast<size_t>(n_rows) > e->sw_planes_rows) {
+    if (e->db.planes) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->db.planes)); e->db.planes = nullptr; }
+    CU(cudaMalloc(&e->db.planes, static_cast<size_t>(n_rows) * 512 * sizeof(__nv_bfloat16) + 1024));
+    e->sw_planes_rows = static_cast<size_t>(n_rows);
+  }
+  e->db.D = D; e->db.n_rows = n_rows; e->db.row_offset = row_offset;
+  CU(search_prepare_db(e->db, static_cast<cudaStream_t>(stream), &e->lc));
+  return 0;
+}
+
+static int ensure_search_work(t2l_engine* e, int nq) {
+  if (nq <= e->sw.nq_cap) return 0;
+  CU(cudaDeviceSynchronize());
+  free_search_work(e);
+  const size_t cap = static_cast<size_t>(nq) + 128;
+  const int sc = 16;
+  CU(cudaMalloc(&e->sw.q_planes, cap * 512 * sizeof(__nv_bfloat16)));
+  CU(cudaMalloc(&e->sw.q_norm, cap * sizeof(float)));
+  CU(cudaMalloc(&e->sw.cand_score, cap * sc * 16 * sizeof(float)));
+  CU(cudaMalloc(&e->sw.cand_idx, cap * sc * 16 * sizeof(int32_t)));
+  CU(cudaMalloc(&e->sw.cand_thr, cap * sc * sizeof(float)));
+  CU(cudaMalloc(&e->sw.flags, cap * sizeof(int32_t)));
+  e->sw.nq_cap = static_cast<int>(cap);
+  e->sw.splits_cap = sc;
+  return 0;
+}
+
+extern "C" int t2l_search_topk(t2l_engine* e, const float* Q, int nq, int k, int64_t* out_idx, double* out_score, int32_t* out_n_fallback,
+                               void* stream) {
+  if (!e) return 1;
+  if (!Q || !out_idx || !out_score || nq < 0) return fail(e, "search_topk: bad argument");
+  if (k < 1 || k > T2L_MAX_TOPK) return fail(e, "search_topk: k must be in 1..%d (use t2l_search_topk_exact beyond)", T2L_MAX_TOPK);
+  if (!e->db.D && e->db.n_rows != 0) return fail(e, "search_topk: t2l_db_build has not been called");
+  CU(cudaSetDevice(e->device));
+  if (ensure_search_work(e, nq)) return 1;
+  CU(search_topk(e->db, e->sw, Q, nq, k, out_idx, out_score, out_n_fallback, static_cast<cudaStream_t>(stream), &e->lc));
+  return 0;
+}
+
+extern "C" int t2l_search_topk_exact(t2l_engine* e, const float* Q, int nq, int k, int64_t* out_idx, double* out_score, void* stream) {
+  if (!e) return 1;
+  if (!Q || !out_idx || !out_score || nq < 0 || k < 1 || k > 16) return fail(e, "search_topk_exact: bad argument (k in 1..16)");
+  CU(cudaSetDevice(e->device));
+  CU(search_topk_exact(e->db, Q, nq, k, out_idx, out_score, nullptr, static_cast<cudaStream_t>(stream), &e->lc));
+  return 0;
+}
+
+extern "C" int t2l_merge_topk(t2l_engine* e, const int64_t* idx_all, const double* score_all, int n_shards, int nq, int k, int64_t* out_idx,
+                              double* out_score, void* stream) {
+  if (!e) return 1;
+  if (!idx_all || !score_all || !out_idx || !out_score) return fail(e, "merge_topk: NULL buffer");
+  CU(cudaSetDevice(e->device));
+  CU(merge_topk(idx_all, score_all, n_shards, nq, k, out_idx, out_score, static_cast<cudaStream_t>(stream), &e->lc));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// test hook
+// ---------------------------------------------------------------------------------------------
+extern "C" int t2l_debug_linear(t2l_engine* e, int path, const float* A, int lda, const float* Wt, int ldw, const float* bias, float* C, int ldc,
+                                int M, int N, int K, int act, int segmax, void* stream) {
+  if (!e) return 1;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Linear l;
+  l.A = A; l.lda = lda; l.W = Wt; l.ldw = ldw; l.bias = bias; l.C = C; l.ldc = ldc; l.M = M; l.N = N; l.K = K; l.act = act;
+  if (path == 1) {
+    l.segmax = segmax;
+    CU(linear_umma(l, st, &e->lc));
+    return 0;
+  }
+  if (!segmax) { CU(linear_simt(l, st, &e->lc)); return 0; }
+  if (ensure_arena(e, static_cast<size_t>(M) * N * 4 + 4096)) return 1;
+  float* tmp = e->arena.get<float>(static_cast<size_t>(M) * N);
+  l.C = tmp; l.ldc = N; l.act = 1;
+  CU(linear_simt(l, st, &e->lc));
+  CU(segmax32(tmp, N, C, ldc, nullptr, 0, M / 32, N, st, &e->lc));
+  return 0;
+}

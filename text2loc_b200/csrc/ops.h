@@ -1,0 +1,118 @@
+// Host-callable launchers of the engine's kernels (internal; the public surface is
+// include/text2loc_b200.h).  Every launcher enqueues on `st`, never synchronises, and returns
+// cudaGetLastError() of its launches.  All pointers are device pointers.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace t2l {
+
+struct Launches {  // running count for t2l_launch_count()
+  int64_t n = 0;
+};
+
+// ---- linear.cu ---------------------------------------------------------------------------
+enum LinearPath { kPathSimt = 0, kPathUmma = 1 };
+
+struct Linear {
+  const float* A; long lda;   // [M, K]
+  const float* W; long ldw;   // [N, K] (torch Linear layout)
+  const float* bias;          // [N] or null
+  float* C; long ldc;         // [M, N]  (segmax: [M/32, N])
+  int M, N, K;
+  int act = 0;                // 0 none, 1 relu
+  const float* residual = nullptr; long ldr = 0;  // added after act (store mode only)
+  int segmax = 0;             // max over 32-row groups after relu
+  const float* side = nullptr; long lds = 0;      // segmax: elementwise max with side[g, :]
+  int round_out = 0;          // round stored values to tf32 (rna)
+};
+// tf32 tensor-core path: needs K-major operands with 16-byte aligned rows (lda, ldw % 4 == 0),
+// N % 32 == 0.  K tails are zero-filled by TMA.
+cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc);
+// exact fp32 path: any shape.
+cudaError_t linear_simt(const Linear& l, cudaStream_t st, Launches* lc);
+
+// out[g, c] = max over rows g*32..g*32+31 of C (already >= 0), optionally max'ed with side[g, c]
+cudaError_t segmax32(const float* C, long ldc, float* out, long ldo, const float* side, long lds, int groups, int N,
+                     cudaStream_t st, Launches* lc);
+
+// ---- geometry.cu (a1: fps + radius of pointnet2.py:26-30, position-only) --------------------
+struct Geometry {           // per object, all levels
+  uint8_t* fps1; uint8_t* fps2; uint8_t* fps3;   // [n,128] [n,64] [n,32] local indices into the level's dense set
+  float* cpos1; float* cpos2; float* cpos3;      // [n,128,3] [n,64,3] [n,32,3] centroid positions
+  uint8_t* nbr1; uint8_t* nbr2; uint8_t* nbr3;   // [n,128,32] [n,64,32] [n,32,32]
+  uint8_t* cnt1; uint8_t* cnt2; uint8_t* cnt3;   // [n,128] [n,64] [n,32]
+};
+cudaError_t fps_all_levels(const float* pts, int n_obj, const Geometry& g, cudaStream_t st, Launches* lc);
+cudaError_t ball_query_all_levels(const float* pts, int n_obj, const Geometry& g, cudaStream_t st, Launches* lc);
+
+// ---- pointnet.cu --------------------------------------------------------------------------
+// x0[n*256, 4] = rgb (padded to 4 floats) from pts
+cudaError_t extract_rgb(const float* pts, int n_obj, float* x0, cudaStream_t st, Launches* lc);
+// First-layer edge activations of one PointConv:
+//   H[(o*M+m)*32 + s, :] = relu(Px[src_point] + Wp * (pos_src - cpos[o,m]) + b1)   s < 32 neighbour slots
+//   Hself[o*M+m, :]      = same for the re-added self-loop edge (dense point with the centroid's
+//                          per-cell global index); empty neighbour slots replicate it.
+// dense positions: level 1 reads pts (stride 6), levels 2/3 read the previous level's cpos.
+struct EdgeGather {
+  const float* Px; int C1;            // [n*P, C1] per dense point
+  const float* dense_pos; int dense_stride;  // [n*P, stride] xyz first
+  const float* cpos;                  // [n*M, 3]
+  const uint8_t* nbr; const uint8_t* cnt;
+  const int32_t* loop_src_obj;        // [n] flat object index feeding this object's self loops
+  const int32_t* loop_half;           // [n] 0/1: which half of that object's dense points
+  const float* Wp;                    // [C1, 3] folded, row pitch 4
+  const float* b1;                    // [C1] folded
+  int n_obj, P, M;
+  float* H; float* Hself;
+};
+cudaError_t edge_gather(const EdgeGather& a, cudaStream_t st, Launches* lc);
+// GA input: A[n*32, 260] = [x3 (256) | cpos3 (3) | 0]
+cudaError_t ga_concat(const float* x3, const float* cpos3, int n_obj, float* A, cudaStream_t st, Launches* lc);
+
+// ---- rowops.cu ----------------------------------------------------------------------------
+// y[r, 0:d] (row pitch ldy) = x[r] / max(||x[r]||, 1e-12)      (F.normalize)
+cudaError_t l2_normalize_rows(const float* x, long ldx, float* y, long ldy, int rows, int d, cudaStream_t st, Launches* lc);
+// y = LayerNorm(x) * w + b, eps 1e-5, one warp per row
+cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const float* b, int rows, int d, cudaStream_t st, Launches* lc);
+// Unmasked multi-head self attention on packed QKV rows [n_seq*S, 3d] (q | k | v), head h uses
+// columns [h*hd, (h+1)*hd); out [n_seq*S, d].  softmax(q k^T / sqrt(hd)) v, fp32.
+cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc);
+// y[g, :] = max over the S rows of group g
+cudaError_t max_over_rows(const float* x, float* y, int groups, int S, int d, cudaStream_t st, Launches* lc);
+// X[b, s, :] = normalize(emb[cell_ptr[b]+s]) for s < min(n_b, 28), else 0   (cell_retrieval.py:85-98)
+cudaError_t scatter_objects(const float* emb, const int32_t* cell_ptr_dev, int n_cells, float* X, cudaStream_t st, Launches* lc);
+// meta[:, 6] -> (cnt - mean) / std  (object_encoder.py:141-143)
+cudaError_t num_feature(const float* meta, int n_obj, float* out, cudaStream_t st, Launches* lc);
+// y = a + b (elementwise)
+cudaError_t add_rows(const float* a, const float* b, float* y, long n, cudaStream_t st, Launches* lc);
+// text: [S, nq] row order helpers are not needed: rows are kept query-major (q*S + s)
+
+// ---- search.cu ----------------------------------------------------------------------------
+struct SearchDb {
+  const float* D = nullptr;        // caller's fp32 rows [N, 256]
+  __nv_bfloat16* planes = nullptr; // [N, 512]  hi | lo
+  float* max_norm = nullptr;       // [1] max row norm (device)
+  int64_t n_rows = 0, row_offset = 0;
+};
+struct SearchWork {
+  __nv_bfloat16* q_planes;  // [nq_cap, 512]
+  float* q_norm;            // [nq_cap]
+  float* cand_score;        // [nq_cap, splits_cap, 16]
+  int32_t* cand_idx;        // [nq_cap, splits_cap, 16]
+  float* cand_thr;          // [nq_cap, splits_cap]
+  int32_t* flags;           // [nq_cap]
+  double* scan;             // [fallback scratch]
+  int nq_cap, splits_cap;
+};
+cudaError_t search_prepare_db(const SearchDb& db, cudaStream_t st, Launches* lc);
+cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q, int nq, int k, int64_t* out_idx,
+                        double* out_score, int32_t* out_n_fallback, cudaStream_t st, Launches* lc);
+cudaError_t search_topk_exact(const SearchDb& db, const float* Q, int nq, int k, int64_t* out_idx, double* out_score,
+                              const int32_t* only_flagged, cudaStream_t st, Launches* lc);
+cudaError_t merge_topk(const int64_t* idx_all, const double* score_all, int n_shards, int nq, int k, int64_t* out_idx,
+                       double* out_score, cudaStream_t st, Launches* lc);
+
+}  // namespace t2l

@@ -1,0 +1,99 @@
+// Feature side of the set-abstraction layers (models/pointcloud/pointnet2.py:31-37, PyG PointConv):
+//   message(j -> i) = local_nn([x_j, pos_j - pos_i]),  out_i = max_j message.
+// The first Linear of local_nn is split so the 32x-redundant part runs once per POINT:
+//   W1 [x_j, dpos] + b = (W1x x_j) + W1p (pos_j - pos_i) + b
+// Px = W1x x_j is a dense GEMM over points (linear.cu); this file adds the exact fp32
+// position term per EDGE, applies ReLU and lays the edge rows out for the second-layer GEMM
+// whose epilogue does the per-centroid max (gemm_epilogues.cuh::SegMaxEpi).
+#include "ops.h"
+#include "common.cuh"
+
+namespace t2l {
+
+__global__ void extract_rgb_kernel(const float* __restrict__ pts, long n_pts, float* __restrict__ x0) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_pts) return;
+  const float* p = pts + i * 6;
+  *reinterpret_cast<float4*>(x0 + i * 4) = make_float4(p[3], p[4], p[5], 0.f);
+}
+
+cudaError_t extract_rgb(const float* pts, int n_obj, float* x0, cudaStream_t st, Launches* lc) {
+  const long n = static_cast<long>(n_obj) * kPoints;
+  if (n <= 0) return cudaSuccess;
+  if (lc) lc->n++;
+  extract_rgb_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(pts, n, x0);
+  return cudaGetLastError();
+}
+
+// One warp per centroid; lane l owns channels l, l+32, ... (coalesced row reads and writes).
+template <int C1>
+__global__ void __launch_bounds__(256) edge_gather_kernel(EdgeGather a) {
+  constexpr int R = C1 / 32;
+  const int lane = threadIdx.x & 31;
+  const long cen = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);  // o * M + m
+  if (cen >= static_cast<long>(a.n_obj) * a.M) return;
+  const int o = static_cast<int>(cen / a.M), m = static_cast<int>(cen % a.M);
+  float wx[R], wy[R], wz[R], b[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int c = r * 32 + lane;
+    wx[r] = a.Wp[c * 4 + 0]; wy[r] = a.Wp[c * 4 + 1]; wz[r] = a.Wp[c * 4 + 2];  // rows padded to 4 floats
+    b[r] = a.b1[c];
+  }
+  const float cx = a.cpos[cen * 3 + 0], cy = a.cpos[cen * 3 + 1], cz = a.cpos[cen * 3 + 2];
+  const int cnt = a.cnt[cen];
+  const long self_row = static_cast<long>(a.loop_src_obj[o]) * a.P + a.loop_half[o] * a.M + m;
+  const uint8_t my_nbr = a.nbr[cen * kMaxNbr + lane];
+  for (int s = 0; s <= kMaxNbr; ++s) {
+    long src = self_row;
+    if (s < cnt) src = static_cast<long>(o) * a.P + __shfl_sync(0xffffffffu, static_cast<int>(my_nbr), s);
+    const float* dp = a.dense_pos + src * a.dense_stride;
+    const float dx = dp[0] - cx, dy = dp[1] - cy, dz = dp[2] - cz;  // pos_j - pos_i (exact fp32 subtraction)
+    const float* px = a.Px + src * C1;
+    float* dst = (s < kMaxNbr) ? a.H + (cen * kMaxNbr + s) * C1 : a.Hself + cen * C1;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float v = px[r * 32 + lane] + b[r];
+      v = fmaf(wx[r], dx, v);
+      v = fmaf(wy[r], dy, v);
+      v = fmaf(wz[r], dz, v);
+      dst[r * 32 + lane] = round_tf32(fmaxf(v, 0.f));  // operand of the tf32 second-layer GEMM
+    }
+  }
+}
+
+cudaError_t edge_gather(const EdgeGather& a, cudaStream_t st, Launches* lc) {
+  const long n_cen = static_cast<long>(a.n_obj) * a.M;
+  if (n_cen <= 0) return cudaSuccess;
+  if (lc) lc->n++;
+  const unsigned grid = static_cast<unsigned>((n_cen + 7) / 8);
+  switch (a.C1) {
+    case 32: edge_gather_kernel<32><<<grid, 256, 0, st>>>(a); break;
+    case 128: edge_gather_kernel<128><<<grid, 256, 0, st>>>(a); break;
+    case 256: edge_gather_kernel<256><<<grid, 256, 0, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// GlobalAbstractionLayer input torch.cat((x, pos), dim=1) (pointnet2.py:46), K padded 259 -> 260
+__global__ void ga_concat_kernel(const float* __restrict__ x3, const float* __restrict__ cpos3, long rows, float* __restrict__ A) {
+  const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* src = reinterpret_cast<const float4*>(x3 + r * 256);
+  float4* dst = reinterpret_cast<float4*>(A + r * 260);
+  dst[lane] = src[lane];
+  dst[lane + 32] = src[lane + 32];
+  if (lane == 0) dst[64] = make_float4(cpos3[r * 3 + 0], cpos3[r * 3 + 1], cpos3[r * 3 + 2], 0.f);
+}
+
+cudaError_t ga_concat(const float* x3, const float* cpos3, int n_obj, float* A, cudaStream_t st, Launches* lc) {
+  const long rows = static_cast<long>(n_obj) * 32;
+  if (rows <= 0) return cudaSuccess;
+  if (lc) lc->n++;
+  ga_concat_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(x3, cpos3, rows, A);
+  return cudaGetLastError();
+}
+
+}  // namespace t2l

@@ -1,0 +1,351 @@
+// Query x database cosine-similarity top-k (training/coarse.py:119-125).
+//
+// The reference scores in float64 on the host, one GEMV + full argsort per query.  Here:
+//   1. candidate pass on the tensor cores: Q and D are split once into bf16 hi|lo planes and the
+//      product hi*hi + hi*lo + lo*hi (three K=256 passes into one fp32 TMEM accumulator,
+//      umma_gemm.cuh) approximates q.d to ~1e-5; the epilogue keeps, per query row and per
+//      database split, the 16 best approximate scores and the threshold below which it dropped;
+//   2. exact re-rank: fp64 dot products of the fp32 originals for those candidates, ordered by
+//      (score desc, row asc);
+//   3. proof: if every split's drop threshold + error bound is below the k-th exact score, no
+//      dropped row can belong to the top-k; otherwise the query is rescanned exactly in fp64.
+// Returned indices are therefore those of the fp64 stable-order oracle by construction.
+#include "ops.h"
+#include "umma_gemm.cuh"
+
+namespace t2l {
+
+constexpr int kCand = 16;         // candidates kept per (query, split)
+constexpr int kMaxSplits = 16;
+constexpr int kMaxK = 12;
+// |approx - exact| <= kEpsRel * ||q|| * max||d||: 3 * 2^-18 from the dropped lo*lo term and
+// the two bf16 residuals, plus fp32 accumulation of 768 products, with a 2x safety factor.
+constexpr float kEpsRel = 2.5e-4f;
+
+// ---- fp32 rows -> bf16 hi | lo planes (+ row norms) ---------------------------------------------
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long rows, __nv_bfloat16* __restrict__ planes,
+                                                           float* __restrict__ norms, float* __restrict__ max_norm) {
+  const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + r * kEmbed;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kEmbed / 32; ++i) {
+    const int c = i * 32 + lane;
+    const float v = xr[c];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    planes[r * 2 * kEmbed + c] = hi;
+    planes[r * 2 * kEmbed + kEmbed + c] = lo;
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) {
+    const float n = sqrtf(ss);
+    if (norms) norms[r] = n;
+    if (max_norm) atomicMax(reinterpret_cast<unsigned int*>(max_norm), __float_as_uint(n));  // n >= 0
+  }
+}
+
+cudaError_t search_prepare_db(const SearchDb& db, cudaStream_t st, Launches* lc) {
+  cudaError_t e = cudaMemsetAsync(db.max_norm, 0, sizeof(float), st);
+  if (e != cudaSuccess || db.n_rows <= 0) return e;
+  if (lc) lc->n++;
+  split_planes_kernel<<<static_cast<unsigned>((db.n_rows + 7) / 8), 256, 0, st>>>(db.D, db.n_rows, db.planes, nullptr, db.max_norm);
+  return cudaGetLastError();
+}
+
+// ---- candidate epilogue -------------------------------------------------------------------------
+struct TopKEpi {
+  struct Params {
+    float* cand_score;  // [nq, n_splits, kCand]
+    int32_t* cand_idx;  // [nq, n_splits, kCand]   -1 = empty
+    float* cand_thr;    // [nq, n_splits]          -inf = nothing was dropped
+    int nq, n_db, n_splits;
+  };
+  static constexpr int kSmemBytes = kCand * 128 * 8;
+  const Params& p;
+  float* s_score;
+  int32_t* s_idx;
+  int t;       // 0..127: row inside the M tile
+  float thr;   // minimum of the kept list once it is full, else -inf
+  int cnt, min_slot;
+  bool active;
+
+  __device__ TopKEpi(const Params& p_, uint8_t* smem, int ew, int lane) : p(p_) {
+    s_score = reinterpret_cast<float*>(smem);
+    s_idx = reinterpret_cast<int32_t*>(smem + kCand * 128 * 4);
+    t = ew * 32 + lane;
+    thr = -INFINITY; cnt = 0; min_slot = 0; active = false;
+  }
+  __device__ void begin_unit(int m_tile, int) {
+    active = (m_tile * 128 + t) < p.nq;
+    thr = active ? -INFINITY : INFINITY;
+    cnt = 0;
+    min_slot = 0;
+  }
+  __device__ __noinline__ void insert(float s, int col) {
+    if (col >= p.n_db) return;
+    if (cnt < kCand) {
+      s_score[cnt * 128 + t] = s;
+      s_idx[cnt * 128 + t] = col;
+      if (++cnt < kCand) return;
+    } else {
+      s_score[min_slot * 128 + t] = s;
+      s_idx[min_slot * 128 + t] = col;
+    }
+    float m = s_score[t];
+    int ms = 0;
+#pragma unroll
+    for (int i = 1; i < kCand; ++i) {
+      const float v = s_score[i * 128 + t];
+      if (v < m) { m = v; ms = i; }
+    }
+    thr = m;
+    min_slot = ms;
+  }
+  __device__ void chunk(int, int, int col0, float (&v)[32]) {
+    float cmax = v[0];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, v[i]);
+    if (!(cmax > thr)) return;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (v[i] > thr) insert(v[i], col0 + i);
+  }
+  __device__ void end_unit(int m_tile, int split) {
+    if (!active) return;
+    const long row = static_cast<long>(m_tile) * 128 + t;
+    const long base = (row * p.n_splits + split) * kCand;
+    for (int i = 0; i < kCand; ++i) {
+      p.cand_score[base + i] = (i < cnt) ? s_score[i * 128 + t] : -INFINITY;
+      p.cand_idx[base + i] = (i < cnt) ? s_idx[i * 128 + t] : -1;
+    }
+    p.cand_thr[row * p.n_splits + split] = (cnt == kCand) ? thr : -INFINITY;
+  }
+};
+
+// ---- canonical fp64 dot: the ONE definition of an exact score -------------------------------------
+// lane l accumulates elements l, l+32, ..., l+224 in that order, then a fixed xor butterfly.
+// Products of two fp32 values are exact in fp64, so only the 8+5 additions round.
+__device__ __forceinline__ double warp_dot256(const float* __restrict__ a, const float* __restrict__ b, int lane) {
+  double acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < kEmbed / 32; ++i) acc = fma(static_cast<double>(a[i * 32 + lane]), static_cast<double>(b[i * 32 + lane]), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+__device__ __forceinline__ bool better(double sa, long ia, double sb, long ib) {  // (score desc, index asc); idx < 0 = empty
+  if (ia < 0) return false;
+  if (ib < 0) return true;
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+// Select the top-k of `n` candidates held in per-warp smem arrays; writes them in order.
+// Entries are consumed (their index is set to -1).
+__device__ void warp_select_topk(double* s_sc, long* s_ix, int n, int k, int lane, double* out_sc, long* out_ix) {
+  for (int r = 0; r < k; ++r) {
+    double bs = 0.0;
+    long bi = -1;
+    int bp = -1;
+    for (int c = lane; c < n; c += 32)
+      if (better(s_sc[c], s_ix[c], bs, bi)) { bs = s_sc[c]; bi = s_ix[c]; bp = c; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+      if (better(os, oi, bs, bi)) { bs = os; bi = oi; bp = op; }
+    }
+    if (lane == 0) {
+      out_sc[r] = (bi >= 0) ? bs : -INFINITY;
+      out_ix[r] = bi;
+      if (bp >= 0) s_ix[bp] = -1;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- exact re-rank + proof (one warp per query) ----------------------------------------------------
+constexpr int kRerankWarps = 4;
+
+__global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const float* __restrict__ Q, const float* __restrict__ D, const float* __restrict__ cand_score,
+                                                                   const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_thr,
+                                                                   const float* __restrict__ q_norm, const float* __restrict__ max_norm, int nq, int n_splits,
+                                                                   int k, long row_offset, int64_t* __restrict__ out_idx, double* __restrict__ out_score,
+                                                                   int32_t* __restrict__ flags, int32_t* __restrict__ n_fallback) {
+  __shared__ double s_sc[kRerankWarps][kMaxSplits * kCand];
+  __shared__ long s_ix[kRerankWarps][kMaxSplits * kCand];
+  __shared__ double s_osc[kRerankWarps][kMaxK];
+  __shared__ long s_oix[kRerankWarps][kMaxK];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * kRerankWarps + w;
+  if (q >= nq) return;
+  const int C = n_splits * kCand;
+  const float* qr = Q + static_cast<long>(q) * kEmbed;
+  for (int c = 0; c < C; ++c) {
+    const int idx = cand_idx[static_cast<long>(q) * C + c];  // warp-uniform
+    double s = 0.0;
+    if (idx >= 0) s = warp_dot256(qr, D + static_cast<long>(idx) * kEmbed, lane);
+    if (lane == 0) { s_sc[w][c] = s; s_ix[w][c] = idx; }
+  }
+  __syncwarp();
+  warp_select_topk(s_sc[w], s_ix[w], C, k, lane, s_osc[w], s_oix[w]);
+  // proof: every dropped row has approx <= thr_s, hence exact <= thr_s + eps; it cannot enter
+  // (or tie into) the top-k if thr_s + eps < k-th exact score.
+  const double kth = s_osc[w][k - 1];
+  const float eps = kEpsRel * q_norm[q] * max_norm[0];
+  bool fail = false;
+  for (int s = lane; s < n_splits; s += 32) {
+    const float thr = cand_thr[static_cast<long>(q) * n_splits + s];
+    if (thr != -INFINITY && !(static_cast<double>(thr) + static_cast<double>(eps) < kth)) fail = true;
+  }
+  fail = __any_sync(0xffffffffu, fail);
+  if (lane < k) {
+    const long ix = s_oix[w][lane];
+    out_idx[static_cast<long>(q) * k + lane] = ix >= 0 ? ix + row_offset : -1;
+    out_score[static_cast<long>(q) * k + lane] = s_osc[w][lane];
+  }
+  if (lane == 0) {
+    flags[q] = fail ? 1 : 0;
+    if (fail && n_fallback) atomicAdd(n_fallback, 1);
+  }
+}
+
+// ---- exact fp64 scan (one CTA per query) -------------------------------------------------------------
+constexpr int kScanWarps = 8;
+
+__global__ void __launch_bounds__(kScanWarps * 32) exact_scan_kernel(const float* __restrict__ Q, const float* __restrict__ D, long n_rows, int nq, int k,
+                                                                     long row_offset, const int32_t* __restrict__ only_flagged,
+                                                                     int64_t* __restrict__ out_idx, double* __restrict__ out_score) {
+  __shared__ double s_sc[kScanWarps * kCand];
+  __shared__ long s_ix[kScanWarps * kCand];
+  __shared__ double s_osc[kCand];
+  __shared__ long s_oix[kCand];
+  const int q = blockIdx.x;
+  if (q >= nq || (only_flagged && !only_flagged[q])) return;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* my_sc = s_sc + w * kCand;
+  long* my_ix = s_ix + w * kCand;
+  if (lane < kCand) { my_sc[lane] = -INFINITY; my_ix[lane] = -1; }
+  __syncwarp();
+  const float* qr = Q + static_cast<long>(q) * kEmbed;
+  int cnt = 0;
+  for (long r = w; r < n_rows; r += kScanWarps) {
+    const double s = warp_dot256(qr, D + r * kEmbed, lane);
+    // per-warp list sorted by (score desc, row asc); rows arrive in ascending order, so a row
+    // that ties an entry ranks after it
+    if (cnt < k || s > my_sc[k - 1]) {
+      if (lane == 0) {
+        int pos = cnt < k ? cnt : k - 1;
+        while (pos > 0 && my_sc[pos - 1] < s) { my_sc[pos] = my_sc[pos - 1]; my_ix[pos] = my_ix[pos - 1]; --pos; }
+        my_sc[pos] = s;
+        my_ix[pos] = r;
+      }
+      if (cnt < k) ++cnt;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (w == 0) {
+    warp_select_topk(s_sc, s_ix, kScanWarps * kCand, k, lane, s_osc, s_oix);
+    if (lane < k) {
+      const long ix = s_oix[lane];
+      out_idx[static_cast<long>(q) * k + lane] = ix >= 0 ? ix + row_offset : -1;
+      out_score[static_cast<long>(q) * k + lane] = s_osc[lane];
+    }
+  }
+}
+
+cudaError_t search_topk_exact(const SearchDb& db, const float* Q, int nq, int k, int64_t* out_idx, double* out_score,
+                              const int32_t* only_flagged, cudaStream_t st, Launches* lc) {
+  if (nq <= 0) return cudaSuccess;
+  if (k < 1 || k > kCand) return cudaErrorInvalidValue;
+  if (lc) lc->n++;
+  exact_scan_kernel<<<nq, kScanWarps * 32, 0, st>>>(Q, db.D, db.n_rows, nq, k, db.row_offset, only_flagged, out_idx, out_score);
+  return cudaGetLastError();
+}
+
+// ---- the search ----------------------------------------------------------------------------------------
+cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q, int nq, int k, int64_t* out_idx,
+                        double* out_score, int32_t* out_n_fallback, cudaStream_t st, Launches* lc) {
+  if (nq <= 0) return cudaSuccess;
+  if (k < 1 || k > kMaxK || nq > w.nq_cap) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if (out_n_fallback && (e = cudaMemsetAsync(out_n_fallback, 0, sizeof(int32_t), st)) != cudaSuccess) return e;
+  if (db.n_rows <= 0) return search_topk_exact(db, Q, nq, k, out_idx, out_score, nullptr, st, lc);
+
+  using Cfg = GemmCfg<256, true>;
+  if (lc) lc->n += 3;
+  split_planes_kernel<<<(nq + 7) / 8, 256, 0, st>>>(Q, nq, w.q_planes, w.q_norm, nullptr);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+  CUtensorMap ta, tb;
+  if (make_operand_map(&ta, w.q_planes, true, nq, 2 * kEmbed, 2 * kEmbed, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
+  if (make_operand_map(&tb, db.planes, true, db.n_rows, 2 * kEmbed, 2 * kEmbed, Cfg::BLOCK_N)) return cudaErrorInvalidValue;
+  GemmShape s;
+  s.M = nq;
+  s.N = static_cast<int>(db.n_rows);
+  s.m_tiles = (nq + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  s.n_tiles = (s.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
+  int want = (2 * tma_api().num_sms + s.m_tiles - 1) / s.m_tiles;  // aim for ~2 units per SM
+  int n_splits = want < 1 ? 1 : want;
+  if (n_splits > s.n_tiles) n_splits = s.n_tiles;
+  if (n_splits > kMaxSplits) n_splits = kMaxSplits;
+  if (n_splits > w.splits_cap) n_splits = w.splits_cap;
+  s.tiles_per_split = (s.n_tiles + n_splits - 1) / n_splits;
+  n_splits = (s.n_tiles + s.tiles_per_split - 1) / s.tiles_per_split;
+  s.n_splits = n_splits;
+  s.ks.n_pass = 3;
+  s.ks.kb_per_pass = kEmbed / Cfg::BLOCK_K;
+  s.ks.a_off[0] = 0;      s.ks.b_off[0] = 0;       // hi * hi
+  s.ks.a_off[1] = 0;      s.ks.b_off[1] = kEmbed;  // hi * lo
+  s.ks.a_off[2] = kEmbed; s.ks.b_off[2] = 0;       // lo * hi
+  TopKEpi::Params ep{w.cand_score, w.cand_idx, w.cand_thr, nq, s.N, n_splits};
+  if ((e = launch_umma_gemm<Cfg, TopKEpi>(ta, tb, s, ep, st)) != cudaSuccess) return e;
+
+  rerank_kernel<<<(nq + kRerankWarps - 1) / kRerankWarps, kRerankWarps * 32, 0, st>>>(
+      Q, db.D, w.cand_score, w.cand_idx, w.cand_thr, w.q_norm, db.max_norm, nq, n_splits, k, db.row_offset, out_idx, out_score, w.flags,
+      out_n_fallback);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  return search_topk_exact(db, Q, nq, k, out_idx, out_score, w.flags, st, lc);
+}
+
+// ---- merge of per-shard lists (one warp per query) -----------------------------------------------------
+__global__ void __launch_bounds__(128) merge_kernel(const int64_t* __restrict__ idx_all, const double* __restrict__ score_all, int n_shards, int nq, int k,
+                                                    int64_t* __restrict__ out_idx, double* __restrict__ out_score) {
+  __shared__ double s_sc[4][kMaxSplits * kCand];
+  __shared__ long s_ix[4][kMaxSplits * kCand];
+  __shared__ double s_osc[4][kCand];
+  __shared__ long s_oix[4][kCand];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + w;
+  if (q >= nq) return;
+  const int C = n_shards * k;
+  for (int c = lane; c < C; c += 32) {
+    const int g = c / k, j = c % k;
+    const long src = (static_cast<long>(g) * nq + q) * k + j;
+    s_sc[w][c] = score_all[src];
+    s_ix[w][c] = idx_all[src];
+  }
+  __syncwarp();
+  warp_select_topk(s_sc[w], s_ix[w], C, k, lane, s_osc[w], s_oix[w]);
+  if (lane < k) {
+    out_idx[static_cast<long>(q) * k + lane] = s_oix[w][lane];
+    out_score[static_cast<long>(q) * k + lane] = s_osc[w][lane];
+  }
+}
+
+cudaError_t merge_topk(const int64_t* idx_all, const double* score_all, int n_shards, int nq, int k, int64_t* out_idx,
+                       double* out_score, cudaStream_t st, Launches* lc) {
+  if (nq <= 0) return cudaSuccess;
+  if (k < 1 || k > kCand || n_shards < 1 || n_shards * k > kMaxSplits * kCand) return cudaErrorInvalidValue;
+  if (lc) lc->n++;
+  merge_kernel<<<(nq + 3) / 4, 128, 0, st>>>(idx_all, score_all, n_shards, nq, k, out_idx, out_score);
+  return cudaGetLastError();
+}
+
+}  // namespace t2l

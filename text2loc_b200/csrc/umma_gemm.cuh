@@ -1,0 +1,252 @@
+// Persistent, warp-specialised tcgen05 GEMM skeleton for sm_100a.
+//
+//   D[M,N] (fp32, TMEM) = A[M,K] * B[N,K]^T      both operands K-major (row-major, K contiguous)
+//
+// One CTA per SM loops over work units; a unit is one 128-row M tile and a contiguous range
+// of N tiles.  Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
+// warp 2 = TMEM allocator, warps 4..7 = epilogue (one TMEM lane quadrant each).  Three
+// pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, double-buffered
+// accumulator so the epilogue of tile t overlaps the MMAs of tile t+1), and the static
+// unit schedule.  Operand tiles are 128-byte rows (32 tf32 / 64 bf16 per k-block) with the
+// 128B TMA swizzle, which is what the UMMA shared-memory descriptor in common.cuh describes.
+//
+// The K loop is a list of "passes": pass p reads A columns a_off[p].. and B columns b_off[p]..
+// for kb_per_pass k-blocks.  One pass is an ordinary GEMM; three passes over [hi|lo] operand
+// planes give the error-compensated split product hi*hi + hi*lo + lo*hi in one accumulator.
+//
+// The epilogue is a policy class (see gemm_epilogues.cuh, search.cu):
+//   struct Epi { struct Params; static constexpr int kSmemBytes;
+//     __device__ Epi(const Params&, uint8_t* smem, int epi_warp, int lane);
+//     __device__ void begin_unit(int m_tile, int split);
+//     __device__ void chunk(int m_tile, int n_tile, int col0, float (&v)[32]);   // 32 fp32 columns of this thread's row
+//     __device__ void end_unit(int m_tile, int split); };
+#pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace t2l {
+
+struct KSchedule {
+  int n_pass;       // 1..3
+  int kb_per_pass;  // k-blocks per pass
+  int a_off[3];     // element offset along K of A for each pass
+  int b_off[3];     // element offset along K of B for each pass
+};
+
+struct GemmShape {
+  int M, N;
+  int m_tiles, n_tiles;
+  int n_splits;         // units per M tile
+  int tiles_per_split;  // N tiles per unit
+  KSchedule ks;
+};
+
+template <int kBlockN, bool kBf16>
+struct GemmCfg {
+  static constexpr int BLOCK_M = 128;
+  static constexpr int BLOCK_N = kBlockN;
+  static constexpr int ELEM_BYTES = kBf16 ? 2 : 4;
+  static constexpr int BLOCK_K = 128 / ELEM_BYTES;  // one 128-byte swizzle atom per row
+  static constexpr int UMMA_K = 32 / ELEM_BYTES;    // 8 (tf32) / 16 (bf16)
+  static constexpr int A_BYTES = BLOCK_M * 128;
+  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers
+  static constexpr int BAR_BYTES = 256;
+  static constexpr uint32_t IDESC = umma_idesc(kBf16 ? 1u : 2u, BLOCK_M, BLOCK_N);
+  static constexpr bool IS_BF16 = kBf16;
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two >= 32");
+  template <class Epi>
+  static constexpr int smem_bytes() { return 1024 + STAGES * STAGE_BYTES + BAR_BYTES + Epi::kSmemBytes; }
+};
+
+constexpr int kGemmThreads = 256;
+
+template <class Cfg, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const GemmShape shape, const typename Epi::Params ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* epi_smem = smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int n_units = shape.m_tiles * shape.n_splits;
+  const int kb_total = shape.ks.n_pass * shape.ks.kb_per_pass;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int m_tile = u / shape.n_splits, split = u % shape.n_splits;
+        const int nt0 = split * shape.tiles_per_split;
+        const int nt1 = min(nt0 + shape.tiles_per_split, shape.n_tiles);
+        for (int nt = nt0; nt < nt1; ++nt) {
+          for (int p = 0; p < shape.ks.n_pass; ++p) {
+            for (int kk = 0; kk < shape.ks.kb_per_pass; ++kk) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+              uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
+              tma_load_2d(&tm_a, &full_bar[stage], sa, shape.ks.a_off[p] + kk * Cfg::BLOCK_K, m_tile * Cfg::BLOCK_M, kEvictNormal);
+              tma_load_2d(&tm_b, &full_bar[stage], sa + Cfg::A_BYTES, shape.ks.b_off[p] + kk * Cfg::BLOCK_K, nt * Cfg::BLOCK_N, kEvictLast);
+              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int split = u % shape.n_splits;
+      const int nt0 = split * shape.tiles_per_split;
+      const int nt1 = min(nt0 + shape.tiles_per_split, shape.n_tiles);
+      for (int nt = nt0; nt < nt1; ++nt) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + acc * Cfg::BLOCK_N;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
+            const uint64_t adesc = umma_desc_sw128(sa);
+            const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+            for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
+              // advance 32 bytes (one UMMA_K slice) inside the swizzle atom: +2 in 16-byte units
+              if (Cfg::IS_BF16) umma_f16(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, (kb | k) != 0);
+              else umma_tf32(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, (kb | k) != 0);
+            }
+            tc_commit(&empty_bar[stage]);                         // smem slot free once these MMAs retire
+            if (kb == kb_total - 1) tc_commit(&tmem_full[acc]);  // accumulator ready
+          }
+          __syncwarp();
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
+    Epi epi(ep, epi_smem, ew, lane);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int m_tile = u / shape.n_splits, split = u % shape.n_splits;
+      const int nt0 = split * shape.tiles_per_split;
+      const int nt1 = min(nt0 + shape.tiles_per_split, shape.n_tiles);
+      epi.begin_unit(m_tile, split);
+      for (int nt = nt0; nt < nt1; ++nt) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * Cfg::BLOCK_N;
+#pragma unroll 1
+        for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
+          float v[32];
+          tmem_ld_32x32(t_addr + c * 32, v);
+          tmem_ld_wait();
+          epi.chunk(m_tile, nt, nt * Cfg::BLOCK_N + c * 32, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      epi.end_unit(m_tile, split);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------
+struct TmaApi {
+  typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeTiled encode = nullptr;
+  int num_sms = 0;
+};
+const TmaApi& tma_api();  // resolved once via cudaGetDriverEntryPoint (api.cu)
+
+// 2-D K-major operand [rows, k_elems] with row pitch `ld` elements; box = 128 bytes x box_rows.
+// Out-of-bounds elements (row or K tails) are zero-filled by the TMA unit.
+inline int make_operand_map(CUtensorMap* tm, const void* base, bool bf16, long rows, long k_elems, long ld, int box_rows) {
+  const int esz = bf16 ? 2 : 4;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_elems), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15)) return -1;
+  CUresult r = tma_api().encode(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                                const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+template <class Cfg, class Epi>
+cudaError_t launch_umma_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmShape& shape,
+                             const typename Epi::Params& ep, cudaStream_t stream) {
+  constexpr int smem = Cfg::template smem_bytes<Epi>();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<Cfg, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int n_units = shape.m_tiles * shape.n_splits;
+  if (n_units <= 0) return cudaSuccess;
+  const int grid = n_units < tma_api().num_sms ? n_units : tma_api().num_sms;
+  umma_gemm_kernel<Cfg, Epi><<<grid, kGemmThreads, smem, stream>>>(tm_a, tm_b, shape, ep);
+  return cudaGetLastError();
+}
+
+}  // namespace t2l

@@ -1,0 +1,166 @@
+"""Thin torch-facing wrapper over the C ABI: tensors in, tensors out, raw pointers across.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in
+libtext2loc_b200.so.  Work is enqueued on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib, weights
+
+EMBED_DIM = 256
+T5_DIM = 1024
+NUM_POINTS = 256
+MAX_TOPK_FAST = 12
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class Engine:
+    """One engine per CUDA device (t2l_create / t2l_destroy)."""
+
+    def __init__(self, device=None):
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise EngineError("text2loc_b200 needs a CUDA (sm_100a) device; there is no CPU path")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise EngineError(f"text2loc_b200 runs on CUDA devices only, got {self.device}")
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", index)
+        h = ctypes.c_void_p()
+        if self._lib.t2l_create(index, ctypes.byref(h)) != 0:
+            raise EngineError(self._lib.t2l_last_error(None).decode())
+        self._h = h
+        self._db = None  # keeps the database tensor alive (the engine holds a raw pointer to it)
+        self.has_weights = False
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.t2l_destroy(h)
+            self._h = None
+
+    # ---- plumbing -------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(self._lib.t2l_last_error(self._h).decode())
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, t, dtype):
+        t = torch.as_tensor(t)
+        if t.device != self.device or t.dtype != dtype or not t.is_contiguous():
+            t = t.to(device=self.device, dtype=dtype).contiguous()
+        return t
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.t2l_launch_count(self._h))
+
+    # ---- weights --------------------------------------------------------------------------
+    def load_state_dict(self, state_dict: dict):
+        """Reference checkpoint keys -> folded engine weights (text2loc_b200/weights.py)."""
+        for name, arr in weights.engine_weights(state_dict).items():
+            arr = np.ascontiguousarray(arr, dtype=np.float32)
+            self._check(self._lib.t2l_set_weight(
+                self._h, name.encode(), arr.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), arr.shape[0], arr.shape[1]))
+        self._check(self._lib.t2l_finalize_weights(self._h))
+        self.has_weights = True
+
+    # ---- encoders -------------------------------------------------------------------------
+    def encode_cells(self, pts, meta, cell_ptr) -> torch.Tensor:
+        """pts [n,256,6], meta [n,7], cell_ptr int32 [B+1] (host) -> unit rows [B,256] on device."""
+        pts = self._dev(pts, torch.float32)
+        meta = self._dev(meta, torch.float32)
+        cp = np.ascontiguousarray(np.asarray(cell_ptr.cpu() if torch.is_tensor(cell_ptr) else cell_ptr), dtype=np.int32)
+        n_cells = len(cp) - 1
+        if pts.dim() != 3 or pts.shape[1:] != (NUM_POINTS, 6) or meta.shape != (pts.shape[0], 7) or cp[-1] != pts.shape[0]:
+            raise EngineError(f"encode_cells: bad shapes pts {tuple(pts.shape)} meta {tuple(meta.shape)} cell_ptr[-1]={cp[-1]}")
+        out = torch.empty((n_cells, EMBED_DIM), dtype=torch.float32, device=self.device)
+        self._check(self._lib.t2l_encode_cells(
+            self._h, _ptr(pts), _ptr(meta), cp.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), n_cells, _ptr(out), self._stream()))
+        return out
+
+    def encode_objects_debug(self, pts, cell_ptr) -> dict:
+        """PointNet++ features2 and the FPS / ball-query index sets (parity tests)."""
+        pts = self._dev(pts, torch.float32)
+        cp = np.ascontiguousarray(np.asarray(cell_ptr.cpu() if torch.is_tensor(cell_ptr) else cell_ptr), dtype=np.int32)
+        n = pts.shape[0]
+        u8 = lambda *s: torch.zeros(s, dtype=torch.uint8, device=self.device)
+        r = dict(features2=torch.empty((n, 256), dtype=torch.float32, device=self.device),
+                 fps1=u8(n, 128), fps2=u8(n, 64), fps3=u8(n, 32), nbr1=u8(n, 128, 32), nbr2=u8(n, 64, 32), nbr3=u8(n, 32, 32),
+                 cnt1=u8(n, 128), cnt2=u8(n, 64), cnt3=u8(n, 32))
+        self._check(self._lib.t2l_encode_objects_debug(
+            self._h, _ptr(pts), cp.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(cp) - 1,
+            *[_ptr(r[k]) for k in ("features2", "fps1", "fps2", "fps3", "nbr1", "nbr2", "nbr3", "cnt1", "cnt2", "cnt3")], self._stream()))
+        return r
+
+    def encode_text(self, t5, n_sent: int) -> torch.Tensor:
+        """t5 [nq*n_sent, n_tok, 1024] (T5 last_hidden_state) -> unit rows [nq,256] on device."""
+        t5 = self._dev(t5, torch.float32)
+        if t5.dim() != 3 or t5.shape[2] != T5_DIM or t5.shape[0] % n_sent:
+            raise EngineError(f"encode_text: bad shape {tuple(t5.shape)} for n_sent={n_sent}")
+        nq = t5.shape[0] // n_sent
+        out = torch.empty((nq, EMBED_DIM), dtype=torch.float32, device=self.device)
+        self._check(self._lib.t2l_encode_text(self._h, _ptr(t5), nq, n_sent, t5.shape[1], _ptr(out), self._stream()))
+        return out
+
+    # ---- search ---------------------------------------------------------------------------
+    def db_build(self, D, row_offset: int = 0):
+        D = self._dev(D, torch.float32)
+        if D.dim() != 2 or D.shape[1] != EMBED_DIM:
+            raise EngineError(f"db_build: database must be [N,256], got {tuple(D.shape)}")
+        self._db = D
+        self._check(self._lib.t2l_db_build(self._h, _ptr(D), D.shape[0], int(row_offset), self._stream()))
+
+    def search_topk(self, Q, k: int, exact: bool = False):
+        """-> (idx int64 [nq,k], score float64 [nq,k], n_fallback int tensor [1]); order (score desc, row asc)."""
+        if self._db is None:
+            raise EngineError("search_topk: call db_build first")
+        Q = self._dev(Q, torch.float32)
+        if Q.dim() != 2 or Q.shape[1] != EMBED_DIM:
+            raise EngineError(f"search_topk: queries must be [nq,256], got {tuple(Q.shape)}")
+        nq = Q.shape[0]
+        idx = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        sc = torch.empty((nq, k), dtype=torch.float64, device=self.device)
+        nfb = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if exact or k > MAX_TOPK_FAST:
+            self._check(self._lib.t2l_search_topk_exact(self._h, _ptr(Q), nq, k, _ptr(idx), _ptr(sc), self._stream()))
+        else:
+            self._check(self._lib.t2l_search_topk(self._h, _ptr(Q), nq, k, _ptr(idx), _ptr(sc), _ptr(nfb), self._stream()))
+        return idx, sc, nfb
+
+    def merge_topk(self, idx_all, score_all):
+        """[G,nq,k] per-shard lists -> global (idx, score) [nq,k]."""
+        idx_all = self._dev(idx_all, torch.int64)
+        score_all = self._dev(score_all, torch.float64)
+        G, nq, k = idx_all.shape
+        idx = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        sc = torch.empty((nq, k), dtype=torch.float64, device=self.device)
+        self._check(self._lib.t2l_merge_topk(self._h, _ptr(idx_all), _ptr(score_all), G, nq, k, _ptr(idx), _ptr(sc), self._stream()))
+        return idx, sc
+
+    # ---- test hook --------------------------------------------------------------------------
+    def debug_linear(self, A, W, bias=None, act=0, segmax=False, path=1):
+        rowmajor = lambda t: t if (t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1) else self._dev(t, torch.float32)
+        A, W = rowmajor(A), rowmajor(W)  # row-padded views (stride(0) > K) are passed through as lda / ldw
+        bias = self._dev(bias, torch.float32) if bias is not None else None
+        M, K = A.shape
+        N = W.shape[0]
+        C = torch.empty((M // 32 if segmax else M, N), dtype=torch.float32, device=self.device)
+        self._check(self._lib.t2l_debug_linear(self._h, path, _ptr(A), A.stride(0), _ptr(W), W.stride(0), _ptr(bias), _ptr(C), N,
+                                               M, N, K, act, int(segmax), self._stream()))
+        return C

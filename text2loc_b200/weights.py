@@ -1,0 +1,85 @@
+"""Reference checkpoint -> engine weights.
+
+Takes a ``CellRetrievalNetwork.state_dict()`` (key layout: SURVEY.md Appendix B; the same keys
+``training/coarse.py:327-332`` saves and ``evaluation/coarse.py:123`` loads with strict=False)
+and produces the flat, BatchNorm-folded tensors the C ABI's ``t2l_set_weight`` expects.
+
+Folding (eval mode, models/language_encoder.py:28-31):  y = (Wx + b - mu) / sqrt(var + 1e-5) * g + beta
+  ->  W' = diag(g / sqrt(var + eps)) W,   b' = (b - mu) * g / sqrt(var + eps) + beta
+computed in float64 and rounded once to float32.
+
+The first Linear of each PointConv MLP is split by input columns ([x_j | pos_j - pos_i],
+PyG PointConv.message): ``w1x`` acts on the point features (once per point), ``w1p`` on the
+relative position (once per edge).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+BN_EPS = 1e-5
+
+
+def _np(v):
+    if hasattr(v, "detach"):
+        v = v.detach().cpu().numpy()
+    return np.asarray(v)
+
+
+def fold_linear_bn(sd, prefix):
+    """<prefix>.0 = Linear, <prefix>.1 = BatchNorm1d  ->  (W', b') float32."""
+    W = _np(sd[prefix + ".0.weight"]).astype(np.float64)
+    b = _np(sd[prefix + ".0.bias"]).astype(np.float64)
+    g = _np(sd[prefix + ".1.weight"]).astype(np.float64)
+    beta = _np(sd[prefix + ".1.bias"]).astype(np.float64)
+    mu = _np(sd[prefix + ".1.running_mean"]).astype(np.float64)
+    var = _np(sd[prefix + ".1.running_var"]).astype(np.float64)
+    s = g / np.sqrt(var + BN_EPS)
+    return (W * s[:, None]).astype(np.float32), ((b - mu) * s + beta).astype(np.float32)
+
+
+def _attn(out, sd, src, dst):
+    f = lambda k: _np(sd[f"{src}.{k}"]).astype(np.float32)
+    out[dst + ".in_w"] = f("self_attn.in_proj_weight")
+    out[dst + ".in_b"] = f("self_attn.in_proj_bias")
+    out[dst + ".out_w"] = f("self_attn.out_proj.weight")
+    out[dst + ".out_b"] = f("self_attn.out_proj.bias")
+    out[dst + ".l1_w"] = f("linear1.weight")
+    out[dst + ".l1_b"] = f("linear1.bias")
+    out[dst + ".l2_w"] = f("linear2.weight")
+    out[dst + ".l2_b"] = f("linear2.bias")
+    out[dst + ".n1_w"] = f("norm1.weight")
+    out[dst + ".n1_b"] = f("norm1.bias")
+    out[dst + ".n2_w"] = f("norm2.weight")
+    out[dst + ".n2_b"] = f("norm2.bias")
+
+
+def engine_weights(sd: dict) -> dict:
+    """name -> float32 2-D array (biases and norm vectors as [1, n])."""
+    out = {}
+    pn = "object_encoder.pointnet"
+    for i, c_in in ((1, 3), (2, 64), (3, 128)):
+        w1, b1 = fold_linear_bn(sd, f"{pn}.sa{i}.point_conv.local_nn.0")
+        w2, b2 = fold_linear_bn(sd, f"{pn}.sa{i}.point_conv.local_nn.1")
+        assert w1.shape[1] == c_in + 3
+        out[f"sa{i}.w1x"], out[f"sa{i}.w1p"], out[f"sa{i}.b1"] = w1[:, :c_in], w1[:, c_in:], b1
+        out[f"sa{i}.w2"], out[f"sa{i}.b2"] = w2, b2
+    out["ga.w1"], out["ga.b1"] = fold_linear_bn(sd, f"{pn}.ga.mlp.0")
+    out["ga.w2"], out["ga.b2"] = fold_linear_bn(sd, f"{pn}.ga.mlp.1")
+    for n in ("lin1", "lin2"):
+        out[n + ".w"], out[n + ".b"] = _np(sd[f"{pn}.{n}.weight"]), _np(sd[f"{pn}.{n}.bias"])
+    oe = "object_encoder"
+    out["mlp_pointnet.w"], out["mlp_pointnet.b"] = fold_linear_bn(sd, f"{oe}.mlp_pointnet.0")
+    for src, dst in (("color_encoder", "color"), ("pos_encoder", "pos"), ("num_encoder", "num")):
+        out[dst + ".w1"], out[dst + ".b1"] = fold_linear_bn(sd, f"{oe}.{src}.0")
+        out[dst + ".w2"], out[dst + ".b2"] = fold_linear_bn(sd, f"{oe}.{src}.1")
+    out["merge.w"], out["merge.b"] = fold_linear_bn(sd, f"{oe}.mlp_merge.0")
+    _attn(out, sd, "obj_inter_module.0", "obj_attn0")
+    _attn(out, sd, "obj_inter_module.1", "obj_attn1")
+    _attn(out, sd, "language_encoder.intra_module.0", "txt_intra")
+    _attn(out, sd, "language_encoder.inter_module.0", "txt_inter")
+    out["txt_mlp.w"], out["txt_mlp.b"] = fold_linear_bn(sd, "language_encoder.inter_mlp.0")
+    return {k: np.ascontiguousarray(np.atleast_2d(np.asarray(v, dtype=np.float32))) for k, v in out.items()}
+
+
+REQUIRED_PREFIXES = ("object_encoder.pointnet.sa1", "object_encoder.mlp_merge", "obj_inter_module.0",
+                     "language_encoder.intra_module.0", "language_encoder.inter_mlp.0", "language_encoder.inter_module.0")
