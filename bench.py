@@ -248,8 +248,7 @@ def run_engine_arm(args):
         return t2ld.sharded_search(eng, q_local, K_TOP, queries_are_sharded=world > 1)
 
     def step_e2e():
-        t5 = t5_h.to(dev, non_blocking=True)
-        q_local = model.encode_text_features(t5, N_SENT)
+        q_local = model.encode_text_features(t5_h, N_SENT)  # pinned host input: the engine streams it H2D in chunks
         idx, score, nfb = t2ld.sharded_search(eng, q_local, K_TOP, queries_are_sharded=world > 1)
         return idx.to("cpu", non_blocking=True), score.to("cpu", non_blocking=True), nfb
 
@@ -268,7 +267,7 @@ def run_engine_arm(args):
 
     with ClockSampler(local_rank) as clocks:
         ms_step, launches, out = timed(step_resident, args.steps, args.warmup)
-    ms_e2e, _, out_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+        ms_e2e, _, out_e2e = timed(step_e2e, args.steps, args.warmup)
     idx, score, nfb = out
 
     # stage split (resident), one extra pass with events between the stages

@@ -18,6 +18,7 @@ from text2loc_b200.engine import Engine  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--small", action="store_true", help="one chunk of each stage only (for --set full captures)")
+ap.add_argument("--skip-cells", action="store_true", help="profile the query step only")
 ap.add_argument("--cells", type=int, default=0)
 ap.add_argument("--queries", type=int, default=0)
 args = ap.parse_args()
@@ -36,8 +37,9 @@ eng.search_topk(q, 10)
 torch.cuda.synchronize()
 
 torch.cuda.profiler.start()
-D = eng.encode_cells(pts, meta, ptr)
-eng.db_build(D)
+if not args.skip_cells:
+    D = eng.encode_cells(pts, meta, ptr)
+    eng.db_build(D)
 q = eng.encode_text(t5, 6)
 idx, sc, nfb = eng.search_topk(q, 10)
 torch.cuda.synchronize()

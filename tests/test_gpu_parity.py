@@ -84,6 +84,18 @@ def test_encode_text_shapes(eng, state_dict):
         assert row_rel_err(got, want) < EMB_TOL, (nq, S, L)
 
 
+def test_encode_text_host_streaming_equals_device(eng):
+    """Host (pinned) input is uploaded in chunks on a side stream; same result as a resident tensor."""
+    from text2loc_b200 import synth
+
+    t5 = torch.from_numpy(synth.make_t5_features(77, 1000, 6, 12))  # > 2 engine chunks of 455 queries
+    a = eng.encode_text(t5.pin_memory(), 6)
+    b = eng.encode_text(t5.cuda(), 6)
+    c = eng.encode_text(t5, 6)  # pageable host memory also works (copies are then synchronous)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(c, b)
+
+
 # ---- search ----------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("n,nq,k", [(3000, 64, 10), (20000, 1000, 10), (257, 130, 5), (100000, 512, 10), (1000, 1, 1), (5000, 300, 12)])

@@ -1,0 +1,98 @@
+"""CPU tests of the host side: the C-ABI library builds, loads and exports every symbol the header
+declares (no compute without a GPU), weight folding, input packing, the failure mode without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from text2loc_b200 import _lib
+
+    _lib.build()
+    return _lib.load()
+
+
+def test_library_exports_every_header_symbol(lib):
+    from text2loc_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "text2loc_b200.h")).read()
+    declared = set(re.findall(r"\b(t2l_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert getattr(raw, name) is not None
+    assert lib.t2l_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_engine_fails_loudly_without_cuda(lib):
+    from text2loc_b200.engine import Engine, EngineError
+
+    h = ctypes.c_void_p()
+    assert lib.t2l_create(0, ctypes.byref(h)) != 0
+    assert b"no CPU path" in lib.t2l_last_error(None)
+    with pytest.raises(EngineError):
+        Engine()
+
+
+def test_bn_folding_matches_torch_modules(state_dict):
+    from text2loc_b200 import weights
+
+    sd = {k: torch.as_tensor(np.asarray(v)) for k, v in state_dict.items()}
+    pre = "object_encoder.mlp_merge.0"
+    lin = torch.nn.Linear(1024, 256)
+    bn = torch.nn.BatchNorm1d(256)
+    lin.load_state_dict({"weight": sd[pre + ".0.weight"], "bias": sd[pre + ".0.bias"]})
+    bn.load_state_dict({k: sd[f"{pre}.1.{k}"] for k in ("weight", "bias", "running_mean", "running_var", "num_batches_tracked")})
+    bn.eval()
+    x = torch.randn(16, 1024)
+    W, b = weights.fold_linear_bn(state_dict, pre)
+    with torch.no_grad():
+        want = bn(lin(x))
+    got = x @ torch.from_numpy(W).T + torch.from_numpy(b)
+    assert (got - want).abs().max() < 1e-5
+
+
+def test_engine_weight_names_cover_what_the_engine_requires(state_dict):
+    from text2loc_b200 import weights
+
+    ew = weights.engine_weights(state_dict)
+    api = open(os.path.join(ROOT, "text2loc_b200", "csrc", "api.cu")).read()
+    required = set(re.findall(r'"((?:sa\d|ga|lin\d|mlp_pointnet|color|pos|num|merge|txt_mlp)\.[a-z0-9]+)"', api))
+    for a in ("obj_attn0", "obj_attn1", "txt_intra", "txt_inter"):
+        required |= {f"{a}.{p}" for p in ("in_w", "in_b", "out_w", "out_b", "l1_w", "l1_b", "l2_w", "l2_b", "n1_w", "n1_b", "n2_w", "n2_b")}
+    assert required <= set(ew), required - set(ew)
+    assert ew["sa2.w1x"].shape == (128, 64) and ew["sa2.w1p"].shape == (128, 3) and ew["ga.w1"].shape == (512, 259)
+    assert all(v.dtype == np.float32 and v.ndim == 2 for v in ew.values())
+
+
+def test_pack_cells_layout_and_errors():
+    from text2loc_b200 import dataio, synth
+
+    cells = synth.make_cell_objects(1, 2, [2, 3], max_raw=100)
+    np.random.seed(0)
+    batches = [dataio.batch_object_points(o, dataio.FixedPoints(256)) for o in cells]
+    pts, meta, ptr = dataio.pack_cells(cells, batches)
+    assert pts.shape == (5, 256, 6) and meta.shape == (5, 7) and ptr.tolist() == [0, 2, 5]
+    assert torch.equal(pts[2, :, 0:3], batches[1].pos[:256]) and torch.equal(pts[2, :, 3:6], batches[1].x[:256])
+    assert np.allclose(meta[3, 3:6].numpy(), cells[1][1].get_center(), atol=1e-6) and meta[3, 6] == len(cells[1][1].xyz)
+    bad = dataio.PointsBatch(batches[0].x[:300], batches[0].pos[:300])
+    with pytest.raises(ValueError):
+        dataio.pack_cells(cells[:1], [bad])
+
+
+def test_packed_generator_matches_object_generator_statistics():
+    from text2loc_b200 import synth
+
+    pts, meta, ptr = synth.make_packed_cells(0, 50, 8)
+    assert pts.shape == (400, 256, 6) and ptr[-1] == 400 and pts.dtype == np.float32
+    assert 0 <= pts[:, :, 3:].min() and pts[:, :, 3:].max() <= 1 and 30 <= meta[:, 6].min() and meta[:, 6].max() <= 5000
+    span = pts[:, :, :3].max(axis=1) - pts[:, :, :3].min(axis=1)
+    assert span.max() < 0.31  # objects are smaller than every ball-query radius's diameter: the 32-neighbour cap is hit

@@ -29,9 +29,14 @@ struct Weight {
 struct Arena {
   uint8_t* base = nullptr;
   size_t cap = 0, off = 0;
+  bool overflow = false;
   template <class T>
   T* get(size_t n) {
     off = (off + 255) & ~size_t(255);
+    if (off + n * sizeof(T) > cap) {  // never hand out an out-of-bounds pointer; the caller fails the call
+      overflow = true;
+      return reinterpret_cast<T*>(base);
+    }
     T* p = reinterpret_cast<T*>(base + off);
     off += n * sizeof(T);
     return p;
@@ -73,6 +78,7 @@ static int fail(t2l_engine* e, const char* fmt, ...) {
   } while (0)
 
 static int ensure_arena(t2l_engine* e, size_t bytes) {
+  e->arena.overflow = false;
   if (e->arena.cap >= bytes) { e->arena.off = 0; return 0; }
   if (e->arena.base) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->arena.base)); e->arena.base = nullptr; e->arena.cap = 0; }
   bytes += bytes / 8;
@@ -145,6 +151,14 @@ static bool is_tf32_operand(const std::string& n) {
   return false;
 }
 
+static bool is_split3_operand(const std::string& n) {
+  // weights of the fp32-accurate tensor-core layers: stored as [hi | lo] tf32 planes
+  static const char* pre[] = {"obj_attn0", "obj_attn1", "txt_inter"};
+  static const char* parts[] = {".in_w", ".out_w", ".l1_w", ".l2_w"};
+  for (const char* p : pre) for (const char* q : parts) if (n == std::string(p) + q) return true;
+  return n == "txt_mlp.w";
+}
+
 static float host_round_tf32(float x) {
   uint32_t u;
   memcpy(&u, &x, 4);
@@ -158,13 +172,21 @@ extern "C" int t2l_set_weight(t2l_engine* e, const char* name, const float* data
   CU(cudaSetDevice(e->device));
   Weight& w = e->w[name];
   if (w.dev) { CU(cudaFree(w.dev)); w.dev = nullptr; }
-  w.rows = rows; w.cols = cols; w.ld = (cols + 3) & ~3;
+  const bool split3 = is_split3_operand(name);
+  if (split3 && (cols % 32)) return fail(e, "t2l_set_weight: '%s' needs cols %% 32 == 0", name);
+  w.rows = rows; w.cols = cols; w.ld = split3 ? 2 * cols : ((cols + 3) & ~3);
   std::vector<float> host(static_cast<size_t>(rows) * w.ld, 0.f);
   const bool rnd = is_tf32_operand(name);
   for (int r = 0; r < rows; ++r)
     for (int c = 0; c < cols; ++c) {
       const float v = data[static_cast<size_t>(r) * cols + c];
-      host[static_cast<size_t>(r) * w.ld + c] = rnd ? host_round_tf32(v) : v;
+      if (split3) {
+        const float hi = host_round_tf32(v);
+        host[static_cast<size_t>(r) * w.ld + c] = hi;
+        host[static_cast<size_t>(r) * w.ld + cols + c] = host_round_tf32(v - hi);
+      } else {
+        host[static_cast<size_t>(r) * w.ld + c] = rnd ? host_round_tf32(v) : v;
+      }
     }
   CU(cudaMalloc(&w.dev, host.size() * sizeof(float)));
   CU(cudaMemcpy(w.dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -210,9 +232,25 @@ static cudaError_t lin(t2l_engine* e, bool umma, const float* A, long lda, int M
   return umma ? linear_umma(l, st, &e->lc) : linear_simt(l, st, &e->lc);
 }
 
+// fp32-accurate layer on the tensor cores: split A into [hi | lo] tf32 planes, three-pass GEMM
+// against the weight's planes (hi*hi + lo*hi + hi*lo).  Error ~2^-21 per product, i.e. fp32 level.
+static cudaError_t lin3(t2l_engine* e, const float* A, long lda, int M, const std::string& wname, const std::string& bname, float* C,
+                        long ldc, int act, cudaStream_t st, const float* residual = nullptr, long ldr = 0) {
+  const Weight& w = W(e, wname);
+  float* planes = e->arena.get<float>(static_cast<size_t>(M) * 2 * w.cols);
+  cudaError_t err = split_tf32_planes(A, lda, planes, M, w.cols, st, &e->lc);
+  if (err != cudaSuccess) return err;
+  Linear l;
+  l.A = planes; l.lda = 2L * w.cols; l.W = w.dev; l.ldw = w.ld; l.bias = bname.empty() ? nullptr : W(e, bname).dev;
+  l.C = C; l.ldc = ldc; l.M = M; l.N = w.rows; l.K = w.cols; l.act = act; l.residual = residual; l.ldr = ldr; l.passes = 3;
+  return linear_umma(l, st, &e->lc);
+}
+
 // One post-norm nn.TransformerEncoderLayer on packed rows [n_seq * S, d] (sequence-major).
-// umma: run the four projections on the tf32 tensor-core path (text token layer only).
-static int encoder_layer(t2l_engine* e, const std::string& pfx, bool umma, const float* X, float* Xout, int n_seq, int S, int d, int ffn,
+// fast: single-pass tf32 projections (text token layer, where the FLOPs are); otherwise the
+// three-pass split product, which keeps fp32 accuracy (the object and sentence layers amplify
+// operand rounding the most, DESIGN.md precision table).
+static int encoder_layer(t2l_engine* e, const std::string& pfx, bool fast, const float* X, float* Xout, int n_seq, int S, int d, int ffn,
                          cudaStream_t st) {
   const int rows = n_seq * S;
   Arena& a = e->arena;
@@ -221,12 +259,21 @@ static int encoder_layer(t2l_engine* e, const std::string& pfx, bool umma, const
   float* y = a.get<float>(static_cast<size_t>(rows) * d);
   float* x1 = a.get<float>(static_cast<size_t>(rows) * d);
   float* h = a.get<float>(static_cast<size_t>(rows) * ffn);
-  CU(lin(e, umma, X, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st));
-  CU(mha_small(qkv, att, n_seq, S, d, 4, st, &e->lc));
-  CU(lin(e, umma, att, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, X, d));
-  CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc));
-  CU(lin(e, umma, x1, d, rows, pfx + ".l1_w", pfx + ".l1_b", h, ffn, 1, st, nullptr, 0, umma ? 1 : 0));
-  CU(lin(e, umma, h, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x1, d));
+  if (fast) {
+    CU(lin(e, true, X, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st));
+    CU(mha_small(qkv, att, n_seq, S, d, 4, st, &e->lc, /*round_out=*/1));
+    CU(lin(e, true, att, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, X, d));
+    CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc));
+    CU(lin(e, true, x1, d, rows, pfx + ".l1_w", pfx + ".l1_b", h, ffn, 1, st, nullptr, 0, 1));
+    CU(lin(e, true, h, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x1, d));
+  } else {
+    CU(lin3(e, X, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st));
+    CU(mha_small(qkv, att, n_seq, S, d, 4, st, &e->lc));
+    CU(lin3(e, att, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, X, d));
+    CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc));
+    CU(lin3(e, x1, d, rows, pfx + ".l1_w", pfx + ".l1_b", h, ffn, 1, st));
+    CU(lin3(e, h, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x1, d));
+  }
   CU(layer_norm_rows(y, Xout, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, rows, d, st, &e->lc));
   return 0;
 }
@@ -242,7 +289,7 @@ struct ObjDebug {
 
 static size_t obj_chunk_bytes(size_t n, size_t cells) {
   // generous upper bound of everything encode_chunk carves from the arena
-  return n * (size_t(1) << 21) + n * 700000 + cells * size_t(28) * 256 * 4 * 12 + (size_t(1) << 20);
+  return n * (size_t(1) << 21) + n * 700000 + cells * size_t(28) * 256 * 4 * 32 + (size_t(1) << 20);
 }
 
 static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr, int c0, int c1, float* out,
@@ -365,6 +412,7 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
   if (encoder_layer(e, "obj_attn1", false, Xb, X, B, 28, 256, 512, st)) return 1;
   CU(max_over_rows(X, pooled, B, 28, 256, st, &e->lc));
   CU(l2_normalize_rows(pooled, 256, out + static_cast<size_t>(c0) * 256, 256, B, 256, st, &e->lc));
+  if (a.overflow) return fail(e, "internal: workspace arena too small for %d objects / %d cells", n, B);
   return 0;
 }
 
@@ -417,7 +465,7 @@ extern "C" int t2l_encode_text(t2l_engine* e, const float* t5, int nq, int S, in
     const int nqc = (nq - q0 < qc) ? nq - q0 : qc;
     const int n_seq = nqc * S;               // sentences
     const size_t T = static_cast<size_t>(n_seq) * L;  // tokens
-    if (ensure_arena(e, T * (3 * d + 3 * d + 4 * d + d) * 4 + static_cast<size_t>(n_seq) * (d + 16 * 256) * 4 + (size_t(1) << 22))) return 1;
+    if (ensure_arena(e, T * (3 * d + 3 * d + 4 * d + d) * 4 + static_cast<size_t>(n_seq) * (d + 64 * 256) * 4 + (size_t(1) << 22))) return 1;
     Arena& a = e->arena;
     const float* X = t5 + static_cast<size_t>(q0) * S * L * d;
     // intra_module: one encoder layer over the tokens of each sentence, no key-padding mask (:130-131)
@@ -429,12 +477,13 @@ extern "C" int t2l_encode_text(t2l_engine* e, const float* t5, int nq, int S, in
     float* z2 = a.get<float>(static_cast<size_t>(n_seq) * 256);
     float* zq = a.get<float>(static_cast<size_t>(nqc) * 256);
     CU(max_over_rows(X2, pooled, n_seq, L, d, st, &e->lc));
-    CU(lin(e, false, pooled, d, n_seq, "txt_mlp.w", "txt_mlp.b", z, 256, 0, st));
+    CU(lin3(e, pooled, d, n_seq, "txt_mlp.w", "txt_mlp.b", z, 256, 0, st));
     // inter_module over the S sentences of each query with the extra residual `x += layer(x)` (:143-145)
     if (encoder_layer(e, "txt_inter", false, z, z2, nqc, S, 256, 1024, st)) return 1;
     CU(add_rows(z, z2, z2, static_cast<long>(n_seq) * 256, st, &e->lc));
     CU(max_over_rows(z2, zq, nqc, S, 256, st, &e->lc));                       // max over sentences (:147)
     CU(l2_normalize_rows(zq, 256, out + static_cast<size_t>(q0) * 256, 256, nqc, 256, st, &e->lc));  // cell_retrieval.py:61
+    if (a.overflow) return fail(e, "internal: workspace arena too small for %zu tokens", T);
   }
   return 0;
 }

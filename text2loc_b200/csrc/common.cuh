@@ -150,6 +150,17 @@ T2L_DEVICE void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
       : "r"(taddr));
 }
 T2L_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.ld is asynchronous: its destination registers are only valid after wait::ld.  The
+// compiler does not know that, so after the wait the values are passed through an empty
+// volatile asm (volatile asms keep their order), which pins every use behind the wait.
+T2L_DEVICE void tmem_ld_wait(float (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                    "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+  asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                    "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
 
 // ---------------------------------------------------------------------------------------
 // misc

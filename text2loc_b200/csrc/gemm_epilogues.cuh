@@ -1,4 +1,9 @@
 // Epilogue policies for umma_gemm_kernel (see umma_gemm.cuh for the interface).
+//
+// Global loads the epilogue needs (bias, the SegMax side input) are issued in begin_tile(), i.e.
+// BEFORE the warp blocks on the accumulator barrier, so their latency hides behind the MMAs of
+// the tile instead of sitting on the epilogue's critical path (profiles/r01: the v1 epilogue spent
+// ~1.2k cycles per 32-column chunk in long-scoreboard stalls on exactly these loads).
 #pragma once
 
 #include "common.cuh"
@@ -6,10 +11,11 @@
 namespace t2l {
 
 enum : int { kActNone = 0, kActRelu = 1 };
+constexpr int kEpiBiasSmem = 4 * 256 * 4;  // one 256-float bias slice per epilogue warp
 
 // C[row, col] = act(acc + bias[col]) (+ residual[row, col]);  optional tf32 rounding of the
 // stored value when the consumer is another tf32 GEMM (round-to-nearest instead of the
-// truncation the tensor core would apply to a raw fp32 operand).
+// truncation the tensor core applies to a raw fp32 operand).
 struct StoreEpi {
   struct Params {
     float* C;
@@ -21,42 +27,48 @@ struct StoreEpi {
     int act;
     int round_out;
   };
-  static constexpr int kSmemBytes = 0;
+  static constexpr int kSmemBytes = kEpiBiasSmem;
   const Params& p;
-  int ew, lane;
-  __device__ StoreEpi(const Params& p_, uint8_t*, int ew_, int lane_) : p(p_), ew(ew_), lane(lane_) {}
+  float* s_bias;
+  int ew, lane, block_n;
+  __device__ StoreEpi(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_)
+      : p(p_), s_bias(reinterpret_cast<float*>(smem) + ew_ * 256), ew(ew_), lane(lane_), block_n(block_n_) {}
   __device__ void begin_unit(int, int) {}
   __device__ void end_unit(int, int) {}
-  __device__ void chunk(int m_tile, int, int col0, float (&v)[32]) {
+  __device__ void begin_tile(int, int, int col0) {
+    __syncwarp();
+    for (int i = lane; i < block_n; i += 32) s_bias[i] = (p.bias && col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
+    __syncwarp();
+  }
+  __device__ void chunk(int m_tile, int, int c, int col0, float (&v)[32]) {
     const long row = static_cast<long>(m_tile) * 128 + ew * 32 + lane;
     if (row >= p.M || col0 >= p.N) return;
     float* dst = p.C + row * p.ldc + col0;
-    const float* res = p.residual ? p.residual + row * p.ldr + col0 : nullptr;
+    float4 r[8];
+    if (p.residual) {
+      const float4* res = reinterpret_cast<const float4*>(p.residual + row * p.ldr + col0);
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float4 o;
-      float* of = reinterpret_cast<float*>(&o);
+      for (int i = 0; i < 8; ++i) r[i] = __ldg(res + i);  // all eight loads in flight before the first use
+    }
+    const float4* sb = reinterpret_cast<const float4*>(s_bias + c * 32);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float x = v[i + j];
-        if (p.bias) x += __ldg(p.bias + col0 + i + j);
-        if (p.act == kActRelu) x = fmaxf(x, 0.f);
-        of[j] = x;
-      }
-      if (res) {
-        const float4 r = *reinterpret_cast<const float4*>(res + i);
-        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-      }
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = sb[i];  // same address in every lane: broadcast
+      float4 o = make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w);
+      if (p.act == kActRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      if (p.residual) { o.x += r[i].x; o.y += r[i].y; o.z += r[i].z; o.w += r[i].w; }
       if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-      *reinterpret_cast<float4*>(dst + i) = o;
+      reinterpret_cast<float4*>(dst)[i] = o;
     }
   }
 };
 
 // out[g, col] = max over the 32 rows of group g of relu(acc + bias[col]), optionally also
 // max'ed with side[g, col].  A group is 32 consecutive rows = exactly one epilogue warp's TMEM
-// lane quadrant, so the reduction is a warp reduction.  Post-ReLU values are >= +0, whose
-// IEEE bit patterns order like unsigned integers, so redux.sync.max.u32 does the max.
+// lane quadrant, so the reduction is a warp reduction: a 5-stage exchange butterfly in which
+// every stage halves the columns a lane still holds (16+8+4+2+1 = 31 shuffles for all 32
+// columns), after which lane l owns the maximum of column l.  (v1 used 32 redux.sync per chunk,
+// which serialised at ~44 cycles each -- profiles/r01.)
 // This is PointConv's max aggregation (pointnet2.py:35) and GA's global_max_pool (:48).
 struct SegMaxEpi {
   struct Params {
@@ -68,24 +80,47 @@ struct SegMaxEpi {
     int M, N;           // M % 32 == 0
     int round_out;
   };
-  static constexpr int kSmemBytes = 0;
+  static constexpr int kSmemBytes = kEpiBiasSmem;
   const Params& p;
-  int ew, lane;
-  __device__ SegMaxEpi(const Params& p_, uint8_t*, int ew_, int lane_) : p(p_), ew(ew_), lane(lane_) {}
+  float* s_bias;
+  int ew, lane, block_n;
+  float side_v[8];  // this lane's side value for each 32-column chunk of the tile
+  __device__ SegMaxEpi(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_)
+      : p(p_), s_bias(reinterpret_cast<float*>(smem) + ew_ * 256), ew(ew_), lane(lane_), block_n(block_n_) {}
   __device__ void begin_unit(int, int) {}
   __device__ void end_unit(int, int) {}
-  __device__ void chunk(int m_tile, int, int col0, float (&v)[32]) {
+  __device__ void begin_tile(int m_tile, int, int col0) {
+    const long row0 = static_cast<long>(m_tile) * 128 + ew * 32;
+    const bool live = row0 < p.M;
+    __syncwarp();
+    for (int i = lane; i < block_n; i += 32) s_bias[i] = (col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int col = col0 + c * 32 + lane;
+      side_v[c] = (p.side && live && c * 32 < block_n && col < p.N) ? __ldg(p.side + (row0 >> 5) * p.lds + col) : 0.f;
+    }
+    __syncwarp();
+  }
+  __device__ void chunk(int m_tile, int, int c, int col0, float (&v)[32]) {
     const long row0 = static_cast<long>(m_tile) * 128 + ew * 32;
     if (row0 >= p.M || col0 >= p.N) return;  // warp-uniform
     const long g = row0 >> 5;
-    float keep = 0.f;
+    float x[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float x = fmaxf(v[i] + __ldg(p.bias + col0 + i), 0.f);
-      const uint32_t m = __reduce_max_sync(0xffffffffu, __float_as_uint(x) & 0x7fffffffu);  // mask: relu may leave -0
-      if (lane == i) keep = __uint_as_float(m);
+    for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(x)[i] = reinterpret_cast<const float4*>(s_bias + c * 32)[i];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = fmaxf(v[i] + x[i], 0.f);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;  // this lane keeps the upper half of the surviving columns
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = upper ? x[i] : x[i + off];
+        const float mine = upper ? x[i + off] : x[i];
+        x[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, off));
+      }
     }
-    if (p.side) keep = fmaxf(keep, __ldg(p.side + g * p.lds + col0 + lane));
+    float keep = fmaxf(x[0], side_v[c]);  // side values are post-ReLU (>= 0); 0 when absent
     if (p.round_out) keep = round_tf32(keep);
     p.out[g * p.ldo + col0 + lane] = keep;
   }

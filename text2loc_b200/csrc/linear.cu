@@ -14,23 +14,27 @@ template <int BN, class Epi>
 static cudaError_t run_umma(const Linear& l, const typename Epi::Params& ep, cudaStream_t st) {
   using Cfg = GemmCfg<BN, false>;
   CUtensorMap ta, tb;
-  if (make_operand_map(&ta, l.A, false, l.M, l.K, l.lda, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
-  if (make_operand_map(&tb, l.W, false, l.N, l.K, l.ldw, BN)) return cudaErrorInvalidValue;
+  const int kw = l.passes == 3 ? 2 * l.K : l.K;  // physical operand width
+  if (make_operand_map(&ta, l.A, false, l.M, kw, l.lda, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
+  if (make_operand_map(&tb, l.W, false, l.N, kw, l.ldw, BN)) return cudaErrorInvalidValue;
   GemmShape s;
   s.M = l.M; s.N = l.N;
   s.m_tiles = (l.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   s.n_tiles = (l.N + BN - 1) / BN;
   s.n_splits = s.n_tiles;
   s.tiles_per_split = 1;
-  s.ks.n_pass = 1;
+  s.ks.n_pass = l.passes;
   s.ks.kb_per_pass = (l.K + Cfg::BLOCK_K - 1) / Cfg::BLOCK_K;
-  s.ks.a_off[0] = s.ks.b_off[0] = 0;
+  s.ks.a_off[0] = 0;   s.ks.b_off[0] = 0;    // hi * hi
+  s.ks.a_off[1] = l.K; s.ks.b_off[1] = 0;    // lo * hi
+  s.ks.a_off[2] = 0;   s.ks.b_off[2] = l.K;  // hi * lo
   return launch_umma_gemm<Cfg, Epi>(ta, tb, s, ep, st);
 }
 
 cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
   if (l.M <= 0) return cudaSuccess;
   if ((l.N % 32) || (l.lda % 4) || (l.ldw % 4)) return cudaErrorInvalidValue;
+  if (l.passes != 1 && (l.passes != 3 || l.K % 32)) return cudaErrorInvalidValue;
   if (lc) lc->n++;
   const bool wide = (l.N % 256) == 0;
   if (l.segmax) {
@@ -40,6 +44,29 @@ cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
   }
   StoreEpi::Params ep{l.C, l.ldc, l.bias, l.residual, l.ldr, l.M, l.N, l.act, l.round_out};
   return wide ? run_umma<256, StoreEpi>(l, ep, st) : run_umma<128, StoreEpi>(l, ep, st);
+}
+
+// fp32 -> [hi | lo] tf32 planes: x = hi + lo up to 2^-22 |x|
+__global__ void split_tf32_kernel(const float* __restrict__ x, long ldx, float* __restrict__ planes, long rows, int K4) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * K4) return;
+  const long r = i / K4;
+  const int c = static_cast<int>(i % K4);
+  const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + 4 * c);
+  float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+  float4 lo = make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+  float4* dst = reinterpret_cast<float4*>(planes + r * 8 * K4);
+  dst[c] = hi;
+  dst[K4 + c] = lo;
+}
+
+cudaError_t split_tf32_planes(const float* x, long ldx, float* planes, int rows, int K, cudaStream_t st, Launches* lc) {
+  if (rows <= 0) return cudaSuccess;
+  if ((K % 4) || (ldx % 4)) return cudaErrorInvalidValue;
+  if (lc) lc->n++;
+  const long n = static_cast<long>(rows) * (K / 4);
+  split_tf32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(x, ldx, planes, rows, K / 4);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------

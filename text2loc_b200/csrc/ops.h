@@ -27,10 +27,14 @@ struct Linear {
   int segmax = 0;             // max over 32-row groups after relu
   const float* side = nullptr; long lds = 0;      // segmax: elementwise max with side[g, :]
   int round_out = 0;          // round stored values to tf32 (rna)
+  int passes = 1;             // 3: A and W are [hi | lo] tf32 planes of logical width K (row pitch >= 2K):
+                              //    hi*hi + lo*hi + hi*lo in one accumulator, fp32-level accuracy on the tensor cores
 };
 // tf32 tensor-core path: needs K-major operands with 16-byte aligned rows (lda, ldw % 4 == 0),
 // N % 32 == 0.  K tails are zero-filled by TMA.
 cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc);
+// planes[r, 0:K] = rna_tf32(x[r]), planes[r, K:2K] = rna_tf32(x[r] - hi): operand of a passes=3 GEMM
+cudaError_t split_tf32_planes(const float* x, long ldx, float* planes, int rows, int K, cudaStream_t st, Launches* lc);
 // exact fp32 path: any shape.
 cudaError_t linear_simt(const Linear& l, cudaStream_t st, Launches* lc);
 
@@ -79,7 +83,7 @@ cudaError_t l2_normalize_rows(const float* x, long ldx, float* y, long ldy, int 
 cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const float* b, int rows, int d, cudaStream_t st, Launches* lc);
 // Unmasked multi-head self attention on packed QKV rows [n_seq*S, 3d] (q | k | v), head h uses
 // columns [h*hd, (h+1)*hd); out [n_seq*S, d].  softmax(q k^T / sqrt(hd)) v, fp32.
-cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc);
+cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out = 0);
 // y[g, :] = max over the S rows of group g
 cudaError_t max_over_rows(const float* x, float* y, int groups, int S, int d, cudaStream_t st, Launches* lc);
 // X[b, s, :] = normalize(emb[cell_ptr[b]+s]) for s < min(n_b, 28), else 0   (cell_retrieval.py:85-98)

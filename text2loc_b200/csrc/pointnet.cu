@@ -26,9 +26,17 @@ cudaError_t extract_rgb(const float* pts, int n_obj, float* x0, cudaStream_t st,
 }
 
 // One warp per centroid; lane l owns channels l, l+32, ... (coalesced row reads and writes).
+// The 33 edge rows are independent, so they are processed four at a time with all gathers
+// (4 x (position + C1/32 feature loads)) issued before the first use: the v1 kernel walked the
+// rows one by one and was bound by exposed L2 latency (profiles/r01: 12-16 % of DRAM bandwidth).
 template <int C1>
 __global__ void __launch_bounds__(256) edge_gather_kernel(EdgeGather a) {
   constexpr int R = C1 / 32;
+  constexpr int U = 4;
+  const float* __restrict__ Px = a.Px;
+  const float* __restrict__ dense_pos = a.dense_pos;
+  float* __restrict__ H = a.H;
+  float* __restrict__ Hself = a.Hself;
   const int lane = threadIdx.x & 31;
   const long cen = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);  // o * M + m
   if (cen >= static_cast<long>(a.n_obj) * a.M) return;
@@ -43,21 +51,37 @@ __global__ void __launch_bounds__(256) edge_gather_kernel(EdgeGather a) {
   const float cx = a.cpos[cen * 3 + 0], cy = a.cpos[cen * 3 + 1], cz = a.cpos[cen * 3 + 2];
   const int cnt = a.cnt[cen];
   const long self_row = static_cast<long>(a.loop_src_obj[o]) * a.P + a.loop_half[o] * a.M + m;
-  const uint8_t my_nbr = a.nbr[cen * kMaxNbr + lane];
-  for (int s = 0; s <= kMaxNbr; ++s) {
-    long src = self_row;
-    if (s < cnt) src = static_cast<long>(o) * a.P + __shfl_sync(0xffffffffu, static_cast<int>(my_nbr), s);
-    const float* dp = a.dense_pos + src * a.dense_stride;
-    const float dx = dp[0] - cx, dy = dp[1] - cy, dz = dp[2] - cz;  // pos_j - pos_i (exact fp32 subtraction)
-    const float* px = a.Px + src * C1;
-    float* dst = (s < kMaxNbr) ? a.H + (cen * kMaxNbr + s) * C1 : a.Hself + cen * C1;
+  const int my_nbr = a.nbr[cen * kMaxNbr + lane];
+  for (int s0 = 0; s0 <= kMaxNbr; s0 += U) {
+    long src[U];
+    float dx[U], dy[U], dz[U], px[U][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      float v = px[r * 32 + lane] + b[r];
-      v = fmaf(wx[r], dx, v);
-      v = fmaf(wy[r], dy, v);
-      v = fmaf(wz[r], dz, v);
-      dst[r * 32 + lane] = round_tf32(fmaxf(v, 0.f));  // operand of the tf32 second-layer GEMM
+    for (int u = 0; u < U; ++u) {
+      const int s = s0 + u;
+      const int nb = __shfl_sync(0xffffffffu, my_nbr, s & 31);
+      src[u] = (s < cnt) ? static_cast<long>(o) * a.P + nb : self_row;  // empty slots replicate the self-loop edge
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float* dp = dense_pos + src[u] * a.dense_stride;
+      dx[u] = dp[0]; dy[u] = dp[1]; dz[u] = dp[2];
+#pragma unroll
+      for (int r = 0; r < R; ++r) px[u][r] = Px[src[u] * C1 + r * 32 + lane];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int s = s0 + u;
+      if (s > kMaxNbr) break;
+      const float ex = dx[u] - cx, ey = dy[u] - cy, ez = dz[u] - cz;  // pos_j - pos_i (exact fp32 subtraction)
+      float* dst = (s < kMaxNbr) ? H + (cen * kMaxNbr + s) * C1 : Hself + cen * C1;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float v = px[u][r] + b[r];
+        v = fmaf(wx[r], ex, v);
+        v = fmaf(wy[r], ey, v);
+        v = fmaf(wz[r], ez, v);
+        dst[r * 32 + lane] = round_tf32(fmaxf(v, 0.f));  // operand of the tf32 second-layer GEMM
+      }
     }
   }
 }

@@ -79,12 +79,15 @@ cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const floa
 // ---- small-sequence attention core -----------------------------------------------------------
 // One warp per (sequence, head, query row).  S <= 32.  Lanes split the head dimension for the
 // q.k dot products (coalesced row reads, warp-sum), lane j then holds score j for the softmax,
-// and lanes split the head dimension again for P.V.  No mask: padded slots/tokens attend like
-// real ones, exactly as the reference (cell_retrieval.py:101-103, language_encoder.py:130-131).
+// and lanes split the head dimension again for P.V.  Key/value rows are fetched four at a time
+// so the L2 latency of one group hides behind the arithmetic of the previous one.  No mask:
+// padded slots/tokens attend like real ones, exactly as the reference
+// (cell_retrieval.py:101-103, language_encoder.py:130-131).
 template <int HD>
 __global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict__ qkv, float* __restrict__ out, long n_rows_total, int S, int d,
-                                                        int n_heads, float scale) {
+                                                        int n_heads, float scale, int round_out) {
   constexpr int R = HD / 32;
+  constexpr int U = 4;
   const long wid = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (wid >= n_rows_total * n_heads) return;
@@ -93,17 +96,28 @@ __global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict_
   const long seq0 = (row / S) * S;
   const long ld = 3L * d;
   const float* q = qkv + row * ld + h * HD;
+  const float* kbase = qkv + seq0 * ld + d + h * HD + lane;
+  const float* vbase = qkv + seq0 * ld + 2 * d + h * HD + lane;
   float qv[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) qv[r] = q[r * 32 + lane];
   float my_score = -INFINITY;
-  for (int j = 0; j < S; ++j) {
-    const float* kj = qkv + (seq0 + j) * ld + d + h * HD;
-    float p = 0.f;
+  for (int j0 = 0; j0 < S; j0 += U) {
+    float kv[U][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) p = fmaf(qv[r], kj[r * 32 + lane], p);
-    p = warp_sum(p) * scale;
-    if (lane == j) my_score = p;
+    for (int u = 0; u < U; ++u) {
+      const int j = min(j0 + u, S - 1);
+#pragma unroll
+      for (int r = 0; r < R; ++r) kv[u][r] = kbase[j * ld + r * 32];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float p = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) p = fmaf(qv[r], kv[u][r], p);
+      p = warp_sum(p) * scale;
+      if (lane == j0 + u && j0 + u < S) my_score = p;
+    }
   }
   const float mx = warp_max(my_score);
   const float e = (lane < S) ? expf(my_score - mx) : 0.f;
@@ -111,18 +125,27 @@ __global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict_
   float acc[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = 0.f;
-  for (int j = 0; j < S; ++j) {
-    const float pj = __shfl_sync(0xffffffffu, prob, j);
-    const float* vj = qkv + (seq0 + j) * ld + 2 * d + h * HD;
+  for (int j0 = 0; j0 < S; j0 += U) {
+    float vv[U][R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) acc[r] = fmaf(pj, vj[r * 32 + lane], acc[r]);
+    for (int u = 0; u < U; ++u) {
+      const int j = min(j0 + u, S - 1);
+#pragma unroll
+      for (int r = 0; r < R; ++r) vv[u][r] = vbase[j * ld + r * 32];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float pj = (j0 + u < S) ? __shfl_sync(0xffffffffu, prob, (j0 + u) & 31) : 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fmaf(pj, vv[u][r], acc[r]);
+    }
   }
   float* o = out + row * d + h * HD;
 #pragma unroll
-  for (int r = 0; r < R; ++r) o[r * 32 + lane] = acc[r];
+  for (int r = 0; r < R; ++r) o[r * 32 + lane] = round_out ? round_tf32(acc[r]) : acc[r];
 }
 
-cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc) {
+cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out) {
   if (n_seq <= 0) return cudaSuccess;
   if (S > 32 || S < 1) return cudaErrorInvalidValue;
   if (lc) lc->n++;
@@ -130,8 +153,8 @@ cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int
   const int hd = d / n_heads;
   const unsigned grid = static_cast<unsigned>((rows * n_heads + 7) / 8);
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
-  if (hd == 64) mha_small_kernel<64><<<grid, 256, 0, st>>>(qkv, out, rows, S, d, n_heads, scale);
-  else if (hd == 256) mha_small_kernel<256><<<grid, 256, 0, st>>>(qkv, out, rows, S, d, n_heads, scale);
+  if (hd == 64) mha_small_kernel<64><<<grid, 256, 0, st>>>(qkv, out, rows, S, d, n_heads, scale, round_out);
+  else if (hd == 256) mha_small_kernel<256><<<grid, 256, 0, st>>>(qkv, out, rows, S, d, n_heads, scale, round_out);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

@@ -73,7 +73,7 @@ struct TopKEpi {
   int cnt, min_slot;
   bool active;
 
-  __device__ TopKEpi(const Params& p_, uint8_t* smem, int ew, int lane) : p(p_) {
+  __device__ TopKEpi(const Params& p_, uint8_t* smem, int ew, int lane, int) : p(p_) {
     s_score = reinterpret_cast<float*>(smem);
     s_idx = reinterpret_cast<int32_t*>(smem + kCand * 128 * 4);
     t = ew * 32 + lane;
@@ -105,7 +105,8 @@ struct TopKEpi {
     thr = m;
     min_slot = ms;
   }
-  __device__ void chunk(int, int, int col0, float (&v)[32]) {
+  __device__ void begin_tile(int, int, int) {}
+  __device__ void chunk(int, int, int, int col0, float (&v)[32]) {
     float cmax = v[0];
 #pragma unroll
     for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, v[i]);

@@ -16,9 +16,10 @@
 //
 // The epilogue is a policy class (see gemm_epilogues.cuh, search.cu):
 //   struct Epi { struct Params; static constexpr int kSmemBytes;
-//     __device__ Epi(const Params&, uint8_t* smem, int epi_warp, int lane);
+//     __device__ Epi(const Params&, uint8_t* smem, int epi_warp, int lane, int block_n);
 //     __device__ void begin_unit(int m_tile, int split);
-//     __device__ void chunk(int m_tile, int n_tile, int col0, float (&v)[32]);   // 32 fp32 columns of this thread's row
+//     __device__ void begin_tile(int m_tile, int n_tile, int col0);   // BEFORE the accumulator is waited for: issue global loads here
+//     __device__ void chunk(int m_tile, int n_tile, int c, int col0, float (&v)[32]);   // 32 fp32 columns of this thread's row
 //     __device__ void end_unit(int m_tile, int split); };
 #pragma once
 
@@ -168,7 +169,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else if (warp >= 4) {
     // ================= epilogue =================
     const int ew = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
-    Epi epi(ep, epi_smem, ew, lane);
+    Epi epi(ep, epi_smem, ew, lane, Cfg::BLOCK_N);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -177,15 +178,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int nt1 = min(nt0 + shape.tiles_per_split, shape.n_tiles);
       epi.begin_unit(m_tile, split);
       for (int nt = nt0; nt < nt1; ++nt) {
+        epi.begin_tile(m_tile, nt, nt * Cfg::BLOCK_N);  // bias / side-input loads fly while the MMAs finish
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * Cfg::BLOCK_N;
-#pragma unroll 1
+        // software-pipelined drain: the TMEM load of chunk c+1 is in flight while chunk c is processed
+        float v[2][32];
+        tmem_ld_32x32(t_addr, v[0]);
+#pragma unroll
         for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
-          float v[32];
-          tmem_ld_32x32(t_addr + c * 32, v);
-          tmem_ld_wait();
-          epi.chunk(m_tile, nt, nt * Cfg::BLOCK_N + c * 32, v);
+          tmem_ld_wait(v[c & 1]);
+          if (c + 1 < Cfg::BLOCK_N / 32) tmem_ld_32x32(t_addr + (c + 1) * 32, v[(c + 1) & 1]);
+          epi.chunk(m_tile, nt, c, nt * Cfg::BLOCK_N + c * 32, v[c & 1]);
         }
         tc_fence_before();
         __syncwarp();

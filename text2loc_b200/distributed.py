@@ -31,7 +31,10 @@ def all_gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:
     if ws == 1:
         return x.unsqueeze(0)
     out = torch.empty((ws,) + tuple(x.shape), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    if x.is_cuda:
+        dist.all_gather_into_tensor(out, x.contiguous(), group=group)  # one NCCL all-gather over NVLink
+    else:
+        dist.all_gather(list(out.unbind(0)), x.contiguous(), group=group)  # gloo (CPU tests)
     return out
 
 

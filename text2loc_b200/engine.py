@@ -108,15 +108,48 @@ class Engine:
             *[_ptr(r[k]) for k in ("features2", "fps1", "fps2", "fps3", "nbr1", "nbr2", "nbr3", "cnt1", "cnt2", "cnt3")], self._stream()))
         return r
 
+    TOKENS_PER_CHUNK = 32768  # the engine's internal text chunk (api.cu: tok_chunk)
+
     def encode_text(self, t5, n_sent: int) -> torch.Tensor:
-        """t5 [nq*n_sent, n_tok, 1024] (T5 last_hidden_state) -> unit rows [nq,256] on device."""
-        t5 = self._dev(t5, torch.float32)
-        if t5.dim() != 3 or t5.shape[2] != T5_DIM or t5.shape[0] % n_sent:
-            raise EngineError(f"encode_text: bad shape {tuple(t5.shape)} for n_sent={n_sent}")
-        nq = t5.shape[0] // n_sent
+        """t5 [nq*n_sent, n_tok, 1024] (T5 last_hidden_state) -> unit rows [nq,256] on device.
+
+        A HOST tensor (ideally pinned) is streamed: the H2D copy of chunk i+1 runs on a side
+        stream while the engine works on chunk i, so PCIe time hides behind compute."""
+        t5 = torch.as_tensor(t5)
+        if t5.dim() != 3 or t5.shape[2] != T5_DIM or t5.shape[0] % n_sent or t5.dtype != torch.float32:
+            raise EngineError(f"encode_text: need float32 [nq*{n_sent}, n_tok, 1024], got {t5.dtype} {tuple(t5.shape)}")
+        nq, n_tok = t5.shape[0] // n_sent, t5.shape[1]
         out = torch.empty((nq, EMBED_DIM), dtype=torch.float32, device=self.device)
-        self._check(self._lib.t2l_encode_text(self._h, _ptr(t5), nq, n_sent, t5.shape[1], _ptr(out), self._stream()))
+        if t5.is_cuda:
+            self._encode_text_dev(self._dev(t5, torch.float32), n_sent, out)
+            return out
+        t5 = t5.contiguous()
+        cq = max(1, self.TOKENS_PER_CHUNK // (n_sent * n_tok))
+        rows_per_chunk = cq * n_sent
+        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < rows_per_chunk or self._stage[0].shape[1] != n_tok:
+            self._stage = [torch.empty((rows_per_chunk, n_tok, T5_DIM), dtype=torch.float32, device=self.device) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._stage_done = [None, None]
+        cur = torch.cuda.current_stream(self.device)
+        for i, q0 in enumerate(range(0, nq, cq)):
+            q1 = min(nq, q0 + cq)
+            b = i % 2
+            n_rows = (q1 - q0) * n_sent
+            with torch.cuda.stream(self._copy_stream):
+                if self._stage_done[b] is not None:
+                    self._copy_stream.wait_event(self._stage_done[b])  # the engine is done reading this buffer
+                self._stage[b][:n_rows].copy_(t5[q0 * n_sent:q1 * n_sent], non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(self._copy_stream)
+            cur.wait_event(copied)
+            self._encode_text_dev(self._stage[b][:n_rows], n_sent, out[q0:q1])
+            self._stage_done[b] = torch.cuda.Event()
+            self._stage_done[b].record(cur)
         return out
+
+    def _encode_text_dev(self, t5: torch.Tensor, n_sent: int, out: torch.Tensor):
+        nq = t5.shape[0] // n_sent
+        self._check(self._lib.t2l_encode_text(self._h, _ptr(t5), nq, n_sent, t5.shape[1], _ptr(out), self._stream()))
 
     # ---- search ---------------------------------------------------------------------------
     def db_build(self, D, row_offset: int = 0):
