@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -58,6 +59,7 @@ struct t2l_engine {
   SearchWork sw{};
   size_t sw_planes_rows = 0;
   int obj_chunk = 2048;      // objects per encode chunk (cell-aligned)
+  bool fused_sa = true;      // sa_fused.cu; false = v1 edge_gather -> H -> SegMax GEMM (kept for A/B checks, T2L_UNFUSED_SA=1)
   int tok_chunk = 32768;     // tokens per text chunk (query-aligned)
 };
 
@@ -116,6 +118,7 @@ extern "C" int t2l_create(int device, t2l_engine** out) {
   g_tma.num_sms = prop.multiProcessorCount;
   e = new t2l_engine();
   e->device = device;
+  if (const char* v = getenv("T2L_UNFUSED_SA")) e->fused_sa = !(v[0] == '1');
   if (cudaMalloc(&e->db.max_norm, sizeof(float)) != cudaSuccess) { delete e; return fail(nullptr, "t2l_create: cudaMalloc failed"); }
   *out = e;
   return 0;
@@ -351,10 +354,23 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
     eg.loop_src_obj = loop_src; eg.loop_half = loop_half; eg.Wp = W(e, nm + ".w1p").dev; eg.b1 = W(e, nm + ".b1").dev;
     eg.n_obj = n; eg.P = L.P; eg.M = L.M; eg.H = H; eg.Hself = Hs;
     if (W(e, nm + ".w1p").ld != 4) return fail(e, "internal: w1p pitch");
-    CU(edge_gather(eg, st, &e->lc));
-    // second Linear + ReLU; max over each centroid's 32 slots in the GEMM epilogue, joined with the self-loop row
-    CU(lin(e, true, Hs, L.C1, n * L.M, nm + ".w2", nm + ".b2", S, L.C2, 1, st));
-    CU(lin(e, true, H, L.C1, n * L.M * 32, nm + ".w2", nm + ".b2", L.xout, L.C2, 1, st, nullptr, 0, /*round_out=*/1, /*segmax=*/1, S, L.C2));
+    if (e->fused_sa) {
+      // self-loop edges: one row per centroid through the same MLP -> side input of the fused kernel
+      CU(self_edge_rows(eg, st, &e->lc));
+      CU(lin(e, true, Hs, L.C1, n * L.M, nm + ".w2", nm + ".b2", S, L.C2, 1, st));
+      // gather + edge MLP + max over each centroid's 32 slots in one kernel (A operand built in smem)
+      SaFused sf;
+      sf.Px = L.Px; sf.C1 = L.C1; sf.C2 = L.C2; sf.dense_pos = L.dense; sf.dense_stride = L.dstride; sf.cpos = L.cpos;
+      sf.nbr = L.nbr; sf.cnt = L.cnt; sf.loop_src_obj = loop_src; sf.loop_half = loop_half; sf.Wp = eg.Wp; sf.b1 = eg.b1;
+      sf.W2 = W(e, nm + ".w2").dev; sf.ldw2 = W(e, nm + ".w2").ld; sf.b2 = W(e, nm + ".b2").dev; sf.side = S; sf.out = L.xout;
+      sf.n_obj = n; sf.P = L.P; sf.M = L.M; sf.rec = reinterpret_cast<float4*>(H);  // H is free on the fused path
+      CU(sa_fused(sf, st, &e->lc));
+    } else {
+      CU(edge_gather(eg, st, &e->lc));
+      // second Linear + ReLU; max over each centroid's 32 slots in the GEMM epilogue, joined with the self-loop row
+      CU(lin(e, true, Hs, L.C1, n * L.M, nm + ".w2", nm + ".b2", S, L.C2, 1, st));
+      CU(lin(e, true, H, L.C1, n * L.M * 32, nm + ".w2", nm + ".b2", L.xout, L.C2, 1, st, nullptr, 0, /*round_out=*/1, /*segmax=*/1, S, L.C2));
+    }
   }
 
   // GlobalAbstraction: mlp([x | pos]) then max over the object's 32 points (pointnet2.py:45-49)

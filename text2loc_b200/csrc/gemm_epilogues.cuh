@@ -31,11 +31,14 @@ struct StoreEpi {
   const Params& p;
   float* s_bias;
   int ew, lane, block_n;
+  int bias_col0 = -1;  // column slice currently staged in s_bias (tiles of one N column share it)
   __device__ StoreEpi(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_)
       : p(p_), s_bias(reinterpret_cast<float*>(smem) + ew_ * 256), ew(ew_), lane(lane_), block_n(block_n_) {}
   __device__ void begin_unit(int, int) {}
   __device__ void end_unit(int, int) {}
   __device__ void begin_tile(int, int, int col0) {
+    if (col0 == bias_col0) return;
+    bias_col0 = col0;
     __syncwarp();
     for (int i = lane; i < block_n; i += 32) s_bias[i] = (p.bias && col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
     __syncwarp();
@@ -85,6 +88,7 @@ struct SegMaxEpi {
   float* s_bias;
   int ew, lane, block_n;
   float side_v[8];  // this lane's side value for each 32-column chunk of the tile
+  int bias_col0 = -1;
   __device__ SegMaxEpi(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_)
       : p(p_), s_bias(reinterpret_cast<float*>(smem) + ew_ * 256), ew(ew_), lane(lane_), block_n(block_n_) {}
   __device__ void begin_unit(int, int) {}
@@ -92,13 +96,15 @@ struct SegMaxEpi {
   __device__ void begin_tile(int m_tile, int, int col0) {
     const long row0 = static_cast<long>(m_tile) * 128 + ew * 32;
     const bool live = row0 < p.M;
-    __syncwarp();
-    for (int i = lane; i < block_n; i += 32) s_bias[i] = (col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 8; ++c) {  // issued first: consumed only after the accumulator wait
       const int col = col0 + c * 32 + lane;
       side_v[c] = (p.side && live && c * 32 < block_n && col < p.N) ? __ldg(p.side + (row0 >> 5) * p.lds + col) : 0.f;
     }
+    if (col0 == bias_col0) return;
+    bias_col0 = col0;
+    __syncwarp();
+    for (int i = lane; i < block_n; i += 32) s_bias[i] = (col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
     __syncwarp();
   }
   __device__ void chunk(int m_tile, int, int c, int col0, float (&v)[32]) {

@@ -73,6 +73,21 @@ struct EdgeGather {
   float* H; float* Hself;
 };
 cudaError_t edge_gather(const EdgeGather& a, cudaStream_t st, Launches* lc);
+// Fused PointConv layer (sa_fused.cu): gathers, first-layer edge activations, second Linear on the
+// tensor cores and the per-centroid max in ONE kernel; `side` [n*M, C2] carries the self-loop edges.
+struct SaFused {
+  const float* Px; int C1; int C2;
+  const float* dense_pos; int dense_stride; const float* cpos;
+  const uint8_t* nbr; const uint8_t* cnt; const int32_t* loop_src_obj; const int32_t* loop_half;
+  const float* Wp; const float* b1;      // [C1,4], [C1]
+  const float* W2; long ldw2; const float* b2;  // [C2, C1] tf32-rounded, [C2]
+  const float* side; float* out;         // [n*M, C2]
+  float4* rec;                           // scratch [n*M*32]: per-edge (Px row offset, pos_j - pos_i)
+  int n_obj, P, M;
+};
+cudaError_t sa_fused(const SaFused& a, cudaStream_t st, Launches* lc);
+// Hself[o*M+m, :] only (the re-added self-loop edge of every centroid)
+cudaError_t self_edge_rows(const EdgeGather& a, cudaStream_t st, Launches* lc);
 // GA input: A[n*32, 260] = [x3 (256) | cpos3 (3) | 0]
 cudaError_t ga_concat(const float* x3, const float* cpos3, int n_obj, float* A, cudaStream_t st, Launches* lc);
 

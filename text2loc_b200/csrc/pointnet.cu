@@ -100,6 +100,42 @@ cudaError_t edge_gather(const EdgeGather& a, cudaStream_t st, Launches* lc) {
   return cudaGetLastError();
 }
 
+// Self-loop edge rows only (one per centroid): A operand of the small side GEMM next to sa_fused.
+template <int C1>
+__global__ void __launch_bounds__(256) self_edge_kernel(EdgeGather a) {
+  constexpr int R = C1 / 32;
+  const int lane = threadIdx.x & 31;
+  const long cen = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (cen >= static_cast<long>(a.n_obj) * a.M) return;
+  const int o = static_cast<int>(cen / a.M), m = static_cast<int>(cen % a.M);
+  const long src = static_cast<long>(a.loop_src_obj[o]) * a.P + a.loop_half[o] * a.M + m;
+  const float* dp = a.dense_pos + src * a.dense_stride;
+  const float ex = dp[0] - a.cpos[cen * 3 + 0], ey = dp[1] - a.cpos[cen * 3 + 1], ez = dp[2] - a.cpos[cen * 3 + 2];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int c = r * 32 + lane;
+    float v = a.Px[src * C1 + c] + a.b1[c];
+    v = fmaf(a.Wp[c * 4 + 0], ex, v);
+    v = fmaf(a.Wp[c * 4 + 1], ey, v);
+    v = fmaf(a.Wp[c * 4 + 2], ez, v);
+    a.Hself[cen * C1 + c] = round_tf32(fmaxf(v, 0.f));
+  }
+}
+
+cudaError_t self_edge_rows(const EdgeGather& a, cudaStream_t st, Launches* lc) {
+  const long n_cen = static_cast<long>(a.n_obj) * a.M;
+  if (n_cen <= 0) return cudaSuccess;
+  if (lc) lc->n++;
+  const unsigned grid = static_cast<unsigned>((n_cen + 7) / 8);
+  switch (a.C1) {
+    case 32: self_edge_kernel<32><<<grid, 256, 0, st>>>(a); break;
+    case 128: self_edge_kernel<128><<<grid, 256, 0, st>>>(a); break;
+    case 256: self_edge_kernel<256><<<grid, 256, 0, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
 // GlobalAbstractionLayer input torch.cat((x, pos), dim=1) (pointnet2.py:46), K padded 259 -> 260
 __global__ void ga_concat_kernel(const float* __restrict__ x3, const float* __restrict__ cpos3, long rows, float* __restrict__ A) {
   const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);

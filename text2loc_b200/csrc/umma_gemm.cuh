@@ -71,7 +71,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const GemmShape shape, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for the 128B swizzle atoms; offset arithmetic on the __shared__ array keeps the
+  // pointer in the shared address space (integer round trips degrade every access to generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
@@ -109,23 +111,25 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int m_tile = u / shape.n_splits, split = u % shape.n_splits;
-        const int nt0 = split * shape.tiles_per_split;
-        const int nt1 = min(nt0 + shape.tiles_per_split, shape.n_tiles);
-        for (int nt = nt0; nt < nt1; ++nt) {
-          for (int p = 0; p < shape.ks.n_pass; ++p) {
-            for (int kk = 0; kk < shape.ks.kb_per_pass; ++kk) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
+    // the whole warp walks the schedule (converged), one elected lane issues: same reason as the MMA warp
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int m_tile = u / shape.n_splits, split = u % shape.n_splits;
+      const int nt0 = split * shape.tiles_per_split;
+      const int nt1 = min(nt0 + shape.tiles_per_split, shape.n_tiles);
+      for (int nt = nt0; nt < nt1; ++nt) {
+        for (int p = 0; p < shape.ks.n_pass; ++p) {
+          for (int kk = 0; kk < shape.ks.kb_per_pass; ++kk) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
               mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
               uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
               tma_load_2d(&tm_a, &full_bar[stage], sa, shape.ks.a_off[p] + kk * Cfg::BLOCK_K, m_tile * Cfg::BLOCK_M, kEvictNormal);
               tma_load_2d(&tm_b, &full_bar[stage], sa + Cfg::A_BYTES, shape.ks.b_off[p] + kk * Cfg::BLOCK_K, nt * Cfg::BLOCK_N, kEvictLast);
-              if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -147,7 +151,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         for (int kb = 0; kb < kb_total; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          // elect.sync (not `lane == 0`): the compiler then knows a single lane runs the uniform-datapath
+          // UTCHMMA/UTCBAR instructions and emits them straight-line; under a plain lane predicate it wraps
+          // every one in an ELECT/BRA.U.ANY loop (~400 cycles of issue overhead per k-block, profiles/r01)
+          if (elect_one()) {
             const uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
             const uint64_t adesc = umma_desc_sw128(sa);
             const uint64_t bdesc = umma_desc_sw128(sa + Cfg::A_BYTES);
