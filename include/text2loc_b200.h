@@ -72,6 +72,15 @@ int t2l_encode_objects_debug(t2l_engine* e, const float* pts, const int32_t* cel
  *   out  device f32 [n_queries, 256]                   unit rows */
 int t2l_encode_text(t2l_engine* e, const float* t5, int n_queries, int n_sent, int n_tok, float* out, void* stream);
 
+/* The same in two stages, so a caller can stream token features in chunks (H2D overlapped with compute)
+ * and run the sentence stage once over everything:
+ *   tokens:    t5 device f32 [n_sentences, n_tok, 1024] -> pooled device f32 [n_sentences, 1024]
+ *              (intra_module + max over tokens, models/language_encoder.py:130-133)
+ *   sentences: pooled [n_queries * n_sent, 1024] -> out [n_queries, 256]
+ *              (inter_mlp, inter_module with `x += layer(x)`, max over sentences, normalise, :137-148) */
+int t2l_encode_text_tokens(t2l_engine* e, const float* t5, int n_sentences, int n_tok, float* pooled, void* stream);
+int t2l_encode_text_sentences(t2l_engine* e, const float* pooled, int n_queries, int n_sent, float* out, void* stream);
+
 /* Database side of eval_epoch's search loop (training/coarse.py:81-84,105-113): registers this
  * rank's shard of cell embeddings.  D device f32 [n_rows, 256]; the engine keeps a reference to D
  * (it must stay alive and unchanged) and builds its bf16 hi/lo operand planes.  row_offset is

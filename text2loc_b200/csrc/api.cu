@@ -60,7 +60,9 @@ struct t2l_engine {
   size_t sw_planes_rows = 0;
   int obj_chunk = 2048;      // objects per encode chunk (cell-aligned)
   bool fused_sa = true;      // sa_fused.cu; false = v1 edge_gather -> H -> SegMax GEMM (kept for A/B checks, T2L_UNFUSED_SA=1)
-  int tok_chunk = 32768;     // tokens per text chunk (query-aligned)
+  int tok_chunk = 32768;     // tokens per text chunk (sentence-aligned)
+  float* pooled = nullptr;   // [pooled_cap, 1024] max-over-tokens sentence features between the two text stages
+  size_t pooled_cap = 0;
 };
 
 static int fail(t2l_engine* e, const char* fmt, ...) {
@@ -136,6 +138,7 @@ extern "C" void t2l_destroy(t2l_engine* e) {
   cudaDeviceSynchronize();
   for (auto& kv : e->w) cudaFree(kv.second.dev);
   cudaFree(e->arena.base);
+  cudaFree(e->pooled);
   cudaFree(e->db.planes);
   cudaFree(e->db.max_norm);
   free_search_work(e);
@@ -468,40 +471,80 @@ extern "C" int t2l_encode_objects_debug(t2l_engine* e, const float* pts, const i
 // ---------------------------------------------------------------------------------------------
 // encode_text
 // ---------------------------------------------------------------------------------------------
-extern "C" int t2l_encode_text(t2l_engine* e, const float* t5, int nq, int S, int L, float* out, void* stream) {
+// Token level: intra_module (one encoder layer over the tokens of each sentence, no key-padding mask,
+// language_encoder.py:130-131) then max over tokens (:133).  pooled [n_seq, 1024].
+static int text_tokens(t2l_engine* e, const float* t5, int n_seq, int L, float* pooled, cudaStream_t st) {
+  const int d = T2L_T5_DIM;
+  int sc = e->tok_chunk / L;  // sentences per chunk
+  if (sc < 1) sc = 1;
+  if (sc > n_seq) sc = n_seq;
+  if (n_seq == 0) return 0;
+  if (ensure_arena(e, static_cast<size_t>(sc) * L * (11 * static_cast<size_t>(d)) * 4 + (size_t(1) << 22))) return 1;
+  Arena& a = e->arena;
+  for (int s0 = 0; s0 < n_seq; s0 += sc) {
+    const int ns = (n_seq - s0 < sc) ? n_seq - s0 : sc;
+    a.off = 0;
+    const float* X = t5 + static_cast<size_t>(s0) * L * d;
+    float* X2 = a.get<float>(static_cast<size_t>(ns) * L * d);
+    if (encoder_layer(e, "txt_intra", true, X, X2, ns, L, d, 4 * d, st)) return 1;
+    CU(max_over_rows(X2, pooled + static_cast<size_t>(s0) * d, ns, L, d, st, &e->lc));
+  }
+  if (a.overflow) return fail(e, "internal: workspace arena too small for %d sentences", n_seq);
+  return 0;
+}
+
+// Sentence level: inter_mlp = Linear + BN folded, no ReLU (:137), inter_module over the S sentences of
+// each query with the extra residual `x += layer(x)` (:143-145), max over sentences (:147), normalise
+// (cell_retrieval.py:61).
+static int text_sentences(t2l_engine* e, const float* pooled, int nq, int S, float* out, cudaStream_t st) {
+  const int d = T2L_T5_DIM;
+  if (nq == 0) return 0;
+  const size_t n_seq = static_cast<size_t>(nq) * S;
+  if (ensure_arena(e, n_seq * (64 * 256) * 4 + (size_t(1) << 22))) return 1;
+  Arena& a = e->arena;
+  float* z = a.get<float>(n_seq * 256);
+  float* z2 = a.get<float>(n_seq * 256);
+  float* zq = a.get<float>(static_cast<size_t>(nq) * 256);
+  CU(lin3(e, pooled, d, static_cast<int>(n_seq), "txt_mlp.w", "txt_mlp.b", z, 256, 0, st));
+  if (encoder_layer(e, "txt_inter", false, z, z2, nq, S, 256, 1024, st)) return 1;
+  CU(add_rows(z, z2, z2, static_cast<long>(n_seq) * 256, st, &e->lc));
+  CU(max_over_rows(z2, zq, nq, S, 256, st, &e->lc));
+  CU(l2_normalize_rows(zq, 256, out, 256, nq, 256, st, &e->lc));
+  if (a.overflow) return fail(e, "internal: workspace arena too small for %d queries", nq);
+  return 0;
+}
+
+static int text_args_ok(t2l_engine* e, const void* in, const void* out, int n, int S, int L) {
   if (!e) return 1;
   if (!e->finalized) return fail(e, "weights not finalized");
-  if (!t5 || !out || nq < 0 || S < 1 || S > 32 || L < 1 || L > 32) return fail(e, "encode_text: bad argument (n_sent, n_tok must be in 1..32)");
+  if (!in || !out || n < 0 || S < 1 || S > 32 || L < 1 || L > 32) return fail(e, "encode_text: bad argument (n_sent, n_tok must be in 1..32)");
+  return 0;
+}
+
+extern "C" int t2l_encode_text_tokens(t2l_engine* e, const float* t5, int n_sentences, int L, float* pooled, void* stream) {
+  if (text_args_ok(e, t5, pooled, n_sentences, 1, L)) return 1;
+  CU(cudaSetDevice(e->device));
+  return text_tokens(e, t5, n_sentences, L, pooled, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int t2l_encode_text_sentences(t2l_engine* e, const float* pooled, int nq, int S, float* out, void* stream) {
+  if (text_args_ok(e, pooled, out, nq, S, 1)) return 1;
+  CU(cudaSetDevice(e->device));
+  return text_sentences(e, pooled, nq, S, out, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int t2l_encode_text(t2l_engine* e, const float* t5, int nq, int S, int L, float* out, void* stream) {
+  if (text_args_ok(e, t5, out, nq, S, L)) return 1;
   CU(cudaSetDevice(e->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int d = T2L_T5_DIM;
-  int qc = e->tok_chunk / (S * L);
-  if (qc < 1) qc = 1;
-  for (int q0 = 0; q0 < nq; q0 += qc) {
-    const int nqc = (nq - q0 < qc) ? nq - q0 : qc;
-    const int n_seq = nqc * S;               // sentences
-    const size_t T = static_cast<size_t>(n_seq) * L;  // tokens
-    if (ensure_arena(e, T * (3 * d + 3 * d + 4 * d + d) * 4 + static_cast<size_t>(n_seq) * (d + 64 * 256) * 4 + (size_t(1) << 22))) return 1;
-    Arena& a = e->arena;
-    const float* X = t5 + static_cast<size_t>(q0) * S * L * d;
-    // intra_module: one encoder layer over the tokens of each sentence, no key-padding mask (:130-131)
-    float* X2 = a.get<float>(T * d);
-    if (encoder_layer(e, "txt_intra", true, X, X2, n_seq, L, d, 4 * d, st)) return 1;
-    // max over tokens (:133), inter_mlp = Linear + BN folded, no ReLU (:137)
-    float* pooled = a.get<float>(static_cast<size_t>(n_seq) * d);
-    float* z = a.get<float>(static_cast<size_t>(n_seq) * 256);
-    float* z2 = a.get<float>(static_cast<size_t>(n_seq) * 256);
-    float* zq = a.get<float>(static_cast<size_t>(nqc) * 256);
-    CU(max_over_rows(X2, pooled, n_seq, L, d, st, &e->lc));
-    CU(lin3(e, pooled, d, n_seq, "txt_mlp.w", "txt_mlp.b", z, 256, 0, st));
-    // inter_module over the S sentences of each query with the extra residual `x += layer(x)` (:143-145)
-    if (encoder_layer(e, "txt_inter", false, z, z2, nqc, S, 256, 1024, st)) return 1;
-    CU(add_rows(z, z2, z2, static_cast<long>(n_seq) * 256, st, &e->lc));
-    CU(max_over_rows(z2, zq, nqc, S, 256, st, &e->lc));                       // max over sentences (:147)
-    CU(l2_normalize_rows(zq, 256, out + static_cast<size_t>(q0) * 256, 256, nqc, 256, st, &e->lc));  // cell_retrieval.py:61
-    if (a.overflow) return fail(e, "internal: workspace arena too small for %zu tokens", T);
+  const size_t n_seq = static_cast<size_t>(nq) * S;
+  if (n_seq > e->pooled_cap) {
+    if (e->pooled) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->pooled)); e->pooled = nullptr; }
+    CU(cudaMalloc(&e->pooled, (n_seq + 1024) * T2L_T5_DIM * sizeof(float)));
+    e->pooled_cap = n_seq + 1024;
   }
-  return 0;
+  if (text_tokens(e, t5, static_cast<int>(n_seq), L, e->pooled, st)) return 1;
+  return text_sentences(e, e->pooled, nq, S, out, st);
 }
 
 // ---------------------------------------------------------------------------------------------

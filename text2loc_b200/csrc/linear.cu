@@ -10,16 +10,16 @@ namespace t2l {
 // ---------------------------------------------------------------------------------------
 // tcgen05 path
 // ---------------------------------------------------------------------------------------
-template <int BN, class Epi>
+template <int BN, int GROUP, class Epi>
 static cudaError_t run_umma(const Linear& l, const typename Epi::Params& ep, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, false>;
+  using Cfg = GemmCfg<BN, false, GROUP>;
   CUtensorMap ta, tb;
   const int kw = l.passes == 3 ? 2 * l.K : l.K;  // physical operand width
   if (make_operand_map(&ta, l.A, false, l.M, kw, l.lda, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
-  if (make_operand_map(&tb, l.W, false, l.N, kw, l.ldw, BN)) return cudaErrorInvalidValue;
+  if (make_operand_map(&tb, l.W, false, l.N, kw, l.ldw, Cfg::LOAD_N)) return cudaErrorInvalidValue;
   GemmShape s;
   s.M = l.M; s.N = l.N;
-  s.m_tiles = (l.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  s.m_tiles = (l.M + Cfg::BLOCK_M * GROUP - 1) / (Cfg::BLOCK_M * GROUP);
   s.n_tiles = (l.N + BN - 1) / BN;
   s.n_splits = s.n_tiles;
   s.tiles_per_split = 1;
@@ -36,14 +36,18 @@ cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
   if ((l.N % 32) || (l.lda % 4) || (l.ldw % 4)) return cudaErrorInvalidValue;
   if (l.passes != 1 && (l.passes != 3 || l.K % 32)) return cudaErrorInvalidValue;
   if (lc) lc->n++;
+  // N % 256 == 0 and more than one 128-row tile: CTA pairs (256 x 256 tiles, cta_group::2); else single CTAs
   const bool wide = (l.N % 256) == 0;
+  const bool pair = wide && l.M > 128;
   if (l.segmax) {
     if (l.M % 32 || !l.bias) return cudaErrorInvalidValue;
     SegMaxEpi::Params ep{l.C, l.ldc, l.bias, l.side, l.lds, l.M, l.N, l.round_out};
-    return wide ? run_umma<256, SegMaxEpi>(l, ep, st) : run_umma<128, SegMaxEpi>(l, ep, st);
+    if (pair) return run_umma<256, 2, SegMaxEpi>(l, ep, st);
+    return wide ? run_umma<256, 1, SegMaxEpi>(l, ep, st) : run_umma<128, 1, SegMaxEpi>(l, ep, st);
   }
   StoreEpi::Params ep{l.C, l.ldc, l.bias, l.residual, l.ldr, l.M, l.N, l.act, l.round_out};
-  return wide ? run_umma<256, StoreEpi>(l, ep, st) : run_umma<128, StoreEpi>(l, ep, st);
+  if (pair) return run_umma<256, 2, StoreEpi>(l, ep, st);
+  return wide ? run_umma<256, 1, StoreEpi>(l, ep, st) : run_umma<128, 1, StoreEpi>(l, ep, st);
 }
 
 // fp32 -> [hi | lo] tf32 planes: x = hi + lo up to 2^-22 |x|

@@ -279,20 +279,21 @@ cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q,
   if (out_n_fallback && (e = cudaMemsetAsync(out_n_fallback, 0, sizeof(int32_t), st)) != cudaSuccess) return e;
   if (db.n_rows <= 0) return search_topk_exact(db, Q, nq, k, out_idx, out_score, nullptr, st, lc);
 
-  using Cfg = GemmCfg<256, true>;
+  using Cfg = GemmCfg<256, true, 2>;  // CTA pairs: 256 queries x 256 database rows per tile
+  constexpr int kTileM = Cfg::BLOCK_M * Cfg::CTA_GROUP;
   if (lc) lc->n += 3;
   split_planes_kernel<<<(nq + 7) / 8, 256, 0, st>>>(Q, nq, w.q_planes, w.q_norm, nullptr);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
   CUtensorMap ta, tb;
   if (make_operand_map(&ta, w.q_planes, true, nq, 2 * kEmbed, 2 * kEmbed, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
-  if (make_operand_map(&tb, db.planes, true, db.n_rows, 2 * kEmbed, 2 * kEmbed, Cfg::BLOCK_N)) return cudaErrorInvalidValue;
+  if (make_operand_map(&tb, db.planes, true, db.n_rows, 2 * kEmbed, 2 * kEmbed, Cfg::LOAD_N)) return cudaErrorInvalidValue;
   GemmShape s;
   s.M = nq;
   s.N = static_cast<int>(db.n_rows);
-  s.m_tiles = (nq + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  s.m_tiles = (nq + kTileM - 1) / kTileM;
   s.n_tiles = (s.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
-  int want = (2 * tma_api().num_sms + s.m_tiles - 1) / s.m_tiles;  // aim for ~2 units per SM
+  int want = (tma_api().num_sms + s.m_tiles - 1) / s.m_tiles;  // aim for ~2 units per CTA pair
   int n_splits = want < 1 ? 1 : want;
   if (n_splits > s.n_tiles) n_splits = s.n_tiles;
   if (n_splits > kMaxSplits) n_splits = kMaxSplits;

@@ -44,20 +44,27 @@ struct GemmShape {
   KSchedule ks;
 };
 
-template <int kBlockN, bool kBf16>
+// kCtaGroup = 2: a cluster of two CTAs computes a 256 x BLOCK_N tile with one cta_group::2 MMA stream
+// issued by the leader CTA.  CTA r holds A rows [128 r, 128 r + 128) and B rows [BLOCK_N/2 r, ...) of the
+// tile: 32 KB instead of 48 KB per k-block at BLOCK_N = 256, so the ring is 6 deep instead of 4 and the
+// per-SM shared-memory traffic (TMA fill + MMA operand reads), which caps the 1-CTA tf32 kernel at ~68 %
+// of the tensor peak, drops by a third.
+template <int kBlockN, bool kBf16, int kCtaGroup = 1>
 struct GemmCfg {
-  static constexpr int BLOCK_M = 128;
+  static constexpr int CTA_GROUP = kCtaGroup;
+  static constexpr int BLOCK_M = 128;                 // rows per CTA
   static constexpr int BLOCK_N = kBlockN;
+  static constexpr int LOAD_N = kBlockN / kCtaGroup;  // B rows each CTA loads
   static constexpr int ELEM_BYTES = kBf16 ? 2 : 4;
   static constexpr int BLOCK_K = 128 / ELEM_BYTES;  // one 128-byte swizzle atom per row
   static constexpr int UMMA_K = 32 / ELEM_BYTES;    // 8 (tf32) / 16 (bf16)
   static constexpr int A_BYTES = BLOCK_M * 128;
-  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int B_BYTES = LOAD_N * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : 6;
+  static constexpr int STAGES = (STAGE_BYTES > 32768) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers
   static constexpr int BAR_BYTES = 256;
-  static constexpr uint32_t IDESC = umma_idesc(kBf16 ? 1u : 2u, BLOCK_M, BLOCK_N);
+  static constexpr uint32_t IDESC = umma_idesc(kBf16 ? 1u : 2u, BLOCK_M * kCtaGroup, BLOCK_N);
   static constexpr bool IS_BF16 = kBf16;
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two >= 32");
   template <class Epi>
@@ -84,6 +91,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr bool kPair = Cfg::CTA_GROUP == 2;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+  const int cta = kPair ? blockIdx.x >> 1 : blockIdx.x;  // scheduling index (cluster index for pairs)
+  const int n_cta = kPair ? gridDim.x >> 1 : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
@@ -91,22 +102,26 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], Cfg::CTA_GROUP);  // pairs: both producers arrive on the LEADER's barrier
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], 4 * Cfg::CTA_GROUP);  // one arrive per epilogue warp (of both CTAs, on the leader's barrier)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+  if (kPair) cluster_sync_all();  // both CTAs resident before the paired TMEM allocation
+  if (warp == 2) {
+    if (kPair) tmem_alloc_pair(tmem_ptr, Cfg::TMEM_COLS);
+    else tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int n_units = shape.m_tiles * shape.n_splits;
+  const int n_units = shape.m_tiles * shape.n_splits;  // m_tiles counts 128*CTA_GROUP-row tiles
   const int kb_total = shape.ks.n_pass * shape.ks.kb_per_pass;
 
   if (warp == 0) {
@@ -114,19 +129,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // the whole warp walks the schedule (converged), one elected lane issues: same reason as the MMA warp
     int stage = 0;
     uint32_t phase = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    for (int u = cta; u < n_units; u += n_cta) {
       const int m_tile = u / shape.n_splits, split = u % shape.n_splits;
       const int nt0 = split * shape.tiles_per_split;
       const int nt1 = min(nt0 + shape.tiles_per_split, shape.n_tiles);
+      const int a_row = (m_tile * Cfg::CTA_GROUP + static_cast<int>(rank)) * Cfg::BLOCK_M;
       for (int nt = nt0; nt < nt1; ++nt) {
+        const int b_row = nt * Cfg::BLOCK_N + static_cast<int>(rank) * Cfg::LOAD_N;
         for (int p = 0; p < shape.ks.n_pass; ++p) {
           for (int kk = 0; kk < shape.ks.kb_per_pass; ++kk) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (elect_one()) {
-              mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
               uint8_t* sa = stage_base + stage * Cfg::STAGE_BYTES;
-              tma_load_2d(&tm_a, &full_bar[stage], sa, shape.ks.a_off[p] + kk * Cfg::BLOCK_K, m_tile * Cfg::BLOCK_M, kEvictNormal);
-              tma_load_2d(&tm_b, &full_bar[stage], sa + Cfg::A_BYTES, shape.ks.b_off[p] + kk * Cfg::BLOCK_K, nt * Cfg::BLOCK_N, kEvictLast);
+              const int ka = shape.ks.a_off[p] + kk * Cfg::BLOCK_K, kb = shape.ks.b_off[p] + kk * Cfg::BLOCK_K;
+              if (kPair) {
+                tma_load_2d_pair(&tm_a, &full_bar[stage], sa, ka, a_row, kEvictNormal);
+                tma_load_2d_pair(&tm_b, &full_bar[stage], sa + Cfg::A_BYTES, kb, b_row, kEvictLast);
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);  // both CTAs' bytes land on this barrier
+                else mbar_arrive_remote(&full_bar[stage], 0);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                tma_load_2d(&tm_a, &full_bar[stage], sa, ka, a_row, kEvictNormal);
+                tma_load_2d(&tm_b, &full_bar[stage], sa + Cfg::A_BYTES, kb, b_row, kEvictLast);
+              }
             }
             __syncwarp();
             if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -134,13 +159,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
+  } else if (warp == 1 && rank == 0) {
+    // ================= MMA issuer (leader CTA only for pairs) =================
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    for (int u = cta; u < n_units; u += n_cta) {
       const int split = u % shape.n_splits;
       const int nt0 = split * shape.tiles_per_split;
       const int nt1 = min(nt0 + shape.tiles_per_split, shape.n_tiles);
@@ -161,11 +186,22 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
             for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
               // advance 32 bytes (one UMMA_K slice) inside the swizzle atom: +2 in 16-byte units
-              if (Cfg::IS_BF16) umma_f16(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, (kb | k) != 0);
-              else umma_tf32(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, (kb | k) != 0);
+              const uint32_t accum = (kb | k) != 0;
+              if (kPair) {
+                if (Cfg::IS_BF16) umma_f16_pair(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, accum);
+                else umma_tf32_pair(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, accum);
+              } else {
+                if (Cfg::IS_BF16) umma_f16(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, accum);
+                else umma_tf32(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, accum);
+              }
             }
-            tc_commit(&empty_bar[stage]);                         // smem slot free once these MMAs retire
-            if (kb == kb_total - 1) tc_commit(&tmem_full[acc]);  // accumulator ready
+            if (kPair) {  // arrive on the barriers of BOTH CTAs: each has its own producer and epilogue
+              tc_commit_pair(&empty_bar[stage]);
+              if (kb == kb_total - 1) tc_commit_pair(&tmem_full[acc]);
+            } else {
+              tc_commit(&empty_bar[stage]);                         // smem slot free once these MMAs retire
+              if (kb == kb_total - 1) tc_commit(&tmem_full[acc]);  // accumulator ready
+            }
           }
           __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -179,8 +215,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     Epi epi(ep, epi_smem, ew, lane, Cfg::BLOCK_N);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int m_tile = u / shape.n_splits, split = u % shape.n_splits;
+    for (int u = cta; u < n_units; u += n_cta) {
+      const int m_tile = (u / shape.n_splits) * Cfg::CTA_GROUP + static_cast<int>(rank);  // this CTA's 128-row tile
+      const int split = u % shape.n_splits;
       const int nt0 = split * shape.tiles_per_split;
       const int nt1 = min(nt0 + shape.tiles_per_split, shape.n_tiles);
       epi.begin_unit(m_tile, split);
@@ -200,7 +237,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if (kPair && rank != 0) mbar_arrive_remote(&tmem_empty[acc], 0);  // the MMA issuer lives in the leader
+          else mbar_arrive(&tmem_empty[acc]);
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       epi.end_unit(m_tile, split);
@@ -208,10 +248,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all(); else __syncthreads();  // pairs: nobody leaves while the peer may still signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (kPair) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -255,9 +296,21 @@ cudaError_t launch_umma_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, c
   }
   const int n_units = shape.m_tiles * shape.n_splits;
   if (n_units <= 0) return cudaSuccess;
-  const int grid = n_units < tma_api().num_sms ? n_units : tma_api().num_sms;
-  umma_gemm_kernel<Cfg, Epi><<<grid, kGemmThreads, smem, stream>>>(tm_a, tm_b, shape, ep);
-  return cudaGetLastError();
+  const int slots = tma_api().num_sms / Cfg::CTA_GROUP;  // CTAs, or CTA pairs
+  const int n_sched = n_units < slots ? n_units : slots;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(n_sched * Cfg::CTA_GROUP);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = Cfg::CTA_GROUP;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, umma_gemm_kernel<Cfg, Epi>, tm_a, tm_b, shape, ep);
 }
 
 }  // namespace t2l

@@ -131,6 +131,7 @@ class Engine:
             self._copy_stream = torch.cuda.Stream(self.device)
             self._stage_done = [None, None]
         cur = torch.cuda.current_stream(self.device)
+        pooled = torch.empty((nq * n_sent, T5_DIM), dtype=torch.float32, device=self.device)
         for i, q0 in enumerate(range(0, nq, cq)):
             q1 = min(nq, q0 + cq)
             b = i % 2
@@ -142,9 +143,11 @@ class Engine:
                 copied = torch.cuda.Event()
                 copied.record(self._copy_stream)
             cur.wait_event(copied)
-            self._encode_text_dev(self._stage[b][:n_rows], n_sent, out[q0:q1])
+            self._check(self._lib.t2l_encode_text_tokens(  # token stage of this chunk; sentence stage once at the end
+                self._h, _ptr(self._stage[b]), n_rows, n_tok, _ptr(pooled[q0 * n_sent:q1 * n_sent]), self._stream()))
             self._stage_done[b] = torch.cuda.Event()
             self._stage_done[b].record(cur)
+        self._check(self._lib.t2l_encode_text_sentences(self._h, _ptr(pooled), nq, n_sent, _ptr(out), self._stream()))
         return out
 
     def _encode_text_dev(self, t5: torch.Tensor, n_sent: int, out: torch.Tensor):
