@@ -267,7 +267,8 @@ static int encoder_layer(t2l_engine* e, const std::string& pfx, bool fast, const
   float* h = a.get<float>(static_cast<size_t>(rows) * ffn);
   if (fast) {
     CU(lin(e, true, X, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st));
-    CU(mha_small(qkv, att, n_seq, S, d, 4, st, &e->lc, /*round_out=*/1));
+    if (d == 1024) CU(mha_tc256(qkv, att, n_seq, S, st, &e->lc, /*round_out=*/1));
+    else CU(mha_small(qkv, att, n_seq, S, d, 4, st, &e->lc, /*round_out=*/1));
     CU(lin(e, true, att, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, X, d));
     CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc));
     CU(lin(e, true, x1, d, rows, pfx + ".l1_w", pfx + ".l1_b", h, ffn, 1, st, nullptr, 0, 1));

@@ -99,6 +99,8 @@ cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const floa
 // Unmasked multi-head self attention on packed QKV rows [n_seq*S, 3d] (q | k | v), head h uses
 // columns [h*hd, (h+1)*hd); out [n_seq*S, d].  softmax(q k^T / sqrt(hd)) v, fp32.
 cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out = 0);
+// Same contract for d = 1024, 4 heads of 256 (the token layer): warp-level mma.sync tf32 tiles.
+cudaError_t mha_tc256(const float* qkv, float* out, int n_seq, int S, cudaStream_t st, Launches* lc, int round_out = 0);
 // y[g, :] = max over the S rows of group g
 cudaError_t max_over_rows(const float* x, float* y, int groups, int S, int d, cudaStream_t st, Launches* lc);
 // X[b, s, :] = normalize(emb[cell_ptr[b]+s]) for s < min(n_b, 28), else 0   (cell_retrieval.py:85-98)

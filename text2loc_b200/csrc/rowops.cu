@@ -159,6 +159,168 @@ cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int
   return cudaGetLastError();
 }
 
+// ---- tensor-core attention core for the token layer (head_dim 256) ---------------------------------
+// One warp per (sentence, head): scores = Q K^T and O = P V as warp-level mma.sync m16n8k8 tf32 tiles,
+// softmax in the accumulator fragments.  Fragment index tricks keep every global access a
+// coalesced 128-bit one and need no shuffles between the two products:
+//   * the k index of an MMA is a dummy summation index, so a lane's 8 contiguous floats of a Q/K row
+//     serve as the (k = t, k = t+4) elements of four successive k-steps;
+//   * the score accumulator layout (row g, keys 2t / 2t+1) is re-read as the A fragment of P V by
+//     declaring key 8j+2t <-> k = t and key 8j+2t+1 <-> k = t+4, and loading V rows in that order;
+//   * output columns are permuted the same way, so each lane ends with 8 contiguous floats of a row.
+// Operands are rounded to tf32 (rna) like every other tensor-core layer of the token encoder.
+// NO mask: padded tokens attend like real ones (language_encoder.py:130-131).
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tf32_bits(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+template <int MT>  // MT 16-row query tiles (S <= 16 * MT), 2 * MT key tiles of 8
+__global__ void __launch_bounds__(128) mha_tc256_kernel(const float* __restrict__ qkv, float* __restrict__ out, long n_seq, int S, float scale,
+                                                        int round_out) {
+  constexpr int HD = 256, D = 1024, LD = 3 * D, NT = 2 * MT;
+  const long wid = static_cast<long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
+  if (wid >= n_seq * 4) return;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int h = static_cast<int>(wid & 3);
+  const float* base = qkv + (wid >> 2) * S * LD + h * HD;
+  auto row_ptr = [&](int r, int which) { return base + static_cast<long>(min(r, S - 1)) * LD + which * D; };  // clamp: rows >= S are never stored / are masked
+
+  // ---- scores[MT*16, NT*8] = Q K^T
+  float sc[MT][NT][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int n = 0; n < NT; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[m][n][i] = 0.f;
+#pragma unroll 2
+  for (int s = 0; s < HD / 32; ++s) {  // 32 head-dim columns per step: lane owns columns 32 s + 8 t .. + 7 of its rows
+    float4 qa[MT][2][2], kb[NT][2];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        const float4* p = reinterpret_cast<const float4*>(row_ptr(16 * m + 8 * hi + g, 0) + 32 * s + 8 * t);
+        qa[m][hi][0] = p[0]; qa[m][hi][1] = p[1];
+      }
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const float4* p = reinterpret_cast<const float4*>(row_ptr(8 * n + g, 1) + 32 * s + 8 * t);
+      kb[n][0] = p[0]; kb[n][1] = p[1];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // four k-steps: elements (2j, 2j+1) of the lane's 8 floats
+      auto pick = [&](const float4 (&v)[2], int e) { const float* f = reinterpret_cast<const float*>(v); return tf32_bits(f[e]); };
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        const uint32_t a0 = pick(qa[m][0], 2 * j), a1 = pick(qa[m][1], 2 * j), a2 = pick(qa[m][0], 2 * j + 1), a3 = pick(qa[m][1], 2 * j + 1);
+#pragma unroll
+        for (int n = 0; n < NT; ++n) mma_tf32_16x8x8(sc[m][n], a0, a1, a2, a3, pick(kb[n], 2 * j), pick(kb[n], 2 * j + 1));
+      }
+    }
+  }
+  // ---- softmax over keys: row (16 m + g [+8]) lives in the 4 lanes of a quad; keys 8 n + 2 t, + 1
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float& v = sc[m][n][2 * hi + e];
+          v = (8 * n + 2 * t + e < S) ? v * scale : -INFINITY;
+          mx = fmaxf(mx, v);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float& v = sc[m][n][2 * hi + e];
+          v = expf(v - mx);
+          sum += v;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) sc[m][n][2 * hi + e] *= inv;
+    }
+  // ---- O = P V, 32 output columns at a time; lane (g, t) ends with columns 32 s + 8 t .. + 7 of rows g, g + 8
+  uint32_t pa[MT][NT][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {  // C layout (c0,c1 | c2,c3) -> A layout (a0 = c0, a1 = c2, a2 = c1, a3 = c3) under the key permutation
+      pa[m][n][0] = tf32_bits(sc[m][n][0]); pa[m][n][1] = tf32_bits(sc[m][n][2]);
+      pa[m][n][2] = tf32_bits(sc[m][n][1]); pa[m][n][3] = tf32_bits(sc[m][n][3]);
+    }
+#pragma unroll 1
+  for (int s = 0; s < HD / 32; ++s) {
+    float o[MT][4][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[m][j][i] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {  // k-step over keys 8 n .. 8 n + 7: k = t <-> key 8 n + 2 t, k = t + 4 <-> key 8 n + 2 t + 1
+      const float4 v0 = *reinterpret_cast<const float4*>(row_ptr(8 * n + 2 * t, 2) + 32 * s + 4 * g);
+      const float4 v1 = *reinterpret_cast<const float4*>(row_ptr(8 * n + 2 * t + 1, 2) + 32 * s + 4 * g);
+      const float f0[4] = {v0.x, v0.y, v0.z, v0.w}, f1[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // n-tile j: output column (n index g) = 32 s + 4 g + j
+        const uint32_t b0 = tf32_bits(f0[j]), b1 = tf32_bits(f1[j]);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) mma_tf32_16x8x8(o[m][j], pa[m][n][0], pa[m][n][1], pa[m][n][2], pa[m][n][3], b0, b1);
+      }
+    }
+    // accumulator (row g | g+8, n = 2 t | 2 t + 1) of tile j is column 32 s + 8 t + j | + 4 + j
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+      for (int hi = 0; hi < 2; ++hi) {
+        const int r = 16 * m + 8 * hi + g;
+        if (r < S) {
+          float4 lo = make_float4(o[m][0][2 * hi], o[m][1][2 * hi], o[m][2][2 * hi], o[m][3][2 * hi]);
+          float4 up = make_float4(o[m][0][2 * hi + 1], o[m][1][2 * hi + 1], o[m][2][2 * hi + 1], o[m][3][2 * hi + 1]);
+          if (round_out) {
+            lo = make_float4(round_tf32(lo.x), round_tf32(lo.y), round_tf32(lo.z), round_tf32(lo.w));
+            up = make_float4(round_tf32(up.x), round_tf32(up.y), round_tf32(up.z), round_tf32(up.w));
+          }
+          float4* dst = reinterpret_cast<float4*>(out + ((wid >> 2) * S + r) * D + h * HD + 32 * s + 8 * t);
+          dst[0] = lo;
+          dst[1] = up;
+        }
+      }
+  }
+}
+
+cudaError_t mha_tc256(const float* qkv, float* out, int n_seq, int S, cudaStream_t st, Launches* lc, int round_out) {
+  if (n_seq <= 0) return cudaSuccess;
+  if (S < 1 || S > 32) return cudaErrorInvalidValue;
+  if (lc) lc->n++;
+  const unsigned grid = static_cast<unsigned>((static_cast<long>(n_seq) * 4 + 3) / 4);
+  const float scale = 1.f / 16.f;  // 1 / sqrt(256)
+  if (S <= 16) mha_tc256_kernel<1><<<grid, 128, 0, st>>>(qkv, out, n_seq, S, scale, round_out);
+  else mha_tc256_kernel<2><<<grid, 128, 0, st>>>(qkv, out, n_seq, S, scale, round_out);
+  return cudaGetLastError();
+}
+
 // ---- max over the rows of a group ---------------------------------------------------------------
 __global__ void max_over_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int groups, int S, int d4) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
