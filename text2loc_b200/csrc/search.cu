@@ -57,6 +57,10 @@ cudaError_t search_prepare_db(const SearchDb& db, cudaStream_t st, Launches* lc)
 }
 
 // ---- candidate epilogue -------------------------------------------------------------------------
+// Each epilogue thread owns one query row and keeps its 16 best approximate scores of the current
+// split in REGISTERS as a descending sorted list; inserting is a branch-free 16-step compare-exchange
+// chain taken only when a score beats the list minimum (the drop threshold).  Everything the thread
+// ever dropped is therefore <= the final minimum, which is what the re-rank proof needs.
 struct TopKEpi {
   struct Params {
     float* cand_score;  // [nq, n_splits, kCand]
@@ -64,66 +68,62 @@ struct TopKEpi {
     float* cand_thr;    // [nq, n_splits]          -inf = nothing was dropped
     int nq, n_db, n_splits;
   };
-  static constexpr int kSmemBytes = kCand * 128 * 8;
+  static constexpr int kSmemBytes = 32 * 128 * 4;  // one 32-float column per epilogue thread (candidate staging)
   const Params& p;
-  float* s_score;
-  int32_t* s_idx;
-  int t;       // 0..127: row inside the M tile
-  float thr;   // minimum of the kept list once it is full, else -inf
-  int cnt, min_slot;
+  float* s_v;
+  int t;  // 0..127: row inside this CTA's 128-row tile
+  float ls[kCand];
+  int li[kCand];
   bool active;
 
-  __device__ TopKEpi(const Params& p_, uint8_t* smem, int ew, int lane, int) : p(p_) {
-    s_score = reinterpret_cast<float*>(smem);
-    s_idx = reinterpret_cast<int32_t*>(smem + kCand * 128 * 4);
-    t = ew * 32 + lane;
-    thr = -INFINITY; cnt = 0; min_slot = 0; active = false;
-  }
+  __device__ TopKEpi(const Params& p_, uint8_t* smem, int ew, int lane, int)
+      : p(p_), s_v(reinterpret_cast<float*>(smem)), t(ew * 32 + lane), active(false) {}
   __device__ void begin_unit(int m_tile, int) {
     active = (m_tile * 128 + t) < p.nq;
-    thr = active ? -INFINITY : INFINITY;
-    cnt = 0;
-    min_slot = 0;
-  }
-  __device__ __noinline__ void insert(float s, int col) {
-    if (col >= p.n_db) return;
-    if (cnt < kCand) {
-      s_score[cnt * 128 + t] = s;
-      s_idx[cnt * 128 + t] = col;
-      if (++cnt < kCand) return;
-    } else {
-      s_score[min_slot * 128 + t] = s;
-      s_idx[min_slot * 128 + t] = col;
-    }
-    float m = s_score[t];
-    int ms = 0;
 #pragma unroll
-    for (int i = 1; i < kCand; ++i) {
-      const float v = s_score[i * 128 + t];
-      if (v < m) { m = v; ms = i; }
-    }
-    thr = m;
-    min_slot = ms;
+    for (int i = 0; i < kCand; ++i) { ls[i] = active ? -INFINITY : INFINITY; li[i] = -1; }
   }
   __device__ void begin_tile(int, int, int) {}
+  __device__ __forceinline__ void insert(float x, int xi) {
+#pragma unroll
+    for (int i = 0; i < kCand; ++i) {  // x sinks through the descending list; the old minimum falls out
+      const bool gt = x > ls[i];
+      const float s_keep = gt ? x : ls[i], s_next = gt ? ls[i] : x;
+      const int i_keep = gt ? xi : li[i], i_next = gt ? li[i] : xi;
+      ls[i] = s_keep; li[i] = i_keep; x = s_next; xi = i_next;
+    }
+  }
   __device__ void chunk(int, int, int, int col0, float (&v)[32]) {
-    float cmax = v[0];
+    if (col0 + 32 > p.n_db) {  // database tail: zero-filled rows must not compete
 #pragma unroll
-    for (int i = 1; i < 32; ++i) cmax = fmaxf(cmax, v[i]);
-    if (!(cmax > thr)) return;
+      for (int i = 0; i < 32; ++i) v[i] = (col0 + i < p.n_db) ? v[i] : -INFINITY;
+    }
+    const float thr = ls[kCand - 1];
+    uint32_t mask = 0;
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (v[i] > thr) insert(v[i], col0 + i);
+    for (int i = 0; i < 32; ++i) mask |= (v[i] > thr) ? (1u << i) : 0u;
+    if (mask == 0) return;  // the common case once the list has warmed up
+    // rare path: park the 32 scores in shared memory so ONE copy of the insertion chain can walk the
+    // set bits with a dynamic index (32 unrolled copies thrashed the instruction cache: 3x slower)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s_v[i * 128 + t] = v[i];
+    while (mask) {
+      const int i = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float x = s_v[i * 128 + t];
+      if (x > ls[kCand - 1]) insert(x, col0 + i);
+    }
   }
   __device__ void end_unit(int m_tile, int split) {
     if (!active) return;
     const long row = static_cast<long>(m_tile) * 128 + t;
     const long base = (row * p.n_splits + split) * kCand;
+#pragma unroll
     for (int i = 0; i < kCand; ++i) {
-      p.cand_score[base + i] = (i < cnt) ? s_score[i * 128 + t] : -INFINITY;
-      p.cand_idx[base + i] = (i < cnt) ? s_idx[i * 128 + t] : -1;
+      p.cand_score[base + i] = ls[i];
+      p.cand_idx[base + i] = li[i];
     }
-    p.cand_thr[row * p.n_splits + split] = (cnt == kCand) ? thr : -INFINITY;
+    p.cand_thr[row * p.n_splits + split] = (li[kCand - 1] >= 0) ? ls[kCand - 1] : -INFINITY;  // list not full: nothing was dropped
   }
 };
 
@@ -293,7 +293,9 @@ cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q,
   s.N = static_cast<int>(db.n_rows);
   s.m_tiles = (nq + kTileM - 1) / kTileM;
   s.n_tiles = (s.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
-  int want = (tma_api().num_sms + s.m_tiles - 1) / s.m_tiles;  // aim for ~2 units per CTA pair
+  // database splits: only as many as it takes to give every CTA pair a unit; each split costs every
+  // query another ~16 (1 + ln(rows/16)) list insertions and another 16 candidates to re-rank
+  int want = (tma_api().num_sms / Cfg::CTA_GROUP) / s.m_tiles;
   int n_splits = want < 1 ? 1 : want;
   if (n_splits > s.n_tiles) n_splits = s.n_tiles;
   if (n_splits > kMaxSplits) n_splits = kMaxSplits;
