@@ -128,7 +128,8 @@ extern "C" int t2l_create(int device, t2l_engine** out) {
 
 static void free_search_work(t2l_engine* e) {
   cudaFree(e->sw.q_planes); cudaFree(e->sw.q_norm); cudaFree(e->sw.cand_score); cudaFree(e->sw.cand_idx);
-  cudaFree(e->sw.cand_thr); cudaFree(e->sw.flags);
+  cudaFree(e->sw.cand_thr); cudaFree(e->sw.flags); cudaFree(e->sw.n_fail); cudaFree(e->sw.fail_ids); cudaFree(e->sw.fail_thr);
+  cudaFree(e->sw.q2_planes); cudaFree(e->sw.cand2_idx); cudaFree(e->sw.cand2_cnt);
   e->sw = SearchWork{};
 }
 
@@ -577,6 +578,12 @@ static int ensure_search_work(t2l_engine* e, int nq) {
   CU(cudaMalloc(&e->sw.cand_idx, cap * sc * 16 * sizeof(int32_t)));
   CU(cudaMalloc(&e->sw.cand_thr, cap * sc * sizeof(float)));
   CU(cudaMalloc(&e->sw.flags, cap * sizeof(int32_t)));
+  CU(cudaMalloc(&e->sw.n_fail, sizeof(int32_t)));
+  CU(cudaMalloc(&e->sw.fail_ids, cap * sizeof(int32_t)));
+  CU(cudaMalloc(&e->sw.fail_thr, cap * sizeof(float)));
+  CU(cudaMalloc(&e->sw.q2_planes, cap * 512 * sizeof(__nv_bfloat16)));
+  CU(cudaMalloc(&e->sw.cand2_idx, cap * kPass2Cap * sizeof(int32_t)));
+  CU(cudaMalloc(&e->sw.cand2_cnt, cap * sc * sizeof(int32_t)));
   e->sw.nq_cap = static_cast<int>(cap);
   e->sw.splits_cap = sc;
   return 0;

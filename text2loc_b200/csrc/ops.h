@@ -124,10 +124,17 @@ struct SearchWork {
   float* cand_score;        // [nq_cap, splits_cap, 16]
   int32_t* cand_idx;        // [nq_cap, splits_cap, 16]
   float* cand_thr;          // [nq_cap, splits_cap]
-  int32_t* flags;           // [nq_cap]
-  double* scan;             // [fallback scratch]
+  int32_t* flags;           // [nq_cap]  2 = needs the exact rescan (second-pass buffer overflowed)
+  // second pass for queries whose proof failed: collect every row whose approximate score can still reach the top-k
+  int32_t* n_fail;          // [1]
+  int32_t* fail_ids;        // [nq_cap]
+  float* fail_thr;          // [nq_cap]   k-th exact score of pass 1 minus the error bound, rounded down
+  __nv_bfloat16* q2_planes; // [nq_cap, 512] planes of the failed queries, compacted
+  int32_t* cand2_idx;       // [nq_cap, kPass2Cap]
+  int32_t* cand2_cnt;       // [nq_cap, splits_cap]
   int nq_cap, splits_cap;
 };
+constexpr int kPass2Cap = 128;  // candidates per failed query in the second pass (all splits together)
 cudaError_t search_prepare_db(const SearchDb& db, cudaStream_t st, Launches* lc);
 cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q, int nq, int k, int64_t* out_idx,
                         double* out_score, int32_t* out_n_fallback, cudaStream_t st, Launches* lc);

@@ -8,7 +8,11 @@
 //   2. exact re-rank: fp64 dot products of the fp32 originals for those candidates, ordered by
 //      (score desc, row asc);
 //   3. proof: if every split's drop threshold + error bound is below the k-th exact score, no
-//      dropped row can belong to the top-k; otherwise the query is rescanned exactly in fp64.
+//      dropped row can belong to the top-k and the query is done;
+//   4. otherwise (tight clusters, e.g. near-collinear embeddings) a second tensor-core pass over just
+//      those queries COLLECTS every row whose approximate score is >= (k-th exact score so far) - bound:
+//      any true top-k member satisfies that, so an exact re-rank of the collected rows is the exact
+//      answer.  Only if more than 128 rows qualify is the query rescanned exhaustively in fp64.
 // Returned indices are therefore those of the fp64 stable-order oracle by construction.
 #include "ops.h"
 #include "umma_gemm.cuh"
@@ -177,7 +181,8 @@ __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const float* 
                                                                    const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_thr,
                                                                    const float* __restrict__ q_norm, const float* __restrict__ max_norm, int nq, int n_splits,
                                                                    int k, long row_offset, int64_t* __restrict__ out_idx, double* __restrict__ out_score,
-                                                                   int32_t* __restrict__ flags, int32_t* __restrict__ n_fallback) {
+                                                                   int32_t* __restrict__ flags, int32_t* __restrict__ n_fail, int32_t* __restrict__ fail_ids,
+                                                                   float* __restrict__ fail_thr) {
   __shared__ double s_sc[kRerankWarps][kMaxSplits * kCand];
   __shared__ long s_ix[kRerankWarps][kMaxSplits * kCand];
   __shared__ double s_osc[kRerankWarps][kMaxK];
@@ -211,8 +216,105 @@ __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const float* 
     out_score[static_cast<long>(q) * k + lane] = s_osc[w][lane];
   }
   if (lane == 0) {
-    flags[q] = fail ? 1 : 0;
-    if (fail && n_fallback) atomicAdd(n_fallback, 1);
+    flags[q] = 0;
+    if (fail) {  // queue for the second pass: rows with approx >= kth - eps are the only possible top-k members
+      const int slot = atomicAdd(n_fail, 1);
+      fail_ids[slot] = q;
+      fail_thr[slot] = __double2float_rd(kth - static_cast<double>(eps));
+    }
+  }
+}
+
+// ---- second pass: compact the failed queries' operand planes -----------------------------------------
+__global__ void __launch_bounds__(256) gather_fail_planes_kernel(const __nv_bfloat16* __restrict__ q_planes, const int32_t* __restrict__ fail_ids,
+                                                                 const int32_t* __restrict__ n_fail, __nv_bfloat16* __restrict__ q2_planes) {
+  const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (slot >= *n_fail) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* src = reinterpret_cast<const uint4*>(q_planes + static_cast<long>(fail_ids[slot]) * 2 * kEmbed);
+  uint4* dst = reinterpret_cast<uint4*>(q2_planes + static_cast<long>(slot) * 2 * kEmbed);
+  dst[lane] = src[lane];
+  dst[lane + 32] = src[lane + 32];
+}
+
+// Epilogue of the second pass: no ranking, just the row indices whose approximate score reaches the
+// query's threshold (per (query, split) buffer of `cap` entries; the count may exceed cap = overflow).
+struct CollectEpi {
+  struct Params {
+    const float* thr;       // [slots]
+    const int32_t* n_rows;  // [1] live slots
+    int32_t* cand_idx;      // [slots, kPass2Cap]  split s owns [s * cap, (s + 1) * cap)
+    int32_t* cand_cnt;      // [slots, n_splits]
+    int n_db, n_splits, cap;
+  };
+  static constexpr int kSmemBytes = 0;
+  const Params& p;
+  int t, cnt;
+  float T;
+  long base;
+  bool active;
+  __device__ CollectEpi(const Params& p_, uint8_t*, int ew, int lane, int) : p(p_), t(ew * 32 + lane), cnt(0), T(INFINITY), base(0), active(false) {}
+  __device__ void begin_unit(int m_tile, int split) {
+    const long row = static_cast<long>(m_tile) * 128 + t;
+    active = row < *p.n_rows;
+    T = active ? p.thr[row] : INFINITY;
+    cnt = 0;
+    base = row * kPass2Cap + static_cast<long>(split) * p.cap;
+  }
+  __device__ void begin_tile(int, int, int) {}
+  __device__ void chunk(int, int, int, int col0, float (&v)[32]) {
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mask |= (v[i] >= T && col0 + i < p.n_db) ? (1u << i) : 0u;
+    while (mask) {
+      const int i = __ffs(mask) - 1;
+      mask &= mask - 1;
+      if (cnt < p.cap) p.cand_idx[base + cnt] = col0 + i;
+      ++cnt;
+    }
+  }
+  __device__ void end_unit(int m_tile, int split) {
+    if (active) p.cand_cnt[(static_cast<long>(m_tile) * 128 + t) * p.n_splits + split] = cnt;
+  }
+};
+
+// Exact re-rank of the collected rows (one warp per failed query); overflow -> flag for the exhaustive scan.
+__global__ void __launch_bounds__(kRerankWarps * 32) rerank2_kernel(const float* __restrict__ Q, const float* __restrict__ D, const int32_t* __restrict__ fail_ids,
+                                                                    const int32_t* __restrict__ n_fail, const int32_t* __restrict__ cand_idx,
+                                                                    const int32_t* __restrict__ cand_cnt, int n_splits, int cap, int k, long row_offset,
+                                                                    int64_t* __restrict__ out_idx, double* __restrict__ out_score, int32_t* __restrict__ flags) {
+  __shared__ double s_sc[kRerankWarps][kPass2Cap];
+  __shared__ long s_ix[kRerankWarps][kPass2Cap];
+  __shared__ double s_osc[kRerankWarps][kMaxK];
+  __shared__ long s_oix[kRerankWarps][kMaxK];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = blockIdx.x * kRerankWarps + w;
+  if (slot >= *n_fail) return;
+  const int q = fail_ids[slot];
+  int n = 0;
+  bool overflow = false;
+  for (int s = 0; s < n_splits; ++s) {
+    const int c = cand_cnt[static_cast<long>(slot) * n_splits + s];  // warp-uniform
+    if (c > cap) { overflow = true; break; }
+    for (int i = lane; i < c; i += 32) s_ix[w][n + i] = cand_idx[static_cast<long>(slot) * kPass2Cap + s * cap + i];
+    n += c;
+  }
+  if (overflow) {
+    if (lane == 0) flags[q] = 2;
+    return;
+  }
+  __syncwarp();
+  const float* qr = Q + static_cast<long>(q) * kEmbed;
+  for (int c = 0; c < n; ++c) {
+    const double s = warp_dot256(qr, D + s_ix[w][c] * kEmbed, lane);
+    if (lane == 0) s_sc[w][c] = s;
+  }
+  __syncwarp();
+  warp_select_topk(s_sc[w], s_ix[w], n, k, lane, s_osc[w], s_oix[w]);
+  if (lane < k) {
+    const long ix = s_oix[w][lane];
+    out_idx[static_cast<long>(q) * k + lane] = ix >= 0 ? ix + row_offset : -1;
+    out_score[static_cast<long>(q) * k + lane] = s_osc[w][lane];
   }
 }
 
@@ -276,6 +378,7 @@ cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q,
   if (nq <= 0) return cudaSuccess;
   if (k < 1 || k > kMaxK || nq > w.nq_cap) return cudaErrorInvalidValue;
   cudaError_t e;
+  if ((e = cudaMemsetAsync(w.n_fail, 0, sizeof(int32_t), st)) != cudaSuccess) return e;
   if (out_n_fallback && (e = cudaMemsetAsync(out_n_fallback, 0, sizeof(int32_t), st)) != cudaSuccess) return e;
   if (db.n_rows <= 0) return search_topk_exact(db, Q, nq, k, out_idx, out_score, nullptr, st, lc);
 
@@ -313,8 +416,26 @@ cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q,
 
   rerank_kernel<<<(nq + kRerankWarps - 1) / kRerankWarps, kRerankWarps * 32, 0, st>>>(
       Q, db.D, w.cand_score, w.cand_idx, w.cand_thr, w.q_norm, db.max_norm, nq, n_splits, k, db.row_offset, out_idx, out_score, w.flags,
-      out_n_fallback);
+      w.n_fail, w.fail_ids, w.fail_thr);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+
+  // ---- second pass over the queries whose proof failed (count lives on the device: no host sync; the GEMM
+  // skips tiles beyond it).  Same operands, same splits; the epilogue collects instead of ranking.
+  if (lc) lc->n += 3;
+  gather_fail_planes_kernel<<<(nq + 7) / 8, 256, 0, st>>>(w.q_planes, w.fail_ids, w.n_fail, w.q2_planes);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  CUtensorMap ta2;
+  if (make_operand_map(&ta2, w.q2_planes, true, nq, 2 * kEmbed, 2 * kEmbed, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
+  GemmShape s2 = s;
+  s2.m_rows_dev = w.n_fail;
+  const int cap = kPass2Cap / n_splits;
+  CollectEpi::Params ep2{w.fail_thr, w.n_fail, w.cand2_idx, w.cand2_cnt, s.N, n_splits, cap};
+  if ((e = launch_umma_gemm<Cfg, CollectEpi>(ta2, tb, s2, ep2, st)) != cudaSuccess) return e;
+  rerank2_kernel<<<(nq + kRerankWarps - 1) / kRerankWarps, kRerankWarps * 32, 0, st>>>(
+      Q, db.D, w.fail_ids, w.n_fail, w.cand2_idx, w.cand2_cnt, n_splits, cap, k, db.row_offset, out_idx, out_score, w.flags);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (out_n_fallback && (e = cudaMemcpyAsync(out_n_fallback, w.n_fail, sizeof(int32_t), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
+  // exhaustive fp64 rescan only where the second pass overflowed its candidate buffer
   return search_topk_exact(db, Q, nq, k, out_idx, out_score, w.flags, st, lc);
 }
 

@@ -42,6 +42,7 @@ struct GemmShape {
   int n_splits;         // units per M tile
   int tiles_per_split;  // N tiles per unit
   KSchedule ks;
+  const int* m_rows_dev = nullptr;  // optional device scalar: only the first *m_rows_dev rows of A are live (count produced by an earlier kernel)
 };
 
 // kCtaGroup = 2: a cluster of two CTAs computes a 256 x BLOCK_N tile with one cta_group::2 MMA stream
@@ -121,7 +122,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int n_units = shape.m_tiles * shape.n_splits;  // m_tiles counts 128*CTA_GROUP-row tiles
+  int n_units = shape.m_tiles * shape.n_splits;  // m_tiles counts 128*CTA_GROUP-row tiles
+  if (shape.m_rows_dev) {  // every role reads the same value, so they all skip the same units
+    const int live_tiles = (*shape.m_rows_dev + Cfg::BLOCK_M * Cfg::CTA_GROUP - 1) / (Cfg::BLOCK_M * Cfg::CTA_GROUP);
+    n_units = min(n_units, live_tiles * shape.n_splits);
+  }
   const int kb_total = shape.ks.n_pass * shape.ks.kb_per_pass;
 
   if (warp == 0) {
