@@ -239,14 +239,18 @@ def encode_text(sd, t5, n_sent: int, n_heads=4, chunk=256):
 def search_topk(cell_enc, text_enc, k: int):
     """scores = D_f64 @ q_f64 per query; order by (score desc, row index asc) -- the
     reference's np.argsort(-scores) default kind leaves tie order unspecified, the oracle pins
-    it with a stable sort.  Returns (idx int64 [nq,k], score f64 [nq,k])."""
+    it with a stable sort.  Returns (idx int64 [nq,k], score f64 [nq,k]).
+
+    The product is evaluated row by row (einsum, no BLAS): a threaded dgemv may sum identical
+    database rows in different orders (seen on the 16-core GPU host: 301 duplicate rows got
+    scores 1 ulp apart), which would break exact ties by rounding noise instead of by row index."""
     D = np.asarray(cell_enc, dtype=np.float64)  # f32 values widened, as np.zeros(...) does (:81,84)
     Q = np.asarray(text_enc, dtype=np.float64)
     k = min(k, D.shape[0])
     idx = np.empty((Q.shape[0], k), np.int64)
     sc = np.empty((Q.shape[0], k), np.float64)
     for q in range(Q.shape[0]):
-        s = D @ Q[q]
+        s = np.einsum("ij,j->i", D, Q[q])
         o = np.argsort(-1.0 * s, kind="stable")[:k]
         idx[q], sc[q] = o, s[o]
     return idx, sc
