@@ -114,6 +114,12 @@ int64_t t2l_launch_count(const t2l_engine* e);
 int t2l_debug_linear(t2l_engine* e, int path, const float* A, int lda, const float* W, int ldw, const float* bias,
                      float* C, int ldc, int M, int N, int K, int act, int segmax, void* stream);
 
+/* Test hook for the fp16-operand tcgen05 GEMM the token layer runs on (kind::f16, fp32 accumulate):
+ * A device f16 [M, lda], W device f16 [N, ldw] (as raw 16-bit words), bias device f32 [N] or NULL,
+ * C device f32 [M, ldc] or, with out_half != 0, f16 [M, ldc] (saturating at +-65504). */
+int t2l_debug_linear_f16(t2l_engine* e, const void* A, int lda, const void* W, int ldw, const float* bias,
+                         void* C, int ldc, int M, int N, int K, int act, int out_half, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

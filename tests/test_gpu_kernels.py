@@ -47,6 +47,30 @@ def test_umma_gemm_matches_tf32_emulation(eng, M, N, K):
     assert (Cr.double() - want_rna.clamp(min=0)).abs().max().item() < 2e-5 * max(1.0, K / 256) ** 0.5
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 256, 64), (1000, 512, 264), (4096, 1024, 1024), (96, 64, 32), (2000, 3072, 1024),
+                                   (777, 1024, 4096), (32760, 4096, 1024)])
+def test_umma_gemm_f16_operands(eng, M, N, K):
+    """kind::f16 with fp16 operands and fp32 accumulation (the token layer): products of fp16 values are exact in
+    fp32, so the result equals the fp64 product of the same fp16 operands up to fp32 accumulation error; the
+    fp16 output variant is that, rounded to nearest fp16."""
+    g = torch.Generator(device="cuda").manual_seed(M * 5 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    b = torch.randn(N, device="cuda", generator=g)
+    want = A.double() @ W.double().T + b.double()
+    C = eng.debug_linear_f16(A, W, b, act=0)
+    err = (C.double() - want).abs().max().item()
+    print(f"\n[f16 {M}x{N}x{K}] |C-fp64|={err:.3e}")
+    assert err < 2e-5 * max(1.0, K / 256) ** 0.5
+    Ch = eng.debug_linear_f16(A, W, b, act=1, out_half=True)
+    assert Ch.dtype == torch.float16
+    assert (Ch.double() - want.clamp(min=0)).abs().max().item() < 2e-5 * max(1.0, K / 256) ** 0.5 + 2.0 ** -11 * want.abs().max().item()
+    # saturation instead of inf
+    big = eng.debug_linear_f16(A[:128] * 0 + 250.0, W * 0 + 2.0, None, act=0, out_half=True) if K >= 256 else None
+    if big is not None:
+        assert torch.isfinite(big).all() and big.max().item() == 65504.0
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (4224 * 4, 64, 32), (2112 * 3, 128, 128), (1056, 256, 256), (64, 1024, 512)])
 def test_umma_segmax_epilogue(eng, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)

@@ -72,6 +72,40 @@ def test_encode_text_golden(eng, golden):
     assert err < EMB_TOL
 
 
+def test_encode_text_tf32_path_also_within_tolerance(state_dict, golden, monkeypatch):
+    """The token layer runs on fp16 operands by default; T2L_TEXT_TF32=1 keeps the tf32 variant for A/B checks.
+    Both have an 11-bit significand and must meet the same tolerance against the reference's fp32 modules."""
+    from oracle import fake_t5
+    from text2loc_b200.engine import Engine
+
+    monkeypatch.setenv("T2L_TEXT_TF32", "1")
+    e32 = Engine("cuda:0")
+    e32.load_state_dict(state_dict)
+    g = golden("text_small.npz")
+    feat, n_sent = fake_t5.FakeFrontend(int(g["fake_t5_seed"]))([str(t) for t in g["texts"]])
+    err = row_rel_err(e32.encode_text(feat, n_sent).cpu().numpy(), g["text_emb"])
+    print(f"\ntext embedding error of the tf32 token layer: {err:.3e}")
+    assert err < EMB_TOL
+
+
+def test_encode_text_feature_magnitudes(eng, state_dict):
+    """fp16 operands: features 4x larger / 100x smaller than the synthetic default stay in tolerance (fp16 has the
+    range for anything a LayerNorm-ed T5 state can hold); absurd magnitudes saturate at 65504 instead of producing inf."""
+    from oracle import restate
+    from text2loc_b200 import synth
+
+    base = synth.make_t5_features(5, 8, 6, 12)
+    for scale in (4.0, 0.01):
+        t5 = base * np.float32(scale)
+        got = eng.encode_text(t5, 6).cpu().numpy()
+        want = restate.encode_text(state_dict, t5, 6).numpy()
+        err = row_rel_err(got, want)
+        print(f"\nfeature scale {scale}: text embedding error {err:.3e}")
+        assert err < EMB_TOL
+    got = eng.encode_text(base * np.float32(1e6), 6).cpu().numpy()
+    assert np.isfinite(got).all()
+
+
 def test_encode_text_shapes(eng, state_dict):
     """Different token counts / sentence counts, chunk boundary in the middle of the batch."""
     from oracle import restate

@@ -1,6 +1,7 @@
 // C ABI of the engine (include/text2loc_b200.h): handle, weights, workspace arena and the
 // orchestration of the kernels in this directory into encode_cells / encode_text / search.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -23,6 +24,7 @@ static std::string g_create_error;
 
 struct Weight {
   float* dev = nullptr;
+  __half* dev16 = nullptr;  // fp16 copy [rows, cols] of the token-layer weights (kind::f16 GEMMs)
   int rows = 0, cols = 0, ld = 0;
 };
 
@@ -61,6 +63,8 @@ struct t2l_engine {
   int obj_chunk = 2048;      // objects per encode chunk (cell-aligned)
   bool fused_sa = true;      // sa_fused.cu; false = v1 edge_gather -> H -> SegMax GEMM (kept for A/B checks, T2L_UNFUSED_SA=1)
   int tok_chunk = 32768;     // tokens per text chunk (sentence-aligned)
+  bool text_f16 = true;      // token layer on fp16 operands (same 11-bit significand as tf32, twice the MMA rate, half the
+                             // operand bytes); T2L_TEXT_TF32=1 selects the tf32 path for A/B checks
   float* pooled = nullptr;   // [pooled_cap, 1024] max-over-tokens sentence features between the two text stages
   size_t pooled_cap = 0;
 };
@@ -121,6 +125,8 @@ extern "C" int t2l_create(int device, t2l_engine** out) {
   e = new t2l_engine();
   e->device = device;
   if (const char* v = getenv("T2L_UNFUSED_SA")) e->fused_sa = !(v[0] == '1');
+  if (const char* v = getenv("T2L_TEXT_TF32")) e->text_f16 = !(v[0] == '1');
+  if (const char* v = getenv("T2L_OBJ_CHUNK")) { const int n = atoi(v); if (n >= 64 && n <= 65536) e->obj_chunk = n; }
   if (cudaMalloc(&e->db.max_norm, sizeof(float)) != cudaSuccess) { delete e; return fail(nullptr, "t2l_create: cudaMalloc failed"); }
   *out = e;
   return 0;
@@ -137,7 +143,7 @@ extern "C" void t2l_destroy(t2l_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
-  for (auto& kv : e->w) cudaFree(kv.second.dev);
+  for (auto& kv : e->w) { cudaFree(kv.second.dev); cudaFree(kv.second.dev16); }
   cudaFree(e->arena.base);
   cudaFree(e->pooled);
   cudaFree(e->db.planes);
@@ -156,6 +162,10 @@ static bool is_tf32_operand(const std::string& n) {
                               "mlp_pointnet.w", "merge.w", "txt_intra.in_w", "txt_intra.out_w", "txt_intra.l1_w", "txt_intra.l2_w"};
   for (const char* p : pre) if (n == p) return true;
   return false;
+}
+
+static bool is_f16_operand(const std::string& n) {
+  return n == "txt_intra.in_w" || n == "txt_intra.out_w" || n == "txt_intra.l1_w" || n == "txt_intra.l2_w";
 }
 
 static bool is_split3_operand(const std::string& n) {
@@ -179,6 +189,7 @@ extern "C" int t2l_set_weight(t2l_engine* e, const char* name, const float* data
   CU(cudaSetDevice(e->device));
   Weight& w = e->w[name];
   if (w.dev) { CU(cudaFree(w.dev)); w.dev = nullptr; }
+  if (w.dev16) { CU(cudaFree(w.dev16)); w.dev16 = nullptr; }
   const bool split3 = is_split3_operand(name);
   if (split3 && (cols % 32)) return fail(e, "t2l_set_weight: '%s' needs cols %% 32 == 0", name);
   w.rows = rows; w.cols = cols; w.ld = split3 ? 2 * cols : ((cols + 3) & ~3);
@@ -197,6 +208,16 @@ extern "C" int t2l_set_weight(t2l_engine* e, const char* name, const float* data
     }
   CU(cudaMalloc(&w.dev, host.size() * sizeof(float)));
   CU(cudaMemcpy(w.dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (is_f16_operand(name)) {
+    if (cols % 8) return fail(e, "t2l_set_weight: '%s' needs cols %% 8 == 0", name);
+    std::vector<__half> h16(static_cast<size_t>(rows) * cols);
+    for (size_t i = 0; i < h16.size(); ++i) {
+      if (!(fabsf(data[i]) <= 65504.f)) return fail(e, "t2l_set_weight: '%s' has a value outside the fp16 range", name);
+      h16[i] = __float2half_rn(data[i]);
+    }
+    CU(cudaMalloc(&w.dev16, h16.size() * sizeof(__half)));
+    CU(cudaMemcpy(w.dev16, h16.data(), h16.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  }
   e->finalized = false;
   return 0;
 }
@@ -253,6 +274,19 @@ static cudaError_t lin3(t2l_engine* e, const float* A, long lda, int M, const st
   return linear_umma(l, st, &e->lc);
 }
 
+// y = act(x W^T + b) with fp16 operands (A and the weight's fp16 copy), fp32 accumulate; C is fp32 or fp16 (out_half).
+static cudaError_t lin_h(t2l_engine* e, const __half* A, long lda, int M, const std::string& wname, const std::string& bname, void* C,
+                         long ldc, int act, int out_half, cudaStream_t st, const float* residual = nullptr, long ldr = 0) {
+  const Weight& w = W(e, wname);
+  if (!w.dev16) return cudaErrorInvalidValue;
+  Linear l;
+  l.A = reinterpret_cast<const float*>(A); l.lda = lda; l.W = reinterpret_cast<const float*>(w.dev16); l.ldw = w.cols;
+  l.bias = bname.empty() ? nullptr : W(e, bname).dev;
+  l.C = static_cast<float*>(C); l.ldc = ldc; l.M = M; l.N = w.rows; l.K = w.cols; l.act = act; l.residual = residual; l.ldr = ldr;
+  l.half_ops = 1; l.out_half = out_half;
+  return linear_umma(l, st, &e->lc);
+}
+
 // One post-norm nn.TransformerEncoderLayer on packed rows [n_seq * S, d] (sequence-major).
 // fast: single-pass tf32 projections (text token layer, where the FLOPs are); otherwise the
 // three-pass split product, which keeps fp32 accuracy (the object and sentence layers amplify
@@ -266,7 +300,21 @@ static int encoder_layer(t2l_engine* e, const std::string& pfx, bool fast, const
   float* y = a.get<float>(static_cast<size_t>(rows) * d);
   float* x1 = a.get<float>(static_cast<size_t>(rows) * d);
   float* h = a.get<float>(static_cast<size_t>(rows) * ffn);
-  if (fast) {
+  if (fast && e->text_f16 && d == 1024) {
+    // fp16 operands, fp32 accumulation and fp32 residual/LayerNorm stream: x -> fp16 once, the attention core and
+    // LayerNorm1 emit the fp16 A operands of the next GEMMs, the FFN hidden activations exist only in fp16
+    __half* xh = a.get<__half>(static_cast<size_t>(rows) * d);
+    __half* atth = reinterpret_cast<__half*>(att);
+    __half* x1h = a.get<__half>(static_cast<size_t>(rows) * d);
+    __half* hh = reinterpret_cast<__half*>(h);
+    CU(to_half_rows(X, xh, static_cast<long>(rows) * d, st, &e->lc));
+    CU(lin_h(e, xh, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, 0, st));
+    CU(mha_tc256(qkv, att, n_seq, S, st, &e->lc, /*round_out=*/2));
+    CU(lin_h(e, atth, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, 0, st, X, d));
+    CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc, x1h));
+    CU(lin_h(e, x1h, d, rows, pfx + ".l1_w", pfx + ".l1_b", hh, ffn, 1, 1, st));
+    CU(lin_h(e, hh, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, 0, st, x1, d));
+  } else if (fast) {
     CU(lin(e, true, X, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st));
     if (d == 1024) CU(mha_tc256(qkv, att, n_seq, S, st, &e->lc, /*round_out=*/1));
     else CU(mha_small(qkv, att, n_seq, S, d, 4, st, &e->lc, /*round_out=*/1));
@@ -481,7 +529,7 @@ static int text_tokens(t2l_engine* e, const float* t5, int n_seq, int L, float* 
   if (sc < 1) sc = 1;
   if (sc > n_seq) sc = n_seq;
   if (n_seq == 0) return 0;
-  if (ensure_arena(e, static_cast<size_t>(sc) * L * (11 * static_cast<size_t>(d)) * 4 + (size_t(1) << 22))) return 1;
+  if (ensure_arena(e, static_cast<size_t>(sc) * L * (12 * static_cast<size_t>(d)) * 4 + (size_t(1) << 22))) return 1;
   Arena& a = e->arena;
   for (int s0 = 0; s0 < n_seq; s0 += sc) {
     const int ns = (n_seq - s0 < sc) ? n_seq - s0 : sc;
@@ -639,5 +687,16 @@ extern "C" int t2l_debug_linear(t2l_engine* e, int path, const float* A, int lda
   l.C = tmp; l.ldc = N; l.act = 1;
   CU(linear_simt(l, st, &e->lc));
   CU(segmax32(tmp, N, C, ldc, nullptr, 0, M / 32, N, st, &e->lc));
+  return 0;
+}
+
+extern "C" int t2l_debug_linear_f16(t2l_engine* e, const void* A, int lda, const void* Wt, int ldw, const float* bias, void* C, int ldc,
+                                    int M, int N, int K, int act, int out_half, void* stream) {
+  if (!e) return 1;
+  CU(cudaSetDevice(e->device));
+  Linear l;
+  l.A = static_cast<const float*>(A); l.lda = lda; l.W = static_cast<const float*>(Wt); l.ldw = ldw; l.bias = bias;
+  l.C = static_cast<float*>(C); l.ldc = ldc; l.M = M; l.N = N; l.K = K; l.act = act; l.half_ops = 1; l.out_half = out_half;
+  CU(linear_umma(l, static_cast<cudaStream_t>(stream), &e->lc));
   return 0;
 }

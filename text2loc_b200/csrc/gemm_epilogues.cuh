@@ -6,9 +6,13 @@
 // ~1.2k cycles per 32-column chunk in long-scoreboard stalls on exactly these loads).
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace t2l {
+
+constexpr float kHalfMax = 65504.f;  // stores to fp16 saturate instead of producing inf
 
 enum : int { kActNone = 0, kActRelu = 1 };
 constexpr int kEpiBiasSmem = 4 * 256 * 4;  // one 256-float bias slice per epilogue warp
@@ -26,6 +30,7 @@ struct StoreEpi {
     int M, N;
     int act;
     int round_out;
+    int out_half;  // C is __half [M, ldc]: the consumer is an fp16 tensor-core GEMM (same 11-bit significand as tf32)
   };
   static constexpr int kSmemBytes = kEpiBiasSmem;
   const Params& p;
@@ -46,7 +51,6 @@ struct StoreEpi {
   __device__ void chunk(int m_tile, int, int c, int col0, float (&v)[32]) {
     const long row = static_cast<long>(m_tile) * 128 + ew * 32 + lane;
     if (row >= p.M || col0 >= p.N) return;
-    float* dst = p.C + row * p.ldc + col0;
     float4 r[8];
     if (p.residual) {
       const float4* res = reinterpret_cast<const float4*>(p.residual + row * p.ldr + col0);
@@ -54,14 +58,30 @@ struct StoreEpi {
       for (int i = 0; i < 8; ++i) r[i] = __ldg(res + i);  // all eight loads in flight before the first use
     }
     const float4* sb = reinterpret_cast<const float4*>(s_bias + c * 32);
+    uint2 hv[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 b = sb[i];  // same address in every lane: broadcast
       float4 o = make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w);
       if (p.act == kActRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
       if (p.residual) { o.x += r[i].x; o.y += r[i].y; o.z += r[i].z; o.w += r[i].w; }
-      if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-      reinterpret_cast<float4*>(dst)[i] = o;
+      if (p.out_half) {  // 8 bytes per step; the lane's 32 columns are 64 contiguous bytes
+        o.x = fminf(fmaxf(o.x, -kHalfMax), kHalfMax); o.y = fminf(fmaxf(o.y, -kHalfMax), kHalfMax);
+        o.z = fminf(fmaxf(o.z, -kHalfMax), kHalfMax); o.w = fminf(fmaxf(o.w, -kHalfMax), kHalfMax);
+        const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&h0);
+        u.y = *reinterpret_cast<const uint32_t*>(&h1);
+        hv[i] = u;
+      } else {
+        if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        reinterpret_cast<float4*>(p.C + row * p.ldc + col0)[i] = o;
+      }
+    }
+    if (p.out_half) {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + row * p.ldc + col0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[i] = make_uint4(hv[2 * i].x, hv[2 * i].y, hv[2 * i + 1].x, hv[2 * i + 1].y);
     }
   }
 };

@@ -10,13 +10,13 @@ namespace t2l {
 // ---------------------------------------------------------------------------------------
 // tcgen05 path
 // ---------------------------------------------------------------------------------------
-template <int BN, int GROUP, class Epi>
+template <int BN, int GROUP, class Epi, int TYPE = kOpTf32>
 static cudaError_t run_umma(const Linear& l, const typename Epi::Params& ep, cudaStream_t st) {
-  using Cfg = GemmCfg<BN, false, GROUP>;
+  using Cfg = GemmCfg<BN, TYPE, GROUP>;
   CUtensorMap ta, tb;
   const int kw = l.passes == 3 ? 2 * l.K : l.K;  // physical operand width
-  if (make_operand_map(&ta, l.A, false, l.M, kw, l.lda, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
-  if (make_operand_map(&tb, l.W, false, l.N, kw, l.ldw, Cfg::LOAD_N)) return cudaErrorInvalidValue;
+  if (make_operand_map(&ta, l.A, TYPE, l.M, kw, l.lda, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
+  if (make_operand_map(&tb, l.W, TYPE, l.N, kw, l.ldw, Cfg::LOAD_N)) return cudaErrorInvalidValue;
   GemmShape s;
   s.M = l.M; s.N = l.N;
   s.m_tiles = (l.M + Cfg::BLOCK_M * GROUP - 1) / (Cfg::BLOCK_M * GROUP);
@@ -33,8 +33,10 @@ static cudaError_t run_umma(const Linear& l, const typename Epi::Params& ep, cud
 
 cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
   if (l.M <= 0) return cudaSuccess;
-  if ((l.N % 32) || (l.lda % 4) || (l.ldw % 4)) return cudaErrorInvalidValue;
-  if (l.passes != 1 && (l.passes != 3 || l.K % 32)) return cudaErrorInvalidValue;
+  const int row_align = l.half_ops ? 8 : 4;  // 16-byte rows for TMA
+  if ((l.N % 32) || (l.lda % row_align) || (l.ldw % row_align)) return cudaErrorInvalidValue;
+  if (l.passes != 1 && (l.passes != 3 || l.K % 32 || l.half_ops)) return cudaErrorInvalidValue;
+  if (l.half_ops && l.segmax) return cudaErrorInvalidValue;
   if (lc) lc->n++;
   // N % 256 == 0 and more than one 128-row tile: CTA pairs (256 x 256 tiles, cta_group::2); else single CTAs
   const bool wide = (l.N % 256) == 0;
@@ -45,7 +47,11 @@ cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
     if (pair) return run_umma<256, 2, SegMaxEpi>(l, ep, st);
     return wide ? run_umma<256, 1, SegMaxEpi>(l, ep, st) : run_umma<128, 1, SegMaxEpi>(l, ep, st);
   }
-  StoreEpi::Params ep{l.C, l.ldc, l.bias, l.residual, l.ldr, l.M, l.N, l.act, l.round_out};
+  StoreEpi::Params ep{l.C, l.ldc, l.bias, l.residual, l.ldr, l.M, l.N, l.act, l.round_out, l.out_half};
+  if (l.half_ops) {  // fp16 operands (A, W are __half), kind::f16: twice the tf32 rate at the same 11-bit significand
+    if (pair) return run_umma<256, 2, StoreEpi, kOpF16>(l, ep, st);
+    return wide ? run_umma<256, 1, StoreEpi, kOpF16>(l, ep, st) : run_umma<128, 1, StoreEpi, kOpF16>(l, ep, st);
+  }
   if (pair) return run_umma<256, 2, StoreEpi>(l, ep, st);
   return wide ? run_umma<256, 1, StoreEpi>(l, ep, st) : run_umma<128, 1, StoreEpi>(l, ep, st);
 }

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -29,6 +30,8 @@ struct Linear {
   int round_out = 0;          // round stored values to tf32 (rna)
   int passes = 1;             // 3: A and W are [hi | lo] tf32 planes of logical width K (row pitch >= 2K):
                               //    hi*hi + lo*hi + hi*lo in one accumulator, fp32-level accuracy on the tensor cores
+  int half_ops = 0;           // A and W point at __half data (lda, ldw in elements): tcgen05 kind::f16, fp32 accumulate
+  int out_half = 0;           // C points at __half data (ldc in elements); values saturate at +-65504
 };
 // tf32 tensor-core path: needs K-major operands with 16-byte aligned rows (lda, ldw % 4 == 0),
 // N % 32 == 0.  K tails are zero-filled by TMA.
@@ -95,11 +98,16 @@ cudaError_t ga_concat(const float* x3, const float* cpos3, int n_obj, float* A, 
 // y[r, 0:d] (row pitch ldy) = x[r] / max(||x[r]||, 1e-12)      (F.normalize)
 cudaError_t l2_normalize_rows(const float* x, long ldx, float* y, long ldy, int rows, int d, cudaStream_t st, Launches* lc);
 // y = LayerNorm(x) * w + b, eps 1e-5, one warp per row
-cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const float* b, int rows, int d, cudaStream_t st, Launches* lc);
+// (optional y_half: an fp16 copy of the output, the A operand of a following fp16 tensor-core GEMM)
+cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const float* b, int rows, int d, cudaStream_t st, Launches* lc,
+                            __half* y_half = nullptr);
+// y = fp16(x), saturating at +-65504; n % 4 == 0
+cudaError_t to_half_rows(const float* x, __half* y, long n, cudaStream_t st, Launches* lc);
 // Unmasked multi-head self attention on packed QKV rows [n_seq*S, 3d] (q | k | v), head h uses
 // columns [h*hd, (h+1)*hd); out [n_seq*S, d].  softmax(q k^T / sqrt(hd)) v, fp32.
 cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out = 0);
 // Same contract for d = 1024, 4 heads of 256 (the token layer): warp-level mma.sync tf32 tiles.
+// round_out: 0 fp32, 1 fp32 rounded to tf32, 2 `out` is __half [rows, 1024].
 cudaError_t mha_tc256(const float* qkv, float* out, int n_seq, int S, cudaStream_t st, Launches* lc, int round_out = 0);
 // y[g, :] = max over the S rows of group g
 cudaError_t max_over_rows(const float* x, float* y, int groups, int S, int d, cudaStream_t st, Launches* lc);

@@ -2,6 +2,8 @@
 // multi-head attention core, max pooling over a sequence, object scatter into the padded cell
 // tensor.  All are HBM/L2-bound streaming kernels: one warp per row, 128-bit accesses where the
 // row length allows.
+#include <cuda_fp16.h>
+
 #include "ops.h"
 #include "common.cuh"
 
@@ -28,10 +30,32 @@ cudaError_t l2_normalize_rows(const float* x, long ldx, float* y, long ldy, int 
   return cudaGetLastError();
 }
 
+__device__ __forceinline__ float sat_half(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
+
+// ---- fp32 -> fp16 rows (saturating): A operand of the fp16 tensor-core layers -------------------
+__global__ void __launch_bounds__(256) to_half_kernel(const float4* __restrict__ x, uint2* __restrict__ y, long n4) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = x[i];
+  const __half2 h0 = __floats2half2_rn(sat_half(v.x), sat_half(v.y)), h1 = __floats2half2_rn(sat_half(v.z), sat_half(v.w));
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&h0);
+  u.y = *reinterpret_cast<const uint32_t*>(&h1);
+  y[i] = u;
+}
+
+cudaError_t to_half_rows(const float* x, __half* y, long n, cudaStream_t st, Launches* lc) {
+  if (n <= 0) return cudaSuccess;
+  if (n % 4) return cudaErrorInvalidValue;
+  if (lc) lc->n++;
+  to_half_kernel<<<static_cast<unsigned>((n / 4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(y), n / 4);
+  return cudaGetLastError();
+}
+
 // ---- LayerNorm (eps 1e-5, biased variance), one warp per row, d <= 1024 ----------------------
 template <int D>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
-                                                         const float* __restrict__ b, int rows) {
+                                                         const float* __restrict__ b, int rows, __half* __restrict__ yh) {
   constexpr int R = D / 128;  // float4 per lane
   const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -63,15 +87,23 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
     o.z = (v[i].z - mean) * rstd * ww.z + bv.z;
     o.w = (v[i].w - mean) * rstd * ww.w + bv.w;
     yr[i * 32 + lane] = o;
+    if (yh) {  // fp16 copy for the next tensor-core GEMM's A operand
+      const __half2 h0 = __floats2half2_rn(sat_half(o.x), sat_half(o.y)), h1 = __floats2half2_rn(sat_half(o.z), sat_half(o.w));
+      uint2 u;
+      u.x = *reinterpret_cast<const uint32_t*>(&h0);
+      u.y = *reinterpret_cast<const uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(yh + r * D)[i * 32 + lane] = u;
+    }
   }
 }
 
-cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const float* b, int rows, int d, cudaStream_t st, Launches* lc) {
+cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const float* b, int rows, int d, cudaStream_t st, Launches* lc,
+                            __half* y_half) {
   if (rows <= 0) return cudaSuccess;
   if (lc) lc->n++;
   const unsigned grid = (rows + 7) / 8;
-  if (d == 256) layer_norm_kernel<256><<<grid, 256, 0, st>>>(x, y, w, b, rows);
-  else if (d == 1024) layer_norm_kernel<1024><<<grid, 256, 0, st>>>(x, y, w, b, rows);
+  if (d == 256) layer_norm_kernel<256><<<grid, 256, 0, st>>>(x, y, w, b, rows, y_half);
+  else if (d == 1024) layer_norm_kernel<1024><<<grid, 256, 0, st>>>(x, y, w, b, rows, y_half);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
@@ -298,11 +330,21 @@ __global__ void __launch_bounds__(128) mha_tc256_kernel(const float* __restrict_
         if (r < S) {
           float4 lo = make_float4(o[m][0][2 * hi], o[m][1][2 * hi], o[m][2][2 * hi], o[m][3][2 * hi]);
           float4 up = make_float4(o[m][0][2 * hi + 1], o[m][1][2 * hi + 1], o[m][2][2 * hi + 1], o[m][3][2 * hi + 1]);
+          const long o_off = ((wid >> 2) * S + r) * D + h * HD + 32 * s + 8 * t;
+          if (round_out == 2) {  // fp16 output (out is __half [rows, D]): attention outputs are convex combinations of V rows
+            const __half2 h0 = __floats2half2_rn(sat_half(lo.x), sat_half(lo.y)), h1 = __floats2half2_rn(sat_half(lo.z), sat_half(lo.w));
+            const __half2 h2 = __floats2half2_rn(sat_half(up.x), sat_half(up.y)), h3 = __floats2half2_rn(sat_half(up.z), sat_half(up.w));
+            uint4 u;
+            u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+            u.z = *reinterpret_cast<const uint32_t*>(&h2); u.w = *reinterpret_cast<const uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + o_off) = u;
+            continue;
+          }
           if (round_out) {
             lo = make_float4(round_tf32(lo.x), round_tf32(lo.y), round_tf32(lo.z), round_tf32(lo.w));
             up = make_float4(round_tf32(up.x), round_tf32(up.y), round_tf32(up.z), round_tf32(up.w));
           }
-          float4* dst = reinterpret_cast<float4*>(out + ((wid >> 2) * S + r) * D + h * HD + 32 * s + 8 * t);
+          float4* dst = reinterpret_cast<float4*>(out + o_off);
           dst[0] = lo;
           dst[1] = up;
         }

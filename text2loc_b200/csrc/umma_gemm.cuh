@@ -50,13 +50,15 @@ struct GemmShape {
 // tile: 32 KB instead of 48 KB per k-block at BLOCK_N = 256, so the ring is 6 deep instead of 4 and the
 // per-SM shared-memory traffic (TMA fill + MMA operand reads), which caps the 1-CTA tf32 kernel at ~68 %
 // of the tensor peak, drops by a third.
-template <int kBlockN, bool kBf16, int kCtaGroup = 1>
+enum : int { kOpTf32 = 0, kOpBf16 = 1, kOpF16 = 2 };  // operand element type (accumulation is always fp32)
+
+template <int kBlockN, int kType, int kCtaGroup = 1>
 struct GemmCfg {
   static constexpr int CTA_GROUP = kCtaGroup;
   static constexpr int BLOCK_M = 128;                 // rows per CTA
   static constexpr int BLOCK_N = kBlockN;
   static constexpr int LOAD_N = kBlockN / kCtaGroup;  // B rows each CTA loads
-  static constexpr int ELEM_BYTES = kBf16 ? 2 : 4;
+  static constexpr int ELEM_BYTES = kType == kOpTf32 ? 4 : 2;
   static constexpr int BLOCK_K = 128 / ELEM_BYTES;  // one 128-byte swizzle atom per row
   static constexpr int UMMA_K = 32 / ELEM_BYTES;    // 8 (tf32) / 16 (bf16)
   static constexpr int A_BYTES = BLOCK_M * 128;
@@ -65,8 +67,9 @@ struct GemmCfg {
   static constexpr int STAGES = (STAGE_BYTES > 32768) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // two accumulator buffers
   static constexpr int BAR_BYTES = 256;
-  static constexpr uint32_t IDESC = umma_idesc(kBf16 ? 1u : 2u, BLOCK_M * kCtaGroup, BLOCK_N);
-  static constexpr bool IS_BF16 = kBf16;
+  // instruction-descriptor operand format: kind::tf32 -> 2; kind::f16 -> 0 (f16) / 1 (bf16)
+  static constexpr uint32_t IDESC = umma_idesc(kType == kOpTf32 ? 2u : (kType == kOpBf16 ? 1u : 0u), BLOCK_M * kCtaGroup, BLOCK_N);
+  static constexpr bool IS_HALF = kType != kOpTf32;  // 2-byte operands: tcgen05.mma kind::f16
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two >= 32");
   template <class Epi>
   static constexpr int smem_bytes() { return 1024 + STAGES * STAGE_BYTES + BAR_BYTES + Epi::kSmemBytes; }
@@ -193,10 +196,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               // advance 32 bytes (one UMMA_K slice) inside the swizzle atom: +2 in 16-byte units
               const uint32_t accum = (kb | k) != 0;
               if (kPair) {
-                if (Cfg::IS_BF16) umma_f16_pair(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, accum);
+                if (Cfg::IS_HALF) umma_f16_pair(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, accum);
                 else umma_tf32_pair(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, accum);
               } else {
-                if (Cfg::IS_BF16) umma_f16(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, accum);
+                if (Cfg::IS_HALF) umma_f16(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, accum);
                 else umma_tf32(d_addr, adesc + 2 * k, bdesc + 2 * k, Cfg::IDESC, accum);
               }
             }
@@ -275,14 +278,16 @@ const TmaApi& tma_api();  // resolved once via cudaGetDriverEntryPoint (api.cu)
 
 // 2-D K-major operand [rows, k_elems] with row pitch `ld` elements; box = 128 bytes x box_rows.
 // Out-of-bounds elements (row or K tails) are zero-filled by the TMA unit.
-inline int make_operand_map(CUtensorMap* tm, const void* base, bool bf16, long rows, long k_elems, long ld, int box_rows) {
-  const int esz = bf16 ? 2 : 4;
+inline int make_operand_map(CUtensorMap* tm, const void* base, int type, long rows, long k_elems, long ld, int box_rows) {
+  const int esz = type == kOpTf32 ? 4 : 2;
+  const CUtensorMapDataType dt = type == kOpTf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : (type == kOpBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_elems), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * esz};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (strides[0] & 15)) return -1;
-  CUresult r = tma_api().encode(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  CUresult r = tma_api().encode(tm, dt, 2,
                                 const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -189,7 +189,18 @@ class Engine:
         self._check(self._lib.t2l_merge_topk(self._h, _ptr(idx_all), _ptr(score_all), G, nq, k, _ptr(idx), _ptr(sc), self._stream()))
         return idx, sc
 
-    # ---- test hook --------------------------------------------------------------------------
+    # ---- test hooks -------------------------------------------------------------------------
+    def debug_linear_f16(self, A, W, bias=None, act=0, out_half=False):
+        """fp16-operand tcgen05 GEMM (the token layer's): A [M,K], W [N,K] float16 on device."""
+        A, W = self._dev(A, torch.float16), self._dev(W, torch.float16)
+        bias = self._dev(bias, torch.float32) if bias is not None else None
+        M, K = A.shape
+        N = W.shape[0]
+        C = torch.empty((M, N), dtype=torch.float16 if out_half else torch.float32, device=self.device)
+        self._check(self._lib.t2l_debug_linear_f16(self._h, _ptr(A), K, _ptr(W), K, _ptr(bias), _ptr(C), N, M, N, K, act,
+                                                   int(out_half), self._stream()))
+        return C
+
     def debug_linear(self, A, W, bias=None, act=0, segmax=False, path=1):
         rowmajor = lambda t: t if (t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1) else self._dev(t, torch.float32)
         A, W = rowmajor(A), rowmajor(W)  # row-padded views (stride(0) > K) are passed through as lda / ldw
