@@ -180,18 +180,19 @@ def test_search_ties_duplicates_and_clusters(eng):
 
 
 def test_search_second_pass_and_exhaustive_rescan(eng):
-    """Near-collinear rows (what random-weight encoders produce) fail the margin proof for most queries: the
-    second tensor-core pass collects the few rows that can still matter.  300 exact duplicates overflow its
-    128-entry buffer and force the exhaustive fp64 rescan.  All three routes must return the oracle's answer."""
+    """Near-collinear rows (what random-weight encoders produce): once more than 16 rows of a split sit within the
+    error bound of the k-th score the margin proof fails and the second tensor-core pass collects every row that
+    can still matter; 300 exact duplicates (and the tightest queries) overflow its 256-entry buffer and force the
+    exhaustive fp64 rescan.  All three routes must return the oracle's answer."""
     from oracle import restate
     from text2loc_b200 import synth
 
     rng = np.random.default_rng(3)
     base = synth.make_unit_rows(40, 1)[0]
-    D = (base[None, :] + 0.02 * rng.standard_normal((6000, 256))).astype(np.float32)  # cosine ~0.95 between any two rows
+    D = (base[None, :] + 0.004 * rng.standard_normal((6000, 256))).astype(np.float32)  # cosine ~0.998 between any two rows
     D /= np.linalg.norm(D, axis=1, keepdims=True)
     D[1000:1300] = D[999]  # 301 identical rows
-    Q = np.concatenate([D[999:1000], (base[None, :] + 0.02 * rng.standard_normal((200, 256))).astype(np.float32)])
+    Q = np.concatenate([D[999:1000], (base[None, :] + 0.004 * rng.standard_normal((200, 256))).astype(np.float32)])
     eng.db_build(D)
     idx, sc, nfb = eng.search_topk(Q, 10)
     oidx, osc = restate.search_topk(D, Q, 10)
@@ -199,7 +200,7 @@ def test_search_second_pass_and_exhaustive_rescan(eng):
     assert idx[0].tolist() == list(range(999, 1009))  # ties in index order, via the exhaustive rescan
     assert np.abs(sc.cpu().numpy() - osc).max() < 1e-12
     print(f"\nnear-collinear database: {int(nfb)} / {len(Q)} queries took the second pass")
-    assert int(nfb) > len(Q) // 4
+    assert int(nfb) > len(Q) // 8
 
 
 def test_search_small_db_and_row_offset(eng):

@@ -291,8 +291,10 @@ static cudaError_t lin_h(t2l_engine* e, const __half* A, long lda, int M, const 
 // fast: single-pass tf32 projections (text token layer, where the FLOPs are); otherwise the
 // three-pass split product, which keeps fp32 accuracy (the object and sentence layers amplify
 // operand rounding the most, DESIGN.md precision table).
+// pooled_out != nullptr: the layer's output is only needed max-pooled over each sequence (token layer): norm2 and the max
+// are one kernel and Xout is not written.
 static int encoder_layer(t2l_engine* e, const std::string& pfx, bool fast, const float* X, float* Xout, int n_seq, int S, int d, int ffn,
-                         cudaStream_t st) {
+                         cudaStream_t st, float* pooled_out = nullptr) {
   const int rows = n_seq * S;
   Arena& a = e->arena;
   float* qkv = a.get<float>(static_cast<size_t>(rows) * 3 * d);
@@ -308,8 +310,8 @@ static int encoder_layer(t2l_engine* e, const std::string& pfx, bool fast, const
     __half* x1h = a.get<__half>(static_cast<size_t>(rows) * d);
     __half* hh = reinterpret_cast<__half*>(h);
     CU(to_half_rows(X, xh, static_cast<long>(rows) * d, st, &e->lc));
-    CU(lin_h(e, xh, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, 0, st));
-    CU(mha_tc256(qkv, att, n_seq, S, st, &e->lc, /*round_out=*/2));
+    CU(lin_h(e, xh, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, /*out_half=*/1, st));
+    CU(mha_tc256(qkv, att, n_seq, S, st, &e->lc, /*round_out=*/2, /*half_in=*/1));
     CU(lin_h(e, atth, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, 0, st, X, d));
     CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc, x1h));
     CU(lin_h(e, x1h, d, rows, pfx + ".l1_w", pfx + ".l1_b", hh, ffn, 1, 1, st));
@@ -330,7 +332,11 @@ static int encoder_layer(t2l_engine* e, const std::string& pfx, bool fast, const
     CU(lin3(e, x1, d, rows, pfx + ".l1_w", pfx + ".l1_b", h, ffn, 1, st));
     CU(lin3(e, h, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x1, d));
   }
-  CU(layer_norm_rows(y, Xout, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, rows, d, st, &e->lc));
+  if (pooled_out && d == 1024) CU(layer_norm_max_rows(y, pooled_out, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, n_seq, S, d, st, &e->lc));
+  else {
+    CU(layer_norm_rows(y, Xout, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, rows, d, st, &e->lc));
+    if (pooled_out) CU(max_over_rows(Xout, pooled_out, n_seq, S, d, st, &e->lc));
+  }
   return 0;
 }
 
@@ -535,9 +541,7 @@ static int text_tokens(t2l_engine* e, const float* t5, int n_seq, int L, float* 
     const int ns = (n_seq - s0 < sc) ? n_seq - s0 : sc;
     a.off = 0;
     const float* X = t5 + static_cast<size_t>(s0) * L * d;
-    float* X2 = a.get<float>(static_cast<size_t>(ns) * L * d);
-    if (encoder_layer(e, "txt_intra", true, X, X2, ns, L, d, 4 * d, st)) return 1;
-    CU(max_over_rows(X2, pooled + static_cast<size_t>(s0) * d, ns, L, d, st, &e->lc));
+    if (encoder_layer(e, "txt_intra", true, X, nullptr, ns, L, d, 4 * d, st, pooled + static_cast<size_t>(s0) * d)) return 1;
   }
   if (a.overflow) return fail(e, "internal: workspace arena too small for %d sentences", n_seq);
   return 0;

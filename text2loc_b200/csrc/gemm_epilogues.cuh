@@ -19,29 +19,67 @@ constexpr int kEpiBiasSmem = 4 * 256 * 4;  // one 256-float bias slice per epilo
 
 // C[row, col] = act(acc + bias[col]) (+ residual[row, col]);  optional tf32 rounding of the
 // stored value when the consumer is another tf32 GEMM (round-to-nearest instead of the
-// truncation the tensor core applies to a raw fp32 operand).
-struct StoreEpi {
-  struct Params {
-    float* C;
-    long ldc;
-    const float* bias;      // [N] or nullptr
-    const float* residual;  // [M, ldr] or nullptr
-    long ldr;
-    int M, N;
-    int act;
-    int round_out;
-    int out_half;  // C is __half [M, ldc]: the consumer is an fp16 tensor-core GEMM (same 11-bit significand as tf32)
-  };
-  static constexpr int kSmemBytes = kEpiBiasSmem;
+// truncation the tensor core applies to a raw fp32 operand), or an fp16 store.
+//
+// A TMEM load hands every lane 32 columns of ITS OWN row, so a direct store makes each warp
+// instruction touch 32 different 128-byte lines (32 LSU wavefronts per STG.128; at K = 1024 the
+// stores and the residual loads of a tile then cost as many cycles as its MMAs -- profiles/r01,
+// out-proj at 577 TFLOP/s).  Each warp therefore transposes its 32 x 32 block through a private
+// 4 KB shared-memory tile (XOR-swizzled 16-byte chunks, conflict-free both ways) and goes to global
+// memory with full lines: 8 lanes per 128-byte row slice (fp32) or 4 lanes per 64-byte slice (fp16).
+// The residual is read in that same coalesced layout and added after the transpose.
+// The residual (out-proj, FFN2) is the one operand the epilogue fetches from DRAM.  Fetching it chunk by chunk after the
+// accumulator is ready put a full DRAM round trip on every 32-column chunk (~3.4k cycles each, 100 us of a 127 us
+// out-proj launch -- profiles/r01).  So: the kernel announces the NEXT unit to prefetch_unit(), which pulls that tile's
+// residual rows into L2 (cp.async.bulk.prefetch.L2, one 1 KB row slice per lane) a whole tile ahead; the chunk loop then
+// keeps the residual of chunk c+1 in flight in registers while chunk c is transposed and stored.
+struct StoreParams {
+  float* C;
+  long ldc;
+  const float* bias;      // [N] or nullptr
+  const float* residual;  // [M, ldr] or nullptr (fp32 output only)
+  long ldr;
+  int M, N;
+  int act;
+  int round_out;
+  int out_half;  // C is __half [M, ldc]: the consumer is an fp16 tensor-core GEMM (same 11-bit significand as tf32)
+};
+
+template <bool kHalfOut, bool kResidual>
+struct StoreEpiT {
+  using Params = StoreParams;
+  static constexpr int kStageBytes = 32 * 128;  // one 32 x 32 fp32 block per epilogue warp
+  static constexpr int kSmemBytes = kEpiBiasSmem + 4 * kStageBytes;
   const Params& p;
   float* s_bias;
+  uint8_t* stage;
   int ew, lane, block_n;
   int bias_col0 = -1;  // column slice currently staged in s_bias (tiles of one N column share it)
-  __device__ StoreEpi(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_)
-      : p(p_), s_bias(reinterpret_cast<float*>(smem) + ew_ * 256), ew(ew_), lane(lane_), block_n(block_n_) {}
+  float4 res[8];       // residual of the chunk about to be processed (coalesced layout: row 4 j + lane / 8, chunk lane % 8)
+  __device__ StoreEpiT(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_)
+      : p(p_), s_bias(reinterpret_cast<float*>(smem) + ew_ * 256), stage(smem + kEpiBiasSmem + ew_ * kStageBytes), ew(ew_), lane(lane_),
+        block_n(block_n_) {}
   __device__ void begin_unit(int, int) {}
   __device__ void end_unit(int, int) {}
-  __device__ void begin_tile(int, int, int col0) {
+  __device__ __forceinline__ void load_res(long row0, int col0) {
+    const int rr = lane >> 3, ch = lane & 7;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const long row = row0 + 4 * j + rr;
+      res[j] = (row < p.M && col0 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col0) + ch)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __device__ void prefetch_unit(int m_tile, int col0) {
+    if (!kResidual) return;
+    const long row = static_cast<long>(m_tile) * 128 + ew * 32 + lane;
+    if (row < p.M && col0 < p.N) {
+      const int bytes = min(block_n, p.N - col0) * 4;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.residual + row * p.ldr + col0), "r"(bytes) : "memory");
+    }
+  }
+  __device__ void begin_tile(int m_tile, int, int col0) {
+    if (kResidual) load_res(static_cast<long>(m_tile) * 128 + ew * 32, col0);  // chunk 0, in flight while the MMAs finish
     if (col0 == bias_col0) return;
     bias_col0 = col0;
     __syncwarp();
@@ -49,40 +87,67 @@ struct StoreEpi {
     __syncwarp();
   }
   __device__ void chunk(int m_tile, int, int c, int col0, float (&v)[32]) {
-    const long row = static_cast<long>(m_tile) * 128 + ew * 32 + lane;
-    if (row >= p.M || col0 >= p.N) return;
-    float4 r[8];
-    if (p.residual) {
-      const float4* res = reinterpret_cast<const float4*>(p.residual + row * p.ldr + col0);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] = __ldg(res + i);  // all eight loads in flight before the first use
-    }
+    const long row0 = static_cast<long>(m_tile) * 128 + ew * 32;
+    if (row0 >= p.M || col0 >= p.N) return;  // warp-uniform
     const float4* sb = reinterpret_cast<const float4*>(s_bias + c * 32);
-    uint2 hv[8];
+    if (kHalfOut) {
+      // own row -> 64 bytes = four 16-byte chunks at position i ^ ((row >> 1) & 3)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float o[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4 b = sb[2 * i + h];
+          o[4 * h + 0] = v[8 * i + 4 * h + 0] + b.x; o[4 * h + 1] = v[8 * i + 4 * h + 1] + b.y;
+          o[4 * h + 2] = v[8 * i + 4 * h + 2] + b.z; o[4 * h + 3] = v[8 * i + 4 * h + 3] + b.w;
+        }
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float x = o[2 * q], y = o[2 * q + 1];
+          if (p.act == kActRelu) { x = fmaxf(x, 0.f); y = fmaxf(y, 0.f); }
+          x = fminf(fmaxf(x, -kHalfMax), kHalfMax);
+          y = fminf(fmaxf(y, -kHalfMax), kHalfMax);
+          const __half2 hh = __floats2half2_rn(x, y);
+          w[q] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        *reinterpret_cast<uint4*>(stage + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      __syncwarp();
+      __half* Ch = reinterpret_cast<__half*>(p.C);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // 8 rows x 64 bytes per instruction
+        const int r = 8 * j + (lane >> 2), ch = lane & 3;
+        const uint4 t = *reinterpret_cast<const uint4*>(stage + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
+        if (row0 + r < p.M) *reinterpret_cast<uint4*>(Ch + (row0 + r) * p.ldc + col0 + ch * 8) = t;
+      }
+      __syncwarp();
+      return;
+    }
+    const int rr = lane >> 3, ch = lane & 7;
+    float4 cur[8];
+    if (kResidual) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = res[j];
+      if ((c + 1) * 32 < block_n) load_res(row0, col0 + 32);  // next chunk's residual in flight during this one
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float4 b = sb[i];  // same address in every lane: broadcast
       float4 o = make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w);
       if (p.act == kActRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-      if (p.residual) { o.x += r[i].x; o.y += r[i].y; o.z += r[i].z; o.w += r[i].w; }
-      if (p.out_half) {  // 8 bytes per step; the lane's 32 columns are 64 contiguous bytes
-        o.x = fminf(fmaxf(o.x, -kHalfMax), kHalfMax); o.y = fminf(fmaxf(o.y, -kHalfMax), kHalfMax);
-        o.z = fminf(fmaxf(o.z, -kHalfMax), kHalfMax); o.w = fminf(fmaxf(o.w, -kHalfMax), kHalfMax);
-        const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
-        uint2 u;
-        u.x = *reinterpret_cast<const uint32_t*>(&h0);
-        u.y = *reinterpret_cast<const uint32_t*>(&h1);
-        hv[i] = u;
-      } else {
-        if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-        reinterpret_cast<float4*>(p.C + row * p.ldc + col0)[i] = o;
-      }
+      *reinterpret_cast<float4*>(stage + lane * 128 + ((i ^ (lane & 7)) << 4)) = o;
     }
-    if (p.out_half) {
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C) + row * p.ldc + col0);
+    __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) dst[i] = make_uint4(hv[2 * i].x, hv[2 * i].y, hv[2 * i + 1].x, hv[2 * i + 1].y);
+    for (int j = 0; j < 8; ++j) {  // 4 rows x 128 bytes per instruction
+      const int r = 4 * j + rr;
+      float4 o = *reinterpret_cast<const float4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
+      if (kResidual) { o.x += cur[j].x; o.y += cur[j].y; o.z += cur[j].z; o.w += cur[j].w; }
+      if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+      if (row0 + r < p.M) *reinterpret_cast<float4*>(p.C + (row0 + r) * p.ldc + col0 + ch * 4) = o;
     }
+    __syncwarp();
   }
 };
 
@@ -111,6 +176,7 @@ struct SegMaxEpi {
   int bias_col0 = -1;
   __device__ SegMaxEpi(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_)
       : p(p_), s_bias(reinterpret_cast<float*>(smem) + ew_ * 256), ew(ew_), lane(lane_), block_n(block_n_) {}
+  __device__ void prefetch_unit(int, int) {}
   __device__ void begin_unit(int, int) {}
   __device__ void end_unit(int, int) {}
   __device__ void begin_tile(int m_tile, int, int col0) {

@@ -31,6 +31,12 @@ static cudaError_t run_umma(const Linear& l, const typename Epi::Params& ep, cud
   return launch_umma_gemm<Cfg, Epi>(ta, tb, s, ep, st);
 }
 
+template <class Epi, int TYPE>
+static cudaError_t run_store(const Linear& l, const StoreParams& ep, bool wide, bool pair, cudaStream_t st) {
+  if (pair) return run_umma<256, 2, Epi, TYPE>(l, ep, st);
+  return wide ? run_umma<256, 1, Epi, TYPE>(l, ep, st) : run_umma<128, 1, Epi, TYPE>(l, ep, st);
+}
+
 cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
   if (l.M <= 0) return cudaSuccess;
   const int row_align = l.half_ops ? 8 : 4;  // 16-byte rows for TMA
@@ -47,13 +53,16 @@ cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
     if (pair) return run_umma<256, 2, SegMaxEpi>(l, ep, st);
     return wide ? run_umma<256, 1, SegMaxEpi>(l, ep, st) : run_umma<128, 1, SegMaxEpi>(l, ep, st);
   }
-  StoreEpi::Params ep{l.C, l.ldc, l.bias, l.residual, l.ldr, l.M, l.N, l.act, l.round_out, l.out_half};
+  if (l.out_half && l.residual) return cudaErrorInvalidValue;
+  StoreParams ep{l.C, l.ldc, l.bias, l.residual, l.ldr, l.M, l.N, l.act, l.round_out, l.out_half};
   if (l.half_ops) {  // fp16 operands (A, W are __half), kind::f16: twice the tf32 rate at the same 11-bit significand
-    if (pair) return run_umma<256, 2, StoreEpi, kOpF16>(l, ep, st);
-    return wide ? run_umma<256, 1, StoreEpi, kOpF16>(l, ep, st) : run_umma<128, 1, StoreEpi, kOpF16>(l, ep, st);
+    if (l.out_half) return run_store<StoreEpiT<true, false>, kOpF16>(l, ep, wide, pair, st);
+    if (l.residual) return run_store<StoreEpiT<false, true>, kOpF16>(l, ep, wide, pair, st);
+    return run_store<StoreEpiT<false, false>, kOpF16>(l, ep, wide, pair, st);
   }
-  if (pair) return run_umma<256, 2, StoreEpi>(l, ep, st);
-  return wide ? run_umma<256, 1, StoreEpi>(l, ep, st) : run_umma<128, 1, StoreEpi>(l, ep, st);
+  if (l.out_half) return cudaErrorInvalidValue;
+  if (l.residual) return run_store<StoreEpiT<false, true>, kOpTf32>(l, ep, wide, pair, st);
+  return run_store<StoreEpiT<false, false>, kOpTf32>(l, ep, wide, pair, st);
 }
 
 // fp32 -> [hi | lo] tf32 planes: x = hi + lo up to 2^-22 |x|

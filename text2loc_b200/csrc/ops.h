@@ -108,7 +108,12 @@ cudaError_t to_half_rows(const float* x, __half* y, long n, cudaStream_t st, Lau
 cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out = 0);
 // Same contract for d = 1024, 4 heads of 256 (the token layer): warp-level mma.sync tf32 tiles.
 // round_out: 0 fp32, 1 fp32 rounded to tf32, 2 `out` is __half [rows, 1024].
-cudaError_t mha_tc256(const float* qkv, float* out, int n_seq, int S, cudaStream_t st, Launches* lc, int round_out = 0);
+// half_in: qkv is __half [rows, 3072].
+cudaError_t mha_tc256(const void* qkv, float* out, int n_seq, int S, cudaStream_t st, Launches* lc, int round_out = 0, int half_in = 0);
+// y[g, :] = max over the S rows of group g of LayerNorm(x[g*S + s, :]) (d = 1024): norm2 + max over tokens without
+// materialising the normalised rows
+cudaError_t layer_norm_max_rows(const float* x, float* y, const float* w, const float* b, int groups, int S, int d, cudaStream_t st,
+                                Launches* lc);
 // y[g, :] = max over the S rows of group g
 cudaError_t max_over_rows(const float* x, float* y, int groups, int S, int d, cudaStream_t st, Launches* lc);
 // X[b, s, :] = normalize(emb[cell_ptr[b]+s]) for s < min(n_b, 28), else 0   (cell_retrieval.py:85-98)
@@ -139,10 +144,10 @@ struct SearchWork {
   float* fail_thr;          // [nq_cap]   k-th exact score of pass 1 minus the error bound, rounded down
   __nv_bfloat16* q2_planes; // [nq_cap, 512] planes of the failed queries, compacted
   int32_t* cand2_idx;       // [nq_cap, kPass2Cap]
-  int32_t* cand2_cnt;       // [nq_cap, splits_cap]
+  int32_t* cand2_cnt;       // [nq_cap]
   int nq_cap, splits_cap;
 };
-constexpr int kPass2Cap = 128;  // candidates per failed query in the second pass (all splits together)
+constexpr int kPass2Cap = 256;  // candidates per failed query in the second pass (all splits together)
 cudaError_t search_prepare_db(const SearchDb& db, cudaStream_t st, Launches* lc);
 cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q, int nq, int k, int64_t* out_idx,
                         double* out_score, int32_t* out_n_fallback, cudaStream_t st, Launches* lc);

@@ -213,16 +213,41 @@ __device__ __forceinline__ uint32_t tf32_bits(float x) {
   return r;
 }
 
-template <int MT>  // MT 16-row query tiles (S <= 16 * MT), 2 * MT key tiles of 8
-__global__ void __launch_bounds__(128) mha_tc256_kernel(const float* __restrict__ qkv, float* __restrict__ out, long n_seq, int S, float scale,
+// 8 / 4 consecutive elements of a qkv row as fp32 (fp16 -> fp32 is exact, and every fp16 value is a tf32 value)
+template <bool HALF_IN>
+__device__ __forceinline__ void ld8(const void* base, long off, float4& a, float4& b) {
+  if (HALF_IN) {
+    const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const __half*>(base) + off);
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&u.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+    a = make_float4(f0.x, f0.y, f1.x, f1.y);
+    b = make_float4(f2.x, f2.y, f3.x, f3.y);
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(base) + off);
+    a = p[0];
+    b = p[1];
+  }
+}
+template <bool HALF_IN>
+__device__ __forceinline__ float4 ld4(const void* base, long off) {
+  if (HALF_IN) {
+    const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const __half*>(base) + off);
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(f0.x, f0.y, f1.x, f1.y);
+  }
+  return *reinterpret_cast<const float4*>(static_cast<const float*>(base) + off);
+}
+
+template <int MT, bool HALF_IN>  // MT 16-row query tiles (S <= 16 * MT), 2 * MT key tiles of 8
+__global__ void __launch_bounds__(128) mha_tc256_kernel(const void* __restrict__ qkv, float* __restrict__ out, long n_seq, int S, float scale,
                                                         int round_out) {
   constexpr int HD = 256, D = 1024, LD = 3 * D, NT = 2 * MT;
   const long wid = static_cast<long>(blockIdx.x) * 4 + (threadIdx.x >> 5);
   if (wid >= n_seq * 4) return;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int h = static_cast<int>(wid & 3);
-  const float* base = qkv + (wid >> 2) * S * LD + h * HD;
-  auto row_ptr = [&](int r, int which) { return base + static_cast<long>(min(r, S - 1)) * LD + which * D; };  // clamp: rows >= S are never stored / are masked
+  const long base = (wid >> 2) * S * LD + h * HD;
+  auto row_off = [&](int r, int which) { return base + static_cast<long>(min(r, S - 1)) * LD + which * D; };  // clamp: rows >= S are never stored / are masked
 
   // ---- scores[MT*16, NT*8] = Q K^T
   float sc[MT][NT][4];
@@ -238,15 +263,9 @@ __global__ void __launch_bounds__(128) mha_tc256_kernel(const float* __restrict_
 #pragma unroll
     for (int m = 0; m < MT; ++m)
 #pragma unroll
-      for (int hi = 0; hi < 2; ++hi) {
-        const float4* p = reinterpret_cast<const float4*>(row_ptr(16 * m + 8 * hi + g, 0) + 32 * s + 8 * t);
-        qa[m][hi][0] = p[0]; qa[m][hi][1] = p[1];
-      }
+      for (int hi = 0; hi < 2; ++hi) ld8<HALF_IN>(qkv, row_off(16 * m + 8 * hi + g, 0) + 32 * s + 8 * t, qa[m][hi][0], qa[m][hi][1]);
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      const float4* p = reinterpret_cast<const float4*>(row_ptr(8 * n + g, 1) + 32 * s + 8 * t);
-      kb[n][0] = p[0]; kb[n][1] = p[1];
-    }
+    for (int n = 0; n < NT; ++n) ld8<HALF_IN>(qkv, row_off(8 * n + g, 1) + 32 * s + 8 * t, kb[n][0], kb[n][1]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {  // four k-steps: elements (2j, 2j+1) of the lane's 8 floats
       auto pick = [&](const float4 (&v)[2], int e) { const float* f = reinterpret_cast<const float*>(v); return tf32_bits(f[e]); };
@@ -311,8 +330,8 @@ __global__ void __launch_bounds__(128) mha_tc256_kernel(const float* __restrict_
         for (int i = 0; i < 4; ++i) o[m][j][i] = 0.f;
 #pragma unroll
     for (int n = 0; n < NT; ++n) {  // k-step over keys 8 n .. 8 n + 7: k = t <-> key 8 n + 2 t, k = t + 4 <-> key 8 n + 2 t + 1
-      const float4 v0 = *reinterpret_cast<const float4*>(row_ptr(8 * n + 2 * t, 2) + 32 * s + 4 * g);
-      const float4 v1 = *reinterpret_cast<const float4*>(row_ptr(8 * n + 2 * t + 1, 2) + 32 * s + 4 * g);
+      const float4 v0 = ld4<HALF_IN>(qkv, row_off(8 * n + 2 * t, 2) + 32 * s + 4 * g);
+      const float4 v1 = ld4<HALF_IN>(qkv, row_off(8 * n + 2 * t + 1, 2) + 32 * s + 4 * g);
       const float f0[4] = {v0.x, v0.y, v0.z, v0.w}, f1[4] = {v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {  // n-tile j: output column (n index g) = 32 s + 4 g + j
@@ -352,14 +371,74 @@ __global__ void __launch_bounds__(128) mha_tc256_kernel(const float* __restrict_
   }
 }
 
-cudaError_t mha_tc256(const float* qkv, float* out, int n_seq, int S, cudaStream_t st, Launches* lc, int round_out) {
+cudaError_t mha_tc256(const void* qkv, float* out, int n_seq, int S, cudaStream_t st, Launches* lc, int round_out, int half_in) {
   if (n_seq <= 0) return cudaSuccess;
   if (S < 1 || S > 32) return cudaErrorInvalidValue;
   if (lc) lc->n++;
   const unsigned grid = static_cast<unsigned>((static_cast<long>(n_seq) * 4 + 3) / 4);
   const float scale = 1.f / 16.f;  // 1 / sqrt(256)
-  if (S <= 16) mha_tc256_kernel<1><<<grid, 128, 0, st>>>(qkv, out, n_seq, S, scale, round_out);
-  else mha_tc256_kernel<2><<<grid, 128, 0, st>>>(qkv, out, n_seq, S, scale, round_out);
+  if (half_in) {
+    if (S <= 16) mha_tc256_kernel<1, true><<<grid, 128, 0, st>>>(qkv, out, n_seq, S, scale, round_out);
+    else mha_tc256_kernel<2, true><<<grid, 128, 0, st>>>(qkv, out, n_seq, S, scale, round_out);
+  } else {
+    if (S <= 16) mha_tc256_kernel<1, false><<<grid, 128, 0, st>>>(qkv, out, n_seq, S, scale, round_out);
+    else mha_tc256_kernel<2, false><<<grid, 128, 0, st>>>(qkv, out, n_seq, S, scale, round_out);
+  }
+  return cudaGetLastError();
+}
+
+// ---- LayerNorm over the rows of each group, then max over the group's rows: y[g, :] = max_s LN(x[g*S + s, :]) ----
+// (the token layer's norm2 followed by the max over tokens, language_encoder.py:131-133: the normalised
+// [tokens, 1024] tensor is never written).  One warp per group.
+__global__ void __launch_bounds__(256) layer_norm_max_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
+                                                             const float* __restrict__ b, int groups, int S) {
+  constexpr int D = 1024, R = D / 128;
+  const long g = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (g >= groups) return;
+  const int lane = threadIdx.x & 31;
+  float4 ww[R], bv[R], m[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    ww[i] = reinterpret_cast<const float4*>(w)[i * 32 + lane];
+    bv[i] = reinterpret_cast<const float4*>(b)[i * 32 + lane];
+    m[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  }
+  for (int s = 0; s < S; ++s) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (g * S + s) * D);
+    float4 v[R];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      v[i] = xr[i * 32 + lane];
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(sum) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, dd = v[i].w - mean;
+      q += (a * a + bb * bb) + (c * c + dd * dd);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / D) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      m[i].x = fmaxf(m[i].x, (v[i].x - mean) * rstd * ww[i].x + bv[i].x);
+      m[i].y = fmaxf(m[i].y, (v[i].y - mean) * rstd * ww[i].y + bv[i].y);
+      m[i].z = fmaxf(m[i].z, (v[i].z - mean) * rstd * ww[i].z + bv[i].z);
+      m[i].w = fmaxf(m[i].w, (v[i].w - mean) * rstd * ww[i].w + bv[i].w);
+    }
+  }
+  float4* yr = reinterpret_cast<float4*>(y + g * D);
+#pragma unroll
+  for (int i = 0; i < R; ++i) yr[i * 32 + lane] = m[i];
+}
+
+cudaError_t layer_norm_max_rows(const float* x, float* y, const float* w, const float* b, int groups, int S, int d, cudaStream_t st,
+                                Launches* lc) {
+  if (groups <= 0) return cudaSuccess;
+  if (d != 1024 || S < 1) return cudaErrorInvalidValue;
+  if (lc) lc->n++;
+  layer_norm_max_kernel<<<(groups + 7) / 8, 256, 0, st>>>(x, y, w, b, groups, S);
   return cudaGetLastError();
 }
 

@@ -12,7 +12,7 @@
 //   4. otherwise (tight clusters, e.g. near-collinear embeddings) a second tensor-core pass over just
 //      those queries COLLECTS every row whose approximate score is >= (k-th exact score so far) - bound:
 //      any true top-k member satisfies that, so an exact re-rank of the collected rows is the exact
-//      answer.  Only if more than 128 rows qualify is the query rescanned exhaustively in fp64.
+//      answer.  Only if more than 256 rows qualify is the query rescanned exhaustively in fp64.
 // Returned indices are therefore those of the fp64 stable-order oracle by construction.
 #include "ops.h"
 #include "umma_gemm.cuh"
@@ -82,6 +82,7 @@ struct TopKEpi {
 
   __device__ TopKEpi(const Params& p_, uint8_t* smem, int ew, int lane, int)
       : p(p_), s_v(reinterpret_cast<float*>(smem)), t(ew * 32 + lane), active(false) {}
+  __device__ void prefetch_unit(int, int) {}
   __device__ void begin_unit(int m_tile, int) {
     active = (m_tile * 128 + t) < p.nq;
 #pragma unroll
@@ -227,10 +228,12 @@ __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const float* 
 
 // ---- second pass: compact the failed queries' operand planes -----------------------------------------
 __global__ void __launch_bounds__(256) gather_fail_planes_kernel(const __nv_bfloat16* __restrict__ q_planes, const int32_t* __restrict__ fail_ids,
-                                                                 const int32_t* __restrict__ n_fail, __nv_bfloat16* __restrict__ q2_planes) {
+                                                                 const int32_t* __restrict__ n_fail, __nv_bfloat16* __restrict__ q2_planes,
+                                                                 int32_t* __restrict__ cand_cnt) {
   const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (slot >= *n_fail) return;
   const int lane = threadIdx.x & 31;
+  if (lane == 0) cand_cnt[slot] = 0;
   const uint4* src = reinterpret_cast<const uint4*>(q_planes + static_cast<long>(fail_ids[slot]) * 2 * kEmbed);
   uint4* dst = reinterpret_cast<uint4*>(q2_planes + static_cast<long>(slot) * 2 * kEmbed);
   dst[lane] = src[lane];
@@ -238,28 +241,27 @@ __global__ void __launch_bounds__(256) gather_fail_planes_kernel(const __nv_bflo
 }
 
 // Epilogue of the second pass: no ranking, just the row indices whose approximate score reaches the
-// query's threshold (per (query, split) buffer of `cap` entries; the count may exceed cap = overflow).
+// query's threshold.  One kPass2Cap-entry buffer per query shared by all database splits (slots are
+// claimed with an atomic counter; the count may exceed the capacity = overflow).  The order in which
+// rows land in the buffer is irrelevant: the re-rank orders them by (exact score, row).
 struct CollectEpi {
   struct Params {
     const float* thr;       // [slots]
     const int32_t* n_rows;  // [1] live slots
-    int32_t* cand_idx;      // [slots, kPass2Cap]  split s owns [s * cap, (s + 1) * cap)
-    int32_t* cand_cnt;      // [slots, n_splits]
-    int n_db, n_splits, cap;
+    int32_t* cand_idx;      // [slots, kPass2Cap]
+    int32_t* cand_cnt;      // [slots]  zeroed by gather_fail_planes_kernel
+    int n_db;
   };
   static constexpr int kSmemBytes = 0;
   const Params& p;
-  int t, cnt;
+  int t;
   float T;
-  long base;
-  bool active;
-  __device__ CollectEpi(const Params& p_, uint8_t*, int ew, int lane, int) : p(p_), t(ew * 32 + lane), cnt(0), T(INFINITY), base(0), active(false) {}
-  __device__ void begin_unit(int m_tile, int split) {
-    const long row = static_cast<long>(m_tile) * 128 + t;
-    active = row < *p.n_rows;
-    T = active ? p.thr[row] : INFINITY;
-    cnt = 0;
-    base = row * kPass2Cap + static_cast<long>(split) * p.cap;
+  long row;
+  __device__ CollectEpi(const Params& p_, uint8_t*, int ew, int lane, int) : p(p_), t(ew * 32 + lane), T(INFINITY), row(0) {}
+  __device__ void prefetch_unit(int, int) {}
+  __device__ void begin_unit(int m_tile, int) {
+    row = static_cast<long>(m_tile) * 128 + t;
+    T = (row < *p.n_rows) ? p.thr[row] : INFINITY;
   }
   __device__ void begin_tile(int, int, int) {}
   __device__ void chunk(int, int, int, int col0, float (&v)[32]) {
@@ -269,19 +271,17 @@ struct CollectEpi {
     while (mask) {
       const int i = __ffs(mask) - 1;
       mask &= mask - 1;
-      if (cnt < p.cap) p.cand_idx[base + cnt] = col0 + i;
-      ++cnt;
+      const int pos = atomicAdd(p.cand_cnt + row, 1);
+      if (pos < kPass2Cap) p.cand_idx[row * kPass2Cap + pos] = col0 + i;
     }
   }
-  __device__ void end_unit(int m_tile, int split) {
-    if (active) p.cand_cnt[(static_cast<long>(m_tile) * 128 + t) * p.n_splits + split] = cnt;
-  }
+  __device__ void end_unit(int, int) {}
 };
 
 // Exact re-rank of the collected rows (one warp per failed query); overflow -> flag for the exhaustive scan.
 __global__ void __launch_bounds__(kRerankWarps * 32) rerank2_kernel(const float* __restrict__ Q, const float* __restrict__ D, const int32_t* __restrict__ fail_ids,
                                                                     const int32_t* __restrict__ n_fail, const int32_t* __restrict__ cand_idx,
-                                                                    const int32_t* __restrict__ cand_cnt, int n_splits, int cap, int k, long row_offset,
+                                                                    const int32_t* __restrict__ cand_cnt, int k, long row_offset,
                                                                     int64_t* __restrict__ out_idx, double* __restrict__ out_score, int32_t* __restrict__ flags) {
   __shared__ double s_sc[kRerankWarps][kPass2Cap];
   __shared__ long s_ix[kRerankWarps][kPass2Cap];
@@ -291,18 +291,12 @@ __global__ void __launch_bounds__(kRerankWarps * 32) rerank2_kernel(const float*
   const int slot = blockIdx.x * kRerankWarps + w;
   if (slot >= *n_fail) return;
   const int q = fail_ids[slot];
-  int n = 0;
-  bool overflow = false;
-  for (int s = 0; s < n_splits; ++s) {
-    const int c = cand_cnt[static_cast<long>(slot) * n_splits + s];  // warp-uniform
-    if (c > cap) { overflow = true; break; }
-    for (int i = lane; i < c; i += 32) s_ix[w][n + i] = cand_idx[static_cast<long>(slot) * kPass2Cap + s * cap + i];
-    n += c;
-  }
-  if (overflow) {
+  const int n = cand_cnt[slot];  // warp-uniform
+  if (n > kPass2Cap) {
     if (lane == 0) flags[q] = 2;
     return;
   }
+  for (int i = lane; i < n; i += 32) s_ix[w][i] = cand_idx[static_cast<long>(slot) * kPass2Cap + i];
   __syncwarp();
   const float* qr = Q + static_cast<long>(q) * kEmbed;
   for (int c = 0; c < n; ++c) {
@@ -422,17 +416,16 @@ cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q,
   // ---- second pass over the queries whose proof failed (count lives on the device: no host sync; the GEMM
   // skips tiles beyond it).  Same operands, same splits; the epilogue collects instead of ranking.
   if (lc) lc->n += 3;
-  gather_fail_planes_kernel<<<(nq + 7) / 8, 256, 0, st>>>(w.q_planes, w.fail_ids, w.n_fail, w.q2_planes);
+  gather_fail_planes_kernel<<<(nq + 7) / 8, 256, 0, st>>>(w.q_planes, w.fail_ids, w.n_fail, w.q2_planes, w.cand2_cnt);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   CUtensorMap ta2;
   if (make_operand_map(&ta2, w.q2_planes, true, nq, 2 * kEmbed, 2 * kEmbed, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
   GemmShape s2 = s;
   s2.m_rows_dev = w.n_fail;
-  const int cap = kPass2Cap / n_splits;
-  CollectEpi::Params ep2{w.fail_thr, w.n_fail, w.cand2_idx, w.cand2_cnt, s.N, n_splits, cap};
+  CollectEpi::Params ep2{w.fail_thr, w.n_fail, w.cand2_idx, w.cand2_cnt, s.N};
   if ((e = launch_umma_gemm<Cfg, CollectEpi>(ta2, tb, s2, ep2, st)) != cudaSuccess) return e;
   rerank2_kernel<<<(nq + kRerankWarps - 1) / kRerankWarps, kRerankWarps * 32, 0, st>>>(
-      Q, db.D, w.fail_ids, w.n_fail, w.cand2_idx, w.cand2_cnt, n_splits, cap, k, db.row_offset, out_idx, out_score, w.flags);
+      Q, db.D, w.fail_ids, w.n_fail, w.cand2_idx, w.cand2_cnt, k, db.row_offset, out_idx, out_score, w.flags);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (out_n_fallback && (e = cudaMemcpyAsync(out_n_fallback, w.n_fail, sizeof(int32_t), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
   // exhaustive fp64 rescan only where the second pass overflowed its candidate buffer

@@ -17,6 +17,7 @@
 // The epilogue is a policy class (see gemm_epilogues.cuh, search.cu):
 //   struct Epi { struct Params; static constexpr int kSmemBytes;
 //     __device__ Epi(const Params&, uint8_t* smem, int epi_warp, int lane, int block_n);
+//     __device__ void prefetch_unit(int m_tile, int col0);   // the unit this CTA will process AFTER the current one (L2 prefetch hook)
 //     __device__ void begin_unit(int m_tile, int split);
 //     __device__ void begin_tile(int m_tile, int n_tile, int col0);   // BEFORE the accumulator is waited for: issue global loads here
 //     __device__ void chunk(int m_tile, int n_tile, int c, int col0, float (&v)[32]);   // 32 fp32 columns of this thread's row
@@ -228,6 +229,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const int split = u % shape.n_splits;
       const int nt0 = split * shape.tiles_per_split;
       const int nt1 = min(nt0 + shape.tiles_per_split, shape.n_tiles);
+      if (u + n_cta < n_units) {
+        const int u2 = u + n_cta;
+        epi.prefetch_unit((u2 / shape.n_splits) * Cfg::CTA_GROUP + static_cast<int>(rank), (u2 % shape.n_splits) * shape.tiles_per_split * Cfg::BLOCK_N);
+      }
       epi.begin_unit(m_tile, split);
       for (int nt = nt0; nt < nt1; ++nt) {
         epi.begin_tile(m_tile, nt, nt * Cfg::BLOCK_N);  // bias / side-input loads fly while the MMAs finish
