@@ -59,6 +59,25 @@ def peaks():
     return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so pinned staging buffers are allocated on the
+    NUMA node the GPU's PCIe root hangs off (first touch) and H2D copies do not cross the socket interconnect.
+    Best effort: any failure leaves the affinity unchanged."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -187,6 +206,7 @@ def run_engine_arm(args):
         args.gpus = world
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bind_to_gpu_numa_node(local_rank)  # before any pinned allocation: the e2e arm streams 1.2 GB/step/GPU from host memory
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 

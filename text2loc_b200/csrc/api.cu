@@ -60,7 +60,7 @@ struct t2l_engine {
   SearchDb db;
   SearchWork sw{};
   size_t sw_planes_rows = 0;
-  int obj_chunk = 2048;      // objects per encode chunk (cell-aligned)
+  int obj_chunk = 4096;      // objects per encode chunk (cell-aligned); 2048 -> 4096 is +9 % cells/s (fuller grids for the small GEMMs), ~12 GB of workspace
   bool fused_sa = true;      // sa_fused.cu; false = v1 edge_gather -> H -> SegMax GEMM (kept for A/B checks, T2L_UNFUSED_SA=1)
   int tok_chunk = 32768;     // tokens per text chunk (sentence-aligned)
   bool text_f16 = true;      // token layer on fp16 operands (same 11-bit significand as tf32, twice the MMA rate, half the
