@@ -312,52 +312,58 @@ def run_engine_arm(args):
             oidx, _ = restate.search_topk(D_local.cpu().numpy(), q_all[:nchk].cpu().numpy(), K_TOP)
             parity = bool((idx[:nchk].cpu().numpy() == oidx + row_lo).all())
 
-    # ---- roofline of the dominant kernel: the text head's tf32 tcgen05 GEMM (FFN up-projection
-    # shape: M = tokens of one chunk, N = 4096, K = 1024), timed alone with CUDA events
+    # ---- roofline of the dominant kernel: the token layer's fp16-operand tcgen05 GEMM (FFN up-projection
+    # shape: M = tokens of one chunk, N = 4096, K = 1024, fp16 output), timed alone with CUDA events on the
+    # stream it is launched on, L2 flushed between launches
     pk = peaks()
     roof = None
     cpu_base = None
     extra = None
     if rank == 0:
         M, N, K = 32768 // (N_SENT * N_TOK) * (N_SENT * N_TOK), 4096, 1024
-        A = torch.randn(M, K, device=dev)
-        Wt = torch.randn(N, K, device=dev) / 32
+        A = torch.randn(M, K, device=dev).half()
+        Wt = (torch.randn(N, K, device=dev) / 32).half()
         bias = torch.zeros(N, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        for _ in range(3):
-            eng.debug_linear(A, Wt, bias, act=1, path=1)
-        durs = []
-        for _ in range(10):
-            flush.zero_()  # L2 flush between timed launches
-            a, b = ev(), ev()
-            a.record()
-            eng.debug_linear(A, Wt, bias, act=1, path=1)
-            b.record()
-            torch.cuda.synchronize()
-            durs.append(a.elapsed_time(b))
-        dur = float(np.mean(durs))
+
+        def time_alone(fn):
+            for _ in range(3):
+                fn()
+            durs = []
+            for _ in range(10):
+                flush.zero_()  # L2 flush between timed launches
+                a, b = ev(), ev()
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                durs.append(a.elapsed_time(b))
+            return float(np.mean(durs))
+
+        dur = time_alone(lambda: eng.debug_linear_f16(A, Wt, bias, act=1, out_half=True))
         achieved = 2.0 * M * N * K / (dur * 1e-3) / 1e12
-        # cuBLAS tf32 on the same shape, same timing: the tf32 counterpart of MEASURED_PEAKS' bf16 figure
-        torch.backends.cuda.matmul.allow_tf32 = True
-        for _ in range(3):
-            torch.matmul(A, Wt.T)
-        cb = []
-        for _ in range(10):
-            flush.zero_()
-            a, b = ev(), ev()
-            a.record()
-            torch.matmul(A, Wt.T)
-            b.record()
-            torch.cuda.synchronize()
-            cb.append(a.elapsed_time(b))
-        cublas_tf32 = 2.0 * M * N * K / (float(np.mean(cb)) * 1e-3) / 1e12
+        # cuBLAS fp16 on the same shape, same timing: what MEASURED_PEAKS' bf16 figure is for this shape
+        cublas = 2.0 * M * N * K / (time_alone(lambda: torch.matmul(A, Wt.T)) * 1e-3) / 1e12
+        # the tf32 variant of the same kernel (encoder GEMMs of the cell path; T2L_TEXT_TF32=1 token layer)
+        A32, W32 = A.float(), Wt.float()
+        tf32 = 2.0 * M * N * K / (time_alone(lambda: eng.debug_linear(A32, W32, bias, act=1, path=1)) * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01", "traffic.json")
+        if os.path.isfile(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("ffn1_f16_bytes_per_launch")
+        roof = {"bound": "tensor", "kernel": "umma_gemm_kernel<GemmCfg<256,f16,cta_group::2>,StoreEpiT<half,no residual>> "
+                                             "(token-layer FFN1 shape %dx%dx%d, fp16 operands, fp32 accumulate)" % (M, N, K),
+                "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"], "traffic": traffic,
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops burst ({pk['source']}); kind::f16 issues at the bf16 rate",
+                "ms_per_launch": dur, "algorithmic_flop_per_launch": 2.0 * M * N * K,
+                "cublas_f16_same_shape_tflops": cublas, "frac_of_cublas_f16": achieved / cublas,
+                "tf32_variant_tflops": tf32, "tf32_variant_frac_of_half_rate_peak": tf32 / (pk["bf16"] / 2.0),
+                "step_share_text_head": ms_text / (ms_text + ms_search),
+                "text_head_algorithmic_tflops": nq_local * 1.83e9 / (ms_text * 1e-3) / 1e12,
+                "text_head_frac_of_sustained_peak": nq_local * 1.83e9 / (ms_text * 1e-3) / 1e12 / pk["bf16_sustained"]}
         peak_tf32 = pk["bf16"] / 2.0  # tf32 issues at half the bf16 rate on the same tensor pipe
-        roof = {"bound": "tensor", "kernel": "umma_gemm_kernel<GemmCfg<256,tf32>,StoreEpi> (text-head FFN1 shape %dx%dx%d)" % (M, N, K),
-                "achieved": achieved, "peak": peak_tf32, "unit": "TFLOP/s", "frac": achieved / peak_tf32, "traffic": None,
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops ({pk['source']}) / 2 for kind::tf32", "ms_per_launch": dur,
-                "cublas_tf32_same_shape_tflops": cublas_tf32, "frac_of_cublas_tf32": achieved / cublas_tf32,
-                "step_share_text_head": ms_text / (ms_text + ms_search)}
-        del A, Wt, flush
+        del A, Wt, A32, W32, flush
 
         # ---- the other named kernels, each against its own roof (north_star asks for both per kernel)
         extra = {}
@@ -411,7 +417,8 @@ def run_engine_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32 tensor-core encoders (fp32 tails) / bf16x3 split candidates + f64 re-rank", "data": "synthetic",
+            "dtype": "f16 operands / f32 accumulate in the token layer (f32 residual + LayerNorm), tf32 and 3xtf32 elsewhere; "
+                     "search: bf16x3 split candidates + f64 re-rank", "data": "synthetic",
             "config": {"workload": wl["name"], "n_cells": n_db, "n_queries": nq, "k": K_TOP, "objects_per_cell": OBJ_PER_CELL,
                        "sentences_x_tokens": [N_SENT, N_TOK], "timed_region": "text head + search (+ all-gathers, merge), DB pre-encoded",
                        "l2": "inputs larger than L2 (1.2 GB of T5 features per GPU per step)", "parallelism": f"db-rowshard{world}"},
