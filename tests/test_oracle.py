@@ -42,8 +42,10 @@ def test_search_golden(golden):
     D = synth.make_unit_rows(int(g["d_seed"]), int(g["n"]))
     Q = synth.make_unit_rows(int(g["q_seed"]), int(g["nq"]))
     idx, sc = restate.search_topk(D, Q, 10)
-    assert (idx == g["idx"]).all()
-    assert np.array_equal(sc, g["score"])
+    assert (idx == g["idx"]).all()  # the reference's own argsort loop (tie-free data)
+    # the golden scores are the reference's BLAS dgemv; the oracle sums row by row (see search_topk): same fp64
+    # products, different summation order
+    assert np.abs(sc - g["score"]).max() < 1e-14
 
 
 def test_eval_epoch_golden(state_dict, golden):
