@@ -62,6 +62,7 @@ struct t2l_engine {
   size_t sw_planes_rows = 0;
   int obj_chunk = 4096;      // objects per encode chunk (cell-aligned); 2048 -> 4096 is +9 % cells/s (fuller grids for the small GEMMs), ~12 GB of workspace
   bool fused_sa = true;      // sa_fused.cu; false = v1 edge_gather -> H -> SegMax GEMM (kept for A/B checks, T2L_UNFUSED_SA=1)
+  bool obj_sa = true;        // sa_obj.cu (object-resident, fp16 operands); T2L_SA_TF32=1 selects sa_fused.cu (tf32, global gathers)
   int tok_chunk = 32768;     // tokens per text chunk (sentence-aligned)
   bool text_f16 = true;      // token layer on fp16 operands (same 11-bit significand as tf32, twice the MMA rate, half the
                              // operand bytes); T2L_TEXT_TF32=1 selects the tf32 path for A/B checks
@@ -126,6 +127,7 @@ extern "C" int t2l_create(int device, t2l_engine** out) {
   e->device = device;
   if (const char* v = getenv("T2L_UNFUSED_SA")) e->fused_sa = !(v[0] == '1');
   if (const char* v = getenv("T2L_TEXT_TF32")) e->text_f16 = !(v[0] == '1');
+  if (const char* v = getenv("T2L_SA_TF32")) e->obj_sa = !(v[0] == '1');
   if (const char* v = getenv("T2L_OBJ_CHUNK")) { const int n = atoi(v); if (n >= 64 && n <= 65536) e->obj_chunk = n; }
   if (cudaMalloc(&e->db.max_norm, sizeof(float)) != cudaSuccess) { delete e; return fail(nullptr, "t2l_create: cudaMalloc failed"); }
   *out = e;
@@ -165,7 +167,8 @@ static bool is_tf32_operand(const std::string& n) {
 }
 
 static bool is_f16_operand(const std::string& n) {
-  return n == "txt_intra.in_w" || n == "txt_intra.out_w" || n == "txt_intra.l1_w" || n == "txt_intra.l2_w";
+  return n == "txt_intra.in_w" || n == "txt_intra.out_w" || n == "txt_intra.l1_w" || n == "txt_intra.l2_w" || n == "sa1.w2" || n == "sa2.w2" ||
+         n == "sa3.w2";
 }
 
 static bool is_split3_operand(const std::string& n) {
@@ -251,12 +254,12 @@ static const Weight& W(t2l_engine* e, const std::string& n) { return e->w.at(n);
 // y = act(x W^T + b) helper
 static cudaError_t lin(t2l_engine* e, bool umma, const float* A, long lda, int M, const std::string& wname, const std::string& bname,
                        float* C, long ldc, int act, cudaStream_t st, const float* residual = nullptr, long ldr = 0, int round_out = 0,
-                       int segmax = 0, const float* side = nullptr, long lds = 0) {
+                       int segmax = 0, const float* side = nullptr, long lds = 0, int out_half = 0) {
   const Weight& w = W(e, wname);
   Linear l;
   l.A = A; l.lda = lda; l.W = w.dev; l.ldw = w.ld; l.bias = bname.empty() ? nullptr : W(e, bname).dev;
   l.C = C; l.ldc = ldc; l.M = M; l.N = w.rows; l.K = w.cols; l.act = act;
-  l.residual = residual; l.ldr = ldr; l.round_out = round_out; l.segmax = segmax; l.side = side; l.lds = lds;
+  l.residual = residual; l.ldr = ldr; l.round_out = round_out; l.segmax = segmax; l.side = side; l.lds = lds; l.out_half = out_half;
   return umma ? linear_umma(l, st, &e->lc) : linear_simt(l, st, &e->lc);
 }
 
@@ -406,14 +409,27 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
   };
   for (const Level& L : lv) {
     const std::string nm = L.name;
-    // per-point half of the first Linear (no bias; b1 is added with the position term per edge)
-    CU(lin(e, L.px_umma, L.x, L.ldx, n * L.P, nm + ".w1x", "", L.Px, L.C1, 0, st));
+    // per-point half of the first Linear (no bias; b1 is added with the position term per edge); fp16 for the
+    // object-resident kernel (the buffer is reused as __half [n*P, C1])
+    const bool obj = e->fused_sa && e->obj_sa;
+    // (there b1 is folded into Px as well: one add less per edge element)
+    CU(lin(e, L.px_umma, L.x, L.ldx, n * L.P, nm + ".w1x", obj ? nm + ".b1" : "", L.Px, L.C1, 0, st, nullptr, 0, 0, 0, nullptr, 0, obj ? 1 : 0));
     EdgeGather eg;
     eg.Px = L.Px; eg.C1 = L.C1; eg.dense_pos = L.dense; eg.dense_stride = L.dstride; eg.cpos = L.cpos; eg.nbr = L.nbr; eg.cnt = L.cnt;
     eg.loop_src_obj = loop_src; eg.loop_half = loop_half; eg.Wp = W(e, nm + ".w1p").dev; eg.b1 = W(e, nm + ".b1").dev;
     eg.n_obj = n; eg.P = L.P; eg.M = L.M; eg.H = H; eg.Hself = Hs;
     if (W(e, nm + ".w1p").ld != 4) return fail(e, "internal: w1p pitch");
-    if (e->fused_sa) {
+    if (obj) {
+      eg.Px16 = reinterpret_cast<const __half*>(L.Px);
+      CU(self_edge_rows(eg, st, &e->lc));
+      CU(lin(e, true, Hs, L.C1, n * L.M, nm + ".w2", nm + ".b2", S, L.C2, 1, st));
+      SaObj so;
+      so.Px16 = eg.Px16; so.C1 = L.C1; so.C2 = L.C2; so.dense_pos = L.dense; so.dense_stride = L.dstride; so.cpos = L.cpos;
+      so.nbr = L.nbr; so.cnt = L.cnt; so.Wp = eg.Wp; so.b1 = eg.b1; so.W2h = W(e, nm + ".w2").dev16; so.b2 = W(e, nm + ".b2").dev;
+      so.side = S; so.out = L.xout; so.n_obj = n; so.P = L.P; so.M = L.M;
+      if (!so.W2h) return fail(e, "internal: no fp16 copy of %s.w2", L.name);
+      CU(sa_obj(so, st, &e->lc));
+    } else if (e->fused_sa) {
       // self-loop edges: one row per centroid through the same MLP -> side input of the fused kernel
       CU(self_edge_rows(eg, st, &e->lc));
       CU(lin(e, true, Hs, L.C1, n * L.M, nm + ".w2", nm + ".b2", S, L.C2, 1, st));

@@ -60,7 +60,7 @@ cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
     if (l.residual) return run_store<StoreEpiT<false, true>, kOpF16>(l, ep, wide, pair, st);
     return run_store<StoreEpiT<false, false>, kOpF16>(l, ep, wide, pair, st);
   }
-  if (l.out_half) return cudaErrorInvalidValue;
+  if (l.out_half) return run_store<StoreEpiT<true, false>, kOpTf32>(l, ep, wide, pair, st);  // tf32 GEMM feeding an fp16 consumer (Px)
   if (l.residual) return run_store<StoreEpiT<false, true>, kOpTf32>(l, ep, wide, pair, st);
   return run_store<StoreEpiT<false, false>, kOpTf32>(l, ep, wide, pair, st);
 }
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(Linear l) {
       if (l.bias) x += l.bias[c];
       if (l.act == 1) x = fmaxf(x, 0.f);
       if (l.residual) x += l.residual[r * l.ldr + c];
+      if (l.out_half) { reinterpret_cast<__half*>(l.C)[r * l.ldc + c] = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)); continue; }
       if (l.round_out) x = round_tf32(x);
       l.C[r * l.ldc + c] = x;
     }

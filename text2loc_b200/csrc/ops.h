@@ -65,6 +65,7 @@ cudaError_t extract_rgb(const float* pts, int n_obj, float* x0, cudaStream_t st,
 // dense positions: level 1 reads pts (stride 6), levels 2/3 read the previous level's cpos.
 struct EdgeGather {
   const float* Px; int C1;            // [n*P, C1] per dense point
+  const __half* Px16 = nullptr;       // fp16 Px WITH b1 folded in (object-resident path): read instead of Px by self_edge_rows
   const float* dense_pos; int dense_stride;  // [n*P, stride] xyz first
   const float* cpos;                  // [n*M, 3]
   const uint8_t* nbr; const uint8_t* cnt;
@@ -89,6 +90,18 @@ struct SaFused {
   int n_obj, P, M;
 };
 cudaError_t sa_fused(const SaFused& a, cudaStream_t st, Launches* lc);
+// Object-resident variant on fp16 operands (sa_obj.cu): Px as fp16 [n*P, C1], W2 as fp16 [C2, C1]; the edges are
+// taken straight from the ball-query lists and positions (no per-edge records).
+struct SaObj {
+  const __half* Px16; int C1; int C2;    // Px16 = fp16 (W1x x_j + b1)
+  const float* dense_pos; int dense_stride; const float* cpos;
+  const uint8_t* nbr; const uint8_t* cnt;
+  const float* Wp; const float* b1;      // [C1,4], [C1]
+  const __half* W2h; const float* b2;    // [C2, C1] fp16, [C2]
+  const float* side; float* out;         // [n*M, C2]
+  int n_obj, P, M;
+};
+cudaError_t sa_obj(const SaObj& a, cudaStream_t st, Launches* lc);
 // Hself[o*M+m, :] only (the re-added self-loop edge of every centroid)
 cudaError_t self_edge_rows(const EdgeGather& a, cudaStream_t st, Launches* lc);
 // GA input: A[n*32, 260] = [x3 (256) | cpos3 (3) | 0]

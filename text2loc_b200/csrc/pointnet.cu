@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256) self_edge_kernel(EdgeGather a) {
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int c = r * 32 + lane;
-    float v = a.Px[src * C1 + c] + a.b1[c];
+    float v = a.Px16 ? __half2float(a.Px16[src * C1 + c]) : a.Px[src * C1 + c] + a.b1[c];  // the fp16 Px already contains b1
     v = fmaf(a.Wp[c * 4 + 0], ex, v);
     v = fmaf(a.Wp[c * 4 + 1], ey, v);
     v = fmaf(a.Wp[c * 4 + 2], ez, v);
