@@ -191,8 +191,15 @@ sa_obj_kernel(const __grid_constant__ CUtensorMap tm_b, const SaObjParams p, con
       for (int kb = 0; kb < Cfg::KB; ++kb) tma_load_2d(&tm_b, bres_bar, b_res + kb * Cfg::B_BYTES, kb * 64, 0, kEvictLast);
     }
     __syncwarp();
+    constexpr int kSideBytes = M * C2 * 4;  // one object's self-loop rows, contiguous
+    if (o0 < o1 && lane < 8)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(ep.side) + static_cast<long>(o0) * kSideBytes + lane * (kSideBytes / 8)),
+                   "r"(kSideBytes / 8) : "memory");
     for (int o = o0, n = 0; o < o1; ++o, ++n) {
       const int buf = n % Cfg::NOBJ;
+      if (o + 1 < o1 && lane < 8)  // the epilogue reaches the next object's side rows in ~10-20 us
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(ep.side) + static_cast<long>(o + 1) * kSideBytes + lane * (kSideBytes / 8)),
+                     "r"(kSideBytes / 8) : "memory");
       mbar_wait(&obj_empty[buf], (((n / Cfg::NOBJ) & 1) ^ 1));
       if (elect_one()) {
         uint8_t* dst = obj_base + buf * Cfg::OBJ_BYTES;
@@ -248,13 +255,24 @@ sa_obj_kernel(const __grid_constant__ CUtensorMap tm_b, const SaObjParams p, con
     int acc = 0;
     uint32_t acc_phase = 0;
     if (ew * 32 < C2 || Cfg::MH > 1) {
-      for (int tile = 0; tile < n_tiles; ++tile) {
-        const long g0 = (tile0 + tile) * 4;  // first centroid of the tile
-        float side_v[Cfg::MH][4];
+      // The self-loop rows (`side`) are the only global reads of the epilogue.  Loaded at the top of a tile's own iteration
+      // they put one DRAM round trip (~1.4k cycles) on EVERY tile -- the whole per-tile time of SA1 (profiles/r01).  So:
+      // the TMA warp L2-prefetches each object's side block one object ahead, and the values are register-prefetched
+      // kSideAhead tiles ahead here.
+      constexpr int kSideAhead = 2;
+      float side_q[kSideAhead + 1][Cfg::MH][4];
+      auto load_side = [&](int tile, float (&dst)[Cfg::MH][4]) {
+        const long g0 = (tile0 + tile) * 4;
 #pragma unroll
         for (int h = 0; h < Cfg::MH; ++h)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) side_v[h][c] = __ldg(ep.side + (g0 + c) * C2 + h * 128 + ew * 32 + lane);  // in flight during the MMAs
+          for (int c = 0; c < 4; ++c) dst[h][c] = (tile < n_tiles) ? __ldg(ep.side + (g0 + c) * C2 + h * 128 + ew * 32 + lane) : 0.f;
+      };
+#pragma unroll
+      for (int a = 0; a < kSideAhead; ++a) load_side(a, side_q[a]);
+      for (int tile = 0; tile < n_tiles; ++tile) {
+        const long g0 = (tile0 + tile) * 4;  // first centroid of the tile
+        load_side(tile + kSideAhead, side_q[kSideAhead]);
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * Cfg::ACC_COLS;
@@ -270,13 +288,19 @@ sa_obj_kernel(const __grid_constant__ CUtensorMap tm_b, const SaObjParams p, con
           for (int i = 0; i < 8; ++i) m[i] = fmaxf(fmaxf(x[4 * i], x[4 * i + 1]), fmaxf(x[4 * i + 2], x[4 * i + 3]));
           const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
           // bias and ReLU commute with the max over edges (per-channel constant, monotonic rounding)
-          const float keep = fmaxf(fmaxf(mx + bias[q >> 2], 0.f), side_v[q >> 2][q & 3]);
+          const float keep = fmaxf(fmaxf(mx + bias[q >> 2], 0.f), side_q[0][q >> 2][q & 3]);
           ep.out[(g0 + (q & 3)) * C2 + (q >> 2) * 128 + ew * 32 + lane] = round_tf32(keep);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
+#pragma unroll
+        for (int a = 0; a < kSideAhead; ++a)
+#pragma unroll
+          for (int h = 0; h < Cfg::MH; ++h)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) side_q[a][h][c] = side_q[a + 1][h][c];
       }
     } else {
       // channels >= C2 (SA1: 64 real channels in a 128-lane accumulator): nothing to read, just release the buffers
