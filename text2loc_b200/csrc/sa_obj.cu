@@ -333,7 +333,10 @@ sa_obj_kernel(const __grid_constant__ CUtensorMap tm_b, const SaObjParams p, con
       mbar_wait(&obj_full[buf], (n / Cfg::NOBJ) & 1);
 #pragma unroll 1
       for (int tau = 0; tau < Cfg::TPO; ++tau) {
-        if (Cfg::KB == 1 && (u & 1) != group) { ++u; continue; }  // one item per tile: the groups alternate tiles
+        // kTileMode (KB <= 2, four slots): the groups alternate TILES; a group builds all k-blocks of its tile and pays ONE
+        // proxy fence for them (its items always land in the same two slots).  Otherwise (SA3: two slots) they alternate items.
+        constexpr bool kTileMode = Cfg::KB <= 2 && Cfg::STAGES == 4;
+        if (kTileMode && ((u / Cfg::KB) & 1) != group) { u += Cfg::KB; continue; }
         // this tile's edges: source point and pos_j - pos_i of my rows (exact fp32 subtraction, as the reference's message())
         int src_off[Cfg::RPT];
         uint64_t dx[Cfg::RPT], dy[Cfg::RPT], dz[Cfg::RPT];
@@ -347,11 +350,15 @@ sa_obj_kernel(const __grid_constant__ CUtensorMap tm_b, const SaObjParams p, con
           dy[i] = dup2(pos_s[j * POS_STRIDE + 1] - cpos_s[cen * 3 + 1]);
           dz[i] = dup2(pos_s[j * POS_STRIDE + 2] - cpos_s[cen * 3 + 2]);
         }
+        const long u_tile = u;
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB; ++kb, ++u) {
-          if (Cfg::KB > 1 && (u & 1) != group) continue;
+          if (!kTileMode && (u & 1) != group) continue;
           const int stage = static_cast<int>(u % Cfg::STAGES);
           const uint32_t use = static_cast<uint32_t>(u / Cfg::STAGES);
+          uint4 raw[Cfg::RPT];  // all Px reads of the item in flight before anything waits
+#pragma unroll
+          for (int i = 0; i < Cfg::RPT; ++i) raw[i] = *reinterpret_cast<const uint4*>(px_s + src_off[i] + kb * 128);
           // w1p of my 8 channels as pairs: (x, y, z) x 4 pairs
           const int pair0 = (kb * 64 + sub * 8) >> 2;  // index in ulonglong2 units (2 pairs each)
           const ulonglong2 wx01 = tab2[pair0], wx23 = tab2[pair0 + 1];
@@ -364,8 +371,7 @@ sa_obj_kernel(const __grid_constant__ CUtensorMap tm_b, const SaObjParams p, con
 #pragma unroll
           for (int i = 0; i < Cfg::RPT; ++i) {
             const int r = rb + Cfg::RSTEP * i;
-            const uint4 raw = *reinterpret_cast<const uint4*>(px_s + src_off[i] + kb * 128);
-            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+            const uint32_t rw[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
             uint32_t packed[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {  // channels 2q, 2q+1:  Px (+ b1) + w1p . (pos_j - pos_i)
@@ -378,9 +384,19 @@ sa_obj_kernel(const __grid_constant__ CUtensorMap tm_b, const SaObjParams p, con
             // 128B swizzle: 16-byte chunk `sub` of row r lives at chunk position sub ^ (r % 8)
             *reinterpret_cast<uint4*>(abase + r * 128 + ((sub ^ (r & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
           }
-          fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
+          if (!kTileMode) {
+            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
+          }
+        }
+        if (kTileMode) {
+          fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&full_bar[stage]);
+          if (lane == 0) {
+#pragma unroll
+            for (int kb = 0; kb < Cfg::KB; ++kb) mbar_arrive(&full_bar[(u_tile + kb) % Cfg::STAGES]);
+          }
         }
       }
       __syncwarp();
