@@ -374,8 +374,12 @@ def run_engine_arm(args):
         extra["db_encode"] = {"bound": "tensor", "achieved": obj_per_s * flop_per_obj / 1e12, "peak": peak_tf32, "unit": "TFLOP/s",
                               "frac": obj_per_s * flop_per_obj / 1e12 / peak_tf32,
                               "hbm_algorithmic_gbs": obj_per_s * 7196 / 1e9, "hbm_frac": obj_per_s * 7196 / 1e9 / pk["hbm_gbs"],
-                              "note": "algorithmic FLOPs of the whole encode / wall time of encode_cells; the HBM figure north_star asks "
-                                      "for is reported but cannot approach its roof: the stage is ~53 kFLOP/B"}
+                              "frac_of_f16_rate_peak": obj_per_s * flop_per_obj / 1e12 / pk["bf16"],
+                              "note": "algorithmic FLOPs of the whole encode / wall time of encode_cells (FPS, ball query, gathers, attention "
+                                      "and all small layers included). 86 % of those FLOPs are the PointConv second layers, which run as fp16 "
+                                      "tcgen05 MMAs (sa_obj.cu); the rest is tf32 / 3xtf32, so the honest bracket is frac (tf32-rate peak) .. "
+                                      "frac_of_f16_rate_peak. The HBM figure north_star asks for is reported but cannot approach its roof: "
+                                      "the stage is ~53 kFLOP/B"}
         # (b) search at the per-GPU shape of configs[2] (32 768 queries x 12 500 rows) and at 100k rows
         for n_rows in (12500, 100000):
             Dn = torch.from_numpy(synth.make_unit_rows(77, n_rows)).to(dev)

@@ -130,3 +130,45 @@ def test_features2_within_tolerance(eng, state_dict, golden):
     rel = np.abs(got - want).max() / np.abs(want).max()
     print(f"\nfeatures2 max rel-to-max error {rel:.3e}")
     assert rel < 1e-3
+
+
+def test_features2_tf32_global_gather_variant(state_dict, golden, monkeypatch):
+    """The set-abstraction layers run object-resident on fp16 operands by default (sa_obj.cu); T2L_SA_TF32=1 keeps the
+    tf32 kernel that gathers from global memory (sa_fused.cu).  Both must meet the tolerance against the reference."""
+    from text2loc_b200.engine import Engine
+
+    g = golden("cells_small.npz")
+    errs = {}
+    for name, env in (("fp16 object-resident", "0"), ("tf32 global gather", "1")):
+        monkeypatch.setenv("T2L_SA_TF32", env)
+        e = Engine("cuda:0")
+        e.load_state_dict(state_dict)
+        got = e.encode_objects_debug(torch.from_numpy(g["pts"]), g["cell_ptr"])["features2"].cpu().numpy()
+        errs[name] = np.abs(got - g["features2"]).max() / np.abs(g["features2"]).max()
+        assert errs[name] < 1e-3, name
+    print("\nfeatures2 max rel-to-max error:", {k: f"{v:.3e}" for k, v in errs.items()})
+
+
+def test_sa_empty_neighbour_slots(state_dict):
+    """Objects whose points are far apart leave most of the 32 neighbour slots empty (down to the centroid alone): the
+    object-resident kernel replicates slot 0 there, the oracle masks the slots; the max must agree."""
+    from oracle import restate
+    from text2loc_b200 import synth
+    from text2loc_b200.engine import Engine
+
+    e = Engine("cuda:0")
+    e.load_state_dict(state_dict)
+    cells = synth.make_cell_objects(11, 3, [2, 3, 1], max_raw=300)
+    pts, meta, ptr = synth.pack_cells(cells, 11)
+    rng = np.random.default_rng(5)
+    pts = pts.copy()
+    pts[:, :, 0:3] = rng.uniform(0.0, 3.0, size=pts[:, :, 0:3].shape).astype(np.float32)  # radius 0.2-0.4 balls are nearly empty
+    d = e.encode_objects_debug(torch.from_numpy(pts), ptr)
+    want, aux = restate.pointnet2_features2(state_dict, torch.from_numpy(pts), ptr, return_aux=True)
+    cnt1 = (aux["nbr1"].numpy() >= 0).sum(axis=2)
+    assert cnt1.min() < 4 and (d["cnt1"].cpu().numpy() == cnt1).all()
+    got = d["features2"].cpu().numpy()
+    want = want.numpy()
+    rel = np.abs(got - want).max() / np.abs(want).max()
+    print(f"\nsparse objects: features2 max rel-to-max error {rel:.3e}, min neighbours {cnt1.min()}")
+    assert rel < 1e-3
