@@ -24,8 +24,8 @@ static std::string g_create_error;
 
 struct Weight {
   float* dev = nullptr;
-  __half* dev16 = nullptr;  // fp16 copy [rows, cols] of the token-layer weights (kind::f16 GEMMs)
-  int rows = 0, cols = 0, ld = 0;
+  __half* dev16 = nullptr;  // fp16 copy [rows, ld16] (zero-padded rows, 16-byte pitch) of the weights of the kind::f16 GEMMs
+  int rows = 0, cols = 0, ld = 0, ld16 = 0;
 };
 
 // bump allocator over one device arena, reset per chunk
@@ -60,7 +60,8 @@ struct t2l_engine {
   SearchDb db;
   SearchWork sw{};
   size_t sw_planes_rows = 0;
-  int obj_chunk = 4096;      // objects per encode chunk (cell-aligned); 2048 -> 4096 is +9 % cells/s (fuller grids for the small GEMMs), ~12 GB of workspace
+  int obj_chunk = 8192;      // objects per encode chunk (cell-aligned); 2048 -> 4096 -> 8192 is +9 % / +5 % cells/s (fuller grids for the small
+                             // kernels), ~24 GB of workspace
   bool fused_sa = true;      // sa_fused.cu; false = v1 edge_gather -> H -> SegMax GEMM (kept for A/B checks, T2L_UNFUSED_SA=1)
   bool obj_sa = true;        // sa_obj.cu (object-resident, fp16 operands); T2L_SA_TF32=1 selects sa_fused.cu (tf32, global gathers)
   int tok_chunk = 32768;     // tokens per text chunk (sentence-aligned)
@@ -168,7 +169,7 @@ static bool is_tf32_operand(const std::string& n) {
 
 static bool is_f16_operand(const std::string& n) {
   return n == "txt_intra.in_w" || n == "txt_intra.out_w" || n == "txt_intra.l1_w" || n == "txt_intra.l2_w" || n == "sa1.w2" || n == "sa2.w2" ||
-         n == "sa3.w2";
+         n == "sa3.w2" || n == "ga.w1" || n == "ga.w2";
 }
 
 static bool is_split3_operand(const std::string& n) {
@@ -212,12 +213,14 @@ extern "C" int t2l_set_weight(t2l_engine* e, const char* name, const float* data
   CU(cudaMalloc(&w.dev, host.size() * sizeof(float)));
   CU(cudaMemcpy(w.dev, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
   if (is_f16_operand(name)) {
-    if (cols % 8) return fail(e, "t2l_set_weight: '%s' needs cols %% 8 == 0", name);
-    std::vector<__half> h16(static_cast<size_t>(rows) * cols);
-    for (size_t i = 0; i < h16.size(); ++i) {
-      if (!(fabsf(data[i]) <= 65504.f)) return fail(e, "t2l_set_weight: '%s' has a value outside the fp16 range", name);
-      h16[i] = __float2half_rn(data[i]);
-    }
+    w.ld16 = (cols + 7) & ~7;
+    std::vector<__half> h16(static_cast<size_t>(rows) * w.ld16, __float2half_rn(0.f));
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) {
+        const float v = data[static_cast<size_t>(r) * cols + c];
+        if (!(fabsf(v) <= 65504.f)) return fail(e, "t2l_set_weight: '%s' has a value outside the fp16 range", name);
+        h16[static_cast<size_t>(r) * w.ld16 + c] = __float2half_rn(v);
+      }
     CU(cudaMalloc(&w.dev16, h16.size() * sizeof(__half)));
     CU(cudaMemcpy(w.dev16, h16.data(), h16.size() * sizeof(__half), cudaMemcpyHostToDevice));
   }
@@ -279,14 +282,14 @@ static cudaError_t lin3(t2l_engine* e, const float* A, long lda, int M, const st
 
 // y = act(x W^T + b) with fp16 operands (A and the weight's fp16 copy), fp32 accumulate; C is fp32 or fp16 (out_half).
 static cudaError_t lin_h(t2l_engine* e, const __half* A, long lda, int M, const std::string& wname, const std::string& bname, void* C,
-                         long ldc, int act, int out_half, cudaStream_t st, const float* residual = nullptr, long ldr = 0) {
+                         long ldc, int act, int out_half, cudaStream_t st, const float* residual = nullptr, long ldr = 0, int segmax = 0) {
   const Weight& w = W(e, wname);
   if (!w.dev16) return cudaErrorInvalidValue;
   Linear l;
-  l.A = reinterpret_cast<const float*>(A); l.lda = lda; l.W = reinterpret_cast<const float*>(w.dev16); l.ldw = w.cols;
+  l.A = reinterpret_cast<const float*>(A); l.lda = lda; l.W = reinterpret_cast<const float*>(w.dev16); l.ldw = w.ld16;
   l.bias = bname.empty() ? nullptr : W(e, bname).dev;
   l.C = static_cast<float*>(C); l.ldc = ldc; l.M = M; l.N = w.rows; l.K = w.cols; l.act = act; l.residual = residual; l.ldr = ldr;
-  l.half_ops = 1; l.out_half = out_half;
+  l.half_ops = 1; l.out_half = out_half; l.segmax = segmax; l.round_out = segmax ? 1 : 0;
   return linear_umma(l, st, &e->lc);
 }
 
@@ -398,7 +401,8 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
   float* x1 = a.get<float>(N * 128 * 64);
   float* x2 = a.get<float>(N * 64 * 128);
   float* x3 = a.get<float>(N * 32 * 256);
-  CU(extract_rgb(p, n, x0, st, &e->lc));
+  const bool obj_mode = e->fused_sa && e->obj_sa;
+  if (!obj_mode) CU(extract_rgb(p, n, x0, st, &e->lc));  // the object-resident path reads rgb straight from pts (sa1_px16)
 
   struct Level { const char* name; int C1, C2, P, M; const float* x; long ldx; const float* dense; int dstride; const float* cpos;
                  const uint8_t* nbr; const uint8_t* cnt; float* Px; float* xout; bool px_umma; };
@@ -413,7 +417,12 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
     // object-resident kernel (the buffer is reused as __half [n*P, C1])
     const bool obj = e->fused_sa && e->obj_sa;
     // (there b1 is folded into Px as well: one add less per edge element)
-    CU(lin(e, L.px_umma, L.x, L.ldx, n * L.P, nm + ".w1x", obj ? nm + ".b1" : "", L.Px, L.C1, 0, st, nullptr, 0, 0, 0, nullptr, 0, obj ? 1 : 0));
+    if (obj && !L.px_umma) {
+      if (W(e, nm + ".w1x").ld != 4 || L.C1 != 32) return fail(e, "internal: sa1.w1x shape");
+      CU(sa1_px16(p, n, W(e, nm + ".w1x").dev, W(e, nm + ".b1").dev, reinterpret_cast<__half*>(L.Px), st, &e->lc));
+    } else {
+      CU(lin(e, L.px_umma, L.x, L.ldx, n * L.P, nm + ".w1x", obj ? nm + ".b1" : "", L.Px, L.C1, 0, st, nullptr, 0, 0, 0, nullptr, 0, obj ? 1 : 0));
+    }
     EdgeGather eg;
     eg.Px = L.Px; eg.C1 = L.C1; eg.dense_pos = L.dense; eg.dense_stride = L.dstride; eg.cpos = L.cpos; eg.nbr = L.nbr; eg.cnt = L.cnt;
     eg.loop_src_obj = loop_src; eg.loop_half = loop_half; eg.Wp = W(e, nm + ".w1p").dev; eg.b1 = W(e, nm + ".b1").dev;
@@ -421,8 +430,9 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
     if (W(e, nm + ".w1p").ld != 4) return fail(e, "internal: w1p pitch");
     if (obj) {
       eg.Px16 = reinterpret_cast<const __half*>(L.Px);
+      eg.Hself16 = reinterpret_cast<__half*>(Hs);  // the self-loop rows go through the same fp16 second layer as the other edges
       CU(self_edge_rows(eg, st, &e->lc));
-      CU(lin(e, true, Hs, L.C1, n * L.M, nm + ".w2", nm + ".b2", S, L.C2, 1, st));
+      CU(lin_h(e, eg.Hself16, L.C1, n * L.M, nm + ".w2", nm + ".b2", S, L.C2, 1, 0, st));
       SaObj so;
       so.Px16 = eg.Px16; so.C1 = L.C1; so.C2 = L.C2; so.dense_pos = L.dense; so.dense_stride = L.dstride; so.cpos = L.cpos;
       so.nbr = L.nbr; so.cnt = L.cnt; so.Wp = eg.Wp; so.b1 = eg.b1; so.W2h = W(e, nm + ".w2").dev16; so.b2 = W(e, nm + ".b2").dev;
@@ -454,9 +464,17 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
   float* f0 = a.get<float>(N * 1024);
   float* f1 = a.get<float>(N * 512);
   float* f2 = a.get<float>(N * 256);
-  CU(ga_concat(x3, g.cpos3, n, gaA, st, &e->lc));
-  CU(lin(e, true, gaA, 260, n * 32, "ga.w1", "ga.b1", g1, 512, 1, st, nullptr, 0, 1));
-  CU(lin(e, true, g1, 512, n * 32, "ga.w2", "ga.b2", f0, 1024, 1, st, nullptr, 0, 1, 1));
+  if (obj_mode) {  // fp16 operands like the set-abstraction layers (x3 and the centroid positions were tf32-rounded operands before)
+    __half* gaA16 = reinterpret_cast<__half*>(gaA);  // [n*32, 264]
+    __half* g1h = reinterpret_cast<__half*>(g1);     // [n*32, 512]
+    CU(ga_concat_half(x3, g.cpos3, n, gaA16, st, &e->lc));
+    CU(lin_h(e, gaA16, 264, n * 32, "ga.w1", "ga.b1", g1h, 512, 1, /*out_half=*/1, st));
+    CU(lin_h(e, g1h, 512, n * 32, "ga.w2", "ga.b2", f0, 1024, 1, 0, st, nullptr, 0, /*segmax=*/1));
+  } else {
+    CU(ga_concat(x3, g.cpos3, n, gaA, st, &e->lc));
+    CU(lin(e, true, gaA, 260, n * 32, "ga.w1", "ga.b1", g1, 512, 1, st, nullptr, 0, 1));
+    CU(lin(e, true, g1, 512, n * 32, "ga.w2", "ga.b2", f0, 1024, 1, st, nullptr, 0, 1, 1));
+  }
   CU(lin(e, true, f0, 1024, n, "lin1.w", "lin1.b", f1, 512, 1, st, nullptr, 0, 1));  // relu(lin1) (:89)
   CU(lin(e, true, f1, 512, n, "lin2.w", "lin2.b", f2, 256, 1, st, nullptr, 0, 1));   // relu(lin2) = features2 (:90)
 
@@ -479,16 +497,16 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
   const float* m = meta + static_cast<size_t>(o0) * 7;
   CU(lin(e, true, f2, 256, n, "mlp_pointnet.w", "mlp_pointnet.b", t256, 256, 1, st));
   CU(l2_normalize_rows(t256, 256, cat + 0, 1024, n, 256, st, &e->lc));
-  CU(lin(e, false, m + 0, 7, n, "color.w1", "color.b1", t64, 64, 1, st));
-  CU(lin(e, false, t64, 64, n, "color.w2", "color.b2", t256, 256, 1, st));
-  CU(l2_normalize_rows(t256, 256, cat + 256, 1024, n, 256, st, &e->lc));
-  CU(lin(e, false, m + 3, 7, n, "pos.w1", "pos.b1", t64, 64, 1, st));
-  CU(lin(e, false, t64, 64, n, "pos.w2", "pos.b2", t256, 256, 1, st));
-  CU(l2_normalize_rows(t256, 256, cat + 512, 1024, n, 256, st, &e->lc));
-  CU(num_feature(m, n, numf, st, &e->lc));
-  CU(lin(e, false, numf, 1, n, "num.w1", "num.b1", t64, 64, 1, st));
-  CU(lin(e, false, t64, 64, n, "num.w2", "num.b2", t256, 256, 1, st));
-  CU(l2_normalize_rows(t256, 256, cat + 768, 1024, n, 256, st, &e->lc));
+  {
+    if (W(e, "color.w1").ld != 4 || W(e, "pos.w1").ld != 4 || W(e, "num.w1").ld != 4 || W(e, "color.w2").ld != 64 || W(e, "pos.w2").ld != 64 ||
+        W(e, "num.w2").ld != 64 || W(e, "color.w2").rows != 256)
+      return fail(e, "internal: side encoder weight shapes");
+    const float* w1[3] = {W(e, "color.w1").dev, W(e, "pos.w1").dev, W(e, "num.w1").dev};
+    const float* b1[3] = {W(e, "color.b1").dev, W(e, "pos.b1").dev, W(e, "num.b1").dev};
+    const float* w2[3] = {W(e, "color.w2").dev, W(e, "pos.w2").dev, W(e, "num.w2").dev};
+    const float* b2[3] = {W(e, "color.b2").dev, W(e, "pos.b2").dev, W(e, "num.b2").dev};
+    CU(side_encoders(m, n, w1, b1, w2, b2, cat, st, &e->lc));
+  }
   CU(lin(e, true, cat, 1024, n, "merge.w", "merge.b", emb, 256, 1, st));
 
   // intra-cell attention (cell_retrieval.py:85-108); fp32 throughout: these two layers amplify

@@ -42,7 +42,6 @@ cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
   const int row_align = l.half_ops ? 8 : 4;  // 16-byte rows for TMA
   if ((l.N % 32) || (l.lda % row_align) || (l.ldw % row_align)) return cudaErrorInvalidValue;
   if (l.passes != 1 && (l.passes != 3 || l.K % 32 || l.half_ops)) return cudaErrorInvalidValue;
-  if (l.half_ops && l.segmax) return cudaErrorInvalidValue;
   if (lc) lc->n++;
   // N % 256 == 0 and more than one 128-row tile: CTA pairs (256 x 256 tiles, cta_group::2); else single CTAs
   const bool wide = (l.N % 256) == 0;
@@ -50,6 +49,10 @@ cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
   if (l.segmax) {
     if (l.M % 32 || !l.bias) return cudaErrorInvalidValue;
     SegMaxEpi::Params ep{l.C, l.ldc, l.bias, l.side, l.lds, l.M, l.N, l.round_out};
+    if (l.half_ops) {  // GA's second layer: N = 1024
+      if (!wide) return cudaErrorInvalidValue;
+      return pair ? run_umma<256, 2, SegMaxEpi, kOpF16>(l, ep, st) : run_umma<256, 1, SegMaxEpi, kOpF16>(l, ep, st);
+    }
     if (pair) return run_umma<256, 2, SegMaxEpi>(l, ep, st);
     return wide ? run_umma<256, 1, SegMaxEpi>(l, ep, st) : run_umma<128, 1, SegMaxEpi>(l, ep, st);
   }

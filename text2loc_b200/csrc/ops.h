@@ -58,6 +58,8 @@ cudaError_t ball_query_all_levels(const float* pts, int n_obj, const Geometry& g
 // ---- pointnet.cu --------------------------------------------------------------------------
 // x0[n*256, 4] = rgb (padded to 4 floats) from pts
 cudaError_t extract_rgb(const float* pts, int n_obj, float* x0, cudaStream_t st, Launches* lc);
+// Px16[n*256, 32] = fp16(W1x . rgb + b1) for SA1 (w1x [32, ld 4]) straight from pts
+cudaError_t sa1_px16(const float* pts, int n_obj, const float* w1x, const float* b1, __half* px16, cudaStream_t st, Launches* lc);
 // First-layer edge activations of one PointConv:
 //   H[(o*M+m)*32 + s, :] = relu(Px[src_point] + Wp * (pos_src - cpos[o,m]) + b1)   s < 32 neighbour slots
 //   Hself[o*M+m, :]      = same for the re-added self-loop edge (dense point with the centroid's
@@ -75,6 +77,7 @@ struct EdgeGather {
   const float* b1;                    // [C1] folded
   int n_obj, P, M;
   float* H; float* Hself;
+  __half* Hself16 = nullptr;          // self_edge_rows writes fp16 rows here instead of Hself (operand of an fp16 side GEMM)
 };
 cudaError_t edge_gather(const EdgeGather& a, cudaStream_t st, Launches* lc);
 // Fused PointConv layer (sa_fused.cu): gathers, first-layer edge activations, second Linear on the
@@ -106,6 +109,8 @@ cudaError_t sa_obj(const SaObj& a, cudaStream_t st, Launches* lc);
 cudaError_t self_edge_rows(const EdgeGather& a, cudaStream_t st, Launches* lc);
 // GA input: A[n*32, 260] = [x3 (256) | cpos3 (3) | 0]
 cudaError_t ga_concat(const float* x3, const float* cpos3, int n_obj, float* A, cudaStream_t st, Launches* lc);
+// the same as fp16 rows of 264 halfs (K padded to a 16-byte multiple)
+cudaError_t ga_concat_half(const float* x3, const float* cpos3, int n_obj, __half* A, cudaStream_t st, Launches* lc);
 
 // ---- rowops.cu ----------------------------------------------------------------------------
 // y[r, 0:d] (row pitch ldy) = x[r] / max(||x[r]||, 1e-12)      (F.normalize)
@@ -133,6 +138,11 @@ cudaError_t max_over_rows(const float* x, float* y, int groups, int S, int d, cu
 cudaError_t scatter_objects(const float* emb, const int32_t* cell_ptr_dev, int n_cells, float* X, cudaStream_t st, Launches* lc);
 // meta[:, 6] -> (cnt - mean) / std  (object_encoder.py:141-143)
 cudaError_t num_feature(const float* meta, int n_obj, float* out, cudaStream_t st, Launches* lc);
+// cat[:, 256:1024] = [normalize(color_enc(mean rgb)) | normalize(pos_enc(centre)) | normalize(num_enc((count-mean)/std))]
+// from meta [n, 7]; w1[i] [64, ld 4], b1[i] [64], w2[i] [256, 64], b2[i] [256] for i = colour, position, count
+// (models/object_encoder.py:122-145)
+cudaError_t side_encoders(const float* meta, int n_obj, const float* const* w1, const float* const* b1, const float* const* w2, const float* const* b2,
+                          float* cat, cudaStream_t st, Launches* lc);
 // y = a + b (elementwise)
 cudaError_t add_rows(const float* a, const float* b, float* y, long n, cudaStream_t st, Launches* lc);
 // text: [S, nq] row order helpers are not needed: rows are kept query-major (q*S + s)

@@ -5,6 +5,8 @@
 // Px = W1x x_j is a dense GEMM over points (linear.cu); this file adds the exact fp32
 // position term per EDGE, applies ReLU and lays the edge rows out for the second-layer GEMM
 // whose epilogue does the per-centroid max (gemm_epilogues.cuh::SegMaxEpi).
+#include <cuda_fp16.h>
+
 #include "ops.h"
 #include "common.cuh"
 
@@ -22,6 +24,43 @@ cudaError_t extract_rgb(const float* pts, int n_obj, float* x0, cudaStream_t st,
   if (n <= 0) return cudaSuccess;
   if (lc) lc->n++;
   extract_rgb_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(pts, n, x0);
+  return cudaGetLastError();
+}
+
+// SA1's per-point first Linear for the object-resident path: Px16[i, :] = fp16(W1x . rgb_i + b1), 32 channels, K = 3.
+// One thread per (point, 8 channels): reads the point's rgb straight from pts, writes 16 bytes.  (The generic SIMT GEMM
+// spent 112 us per 4 096 objects on this K = 3 layer; this is a 92 MB streaming pass.)
+__global__ void __launch_bounds__(256) px1_kernel(const float* __restrict__ pts, long n_pts, const float* __restrict__ w1x /*[32, ld 4]*/,
+                                                  const float* __restrict__ b1, __half* __restrict__ px16) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long i = idx >> 2;
+  const int q = static_cast<int>(idx & 3);
+  if (i >= n_pts) return;
+  const float r = pts[i * 6 + 3], g = pts[i * 6 + 4], b = pts[i * 6 + 5];
+  uint32_t out[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = q * 8 + p * 2 + e;
+      const float4 w = __ldg(reinterpret_cast<const float4*>(w1x + c * 4));
+      float acc = fmaf(r, w.x, 0.f);
+      acc = fmaf(g, w.y, acc);
+      acc = fmaf(b, w.z, acc);
+      v[e] = fminf(fmaxf(acc + __ldg(b1 + c), -65504.f), 65504.f);
+    }
+    const __half2 h = __floats2half2_rn(v[0], v[1]);
+    out[p] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(px16 + i * 32 + q * 8) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+cudaError_t sa1_px16(const float* pts, int n_obj, const float* w1x, const float* b1, __half* px16, cudaStream_t st, Launches* lc) {
+  const long n = static_cast<long>(n_obj) * kPoints;
+  if (n <= 0) return cudaSuccess;
+  if (lc) lc->n++;
+  px1_kernel<<<static_cast<unsigned>((n * 4 + 255) / 256), 256, 0, st>>>(pts, n, w1x, b1, px16);
   return cudaGetLastError();
 }
 
@@ -118,7 +157,8 @@ __global__ void __launch_bounds__(256) self_edge_kernel(EdgeGather a) {
     v = fmaf(a.Wp[c * 4 + 0], ex, v);
     v = fmaf(a.Wp[c * 4 + 1], ey, v);
     v = fmaf(a.Wp[c * 4 + 2], ez, v);
-    a.Hself[cen * C1 + c] = round_tf32(fmaxf(v, 0.f));
+    if (a.Hself16) a.Hself16[cen * C1 + c] = __float2half_rn(fminf(fmaxf(v, 0.f), 65504.f));
+    else a.Hself[cen * C1 + c] = round_tf32(fmaxf(v, 0.f));
   }
 }
 
@@ -146,6 +186,33 @@ __global__ void ga_concat_kernel(const float* __restrict__ x3, const float* __re
   dst[lane] = src[lane];
   dst[lane + 32] = src[lane + 32];
   if (lane == 0) dst[64] = make_float4(cpos3[r * 3 + 0], cpos3[r * 3 + 1], cpos3[r * 3 + 2], 0.f);
+}
+
+// fp16 variant: A16[n*32, 264] = [x3 (256) | cpos3 (3) | 0 x 5]
+__global__ void ga_concat_half_kernel(const float* __restrict__ x3, const float* __restrict__ cpos3, long rows, __half* __restrict__ A) {
+  const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* src = reinterpret_cast<const float4*>(x3 + r * 256);
+  const float4 a = src[2 * lane], b = src[2 * lane + 1];  // 8 consecutive channels per lane -> one 16-byte store
+  const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w), h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+  uint4 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+  u.z = *reinterpret_cast<const uint32_t*>(&h2); u.w = *reinterpret_cast<const uint32_t*>(&h3);
+  reinterpret_cast<uint4*>(A + r * 264)[lane] = u;
+  if (lane == 0) {
+    const __half2 p0 = __floats2half2_rn(cpos3[r * 3 + 0], cpos3[r * 3 + 1]), p1 = __floats2half2_rn(cpos3[r * 3 + 2], 0.f);
+    uint4 t = make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1), 0u, 0u);
+    reinterpret_cast<uint4*>(A + r * 264)[32] = t;
+  }
+}
+
+cudaError_t ga_concat_half(const float* x3, const float* cpos3, int n_obj, __half* A, cudaStream_t st, Launches* lc) {
+  const long rows = static_cast<long>(n_obj) * 32;
+  if (rows <= 0) return cudaSuccess;
+  if (lc) lc->n++;
+  ga_concat_half_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(x3, cpos3, rows, A);
+  return cudaGetLastError();
 }
 
 cudaError_t ga_concat(const float* x3, const float* cpos3, int n_obj, float* A, cudaStream_t st, Launches* lc) {

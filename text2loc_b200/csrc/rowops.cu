@@ -511,6 +511,92 @@ cudaError_t num_feature(const float* meta, int n_obj, float* out, cudaStream_t s
   return cudaGetLastError();
 }
 
+// ---- colour / position / point-count encoders of ObjectEncoder.forward in ONE kernel ---------------------------
+// (models/object_encoder.py:122-145: three get_mlp([k, 64, 256]) stacks = Linear+BN(folded)+ReLU twice, each followed by
+// F.normalize).  The seven SIMT GEMM launches + three normalisations they replace moved 4 096 x 256 floats each and were
+// launch/latency-bound (24 us apiece, profiles/r01).  Thread c of a 256-thread block owns output channel c: its 64-float
+// second-layer weight row lives in registers and is reused for every object the block visits; the 64 hidden units of
+// eight objects at a time are staged in shared memory.  Same operation order as linear_simt (fma chain over k, then bias).
+struct SideEncoders {
+  const float* w1[3]; const float* b1[3]; const float* w2[3]; const float* b2[3];  // w1 [64, ld 4], w2 [256, 64]
+};
+
+__global__ void __launch_bounds__(256) side_encoders_kernel(const float* __restrict__ meta, int n, SideEncoders w, float* __restrict__ cat) {
+  constexpr int OB = 8;
+  __shared__ float hid[OB][64];
+  __shared__ float red[8][OB];
+  const int c = threadIdx.x, lane = c & 31, wp = c >> 5;
+  const float mean = static_cast<float>(1826.6844940968194), std_ = static_cast<float>(2516.8905096993817);
+  for (int enc = 0; enc < 3; ++enc) {
+    float w2r[64];
+#pragma unroll
+    for (int k = 0; k < 64; k += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(w.w2[enc] + c * 64 + k));
+      w2r[k] = v.x; w2r[k + 1] = v.y; w2r[k + 2] = v.z; w2r[k + 3] = v.w;
+    }
+    const float b2c = __ldg(w.b2[enc] + c);
+    const int h = c & 63;
+    const float4 w1h = __ldg(reinterpret_cast<const float4*>(w.w1[enc] + h * 4));
+    const float b1h = __ldg(w.b1[enc] + h);
+    for (int o0 = blockIdx.x * OB; o0 < n; o0 += gridDim.x * OB) {
+#pragma unroll
+      for (int pass = 0; pass < OB / 4; ++pass) {  // 256 threads = 4 objects x 64 hidden units per pass
+        const int ol = pass * 4 + (c >> 6), o = o0 + ol;
+        float x = 0.f;
+        if (o < n) {
+          const float* m = meta + static_cast<long>(o) * 7;
+          if (enc == 2) {
+            x = fmaf(__fdiv_rn(__fsub_rn(m[6], mean), std_), w1h.x, 0.f);  // (count - mean) / std (object_encoder.py:141-143)
+          } else {
+            x = fmaf(m[enc * 3 + 0], w1h.x, 0.f);
+            x = fmaf(m[enc * 3 + 1], w1h.y, x);
+            x = fmaf(m[enc * 3 + 2], w1h.z, x);
+          }
+          x = fmaxf(x + b1h, 0.f);
+        }
+        hid[ol][h] = x;
+      }
+      __syncthreads();
+      float acc[OB];
+#pragma unroll
+      for (int ol = 0; ol < OB; ++ol) acc[ol] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 64; ++k)
+#pragma unroll
+        for (int ol = 0; ol < OB; ++ol) acc[ol] = fmaf(hid[ol][k], w2r[k], acc[ol]);
+#pragma unroll
+      for (int ol = 0; ol < OB; ++ol) {
+        acc[ol] = fmaxf(acc[ol] + b2c, 0.f);
+        const float ss = warp_sum(acc[ol] * acc[ol]);
+        if (lane == 0) red[wp][ol] = ss;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int ol = 0; ol < OB; ++ol) {
+        if (o0 + ol >= n) break;
+        float ss = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ss += red[q][ol];
+        const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize
+        cat[static_cast<long>(o0 + ol) * 1024 + 256 * (enc + 1) + c] = acc[ol] * inv;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+cudaError_t side_encoders(const float* meta, int n_obj, const float* const* w1, const float* const* b1, const float* const* w2, const float* const* b2,
+                          float* cat, cudaStream_t st, Launches* lc) {
+  if (n_obj <= 0) return cudaSuccess;
+  if (lc) lc->n++;
+  SideEncoders w;
+  for (int i = 0; i < 3; ++i) { w.w1[i] = w1[i]; w.b1[i] = b1[i]; w.w2[i] = w2[i]; w.b2[i] = b2[i]; }
+  const int batches = (n_obj + 7) / 8;
+  const int grid = batches < 296 ? batches : 296;
+  side_encoders_kernel<<<grid, 256, 0, st>>>(meta, n_obj, w, cat);
+  return cudaGetLastError();
+}
+
 __global__ void add_rows_kernel(const float4* __restrict__ a, const float4* __restrict__ b, float4* __restrict__ y, long n4) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
