@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 MASKS="${MASKS:-0 1 2 6 8 14 15 16 32 47}"
-timeout 900 ncu --profile-from-start off -k regex:sa_fused --metrics gpu__time_duration.sum --clock-control none --csv \
+timeout 900 ncu --profile-from-start off -k regex:${KPAT:-sa_fused} --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/sa_bisect.csv python scripts/sa_bisect.py $MASKS > gpurun_out/sa_bisect.log 2>&1; echo "rc=$?"
 python - <<PY
 import csv

@@ -7,7 +7,7 @@ from text2loc_b200.engine import Engine
 
 eng = Engine("cuda:0")
 eng.load_state_dict(synth.make_state_dict(0))
-pts, meta, ptr = synth.make_packed_cells(1, 256, 8)
+pts, meta, ptr = synth.make_packed_cells(1, 512, 8)
 pts, meta = torch.from_numpy(pts).cuda(), torch.from_numpy(meta).cuda()
 eng.encode_cells(pts, meta, ptr)
 torch.cuda.synchronize()

@@ -33,6 +33,8 @@
 // issuer, 2 = TMEM allocator, 4..7 = epilogue (SegMax: one centroid per TMEM lane quadrant), 8..15 =
 // gather.  Pipelines: object buffers full/empty (TMA <-> gather), A ring full/empty (gather <-> MMA),
 // TMEM accumulators full/empty (MMA <-> epilogue).
+#include <cstdlib>
+
 #include "ops.h"
 #include "umma_gemm.cuh"
 #include "gemm_epilogues.cuh"
@@ -54,6 +56,7 @@ struct SaObjParams {
   const float* Wp;
   const float* b1;
   int n_obj;
+  int dbg;  // timing bisect only (T2L_SA_DBG bitmask; results are then wrong): 1 no proxy fence, 2 no output stores, 4 no side loads
 };
 
 template <int C1, int C2, int P, int M, int POS_STRIDE>
@@ -76,9 +79,12 @@ struct SaObjCfg {
   static constexpr int CNT_BYTES = M;
   static constexpr int OBJ_BYTES = PX_BYTES + POS_BYTES + CPOS_BYTES + NBR_BYTES + CNT_BYTES;  // every part a multiple of 16
   static constexpr int NOBJ = (B_RES_BYTES + 2 * OBJ_BYTES + 3 * A_BYTES) <= 190 * 1024 ? 2 : 1;
-  // A ring: an even number of slots, slot parity = owning gather group (each slot then has ONE producer whose waits
-  // on its empty barrier are consecutive phases; a parity wait from a second producer could pass one phase early)
-  static constexpr int STAGES = (B_RES_BYTES + NOBJ * OBJ_BYTES + 4 * A_BYTES) <= 200 * 1024 ? 4 : 2;
+  // A ring: four slots where they fit (slot parity = owning gather group), else three.  With three slots the two groups
+  // alternate on every slot; a parity wait is still unambiguous because the MMA warp consumes items in order: when a group
+  // waits for slot s of item u (previous use: item u-3) it has already filled u-2, whose slot could only be free after
+  // the MMAs of u-5 -- hence of u-6, the use before the one it waits for -- had completed.  So the barrier is never more
+  // than one phase behind the waiter (and cannot be ahead: the next phase needs the item the waiter has not built yet).
+  static constexpr int STAGES = (B_RES_BYTES + NOBJ * OBJ_BYTES + 4 * A_BYTES) <= 200 * 1024 ? 4 : 3;
   static constexpr int ACC_COLS = MH * 128;     // accumulator of one tile: [128 channels] x [128 edge rows] per half
   static constexpr int NACC = 512 / ACC_COLS;
   static constexpr int TMEM_COLS = NACC * ACC_COLS;
@@ -266,7 +272,8 @@ sa_obj_kernel(const __grid_constant__ CUtensorMap tm_b, const SaObjParams p, con
 #pragma unroll
         for (int h = 0; h < Cfg::MH; ++h)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) dst[h][c] = (tile < n_tiles) ? __ldg(ep.side + (g0 + c) * C2 + h * 128 + ew * 32 + lane) : 0.f;
+          for (int c = 0; c < 4; ++c)
+            dst[h][c] = (tile < n_tiles && !(p.dbg & 4)) ? __ldg(ep.side + (g0 + c) * C2 + h * 128 + ew * 32 + lane) : 0.f;
       };
 #pragma unroll
       for (int a = 0; a < kSideAhead; ++a) load_side(a, side_q[a]);
@@ -289,7 +296,7 @@ sa_obj_kernel(const __grid_constant__ CUtensorMap tm_b, const SaObjParams p, con
           const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
           // bias and ReLU commute with the max over edges (per-channel constant, monotonic rounding)
           const float keep = fmaxf(fmaxf(mx + bias[q >> 2], 0.f), side_q[0][q >> 2][q & 3]);
-          ep.out[(g0 + (q & 3)) * C2 + (q >> 2) * 128 + ew * 32 + lane] = round_tf32(keep);
+          if (!(p.dbg & 2) || keep == 12345.f) ep.out[(g0 + (q & 3)) * C2 + (q >> 2) * 128 + ew * 32 + lane] = round_tf32(keep);
         }
         tc_fence_before();
         __syncwarp();
@@ -385,13 +392,13 @@ sa_obj_kernel(const __grid_constant__ CUtensorMap tm_b, const SaObjParams p, con
             *reinterpret_cast<uint4*>(abase + r * 128 + ((sub ^ (r & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
           }
           if (!kTileMode) {
-            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
+            if (!(p.dbg & 1)) fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_bar[stage]);
           }
         }
         if (kTileMode) {
-          fence_proxy_async();
+          if (!(p.dbg & 1)) fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
 #pragma unroll
@@ -423,7 +430,8 @@ static cudaError_t launch_sa_obj(const SaObj& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  SaObjParams p{a.Px16, a.dense_pos, a.cpos, a.nbr, a.cnt, a.Wp, a.b1, a.n_obj};
+  const char* dbg_env = getenv("T2L_SA_DBG");
+  SaObjParams p{a.Px16, a.dense_pos, a.cpos, a.nbr, a.cnt, a.Wp, a.b1, a.n_obj, dbg_env ? atoi(dbg_env) : 0};
   SaObjOut ep{a.out, a.b2, a.side};
   const int grid = a.n_obj < tma_api().num_sms ? a.n_obj : tma_api().num_sms;
   sa_obj_kernel<C1, C2, P, M, POS_STRIDE><<<grid, kSaObjThreads, Cfg::SMEM, st>>>(tb, p, ep);
