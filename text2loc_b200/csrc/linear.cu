@@ -72,8 +72,8 @@ cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
 __global__ void split_tf32_kernel(const float* __restrict__ x, long ldx, float* __restrict__ planes, long rows, int K4) {
   const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= rows * K4) return;
-  const long r = i / K4;
-  const int c = static_cast<int>(i % K4);
+  const long r = (i < (1L << 31)) ? static_cast<long>(static_cast<unsigned>(i) / static_cast<unsigned>(K4)) : i / K4;  // 32-bit divide when it fits
+  const int c = static_cast<int>(i - r * K4);
   const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + 4 * c);
   float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
   float4 lo = make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));

@@ -120,12 +120,13 @@ __global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict_
                                                         int n_heads, float scale, int round_out) {
   constexpr int R = HD / 32;
   constexpr int U = 4;
-  const long wid = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  // 32-bit index math: the 64-bit runtime divisions this replaced cost more instructions than the attention itself
+  const unsigned wid = blockIdx.x * 8u + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (wid >= n_rows_total * n_heads) return;
-  const int h = static_cast<int>(wid % n_heads);
-  const long row = wid / n_heads;  // seq * S + i
-  const long seq0 = (row / S) * S;
+  if (wid >= static_cast<unsigned>(n_rows_total) * static_cast<unsigned>(n_heads)) return;
+  const int h = static_cast<int>(wid % static_cast<unsigned>(n_heads));
+  const long row = wid / static_cast<unsigned>(n_heads);  // seq * S + i
+  const long seq0 = static_cast<long>((static_cast<unsigned>(row) / static_cast<unsigned>(S)) * static_cast<unsigned>(S));
   const long ld = 3L * d;
   const float* q = qkv + row * ld + h * HD;
   const float* kbase = qkv + seq0 * ld + d + h * HD + lane;
@@ -183,6 +184,7 @@ cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int
   if (lc) lc->n++;
   const long rows = static_cast<long>(n_seq) * S;
   const int hd = d / n_heads;
+  if (rows * n_heads >= (1L << 31)) return cudaErrorInvalidValue;
   const unsigned grid = static_cast<unsigned>((rows * n_heads + 7) / 8);
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
   if (hd == 64) mha_small_kernel<64><<<grid, 256, 0, st>>>(qkv, out, rows, S, d, n_heads, scale, round_out);
