@@ -69,6 +69,11 @@ struct t2l_engine {
                              // operand bytes); T2L_TEXT_TF32=1 selects the tf32 path for A/B checks
   float* pooled = nullptr;   // [pooled_cap, 1024] max-over-tokens sentence features between the two text stages
   size_t pooled_cap = 0;
+  // pinned staging ring for the per-chunk index arrays of encode_cells: a pageable cudaMemcpyAsync larger than 64 KB
+  // serialises the host with the stream, so the host could not queue chunk k+1 while chunk k ran (encode times then
+  // varied 60 -> 95 ms between identical runs)
+  struct HostStage { int32_t* ptr = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; } stage[4];
+  unsigned stage_next = 0;
 };
 
 static int fail(t2l_engine* e, const char* fmt, ...) {
@@ -149,6 +154,7 @@ extern "C" void t2l_destroy(t2l_engine* e) {
   for (auto& kv : e->w) { cudaFree(kv.second.dev); cudaFree(kv.second.dev16); }
   cudaFree(e->arena.base);
   cudaFree(e->pooled);
+  for (auto& hs : e->stage) { if (hs.ptr) cudaFreeHost(hs.ptr); if (hs.ev) cudaEventDestroy(hs.ev); }
   cudaFree(e->db.planes);
   cudaFree(e->db.max_norm);
   free_search_work(e);
@@ -369,7 +375,17 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
   const float* p = pts + static_cast<size_t>(o0) * kPoints * 6;
 
   // self-loop source of each object (PyG add_self_loops on per-cell indices) + local cell_ptr
-  std::vector<int32_t> host(2 * static_cast<size_t>(n) + B + 1);
+  const size_t host_n = 2 * static_cast<size_t>(n) + B + 1;
+  auto& hs = e->stage[e->stage_next++ % 4];
+  if (hs.used) CU(cudaEventSynchronize(hs.ev));  // the copy that last read this buffer has finished
+  if (hs.cap < host_n) {
+    if (hs.ptr) CU(cudaFreeHost(hs.ptr));
+    hs.ptr = nullptr;
+    CU(cudaMallocHost(reinterpret_cast<void**>(&hs.ptr), (host_n + 1024) * sizeof(int32_t)));
+    hs.cap = host_n + 1024;
+  }
+  if (!hs.ev) CU(cudaEventCreateWithFlags(&hs.ev, cudaEventDisableTiming));
+  int32_t* host = hs.ptr;
   for (int c = c0; c < c1; ++c)
     for (int o = cell_ptr[c]; o < cell_ptr[c + 1]; ++o) {
       const int b = o - cell_ptr[c];
@@ -377,8 +393,10 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
       host[n + (o - o0)] = b & 1;
     }
   for (int c = c0; c <= c1; ++c) host[2 * static_cast<size_t>(n) + (c - c0)] = cell_ptr[c] - o0;
-  int32_t* d_host = a.get<int32_t>(host.size());
-  CU(cudaMemcpyAsync(d_host, host.data(), host.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  int32_t* d_host = a.get<int32_t>(host_n);
+  CU(cudaMemcpyAsync(d_host, host, host_n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CU(cudaEventRecord(hs.ev, st));
+  hs.used = true;
   const int32_t* loop_src = d_host;
   const int32_t* loop_half = d_host + n;
   const int32_t* cell_ptr_dev = d_host + 2 * static_cast<size_t>(n);
