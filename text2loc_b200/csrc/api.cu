@@ -60,8 +60,8 @@ struct t2l_engine {
   SearchDb db;
   SearchWork sw{};
   size_t sw_planes_rows = 0;
-  int obj_chunk = 8192;      // objects per encode chunk (cell-aligned); 2048 -> 4096 -> 8192 is +9 % / +5 % cells/s (fuller grids for the small
-                             // kernels), ~24 GB of workspace
+  int obj_chunk = 16384;     // objects per encode chunk (cell-aligned); 2048 -> 4096 -> 8192 -> 16384 is +9 % / +5 % / +4 % cells/s (fuller
+                             // grids for the small kernels), ~48 GB of workspace (T2L_OBJ_CHUNK to change)
   bool fused_sa = true;      // sa_fused.cu; false = v1 edge_gather -> H -> SegMax GEMM (kept for A/B checks, T2L_UNFUSED_SA=1)
   bool obj_sa = true;        // sa_obj.cu (object-resident, fp16 operands); T2L_SA_TF32=1 selects sa_fused.cu (tf32, global gathers)
   int tok_chunk = 32768;     // tokens per text chunk (sentence-aligned)
