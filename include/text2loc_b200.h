@@ -50,7 +50,7 @@ int t2l_finalize_weights(t2l_engine* e);
 /* CellRetrievalNetwork.encode_objects (models/cell_retrieval.py:65-110) = PointNet2 features2
  * (models/pointcloud/pointnet2.py:80-90) -> ObjectEncoder.forward (models/object_encoder.py:92-149)
  * -> intra-cell attention, max over slots, L2 normalise.
- *   pts          device f32 [n_objects, 256, 6]   xyz | rgb of each object's 256-sample
+ *   pts          device f32 [n_objects, 256, 6]   xyz | rgb of each object's 256-sample (16-byte aligned)
  *   meta         device f32 [n_objects, 7]        mean rgb | centre | raw point count
  *   cell_ptr     HOST   i32 [n_cells + 1]         object range of each cell
  *   out          device f32 [n_cells, 256]        unit rows */

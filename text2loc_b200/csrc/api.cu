@@ -564,6 +564,7 @@ static int encode_cells_impl(t2l_engine* e, const float* pts, const float* meta,
 extern "C" int t2l_encode_cells(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr_host, int n_cells, float* out,
                                 void* stream) {
   if (!pts || !meta || !out) return fail(e, "encode_cells: NULL buffer");
+  if (reinterpret_cast<uintptr_t>(pts) & 15) return fail(e, "encode_cells: pts must be 16-byte aligned (bulk TMA copies read it)");
   return encode_cells_impl(e, pts, meta, cell_ptr_host, n_cells, out, nullptr, static_cast<cudaStream_t>(stream));
 }
 
