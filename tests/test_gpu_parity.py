@@ -239,6 +239,70 @@ def test_merge_topk_is_shard_count_independent(eng):
         assert np.abs(sc.cpu().numpy() - osc).max() < 1e-12
 
 
+# ---- BASELINE.json's full sizes: properties that do not need the oracle to scale ------------------------
+
+def test_search_full_size_properties(eng):
+    """configs[2]: 100 000 rows x 32 768 queries.  The fp64 oracle only checks a sample; the rest is covered by
+    properties: scores are the exact fp64 dots of the returned rows, lists are sorted by (score desc, row asc),
+    the call is idempotent, and 8 row shards merged equal the unsharded search bit for bit."""
+    from oracle import restate
+    from text2loc_b200 import synth
+
+    N, NQ, K = 100000, 32768, 10
+    D = synth.make_unit_rows(101, N)
+    Q = synth.make_unit_rows(102, NQ)
+    Dt, Qt = torch.from_numpy(D).cuda(), torch.from_numpy(Q).cuda()
+    eng.db_build(Dt)
+    idx, sc, nfb = eng.search_topk(Qt, K)
+    idx2, sc2, _ = eng.search_topk(Qt, K)
+    assert torch.equal(idx, idx2) and torch.equal(sc, sc2)  # idempotent
+    assert int(idx.min()) >= 0 and int(idx.max()) < N
+    # sortedness: score non-increasing, row index increasing inside a tie
+    d = sc[:, 1:] - sc[:, :-1]
+    assert bool((d <= 0).all())
+    assert bool(((d < 0) | (idx[:, 1:] > idx[:, :-1])).all())
+    # returned scores are the fp64 dots of the returned rows (any summation order: 1e-12)
+    g = Dt[idx.reshape(-1)].double().reshape(NQ, K, 256)
+    exact = torch.einsum("qkd,qd->qk", g, Qt.double())
+    assert float((exact - sc).abs().max()) < 1e-12
+    # oracle on a sample of queries
+    pick = np.random.default_rng(0).choice(NQ, 48, replace=False)
+    oidx, _ = restate.search_topk(D, Q[pick], K)
+    assert (idx[torch.from_numpy(pick).cuda()].cpu().numpy() == oidx).all()
+    # 8 shards (BASELINE's 8 x 12 500 rows) merged == unsharded
+    bounds = np.linspace(0, N, 9).astype(int)
+    idxs, scs = [], []
+    for gi in range(8):
+        eng.db_build(Dt[bounds[gi]:bounds[gi + 1]], row_offset=int(bounds[gi]))
+        i, s, _ = eng.search_topk(Qt, K)
+        idxs.append(i)
+        scs.append(s)
+    midx, msc = eng.merge_topk(torch.stack(idxs), torch.stack(scs))
+    assert torch.equal(midx, idx) and torch.equal(msc, sc)
+    print(f"\n100000 x 32768: {int(nfb)} queries took the second pass; sorted, idempotent, exact, shard-independent")
+
+
+def test_encode_cells_full_size_properties(eng, state_dict):
+    """3 000 cells x 8 objects (more than one 16 384-object chunk): cells are independent units, so encoding them in
+    reverse order must give the same rows bit for bit (chunk boundaries fall elsewhere), rows are unit vectors, and a
+    sample agrees with the oracle."""
+    from oracle import restate
+    from text2loc_b200 import synth
+
+    n_cells = 3000
+    pts, meta, ptr = synth.make_packed_cells(77, n_cells, 8)
+    fwd = eng.encode_cells(pts, meta, ptr)
+    order = np.arange(n_cells)[::-1].copy()
+    obj = (order[:, None] * 8 + np.arange(8)[None, :]).reshape(-1)
+    rev = eng.encode_cells(pts[obj], meta[obj], ptr)
+    assert torch.equal(rev.flip(0), fwd)
+    assert float((fwd.norm(dim=1) - 1).abs().max()) < 1e-5
+    sample = [0, 1499, 2047, 2048, 2999]  # includes the cells either side of the chunk boundary
+    sobj = np.concatenate([np.arange(c * 8, c * 8 + 8) for c in sample])
+    want = restate.encode_cells(state_dict, pts[sobj], meta[sobj], np.arange(0, 8 * len(sample) + 1, 8, dtype=np.int32)).numpy()
+    assert row_rel_err(fwd.cpu().numpy()[sample], want) < EMB_TOL
+
+
 # ---- drop-in API ---------------------------------------------------------------------------------------
 
 def make_model(state_dict, fake_seed=0):
