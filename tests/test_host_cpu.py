@@ -96,3 +96,23 @@ def test_packed_generator_matches_object_generator_statistics():
     assert 0 <= pts[:, :, 3:].min() and pts[:, :, 3:].max() <= 1 and 30 <= meta[:, 6].min() and meta[:, 6].max() <= 5000
     span = pts[:, :, :3].max(axis=1) - pts[:, :, :3].min(axis=1)
     assert span.max() < 0.31  # objects are smaller than every ball-query radius's diameter: the 32-neighbour cap is hit
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path through the oracle port) prints one JSON line with the
+    keys the driver reads; it needs no GPU."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "queries/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1
+    assert line["e2e"] == {"value": line["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert "workload" in line["config"]
