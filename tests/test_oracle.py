@@ -149,3 +149,48 @@ def test_restatement_matches_reference_modules_other_seed():
     pts, meta, ptr = dataio.pack_cells(cells, batches)
     got = restate.encode_cells(sd, pts, meta, ptr)
     assert (got - want).abs().max() < 2e-6
+
+
+# ---- precision plan: operand rounding emulated on the CPU -----------------------------
+
+def _emulated_text_error(state_dict, rounder, monkeypatch):
+    """Row-relative error of the text embeddings when both operands of every Linear of the TOKEN layer are passed
+    through `rounder` (what a reduced-precision tensor-core GEMM with fp32 accumulation does); everything else fp32."""
+    import torch.nn.functional as F_
+
+    t5 = synth.make_t5_features(5, 16, 6, 12)
+    want = restate.encode_text(state_dict, t5, 6).numpy()
+    real_linear = F_.linear
+    real_layer = restate.encoder_layer
+
+    def rounded_linear(x, w, b=None):
+        return real_linear(rounder(x), rounder(w), b)
+
+    def layer(sd, prefix, x, n_heads):
+        if "intra_module" in prefix:  # the token layer carries 99 % of the text head's FLOPs
+            monkeypatch.setattr(restate.F, "linear", rounded_linear)
+            try:
+                return real_layer(sd, prefix, x, n_heads)
+            finally:
+                monkeypatch.setattr(restate.F, "linear", real_linear)
+        return real_layer(sd, prefix, x, n_heads)
+
+    monkeypatch.setattr(restate, "encoder_layer", layer)
+    got = restate.encode_text(state_dict, t5, 6).numpy()
+    monkeypatch.setattr(restate, "encoder_layer", real_layer)
+    return float((np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)).max())
+
+
+def test_precision_plan_token_layer_operand_rounding(state_dict, monkeypatch):
+    """fp16 and tf32 (round-to-nearest) operands have the same 11-bit significand: both keep the text embeddings well
+    inside the 1e-3 tolerance; bf16 operands (8 bits) do not -- which is why the engine's token layer is fp16/tf32."""
+    def tf32_rna(t):
+        return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    e_f16 = _emulated_text_error(state_dict, lambda t: t.half().float(), monkeypatch)
+    e_tf32 = _emulated_text_error(state_dict, tf32_rna, monkeypatch)
+    e_bf16 = _emulated_text_error(state_dict, lambda t: t.bfloat16().float(), monkeypatch)
+    print(f"\ntoken-layer operand rounding, text embedding error: fp16 {e_f16:.2e}, tf32 {e_tf32:.2e}, bf16 {e_bf16:.2e}")
+    assert e_f16 < 5e-4 and e_tf32 < 5e-4
+    assert abs(e_f16 - e_tf32) < 2e-4
+    assert e_bf16 > 1e-3
