@@ -194,3 +194,49 @@ def test_precision_plan_token_layer_operand_rounding(state_dict, monkeypatch):
     assert e_f16 < 5e-4 and e_tf32 < 5e-4
     assert abs(e_f16 - e_tf32) < 2e-4
     assert e_bf16 > 1e-3
+
+
+def _emulated_cell_error(state_dict, r16, monkeypatch):
+    """Row-relative error of the cell embeddings when the set-abstraction and global-abstraction MLPs use the engine's
+    rounding points (sa_obj.cu / GA on fp16 operands): Px = r16(W1x x + b1), edge activation r16(relu(Px + W1p.d)),
+    W2 r16, fp32 accumulation, layer outputs rounded to tf32; everything else fp32."""
+    from text2loc_b200 import weights
+
+    fw = {k: torch.from_numpy(v) for k, v in weights.engine_weights(state_dict).items()}
+    real_mlp = restate.mlp
+
+    def tf32(t):
+        return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    def mlp(sd, prefix, x, n_layers, last_relu=True):
+        if "point_conv.local_nn" in prefix:
+            lvl = prefix.split(".sa")[1][0]
+            w1x, w1p, b1 = fw[f"sa{lvl}.w1x"], fw[f"sa{lvl}.w1p"], fw[f"sa{lvl}.b1"][0]
+            w2, b2 = fw[f"sa{lvl}.w2"], fw[f"sa{lvl}.b2"][0]
+            c = w1x.shape[1]
+            xin = x[..., :c] if lvl == "1" else tf32(x[..., :c])  # levels 2/3: tf32 GEMM on the previous level's output
+            px = r16(xin @ (w1x if lvl == "1" else tf32(w1x)).T + b1)
+            a = r16(torch.relu(px + x[..., c:] @ w1p.T))
+            return tf32(torch.relu(a @ r16(w2).T + b2))
+        if ".ga.mlp" in prefix:
+            g1 = r16(torch.relu(r16(x) @ r16(fw["ga.w1"]).T + fw["ga.b1"][0]))
+            return tf32(torch.relu(g1 @ r16(fw["ga.w2"]).T + fw["ga.b2"][0]))
+        return real_mlp(sd, prefix, x, n_layers, last_relu)
+
+    cells = synth.make_cell_objects(21, 6, [3, 8, 1, 5, 12, 2], max_raw=400)
+    pts, meta, ptr = synth.pack_cells(cells, 21)
+    want = restate.encode_cells(state_dict, pts, meta, ptr).numpy()
+    monkeypatch.setattr(restate, "mlp", mlp)
+    got = restate.encode_cells(state_dict, pts, meta, ptr).numpy()
+    monkeypatch.setattr(restate, "mlp", real_mlp)
+    return float((np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)).max())
+
+
+def test_precision_plan_set_abstraction_operand_rounding(state_dict, monkeypatch):
+    """fp16 Px / edge activations / W2 (the object-resident PointConv kernel) keep the cell embeddings inside the
+    tolerance with a wide margin; the same rounding points in bf16 cost an order of magnitude more."""
+    e_f16 = _emulated_cell_error(state_dict, lambda t: t.half().float(), monkeypatch)
+    e_bf16 = _emulated_cell_error(state_dict, lambda t: t.bfloat16().float(), monkeypatch)
+    print(f"\nset-abstraction operand rounding, cell embedding error: fp16 {e_f16:.2e}, bf16 {e_bf16:.2e}")
+    assert e_f16 < 5e-4
+    assert e_bf16 > 3 * e_f16
