@@ -271,7 +271,8 @@ static cudaError_t launch_sa(const SaFused& a, cudaStream_t st) {
   using Cfg = SaCfg<C1, BLOCK_N>;
   CUtensorMap tb;
   if (make_operand_map(&tb, a.W2, false, BLOCK_N, C1, a.ldw2, BLOCK_N)) return cudaErrorInvalidValue;
-  static bool configured = false;
+  static bool configured_dev[64] = {};  // the attribute is per device: one flag per device ordinal
+  bool& configured = configured_dev[current_device() & 63];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(sa_fused_kernel<C1, BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return e;

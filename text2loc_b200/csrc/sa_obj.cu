@@ -424,7 +424,8 @@ static cudaError_t launch_sa_obj(const SaObj& a, cudaStream_t st) {
   using Cfg = SaObjCfg<C1, C2, P, M, POS_STRIDE>;
   CUtensorMap tb;
   if (make_operand_map(&tb, a.W2h, kOpF16, C2, C1, C1, Cfg::MH * 128 > 256 ? 256 : Cfg::MH * 128)) return cudaErrorInvalidValue;
-  static bool configured = false;
+  static bool configured_dev[64] = {};  // the attribute is per device: one flag per device ordinal
+  bool& configured = configured_dev[current_device() & 63];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(sa_obj_kernel<C1, C2, P, M, POS_STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return e;

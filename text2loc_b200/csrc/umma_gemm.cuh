@@ -299,11 +299,18 @@ inline int make_operand_map(CUtensorMap* tm, const void* base, int type, long ro
   return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
 template <class Cfg, class Epi>
 cudaError_t launch_umma_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmShape& shape,
                              const typename Epi::Params& ep, cudaStream_t stream) {
   constexpr int smem = Cfg::template smem_bytes<Epi>();
-  static bool configured = false;
+  static bool configured_dev[64] = {};  // the attribute is per device: one flag per device ordinal
+  bool& configured = configured_dev[current_device() & 63];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<Cfg, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
