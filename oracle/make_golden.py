@@ -12,6 +12,8 @@ on seeded synthetic inputs with the seeded synthetic weights of text2loc_b200/sy
   eval_e2e.npz      training.coarse.eval_epoch(return_encodings=True) + evaluation.coarse.run_coarse
                     on a 24-cell / 40-pose synthetic dataset
   search_small.npz  the training/coarse.py:119-125 loop on random unit rows
+  fine_small.npz    CrossMatch.forward (models/cross_matcher.py:83-129, the fine stage = SURVEY.md section 8f row 1) on
+                    5 cells padded to 16 objects x 6 hints: offsets [5, 2]   (python -m oracle.make_golden fine)
 """
 from __future__ import annotations
 
@@ -66,6 +68,38 @@ def e2e_dataset():
     counts = [int(c) for c in np.random.default_rng(8).integers(1, 13, 24)]
     counts[5] = 31
     return synth.SynthCoarseDataset(seed=3, n_cells=24, n_poses=40, n_obj=counts, max_raw=400)
+
+
+def fine_case():
+    """5 top-k cells padded to pad_size = 16 objects, one 6-hint description per cell."""
+    cells = synth.make_cell_objects(31, 5, [16] * 5, max_raw=500)
+    np.random.seed(7)
+    fixed = dataio.FixedPoints(256)
+    batches = [dataio.batch_object_points(objs, fixed) for objs in cells]
+    rng = np.random.default_rng(6)
+    texts = [" ".join(
+        f"The pose is {synth.DIRECTIONS[rng.integers(5)]} of a {synth.COLOR_WORDS[rng.integers(8)]} {synth.CLASS_WORDS[rng.integers(22)]}."
+        for _ in range(6)) for _ in range(5)]
+    return cells, batches, texts
+
+
+def main_fine():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    sd = synth.make_fine_state_dict(WEIGHT_SEED)
+    model = reference_run.build_fine_model(sd, fake_seed=FAKE_T5_SEED)
+    cells, batches, texts = fine_case()
+    with torch.no_grad():
+        offsets = model(cells, texts, batches).numpy()
+    pts, meta, cell_ptr = dataio.pack_cells(cells, batches)
+    feat, n_sent = fake_t5.FakeFrontend(FAKE_T5_SEED)(texts)
+    got = restate.fine_offsets(sd, pts, meta, cell_ptr, feat, n_sent).numpy()
+    print("fine: restatement vs reference max abs diff", np.abs(got - offsets).max())
+    np.savez_compressed(
+        os.path.join(GOLDEN_DIR, "fine_small.npz"),
+        pts=pts.numpy(), meta=meta.numpy(), cell_ptr=cell_ptr.numpy(), texts=np.array(texts), offsets=offsets,
+        t5_digest=digest(feat.numpy()), n_sent=n_sent, weight_seed=WEIGHT_SEED, fake_t5_seed=FAKE_T5_SEED,
+    )
+    print("fine_small.npz", os.path.getsize(os.path.join(GOLDEN_DIR, "fine_small.npz")))
 
 
 def main():
@@ -140,4 +174,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+
+    if len(sys.argv) > 1 and sys.argv[1] == "fine":
+        main_fine()
+    else:
+        main()

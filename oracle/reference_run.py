@@ -77,6 +77,32 @@ def load(fake_seed: int = 0):
     return _LOADED
 
 
+def fine_args(**over) -> argparse.Namespace:
+    """evaluation/args.py defaults of the fine stage (:41-46, :80-81) on top of the shared ones."""
+    return default_args(fine_embed_dim=128, fine_num_decoder_heads=4, fine_num_decoder_layers=2, pad_size=16, num_mentioned=6,
+                        fine_intra_module_num_heads=4, fine_intra_module_num_layers=1, **over)
+
+
+def build_fine_model(state_dict: dict, args=None, fake_seed: int = 0):
+    """The reference CrossMatch (models/cross_matcher.py:39-129) carrying `state_dict`."""
+    from text2loc_b200.synth import pointnet_state_dict
+
+    ref = load(fake_seed)
+    args = args or fine_args()
+    with contextlib.redirect_stdout(io.StringIO()):
+        from models.cross_matcher import CrossMatch
+    sd = {k: torch.as_tensor(np.asarray(v)) for k, v in state_dict.items()}
+    with tempfile.TemporaryDirectory() as tmp:
+        args.pointnet_path = os.path.join(tmp, "pointnet.pth")
+        torch.save(pointnet_state_dict(sd), args.pointnet_path)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = CrossMatch(ref["KNOWN_CLASS"], ref["COLOR_NAMES"], args)
+    res = model.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all("llm_model" in k for k in res.missing_keys), res.missing_keys
+    return model.eval()
+
+
 def build_model(state_dict: dict, args=None, fake_seed: int = 0):
     """The reference CellRetrievalNetwork carrying `state_dict` (numpy or torch values)."""
     from text2loc_b200.synth import pointnet_state_dict

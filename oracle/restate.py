@@ -234,6 +234,65 @@ def encode_text(sd, t5, n_sent: int, n_heads=4, chunk=256):
     return F.normalize(x.max(dim=0)[0])
 
 
+# ---- fine stage (models/cross_matcher.py:83-129), SURVEY.md section 8f row 1 -------------------------------
+
+def _mha(sd, prefix, q_in, kv_in, n_heads):
+    """nn.MultiheadAttention forward (no masks, eval): q_in [Lq, B, d], kv_in [Lk, B, d]."""
+    Lq, B, d = q_in.shape
+    Lk = kv_in.shape[0]
+    hd = d // n_heads
+    w, b = _t(sd, prefix + ".in_proj_weight"), _t(sd, prefix + ".in_proj_bias")
+    q = F.linear(q_in, w[:d], b[:d])
+    k = F.linear(kv_in, w[d:2 * d], b[d:2 * d])
+    v = F.linear(kv_in, w[2 * d:], b[2 * d:])
+    q = q.reshape(Lq, B, n_heads, hd).permute(1, 2, 0, 3)
+    k = k.reshape(Lk, B, n_heads, hd).permute(1, 2, 0, 3)
+    v = v.reshape(Lk, B, n_heads, hd).permute(1, 2, 0, 3)
+    att = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+    o = (att @ v).permute(2, 0, 1, 3).reshape(Lq, B, d)
+    return F.linear(o, _t(sd, prefix + ".out_proj.weight"), _t(sd, prefix + ".out_proj.bias"))
+
+
+def decoder_layer(sd, prefix, tgt, memory, n_heads):
+    """nn.TransformerDecoderLayer defaults (post-norm, ReLU, eps 1e-5, eval, no masks), inputs [L, B, d]
+    (models/cross_matcher.py:66-72, :113-115)."""
+    d = tgt.shape[-1]
+    ln = lambda x, n: F.layer_norm(x, (d,), _t(sd, f"{prefix}.{n}.weight"), _t(sd, f"{prefix}.{n}.bias"), 1e-5)
+    x = ln(tgt + _mha(sd, prefix + ".self_attn", tgt, tgt, n_heads), "norm1")
+    x = ln(x + _mha(sd, prefix + ".multihead_attn", x, memory, n_heads), "norm2")
+    f = F.linear(F.relu(F.linear(x, _t(sd, prefix + ".linear1.weight"), _t(sd, prefix + ".linear1.bias"))),
+                 _t(sd, prefix + ".linear2.weight"), _t(sd, prefix + ".linear2.bias"))
+    return ln(x + f, "norm3")
+
+
+@torch.no_grad()
+def fine_offsets(sd, pts, meta, cell_ptr, t5, n_hints: int, n_heads=4, n_layers=2):
+    """CrossMatch.forward (models/cross_matcher.py:83-129) on packed inputs: every cell holds the same number of
+    (padded) objects; t5 f32 [B*n_hints, L, 1024] are the hint sentences' T5 states.  Returns offsets [B, 2]."""
+    pts = torch.as_tensor(np.asarray(pts), dtype=torch.float32)
+    meta = torch.as_tensor(np.asarray(meta), dtype=torch.float32)
+    t5 = torch.as_tensor(np.asarray(t5), dtype=torch.float32)
+    cp = np.asarray(cell_ptr, dtype=np.int64)
+    B = len(cp) - 1
+    n_obj = int(cp[1] - cp[0])
+    assert (np.diff(cp) == n_obj).all(), "the fine stage pads every cell to pad_size objects"
+    # textual branch: LanguageEncoder(is_fine=True) = token layer, max over tokens, inter_mlp (language_encoder.py:130-140)
+    le = "language_encoder"
+    x = encoder_layer(sd, f"{le}.intra_module.0", t5.permute(1, 0, 2), n_heads)
+    hints = mlp(sd, f"{le}.inter_mlp", x.permute(1, 0, 2).max(dim=1)[0], 1, last_relu=False).view(B, n_hints, -1)
+    # 3D branch: ObjectEncoder at d = 128, per-object normalise (:98-108)
+    f2 = pointnet2_features2(sd, pts, cell_ptr)
+    obj = F.normalize(object_embeddings(sd, f2, meta), dim=-1).view(B, n_obj, -1)
+    # cascaded cross-attention (:113-121)
+    desc0, desc1 = obj.transpose(0, 1), hints.transpose(0, 1)
+    for i in range(n_layers):
+        desc0 = decoder_layer(sd, f"cross_objects.{i}", desc0, desc1, n_heads)
+        desc1 = decoder_layer(sd, f"cross_hints.{i}", desc1, desc0, n_heads)
+    h = desc1.max(dim=0)[0]
+    h = F.relu(F.linear(h, _t(sd, "mlp_offsets.0.weight"), _t(sd, "mlp_offsets.0.bias")))
+    return F.linear(h, _t(sd, "mlp_offsets.2.weight"), _t(sd, "mlp_offsets.2.bias"))
+
+
 # ---- search (training/coarse.py:81-125) -----------------------------------------------------
 
 def search_topk(cell_enc, text_enc, k: int):

@@ -48,6 +48,18 @@ def test_search_golden(golden):
     assert np.abs(sc - g["score"]).max() < 1e-14
 
 
+def test_fine_stage_golden(golden):
+    """Groundwork for SURVEY.md section 8f row 1 (the fine stage): the restatement of CrossMatch.forward is pinned to
+    the reference's own module (oracle/make_golden.py fine); no engine code consumes it yet."""
+    g = golden("fine_small.npz")
+    sd = synth.make_fine_state_dict(int(g["weight_seed"]))
+    feat, n_sent = fake_t5.FakeFrontend(int(g["fake_t5_seed"]))([str(t) for t in g["texts"]])
+    assert digest(feat.numpy()) == str(g["t5_digest"]) and n_sent == int(g["n_sent"])
+    out = restate.fine_offsets(sd, g["pts"], g["meta"], g["cell_ptr"], feat, n_sent).numpy()
+    assert out.shape == g["offsets"].shape == (5, 2)
+    assert np.abs(out - g["offsets"]).max() < 2e-6
+
+
 def test_eval_epoch_golden(state_dict, golden):
     from oracle.make_golden import e2e_dataset
 

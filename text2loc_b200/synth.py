@@ -94,6 +94,58 @@ def make_state_dict(seed: int = 0) -> dict:
     return sd
 
 
+FINE_EMBED_DIM = 128  # fine_embed_dim, evaluation/args.py:41
+FINE_PAD_SIZE = 16  # pad_size, evaluation/args.py:45
+
+
+def _decoder_layer(rng, sd, prefix, d, ffn):
+    """nn.TransformerDecoderLayer(d, H, dim_feedforward=ffn) key layout (models/cross_matcher.py:66-72)."""
+    for att in ("self_attn", "multihead_attn"):
+        sd[f"{prefix}.{att}.in_proj_weight"] = (rng.standard_normal((3 * d, d)) / np.sqrt(d)).astype(np.float32)
+        sd[f"{prefix}.{att}.in_proj_bias"] = (rng.standard_normal(3 * d) * 0.05).astype(np.float32)
+        _linear(rng, sd, f"{prefix}.{att}.out_proj", d, d)
+    _linear(rng, sd, prefix + ".linear1", ffn, d, gain=1.4)
+    _linear(rng, sd, prefix + ".linear2", d, ffn)
+    for n in ("norm1", "norm2", "norm3"):
+        sd[f"{prefix}.{n}.weight"] = rng.uniform(0.9, 1.1, d).astype(np.float32)
+        sd[f"{prefix}.{n}.bias"] = (rng.standard_normal(d) * 0.05).astype(np.float32)
+
+
+def make_fine_state_dict(seed: int = 0, n_decoder_layers: int = 2) -> dict:
+    """Random 'trained-like' weights under the key names of the reference's fine-stage model
+    ``CrossMatch.state_dict()`` (models/cross_matcher.py:39-78): ObjectEncoder and
+    LanguageEncoder(is_fine=True) at d = 128, the cascaded cross-attention decoder layers and the offset MLP."""
+    rng = np.random.default_rng([seed, 0xF17E])
+    d = FINE_EMBED_DIM
+    sd: dict = {}
+    pn = "object_encoder.pointnet"
+    _mlp(rng, sd, f"{pn}.sa1.point_conv.local_nn", [3 + 3, 32, 64])
+    _mlp(rng, sd, f"{pn}.sa2.point_conv.local_nn", [64 + 3, 128, 128])
+    _mlp(rng, sd, f"{pn}.sa3.point_conv.local_nn", [128 + 3, 256, 256])
+    _mlp(rng, sd, f"{pn}.ga.mlp", [256 + 3, 512, 1024])
+    _linear(rng, sd, f"{pn}.lin1", 512, 1024, gain=1.4)
+    _linear(rng, sd, f"{pn}.lin2", 256, 512, gain=1.4)
+    _linear(rng, sd, f"{pn}.class_classifier", NUM_CLASSES, 256)
+    _linear(rng, sd, f"{pn}.color_classifier", NUM_COLORS, 256)
+    oe = "object_encoder"
+    sd[f"{oe}.class_embedding.weight"] = rng.standard_normal((NUM_CLASSES + 1, d)).astype(np.float32)
+    sd[f"{oe}.color_embedding.weight"] = rng.standard_normal((NUM_COLORS, d)).astype(np.float32)
+    _mlp(rng, sd, f"{oe}.pos_encoder", [3, 64, d])
+    _mlp(rng, sd, f"{oe}.color_encoder", [3, 64, d])
+    _mlp(rng, sd, f"{oe}.num_encoder", [1, 64, d])
+    _mlp(rng, sd, f"{oe}.mlp_pointnet", [256, d])
+    _mlp(rng, sd, f"{oe}.mlp_merge", [4 * d, d])
+    le = "language_encoder"
+    _encoder_layer(rng, sd, f"{le}.intra_module.0", T5_DIM, 4 * T5_DIM)
+    _mlp(rng, sd, f"{le}.inter_mlp", [T5_DIM, d])
+    for i in range(n_decoder_layers):
+        _decoder_layer(rng, sd, f"cross_hints.{i}", d, 4 * d)
+        _decoder_layer(rng, sd, f"cross_objects.{i}", d, 4 * d)
+    _linear(rng, sd, "mlp_offsets.0", d // 2, d, gain=1.4)
+    _linear(rng, sd, "mlp_offsets.2", 2, d // 2)
+    return sd
+
+
 def pointnet_state_dict(sd: dict) -> dict:
     """The sub-dict ObjectEncoder.__init__ loads from args.pointnet_path (models/object_encoder.py:50)."""
     p = "object_encoder.pointnet."
