@@ -151,7 +151,7 @@ def cpu_reference_sample(sd, n_db: int, n_queries_total: int, text_q: int, searc
     import torch
 
     from oracle import restate
-    from text2loc_b200 import synth
+    import synth
 
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
@@ -178,7 +178,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from text2loc_b200 import synth
+    import synth
 
     wl = workload(args.gpus)
     n_db, nq = wl["cells_per_gpu"] * args.gpus, wl["queries_per_gpu"] * args.gpus
@@ -217,7 +217,8 @@ def run_engine_arm(args):
     import torch
     import torch.distributed as dist
 
-    from text2loc_b200 import CellRetrievalNetwork, synth
+    import synth
+    from text2loc_b200 import CellRetrievalNetwork
     from text2loc_b200 import distributed as t2ld
 
     rank = int(os.environ.get("RANK", "0"))

@@ -10,9 +10,14 @@
  *     Nothing throws across the ABI.
  *   - data buffers are CALLER-OWNED DEVICE memory unless a parameter says "host"; the engine
  *     owns weights, the prepared database planes and its workspace.
- *   - all work is enqueued on the caller's cudaStream_t (passed as void*); no hidden device
- *     synchronisation except where documented (t2l_finalize_weights, t2l_create).
+ *   - all work is enqueued on the caller's cudaStream_t (passed as void*).  Device-wide synchronisation
+ *     happens only in t2l_create, t2l_finalize_weights, t2l_destroy and when a call needs MORE workspace
+ *     than any call before it (the arena is re-allocated: cudaFree synchronises); t2l_reserve sizes the
+ *     workspace up front so that steady-state calls never do.
  *   - an engine is bound to one device and is not thread-safe; distinct engines are independent.
+ *     Every entry point switches to the engine's device and restores the caller's current device.
+ *   - the workspace is shared by all calls of an engine: calls issued on one stream are ordered by the
+ *     stream; a call on a different stream first waits (cudaStreamWaitEvent) for the previous call.
  *   - sm_100a only.  There is no CPU or other fallback: on a non-Blackwell device t2l_create fails.
  */
 #ifndef TEXT2LOC_B200_H
@@ -30,6 +35,7 @@ typedef struct t2l_engine t2l_engine;
 #define T2L_T5_DIM 1024      /* t5-large d_model, README.md:127 */
 #define T2L_NUM_POINTS 256   /* pointnet_numpoints, evaluation/args.py:58 */
 #define T2L_OBJECT_SLOTS 28  /* object_size, evaluation/args.py:68 */
+#define T2L_FINE_DIM 128     /* fine_embed_dim, evaluation/args.py:41 */
 #define T2L_MAX_TOPK 12      /* fast path; the reference uses max(top_k) = 10, evaluation/args.py:20 */
 
 /* Engine for CUDA device `device`.  Replaces CellRetrievalNetwork.__init__ + .to(device)
@@ -104,6 +110,21 @@ int t2l_search_topk_exact(t2l_engine* e, const float* Q, int nq, int k, int64_t*
  *   same (score desc, index asc) order, independent of the number of shards. */
 int t2l_merge_topk(t2l_engine* e, const int64_t* idx_all, const double* score_all, int n_shards, int nq, int k,
                    int64_t* out_idx, double* out_score, void* stream);
+
+/* Accuracy bookkeeping of eval_epoch / run_coarse for a whole query batch (training/coarse.py:131-150: top-k hit and
+ * close-by accuracy; evaluation/utils.py:31-54: calc_sample_accuracies).  For every query q and every k in top_k:
+ *   hit[q, k]       = target_row[q] in idx[q, 0:k]
+ *   within[q, k, t] = min(dists[q, 0:k]) <= threshs[t],  dists[q, j] = |query_xy[q] - cell_xy[idx[q, j]]| (float64,
+ *                     evaluated as numpy does: sqrt(dx*dx + dy*dy)); +inf for empty slots and, when scene codes are
+ *                     given, for rows of another scene
+ *   idx device i64 [nq, k];  target_row device i64 [nq] or NULL;  query_xy device f64 [nq, 2];  cell_xy device f64 [N, 2]
+ *   query_scene / cell_scene device i32 [nq] / [N], both or neither;  top_k HOST i32 [n_top] ascending (<= 8);
+ *   threshs HOST f64 [n_thr] (<= 8);  hit device u8 [nq, n_top], within device u8 [nq, n_top, n_thr], dists device
+ *   f64 [nq, k] -- any of the three may be NULL. */
+int t2l_topk_accuracy(t2l_engine* e, const int64_t* idx, int nq, int k, const int64_t* target_row, const double* query_xy,
+                      const double* cell_xy, const int32_t* query_scene, const int32_t* cell_scene,
+                      const int32_t* top_k_host, int n_top, const double* threshs_host, int n_thr,
+                      uint8_t* hit, uint8_t* within, double* dists, void* stream);
 
 /* Number of kernels this engine has launched since creation (bench.py's gpu_launches). */
 int64_t t2l_launch_count(const t2l_engine* e);

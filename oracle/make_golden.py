@@ -12,6 +12,8 @@ on seeded synthetic inputs with the seeded synthetic weights of text2loc_b200/sy
   eval_e2e.npz      training.coarse.eval_epoch(return_encodings=True) + evaluation.coarse.run_coarse
                     on a 24-cell / 40-pose synthetic dataset
   search_small.npz  the training/coarse.py:119-125 loop on random unit rows
+  eval_cfg1.npz     evaluation.coarse.run_coarse + eval_epoch(return_encodings=True) on BASELINE configs[0]: 1 000 cells x
+                    8 objects, 256 queries, seed 1, with the wall time of the reference's run   (python -m oracle.make_golden cfg1)
   fine_small.npz    CrossMatch.forward (models/cross_matcher.py:83-129, the fine stage = SURVEY.md section 8f row 1) on
                     5 cells padded to 16 objects x 6 hints: offsets [5, 2]   (python -m oracle.make_golden fine)
 """
@@ -26,7 +28,8 @@ import numpy as np
 import torch
 from torch.utils.data import DataLoader
 
-from text2loc_b200 import dataio, synth
+import synth
+from text2loc_b200 import dataio
 
 from . import fake_t5, reference_run, restate
 
@@ -100,6 +103,52 @@ def main_fine():
         t5_digest=digest(feat.numpy()), n_sent=n_sent, weight_seed=WEIGHT_SEED, fake_t5_seed=FAKE_T5_SEED,
     )
     print("fine_small.npz", os.path.getsize(os.path.join(GOLDEN_DIR, "fine_small.npz")))
+
+
+def cfg1_dataset():
+    """BASELINE.json configs[0] / SURVEY.md section 8d config 1: 1 000 cells x 8 objects (30..5000 raw points each),
+    256 queries, seed 1."""
+    return synth.SynthCoarseDataset(seed=1, n_cells=1000, n_poses=256, n_obj=8, max_raw=5000)
+
+
+CFG1_NP_SEED = 1
+CFG1_BATCH = 8
+
+
+def main_cfg1():
+    """eval_cfg1.npz: the reference's own evaluation.coarse.run_coarse (evaluation/coarse.py:40-84, which calls
+    training/coarse.py::eval_epoch) on configs[0], all three loops, timed on this container's cores."""
+    import time
+
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    sd = synth.make_state_dict(WEIGHT_SEED)
+    model = reference_run.build_model(sd, fake_seed=FAKE_T5_SEED)
+    ref = reference_run.load()
+    args = reference_run.default_args()
+    args.batch_size = CFG1_BATCH
+    ds = cfg1_dataset()
+    loader = DataLoader(ds, batch_size=args.batch_size, collate_fn=dataio.collate_fn, shuffle=False)
+    np.random.seed(CFG1_NP_SEED)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        retrievals, accuracies = ref["run_coarse"](model, loader, args)
+    t_run = time.perf_counter() - t0
+    np.random.seed(CFG1_NP_SEED)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        acc, acc_close, retr, cell_enc, text_enc = ref["eval_epoch"](model, loader, args, return_encodings=True)
+    assert all((retrievals[i] == retr[i]).all() for i in range(len(ds)))
+    np.savez_compressed(
+        os.path.join(GOLDEN_DIR, "eval_cfg1.npz"),
+        retrievals=np.stack(retrievals), acc=np.array([acc[k] for k in args.top_k]),
+        acc_close=np.array([acc_close[k] for k in args.top_k]),
+        run_coarse_acc=np.array([[accuracies[k][t] for t in args.threshs] for k in args.top_k]),
+        cell_enc=cell_enc.astype(np.float32), text_enc=text_enc.astype(np.float32),  # f32 values held in f64 buffers
+        top_k=np.array(args.top_k), threshs=np.array(args.threshs), np_seed=CFG1_NP_SEED, batch_size=args.batch_size,
+        weight_seed=WEIGHT_SEED, fake_t5_seed=FAKE_T5_SEED, reference_run_coarse_seconds=t_run, reference_cores=os.cpu_count(),
+    )
+    print(f"cfg1: reference run_coarse took {t_run:.1f} s on {os.cpu_count()} cores; acc {acc} close {acc_close}")
+    print("eval_cfg1.npz", os.path.getsize(os.path.join(GOLDEN_DIR, "eval_cfg1.npz")))
 
 
 def main():
@@ -178,5 +227,7 @@ if __name__ == "__main__":
 
     if len(sys.argv) > 1 and sys.argv[1] == "fine":
         main_fine()
+    elif len(sys.argv) > 1 and sys.argv[1] == "cfg1":
+        main_cfg1()
     else:
         main()

@@ -33,13 +33,23 @@ import torch.nn as nn
 
 FPS_RANDOM_START = False
 MAX_NUM_NEIGHBORS = 32
+# torch-cluster's CUDA kernels accumulate `dist += tmp * tmp` per coordinate; nvcc's default -fmad=true would contract that
+# into fma(dz, dz, fma(dy, dy, dx*dx)).  Which form the authors' wheel ran cannot be checked offline, so it is a switch:
+# False (default) = one rounding per operation, True = the contracted form.  The engine's twin is T2L_DIST_FMA=1.
+DIST_FMA = False
 
 
 def _sqdist(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """(dx*dx + dy*dy) + dz*dz, one rounding per op (torch eager never contracts to FMA)."""
+    """(dx*dx + dy*dy) + dz*dz, one rounding per op (torch eager never contracts to FMA); with DIST_FMA the
+    contracted sum, each fma evaluated in float64 (the product of two fp32 values is exact there) and rounded once
+    to fp32 -- identical to a hardware fma except for double-rounding cases of probability ~2^-29 per operation."""
     d = a - b
     dx, dy, dz = d[..., 0], d[..., 1], d[..., 2]
-    return (dx * dx + dy * dy) + dz * dz
+    if not DIST_FMA:
+        return (dx * dx + dy * dy) + dz * dz
+    r = dx * dx
+    r = (dy.double() * dy.double() + r.double()).float()
+    return (dz.double() * dz.double() + r.double()).float()
 
 
 def _segments(batch: torch.Tensor):

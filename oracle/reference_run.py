@@ -85,7 +85,7 @@ def fine_args(**over) -> argparse.Namespace:
 
 def build_fine_model(state_dict: dict, args=None, fake_seed: int = 0):
     """The reference CrossMatch (models/cross_matcher.py:39-129) carrying `state_dict`."""
-    from text2loc_b200.synth import pointnet_state_dict
+    from synth import pointnet_state_dict
 
     ref = load(fake_seed)
     args = args or fine_args()
@@ -105,7 +105,7 @@ def build_fine_model(state_dict: dict, args=None, fake_seed: int = 0):
 
 def build_model(state_dict: dict, args=None, fake_seed: int = 0):
     """The reference CellRetrievalNetwork carrying `state_dict` (numpy or torch values)."""
-    from text2loc_b200.synth import pointnet_state_dict
+    from synth import pointnet_state_dict
 
     ref = load(fake_seed)
     args = args or default_args()

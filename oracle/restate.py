@@ -379,3 +379,46 @@ def eval_epoch(sd, dataloader, args, frontend, return_encodings=False):
     if return_encodings:
         return accuracies, accuracies_close, top_retrievals, cell_encodings, text_encodings
     return accuracies, accuracies_close, top_retrievals
+
+
+# ---- accuracy bookkeeping, the reference's per-query loops (checkers of t2l_topk_accuracy) -------------------
+
+def retrieval_accuracies(retrieved_ids, query_cell_ids, query_poses_w, cells_dict, cell_size, top_k):
+    """training/coarse.py:127-150 given the retrieved id lists: ({k: hit rate}, {k: close-by rate}, dists [nq, k_max])."""
+    accuracies = {k: [] for k in top_k}
+    accuracies_close = {k: [] for k in top_k}
+    all_dists = []
+    for q in range(len(retrieved_ids)):
+        ids = retrieved_ids[q]
+        for k in top_k:
+            accuracies[k].append(query_cell_ids[q] in ids[0:k])
+        poses = [cells_dict[c].get_center()[0:2] for c in ids]
+        dists = np.linalg.norm(query_poses_w[q] - poses, axis=1)
+        all_dists.append(dists)
+        for k in top_k:
+            accuracies_close[k].append(np.any(dists[0:k] <= cell_size / 2))
+    return ({k: np.mean(v) for k, v in accuracies.items()}, {k: np.mean(v) for k, v in accuracies_close.items()}, np.stack(all_dists))
+
+
+def calc_sample_accuracies(pose, top_cells, pos_in_cells, top_k, threshs):
+    """evaluation/utils.py:31-54."""
+    pose_w = pose.pose_w
+    assert len(top_cells) == max(top_k) == len(pos_in_cells)
+    pred_w = np.array([top_cells[i].bbox_w[0:2] + pos_in_cells[i, :] * top_cells[i].cell_size for i in range(len(top_cells))])
+    dists = np.linalg.norm(pose_w[0:2] - pred_w, axis=1)
+    pose_scene_name = pose.cell_id.split("_")[0]
+    cell_scene_names = np.array([cell.id.split("_")[0] for cell in top_cells])
+    dists[pose_scene_name != cell_scene_names] = np.inf
+    return {k: {t: np.min(dists[0:k]) <= t for t in threshs} for k in top_k}
+
+
+def localisation_accuracies(poses, all_cells, retrievals, pos_in_cells, top_k, threshs):
+    """evaluation/coarse.py:69-82: per-sample calc_sample_accuracies, averaged."""
+    cells_dict = {cell.id: cell for cell in all_cells}
+    acc = {k: {t: [] for t in threshs} for k in top_k}
+    for i in range(len(retrievals)):
+        a = calc_sample_accuracies(poses[i], [cells_dict[c] for c in retrievals[i]], pos_in_cells[i], top_k, threshs)
+        for k in top_k:
+            for t in threshs:
+                acc[k][t].append(a[k][t])
+    return {k: {t: np.mean(acc[k][t]) for t in threshs} for k in top_k}

@@ -8,7 +8,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from text2loc_b200 import distributed as t2ld  # noqa: E402
-from text2loc_b200 import synth  # noqa: E402
+import synth  # noqa: E402
 from text2loc_b200.engine import Engine  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])

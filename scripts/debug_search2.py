@@ -4,7 +4,7 @@ import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import restate
-from text2loc_b200 import synth
+import synth
 from text2loc_b200.engine import Engine
 
 eng = Engine("cuda:0")

@@ -5,7 +5,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from text2loc_b200 import synth  # noqa: E402
+import synth  # noqa: E402
 from text2loc_b200.engine import Engine  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000

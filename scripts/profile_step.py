@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from text2loc_b200 import synth  # noqa: E402
+import synth  # noqa: E402
 from text2loc_b200.engine import Engine  # noqa: E402
 
 ap = argparse.ArgumentParser()

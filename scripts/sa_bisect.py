@@ -2,7 +2,7 @@
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from text2loc_b200 import synth
+import synth
 from text2loc_b200.engine import Engine
 
 eng = Engine("cuda:0")

@@ -321,7 +321,7 @@ class SynthCellOnlyDataset:
         self.transform = transform
 
     def __getitem__(self, idx):
-        from .dataio import batch_object_points
+        from text2loc_b200.dataio import batch_object_points
 
         cell = self.cells[idx]
         assert len(cell.objects) >= 1
@@ -342,7 +342,7 @@ class SynthCoarseDataset:
 
     def __init__(self, seed: int, n_cells: int, n_poses: int, n_obj=8, transform=None, max_raw: int = 5000,
                  scene_name: str = "0000", cell_size: float = 30.0, n_hints: int = 6):
-        from .dataio import FixedPoints
+        from text2loc_b200.dataio import FixedPoints
 
         self.transform = transform or FixedPoints(NUM_POINTS)
         rng = np.random.default_rng([seed, 0xDA7A])
@@ -367,7 +367,7 @@ class SynthCoarseDataset:
         self._cells_dict = {c.id: c for c in self.all_cells}
 
     def __getitem__(self, idx):
-        from .dataio import batch_object_points
+        from text2loc_b200.dataio import batch_object_points
 
         pose = self.all_poses[idx]
         cell = self._cells_dict[pose.cell_id]

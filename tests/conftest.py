@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def state_dict():
-    from text2loc_b200 import synth
+    import synth
 
     return synth.make_state_dict(0)
 

@@ -27,7 +27,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import restate
     from text2loc_b200 import distributed as t2ld
-    from text2loc_b200 import synth
+    import synth
 
     D = synth.make_unit_rows(3, 1001)  # not divisible by the world size
     D[900] = D[5]  # an exact tie across the two shards

@@ -92,7 +92,7 @@ def test_encode_text_feature_magnitudes(eng, state_dict):
     """fp16 operands: features 4x larger / 100x smaller than the synthetic default stay in tolerance (fp16 has the
     range for anything a LayerNorm-ed T5 state can hold); absurd magnitudes saturate at 65504 instead of producing inf."""
     from oracle import restate
-    from text2loc_b200 import synth
+    import synth
 
     base = synth.make_t5_features(5, 8, 6, 12)
     for scale in (4.0, 0.01):
@@ -109,7 +109,7 @@ def test_encode_text_feature_magnitudes(eng, state_dict):
 def test_encode_text_shapes(eng, state_dict):
     """Different token counts / sentence counts, chunk boundary in the middle of the batch."""
     from oracle import restate
-    from text2loc_b200 import synth
+    import synth
 
     for nq, S, L in ((3, 6, 9), (5, 4, 17), (2, 1, 1), (40, 6, 12)):
         t5 = synth.make_t5_features(nq + S + L, nq, S, L)
@@ -120,7 +120,7 @@ def test_encode_text_shapes(eng, state_dict):
 
 def test_encode_text_host_streaming_equals_device(eng):
     """Host (pinned) input is uploaded in chunks on a side stream; same result as a resident tensor."""
-    from text2loc_b200 import synth
+    import synth
 
     t5 = torch.from_numpy(synth.make_t5_features(77, 1000, 6, 12))  # > 2 engine chunks of 455 queries
     a = eng.encode_text(t5.pin_memory(), 6)
@@ -135,7 +135,7 @@ def test_encode_text_host_streaming_equals_device(eng):
 @pytest.mark.parametrize("n,nq,k", [(3000, 64, 10), (20000, 1000, 10), (257, 130, 5), (100000, 512, 10), (1000, 1, 1), (5000, 300, 12)])
 def test_search_matches_fp64_oracle(eng, n, nq, k):
     from oracle import restate
-    from text2loc_b200 import synth
+    import synth
 
     D = synth.make_unit_rows(n, n)
     Q = synth.make_unit_rows(nq + 1, nq)
@@ -151,7 +151,7 @@ def test_search_matches_fp64_oracle(eng, n, nq, k):
 
 
 def test_search_golden_reference_loop(eng, golden):
-    from text2loc_b200 import synth
+    import synth
 
     g = golden("search_small.npz")
     eng.db_build(synth.make_unit_rows(int(g["d_seed"]), int(g["n"])))
@@ -164,7 +164,7 @@ def test_search_ties_duplicates_and_clusters(eng):
     """Duplicate rows tie exactly -> index order; a tight cluster forces the margin proof to fail
     and the exact rescan to take over.  Either way the result is the oracle's."""
     from oracle import restate
-    from text2loc_b200 import synth
+    import synth
 
     D = synth.make_unit_rows(5, 4000)
     D[100] = D[7]
@@ -185,7 +185,7 @@ def test_search_second_pass_and_exhaustive_rescan(eng):
     can still matter; 300 exact duplicates (and the tightest queries) overflow its 256-entry buffer and force the
     exhaustive fp64 rescan.  All three routes must return the oracle's answer."""
     from oracle import restate
-    from text2loc_b200 import synth
+    import synth
 
     rng = np.random.default_rng(3)
     base = synth.make_unit_rows(40, 1)[0]
@@ -205,7 +205,7 @@ def test_search_second_pass_and_exhaustive_rescan(eng):
 
 def test_search_small_db_and_row_offset(eng):
     from oracle import restate
-    from text2loc_b200 import synth
+    import synth
 
     D = synth.make_unit_rows(9, 6)
     Q = synth.make_unit_rows(10, 3)
@@ -220,7 +220,7 @@ def test_search_small_db_and_row_offset(eng):
 def test_merge_topk_is_shard_count_independent(eng):
     """Row-shard the DB 1/2/4/8 ways on one GPU, merge the per-shard lists: identical result."""
     from oracle import restate
-    from text2loc_b200 import synth
+    import synth
 
     D = synth.make_unit_rows(11, 10000)
     D[9000] = D[10]  # a tie across shards
@@ -246,7 +246,7 @@ def test_search_full_size_properties(eng):
     properties: scores are the exact fp64 dots of the returned rows, lists are sorted by (score desc, row asc),
     the call is idempotent, and 8 row shards merged equal the unsharded search bit for bit."""
     from oracle import restate
-    from text2loc_b200 import synth
+    import synth
 
     N, NQ, K = 100000, 32768, 10
     D = synth.make_unit_rows(101, N)
@@ -287,7 +287,7 @@ def test_encode_cells_full_size_properties(eng, state_dict):
     reverse order must give the same rows bit for bit (chunk boundaries fall elsewhere), rows are unit vectors, and a
     sample agrees with the oracle."""
     from oracle import restate
-    from text2loc_b200 import synth
+    import synth
 
     n_cells = 3000
     pts, meta, ptr = synth.make_packed_cells(77, n_cells, 8)
@@ -301,6 +301,27 @@ def test_encode_cells_full_size_properties(eng, state_dict):
     sobj = np.concatenate([np.arange(c * 8, c * 8 + 8) for c in sample])
     want = restate.encode_cells(state_dict, pts[sobj], meta[sobj], np.arange(0, 8 * len(sample) + 1, 8, dtype=np.int32)).numpy()
     assert row_rel_err(fwd.cpu().numpy()[sample], want) < EMB_TOL
+
+
+def test_encode_cells_16_objects_per_cell(eng, state_dict):
+    """BASELINE configs[3] cell shape: 16 objects per cell (packed), 300 cells = 4 800 objects; every 20th cell against
+    the oracle, plus the order-independence property on all of them."""
+    from oracle import restate
+    import synth
+
+    pts, meta, ptr = synth.make_packed_cells(41, 300, 16)
+    got = eng.encode_cells(pts, meta, ptr).cpu().numpy()
+    assert np.abs(np.linalg.norm(got, axis=1) - 1).max() < 1e-5
+    sample = list(range(0, 300, 20))
+    sobj = np.concatenate([np.arange(c * 16, c * 16 + 16) for c in sample])
+    want = restate.encode_cells(state_dict, pts[sobj], meta[sobj], np.arange(0, 16 * len(sample) + 1, 16, dtype=np.int32)).numpy()
+    err = row_rel_err(got[sample], want)
+    print(f"\n16 objects/cell: embeddings vs oracle {err:.3e}")
+    assert err < EMB_TOL
+    perm = np.arange(299, -1, -1)
+    pobj = np.concatenate([np.arange(c * 16, c * 16 + 16) for c in perm])
+    rev = eng.encode_cells(pts[pobj], meta[pobj], ptr).cpu().numpy()
+    assert (rev[::-1] == got).all()
 
 
 # ---- drop-in API ---------------------------------------------------------------------------------------
@@ -351,6 +372,114 @@ def test_dropin_eval_epoch_and_run_coarse_golden(state_dict, golden):
     assert len(retrievals) == len(ds) and all(len(r) == 10 for r in retrievals)
     assert set(accuracies.keys()) == set(args.top_k) and set(accuracies[1].keys()) == set(args.threshs)
     assert np.allclose([[accuracies[k][t] for t in args.threshs] for k in args.top_k], g["run_coarse_acc"], atol=0.1)
+    # bookkeeping: the device rows (t2l_topk_accuracy) equal the reference's per-query loops on the SAME retrievals, exactly
+    check_bookkeeping(ds, args, got, acc, acc_close, accuracies)
+    if (got == ref).all():  # identical retrievals => identical accuracies, bit for bit
+        assert [acc[k] for k in args.top_k] == list(g["acc"]) and [acc_close[k] for k in args.top_k] == list(g["acc_close"])
+        assert ([[accuracies[k][t] for t in args.threshs] for k in args.top_k] == g["run_coarse_acc"]).all()
+
+
+def check_bookkeeping(ds, args, got, acc, acc_close, accuracies):
+    from oracle import restate
+
+    cells_dict = {c.id: c for c in ds.all_cells}
+    want_acc, want_close, _ = restate.retrieval_accuracies(
+        got, np.array([p.cell_id for p in ds.all_poses]), np.array([p.pose_w[0:2] for p in ds.all_poses]), cells_dict,
+        ds.all_cells[0].cell_size, args.top_k)
+    assert all(acc[k] == want_acc[k] for k in args.top_k), (acc, want_acc)
+    assert all(acc_close[k] == want_close[k] for k in args.top_k), (acc_close, want_close)
+    want_loc = restate.localisation_accuracies(ds.all_poses, ds.all_cells, got, np.full((len(got), got.shape[1], 2), 0.5), args.top_k, args.threshs)
+    assert all(accuracies[k][t] == want_loc[k][t] for k in args.top_k for t in args.threshs), (accuracies, want_loc)
+
+
+def test_dropin_configs0_against_reference_run_coarse(state_dict, golden):
+    """BASELINE configs[0] at its stated size: 1 000 cells x 8 objects x 256 points, 256 queries, seed 1, through the
+    drop-in run_coarse / eval_epoch, against what the REFERENCE'S OWN evaluation.coarse.run_coarse returned for the same
+    dataset (tests/golden/eval_cfg1.npz, oracle/make_golden.py cfg1).  Reports how many queries' top-10 differ; each of those
+    must sit on a reference k/k+1 score gap smaller than twice the measured embedding error (L3 parity)."""
+    from oracle import restate
+    from oracle.make_golden import cfg1_dataset
+    from text2loc_b200 import dataio, eval_epoch, run_coarse
+
+    g = golden("eval_cfg1.npz")
+    model, args = make_model(state_dict, int(g["fake_t5_seed"]))
+    args.batch_size = int(g["batch_size"])
+    ds = cfg1_dataset()
+    loader = DataLoader(ds, batch_size=args.batch_size, collate_fn=dataio.collate_fn, shuffle=False)
+    np.random.seed(int(g["np_seed"]))
+    retrievals, accuracies = run_coarse(model, loader, args, verbose=False)
+    np.random.seed(int(g["np_seed"]))
+    acc, acc_close, retr, cell_enc, text_enc = eval_epoch(model, loader, args, return_encodings=True)
+    got = np.stack([retr[i] for i in range(len(ds))])
+    assert (np.stack(retrievals) == got).all()
+    ref_cells, ref_text = g["cell_enc"].astype(np.float64), g["text_enc"].astype(np.float64)
+    ec, et = row_rel_err(cell_enc, ref_cells), row_rel_err(text_enc, ref_text)
+    assert ec < EMB_TOL and et < EMB_TOL
+    # L1: the engine's lists are the fp64 stable order of ITS embeddings
+    oidx, _ = restate.search_topk(cell_enc, text_enc, 10)
+    ids = np.array([c.id for c in ds.all_cells])
+    assert (got == ids[oidx]).all()
+    # L3: against the reference's own retrievals
+    ref = g["retrievals"]
+    differing = np.nonzero((got != ref).any(axis=1))[0]
+    s_ref = ref_text @ ref_cells.T
+    worst_gap = 0.0
+    for q in differing:
+        srt = np.sort(s_ref[q])[::-1]
+        gap = float(np.min(np.abs(np.diff(srt[:11]))))
+        worst_gap = max(worst_gap, gap)
+        assert gap < 2 * (ec + et), f"query {q} differs from the reference although its closest top-11 score gap is {gap:.2e}"
+    print(f"\nconfigs[0] vs the reference's run_coarse: embeddings cells {ec:.3e} / text {et:.3e}; "
+          f"{len(differing)} of {len(ds)} queries differ in their top-10 (largest deciding gap {worst_gap:.2e}, bound {2 * (ec + et):.2e}); "
+          f"reference run took {float(g['reference_run_coarse_seconds']):.0f} s on {int(g['reference_cores'])} cores")
+    check_bookkeeping(ds, args, got, acc, acc_close, accuracies)
+    if len(differing) == 0:
+        assert [acc[k] for k in args.top_k] == list(g["acc"]) and [acc_close[k] for k in args.top_k] == list(g["acc_close"])
+        assert ([[accuracies[k][t] for t in args.threshs] for k in args.top_k] == g["run_coarse_acc"]).all()
+
+
+def test_topk_accuracy_kernel_matches_reference_loops(eng):
+    """t2l_topk_accuracy on random retrievals (empty slots, several scenes, targets absent from the database) against
+    the reference's per-query loops (training/coarse.py:131-150, evaluation/utils.py:31-54)."""
+    from oracle import restate
+    import synth
+
+    rng = np.random.default_rng(17)
+    n_c, n_q, k = 300, 500, 10
+    cells = []
+    for i in range(n_c):
+        scene = f"{rng.integers(3):04d}"
+        x0, y0 = rng.uniform(0, 300, 2)
+        cells.append(synth.SynthCell(i, scene, [], 30.0, np.array([x0, y0, 0.0, x0 + 30, y0 + 30, 30.0])))
+    poses = []
+    for _ in range(n_q):
+        c = cells[int(rng.integers(n_c))]
+        poses.append(synth.SynthPose(c.bbox_w[0:3] + rng.uniform(-20, 50, 3), c.id, c.scene_name, ""))
+    idx = np.stack([rng.permutation(n_c)[:k] for _ in range(n_q)]).astype(np.int64)
+    ids = np.array([c.id for c in cells])
+    top_k, threshs = [1, 3, 5, 10], [5, 10, 15]
+    from text2loc_b200 import evaluation
+
+    want_acc, want_close, want_d = restate.retrieval_accuracies(ids[idx], np.array([p.cell_id for p in poses]),
+                                                                np.array([p.pose_w[0:2] for p in poses]), {c.id: c for c in cells}, 30.0, top_k)
+    hit, close, dists = eng.topk_accuracy(idx, np.array([p.pose_w[0:2] for p in poses]), np.array([c.get_center()[0:2] for c in cells]),
+                                          top_k, threshs=[15.0], target_row=evaluation.rows_of_ids(ids, np.array([p.cell_id for p in poses])),
+                                          want_dists=True)
+    assert (dists.cpu().numpy() == want_d).all()  # same float64 arithmetic as numpy's 2-vector norm
+    assert all(hit[:, i].double().mean().item() == want_acc[kk] for i, kk in enumerate(top_k))
+    assert all(close[:, i, 0].double().mean().item() == want_close[kk] for i, kk in enumerate(top_k))
+    pos_in = rng.uniform(0, 1, (n_q, k, 2))
+    want_loc = restate.localisation_accuracies(poses, cells, ids[idx], pos_in, top_k, threshs)
+    got_loc = evaluation.localisation_accuracies(eng, poses, cells, ids[idx], pos_in, top_k, threshs)
+    assert all(got_loc[kk][t] == want_loc[kk][t] for kk in top_k for t in threshs)
+    assert 0 < want_loc[10][15] < 1  # the case is not degenerate
+    # empty slots (-1) are +inf / never hits
+    idx2 = idx.copy()
+    idx2[:, 5:] = -1
+    hit2, close2, d2 = eng.topk_accuracy(idx2, np.array([p.pose_w[0:2] for p in poses]), np.array([c.get_center()[0:2] for c in cells]),
+                                         top_k, threshs=[15.0], target_row=np.full(n_q, -1), want_dists=True)
+    assert torch.isinf(d2[:, 5:]).all() and (d2[:, :5].cpu().numpy() == want_d[:, :5]).all() and int(hit2.sum()) == 0
+    assert (close2[:, 3, 0] == close2[:, 2, 0]).all()
 
 
 def test_dropin_surface(state_dict):
@@ -369,3 +498,11 @@ def test_dropin_surface(state_dict):
 
     with pytest.raises(EngineError):
         CellRetrievalNetwork([], [], bad)
+    # a checkpoint with other dimensions is rejected with a size-mismatch error (load_state_dict raises in the reference too)
+    wrong = {k: np.asarray(v) for k, v in state_dict.items()}
+    wrong["object_encoder.mlp_merge.0.0.weight"] = wrong["object_encoder.mlp_merge.0.0.weight"][:, :512]
+    with pytest.raises(EngineError, match="size mismatch"):
+        make_fresh = CellRetrievalNetwork(["c"] * 22, ["k"] * 8, args, text_frontend=lambda d: None)
+        make_fresh.load_state_dict({k: torch.as_tensor(v) for k, v in wrong.items()}, strict=False)
+    # engine calls leave the caller's current device alone
+    assert torch.cuda.current_device() == 0

@@ -74,7 +74,8 @@ def test_engine_weight_names_cover_what_the_engine_requires(state_dict):
 
 
 def test_pack_cells_layout_and_errors():
-    from text2loc_b200 import dataio, synth
+    import synth
+    from text2loc_b200 import dataio
 
     cells = synth.make_cell_objects(1, 2, [2, 3], max_raw=100)
     np.random.seed(0)
@@ -89,7 +90,7 @@ def test_pack_cells_layout_and_errors():
 
 
 def test_packed_generator_matches_object_generator_statistics():
-    from text2loc_b200 import synth
+    import synth
 
     pts, meta, ptr = synth.make_packed_cells(0, 50, 8)
     assert pts.shape == (400, 256, 6) and ptr[-1] == 400 and pts.dtype == np.float32
@@ -116,3 +117,32 @@ def test_bench_reference_arm_contract():
     cb = line["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     assert "workload" in line["config"]
+
+
+def test_rows_of_ids_maps_strings_to_database_rows():
+    from text2loc_b200.evaluation import rows_of_ids
+
+    db = np.array(["0003_00002", "0000_00010", "0003_00000", "0001_00007"], dtype="<U32")
+    q = np.array([["0001_00007", "0003_00000"], ["nope", "0003_00002"]])
+    assert (rows_of_ids(db, q) == np.array([[3, 2], [-1, 0]])).all()
+    assert rows_of_ids(db, np.array([], dtype="<U32")).shape == (0,)
+
+
+def test_oracle_bookkeeping_restatement_matches_reference_functions():
+    """restate.calc_sample_accuracies / localisation_accuracies against the reference's own evaluation/utils.py."""
+    from oracle import reference_run, restate
+    import synth
+
+    if not reference_run.available():
+        pytest.skip("reference not present")
+    reference_run.load()
+    from evaluation.utils import calc_sample_accuracies as ref_calc
+
+    rng = np.random.default_rng(3)
+    cells = [synth.SynthCell(i, f"{i % 2:04d}", [], 30.0, np.array([10.0 * i, 5.0 * i, 0, 10.0 * i + 30, 5.0 * i + 30, 30])) for i in range(12)]
+    pose = synth.SynthPose(np.array([40.0, 30.0, 1.0]), cells[4].id, cells[4].scene_name, "")
+    top = [cells[i] for i in rng.permutation(12)[:10]]
+    pos = rng.uniform(0, 1, (10, 2))
+    want = ref_calc(pose, top, pos, [1, 3, 5, 10], [5, 10, 15])
+    got = restate.calc_sample_accuracies(pose, top, pos, [1, 3, 5, 10], [5, 10, 15])
+    assert got == want

@@ -9,7 +9,8 @@ import torch
 from torch.utils.data import DataLoader
 
 from oracle import fake_t5, pyg_ops, reference_run, restate
-from text2loc_b200 import dataio, synth
+import synth
+from text2loc_b200 import dataio
 
 
 def digest(a):

@@ -55,6 +55,7 @@ struct t2l_engine {
   std::string err;
   std::map<std::string, Weight> w;
   bool finalized = false;
+  bool fine = false;         // weights are those of the fine-stage model (CrossMatch, d = 128): only t2l_fine_offsets runs
   Arena arena;
   Launches lc;
   SearchDb db;
@@ -64,6 +65,8 @@ struct t2l_engine {
                              // grids for the small kernels), ~48 GB of workspace (T2L_OBJ_CHUNK to change)
   bool fused_sa = true;      // sa_fused.cu; false = v1 edge_gather -> H -> SegMax GEMM (kept for A/B checks, T2L_UNFUSED_SA=1)
   bool obj_sa = true;        // sa_obj.cu (object-resident, fp16 operands); T2L_SA_TF32=1 selects sa_fused.cu (tf32, global gathers)
+  bool obj_sa2 = true;       // sa_obj2.cu: W2 in tensor memory, self-loop edges folded in, paired SA1 tiles; T2L_SA_V1=1 selects sa_obj.cu
+  bool dist_fma = false;     // FPS / ball-query distances with FMA contraction (T2L_DIST_FMA=1; oracle: pyg_ops.DIST_FMA)
   int tok_chunk = 32768;     // tokens per text chunk (sentence-aligned)
   bool text_f16 = true;      // token layer on fp16 operands (same 11-bit significand as tf32, twice the MMA rate, half the
                              // operand bytes); T2L_TEXT_TF32=1 selects the tf32 path for A/B checks
@@ -74,7 +77,37 @@ struct t2l_engine {
   // varied 60 -> 95 ms between identical runs)
   struct HostStage { int32_t* ptr = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; bool used = false; } stage[4];
   unsigned stage_next = 0;
+  // The arena, `pooled` and the search work buffers are shared by every call on this engine.  Calls on ONE stream are
+  // ordered by the stream; a call on a different stream first waits for the event the previous call recorded.
+  cudaEvent_t order_ev = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool order_recorded = false;
 };
+
+namespace {
+// Every entry point runs on the engine's device and restores the caller's current device on return.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess; else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+// Cross-stream ordering of the shared workspace (see t2l_engine::order_ev).
+struct CallScope {
+  t2l_engine* e;
+  cudaStream_t st;
+  bool ok = true;
+  CallScope(t2l_engine* e_, void* stream) : e(e_), st(static_cast<cudaStream_t>(stream)) {
+    if (e->order_recorded && st != e->last_stream) ok = cudaStreamWaitEvent(st, e->order_ev, 0) == cudaSuccess;
+  }
+  ~CallScope() {
+    if (cudaEventRecord(e->order_ev, st) == cudaSuccess) { e->last_stream = st; e->order_recorded = true; }
+  }
+};
+}  // namespace
 
 static int fail(t2l_engine* e, const char* fmt, ...) {
   char buf[512];
@@ -85,6 +118,14 @@ static int fail(t2l_engine* e, const char* fmt, ...) {
   if (e) e->err = buf; else g_create_error = buf;
   return 1;
 }
+
+#define ENTER(e)                     \
+  DeviceGuard _guard((e)->device);   \
+  if (!_guard.ok) return fail(e, "cudaSetDevice(%d) failed", (e)->device)
+#define ENTER_STREAM(e, stream)      \
+  ENTER(e);                          \
+  CallScope _scope(e, stream);       \
+  if (!_scope.ok) return fail(e, "cudaStreamWaitEvent failed")
 
 #define CU(call)                                                                                   \
   do {                                                                                             \
@@ -117,7 +158,8 @@ extern "C" int t2l_create(int device, t2l_engine** out) {
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
     return fail(e, "t2l_create: no CUDA device visible; this engine has no CPU path");
   if (device < 0 || device >= n_dev) return fail(e, "t2l_create: device %d out of range (%d visible)", device, n_dev);
-  CU(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(e, "t2l_create: cudaSetDevice(%d) failed", device);
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(e, "t2l_create: device %d is sm_%d%d; the kernels are sm_100a (Blackwell B200) only", device, prop.major, prop.minor);
@@ -134,8 +176,14 @@ extern "C" int t2l_create(int device, t2l_engine** out) {
   if (const char* v = getenv("T2L_UNFUSED_SA")) e->fused_sa = !(v[0] == '1');
   if (const char* v = getenv("T2L_TEXT_TF32")) e->text_f16 = !(v[0] == '1');
   if (const char* v = getenv("T2L_SA_TF32")) e->obj_sa = !(v[0] == '1');
+  if (const char* v = getenv("T2L_SA_V1")) e->obj_sa2 = !(v[0] == '1');
+  if (const char* v = getenv("T2L_DIST_FMA")) e->dist_fma = v[0] == '1';
   if (const char* v = getenv("T2L_OBJ_CHUNK")) { const int n = atoi(v); if (n >= 64 && n <= 65536) e->obj_chunk = n; }
-  if (cudaMalloc(&e->db.max_norm, sizeof(float)) != cudaSuccess) { delete e; return fail(nullptr, "t2l_create: cudaMalloc failed"); }
+  if (cudaMalloc(&e->db.max_norm, sizeof(float)) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->order_ev, cudaEventDisableTiming) != cudaSuccess) {
+    delete e;
+    return fail(nullptr, "t2l_create: cudaMalloc / cudaEventCreate failed");
+  }
   *out = e;
   return 0;
 }
@@ -149,12 +197,13 @@ static void free_search_work(t2l_engine* e) {
 
 extern "C" void t2l_destroy(t2l_engine* e) {
   if (!e) return;
-  cudaSetDevice(e->device);
+  DeviceGuard guard(e->device);
   cudaDeviceSynchronize();
   for (auto& kv : e->w) { cudaFree(kv.second.dev); cudaFree(kv.second.dev16); }
   cudaFree(e->arena.base);
   cudaFree(e->pooled);
   for (auto& hs : e->stage) { if (hs.ptr) cudaFreeHost(hs.ptr); if (hs.ev) cudaEventDestroy(hs.ev); }
+  if (e->order_ev) cudaEventDestroy(e->order_ev);
   cudaFree(e->db.planes);
   cudaFree(e->db.max_norm);
   free_search_work(e);
@@ -196,7 +245,7 @@ static float host_round_tf32(float x) {
 
 extern "C" int t2l_set_weight(t2l_engine* e, const char* name, const float* data, int rows, int cols) {
   if (!e || !name || !data || rows <= 0 || cols <= 0) return fail(e, "t2l_set_weight: bad argument");
-  CU(cudaSetDevice(e->device));
+  ENTER(e);
   Weight& w = e->w[name];
   if (w.dev) { CU(cudaFree(w.dev)); w.dev = nullptr; }
   if (w.dev16) { CU(cudaFree(w.dev16)); w.dev16 = nullptr; }
@@ -234,26 +283,72 @@ extern "C" int t2l_set_weight(t2l_engine* e, const char* name, const float* data
   return 0;
 }
 
-static const char* kRequired[] = {
-    "sa1.w1x", "sa1.w1p", "sa1.b1", "sa1.w2", "sa1.b2", "sa2.w1x", "sa2.w1p", "sa2.b1", "sa2.w2", "sa2.b2",
-    "sa3.w1x", "sa3.w1p", "sa3.b1", "sa3.w2", "sa3.b2", "ga.w1", "ga.b1", "ga.w2", "ga.b2",
-    "lin1.w", "lin1.b", "lin2.w", "lin2.b", "mlp_pointnet.w", "mlp_pointnet.b",
-    "color.w1", "color.b1", "color.w2", "color.b2", "pos.w1", "pos.b1", "pos.w2", "pos.b2",
-    "num.w1", "num.b1", "num.w2", "num.b2", "merge.w", "merge.b", "txt_mlp.w", "txt_mlp.b"};
-static const char* kAttn[] = {"obj_attn0", "obj_attn1", "txt_intra", "txt_inter"};
-static const char* kAttnParts[] = {"in_w", "in_b", "out_w", "out_b", "l1_w", "l1_b", "l2_w", "l2_b", "n1_w", "n1_b", "n2_w", "n2_b"};
+// Expected (rows, cols) of every weight, as the reference's constructors fix them (models/pointcloud/pointnet2.py:57-63,
+// models/object_encoder.py:33-64, models/cell_retrieval.py:35, models/language_encoder.py:98-103, models/cross_matcher.py:55-78)
+// for embed dim d (256 coarse / 128 fine).  A checkpoint with other dimensions is rejected here -- the reference's
+// load_state_dict raises on a size mismatch even with strict=False -- instead of being read out of bounds by kernels whose
+// leading dimensions are compile-time constants.
+struct ShapeSpec { std::string name; int rows, cols; };
+
+static void attn_shapes(std::vector<ShapeSpec>& v, const std::string& p, int d, int ffn) {
+  v.push_back({p + ".in_w", 3 * d, d}); v.push_back({p + ".in_b", 1, 3 * d});
+  v.push_back({p + ".out_w", d, d});    v.push_back({p + ".out_b", 1, d});
+  v.push_back({p + ".l1_w", ffn, d});   v.push_back({p + ".l1_b", 1, ffn});
+  v.push_back({p + ".l2_w", d, ffn});   v.push_back({p + ".l2_b", 1, d});
+  v.push_back({p + ".n1_w", 1, d}); v.push_back({p + ".n1_b", 1, d}); v.push_back({p + ".n2_w", 1, d}); v.push_back({p + ".n2_b", 1, d});
+}
+
+static std::vector<ShapeSpec> expected_shapes(bool fine) {
+  const int d = fine ? T2L_FINE_DIM : T2L_EMBED_DIM;
+  std::vector<ShapeSpec> v;
+  const int sa[3][3] = {{3, 32, 64}, {64, 128, 128}, {128, 256, 256}};  // in, C1, C2
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = "sa" + std::to_string(i + 1);
+    v.push_back({p + ".w1x", sa[i][1], sa[i][0]}); v.push_back({p + ".w1p", sa[i][1], 3}); v.push_back({p + ".b1", 1, sa[i][1]});
+    v.push_back({p + ".w2", sa[i][2], sa[i][1]});  v.push_back({p + ".b2", 1, sa[i][2]});
+  }
+  v.push_back({"ga.w1", 512, 259}); v.push_back({"ga.b1", 1, 512}); v.push_back({"ga.w2", 1024, 512}); v.push_back({"ga.b2", 1, 1024});
+  v.push_back({"lin1.w", 512, 1024}); v.push_back({"lin1.b", 1, 512}); v.push_back({"lin2.w", 256, 512}); v.push_back({"lin2.b", 1, 256});
+  v.push_back({"mlp_pointnet.w", d, 256}); v.push_back({"mlp_pointnet.b", 1, d});
+  const char* side[3] = {"color", "pos", "num"};
+  for (int i = 0; i < 3; ++i) {
+    const std::string p = side[i];
+    v.push_back({p + ".w1", 64, i == 2 ? 1 : 3}); v.push_back({p + ".b1", 1, 64}); v.push_back({p + ".w2", d, 64}); v.push_back({p + ".b2", 1, d});
+  }
+  v.push_back({"merge.w", d, 4 * d}); v.push_back({"merge.b", 1, d});
+  v.push_back({"txt_mlp.w", d, T2L_T5_DIM}); v.push_back({"txt_mlp.b", 1, d});
+  attn_shapes(v, "txt_intra", T2L_T5_DIM, 4 * T2L_T5_DIM);
+  if (!fine) {
+    attn_shapes(v, "obj_attn0", d, 2 * d);
+    attn_shapes(v, "obj_attn1", d, 2 * d);
+    attn_shapes(v, "txt_inter", d, 4 * d);
+  } else {
+    for (const char* side_name : {"cross_objects", "cross_hints"})
+      for (int i = 0; i < 2; ++i) {
+        const std::string p = std::string(side_name) + std::to_string(i);
+        attn_shapes(v, p, d, 4 * d);  // self-attention block + FFN + norm1 / norm2 (norm2 follows the cross-attention)
+        v.push_back({p + ".ca_in_w", 3 * d, d}); v.push_back({p + ".ca_in_b", 1, 3 * d});
+        v.push_back({p + ".ca_out_w", d, d});    v.push_back({p + ".ca_out_b", 1, d});
+        v.push_back({p + ".n3_w", 1, d}); v.push_back({p + ".n3_b", 1, d});
+      }
+    v.push_back({"offs.w1", d / 2, d}); v.push_back({"offs.b1", 1, d / 2}); v.push_back({"offs.w2", 2, d / 2}); v.push_back({"offs.b2", 1, 2});
+  }
+  return v;
+}
 
 extern "C" int t2l_finalize_weights(t2l_engine* e) {
   if (!e) return 1;
-  for (const char* n : kRequired)
-    if (!e->w.count(n)) return fail(e, "t2l_finalize_weights: missing weight '%s'", n);
-  for (const char* a : kAttn)
-    for (const char* p : kAttnParts) {
-      std::string n = std::string(a) + "." + p;
-      if (!e->w.count(n)) return fail(e, "t2l_finalize_weights: missing weight '%s'", n.c_str());
-    }
-  CU(cudaSetDevice(e->device));
+  const bool fine = e->w.count("offs.w1") != 0;  // the fine-stage model (CrossMatch) carries the offset MLP
+  for (const ShapeSpec& sp : expected_shapes(fine)) {
+    auto it = e->w.find(sp.name);
+    if (it == e->w.end()) return fail(e, "t2l_finalize_weights: missing weight '%s' (%s model)", sp.name.c_str(), fine ? "fine" : "coarse");
+    if (it->second.rows != sp.rows || it->second.cols != sp.cols)
+      return fail(e, "t2l_finalize_weights: size mismatch for '%s': got [%d, %d], the engine is built for [%d, %d]", sp.name.c_str(),
+                  it->second.rows, it->second.cols, sp.rows, sp.cols);
+  }
+  ENTER(e);
   CU(cudaDeviceSynchronize());
+  e->fine = fine;
   e->finalized = true;
   return 0;
 }
@@ -361,16 +456,18 @@ struct ObjDebug {
           *cnt2 = nullptr, *cnt3 = nullptr;
 };
 
-static size_t obj_chunk_bytes(size_t n, size_t cells) {
-  // generous upper bound of everything encode_chunk carves from the arena
-  return n * (size_t(1) << 21) + n * 700000 + cells * size_t(28) * 256 * 4 * 32 + (size_t(1) << 20);
+static size_t obj_chunk_bytes(size_t n, size_t cells, bool obj_mode) {
+  // upper bound of everything encode_chunk carves from the arena.  Object-resident path: ~381 KB per object (geometry 10 KB,
+  // Px 96 KB, self-loop rows 64 KB when they exist, x1..x3 96 KB, GA 97 KB, tails 13 KB); the A/B paths add the 1 MB / object
+  // edge tensor.  Per cell: the two attention layers' buffers (~0.6 MB).  A too-small estimate fails the call (Arena::overflow).
+  return n * (obj_mode ? size_t(440000) : (size_t(1) << 21) + 700000) + cells * size_t(28) * 256 * 4 * 32 + (size_t(1) << 20);
 }
 
 static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr, int c0, int c1, float* out,
                         const ObjDebug* dbg, cudaStream_t st) {
   const int o0 = cell_ptr[c0], o1 = cell_ptr[c1];
   const int n = o1 - o0, B = c1 - c0;
-  if (ensure_arena(e, obj_chunk_bytes(n, B))) return 1;
+  if (ensure_arena(e, obj_chunk_bytes(n, B, e->fused_sa && e->obj_sa))) return 1;
   Arena& a = e->arena;
   const float* p = pts + static_cast<size_t>(o0) * kPoints * 6;
 
@@ -407,19 +504,20 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
   g.cpos1 = a.get<float>(N * 128 * 3); g.cpos2 = a.get<float>(N * 64 * 3); g.cpos3 = a.get<float>(N * 32 * 3);
   g.nbr1 = a.get<uint8_t>(N * 128 * 32); g.nbr2 = a.get<uint8_t>(N * 64 * 32); g.nbr3 = a.get<uint8_t>(N * 32 * 32);
   g.cnt1 = a.get<uint8_t>(N * 128); g.cnt2 = a.get<uint8_t>(N * 64); g.cnt3 = a.get<uint8_t>(N * 32);
-  CU(fps_all_levels(p, n, g, st, &e->lc));
-  CU(ball_query_all_levels(p, n, g, st, &e->lc));
+  CU(fps_all_levels(p, n, g, e->dist_fma, st, &e->lc));
+  CU(ball_query_all_levels(p, n, g, e->dist_fma, st, &e->lc));
 
   float* x0 = a.get<float>(N * 256 * 4);
   float* px = a.get<float>(N * 256 * 32);      // max over levels: 256*32 = 128*128/2 ... sized below
   float* px23 = a.get<float>(N * 128 * 128);   // Px of levels 2 and 3 (n*128*128 == n*64*256)
-  float* H = a.get<float>(N * 32 * 32 * 256);  // edge rows, largest level (1 MB / object)
-  float* Hs = a.get<float>(N * 64 * 128);      // self-loop rows (n*128*32, n*64*128, n*32*256)
-  float* S = a.get<float>(N * 64 * 128);       // second-layer output of the self-loop rows
+  const bool obj_mode = e->fused_sa && e->obj_sa;
+  const bool need_side = !(obj_mode && e->obj_sa2);  // sa_obj2 folds the self-loop edges in: no side tensors
+  float* H = obj_mode ? nullptr : a.get<float>(N * 32 * 32 * 256);  // edge rows / edge records of the A/B paths (1 MB / object)
+  float* Hs = need_side ? a.get<float>(N * 64 * 128) : nullptr;     // self-loop rows (n*128*32, n*64*128, n*32*256)
+  float* S = need_side ? a.get<float>(N * 64 * 128) : nullptr;      // second-layer output of the self-loop rows
   float* x1 = a.get<float>(N * 128 * 64);
   float* x2 = a.get<float>(N * 64 * 128);
   float* x3 = a.get<float>(N * 32 * 256);
-  const bool obj_mode = e->fused_sa && e->obj_sa;
   if (!obj_mode) CU(extract_rgb(p, n, x0, st, &e->lc));  // the object-resident path reads rgb straight from pts (sa1_px16)
 
   struct Level { const char* name; int C1, C2, P, M; const float* x; long ldx; const float* dense; int dstride; const float* cpos;
@@ -446,7 +544,14 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
     eg.loop_src_obj = loop_src; eg.loop_half = loop_half; eg.Wp = W(e, nm + ".w1p").dev; eg.b1 = W(e, nm + ".b1").dev;
     eg.n_obj = n; eg.P = L.P; eg.M = L.M; eg.H = H; eg.Hself = Hs;
     if (W(e, nm + ".w1p").ld != 4) return fail(e, "internal: w1p pitch");
-    if (obj) {
+    if (obj && e->obj_sa2) {
+      SaObj2 so;
+      so.Px16 = reinterpret_cast<const __half*>(L.Px); so.C1 = L.C1; so.C2 = L.C2; so.dense_pos = L.dense; so.dense_stride = L.dstride;
+      so.cpos = L.cpos; so.nbr = L.nbr; so.cnt = L.cnt; so.loop_src_obj = loop_src; so.loop_half = loop_half; so.Wp = eg.Wp;
+      so.W2h = W(e, nm + ".w2").dev16; so.b2 = W(e, nm + ".b2").dev; so.out = L.xout; so.n_obj = n; so.P = L.P; so.M = L.M;
+      if (!so.W2h) return fail(e, "internal: no fp16 copy of %s.w2", L.name);
+      CU(sa_obj2(so, st, &e->lc));
+    } else if (obj) {
       eg.Px16 = reinterpret_cast<const __half*>(L.Px);
       eg.Hself16 = reinterpret_cast<__half*>(Hs);  // the self-loop rows go through the same fp16 second layer as the other edges
       CU(self_edge_rows(eg, st, &e->lc));
@@ -548,7 +653,7 @@ static int encode_cells_impl(t2l_engine* e, const float* pts, const float* meta,
   if (!e) return 1;
   if (!e->finalized) return fail(e, "weights not finalized");
   if (n_cells < 0 || !cell_ptr || cell_ptr[0] != 0) return fail(e, "encode_cells: bad cell_ptr");
-  CU(cudaSetDevice(e->device));
+  ENTER_STREAM(e, st);
   for (int c = 0; c < n_cells; ++c)
     if (cell_ptr[c + 1] <= cell_ptr[c]) return fail(e, "encode_cells: cell %d has no objects (the reference asserts >= 1, cells.py:202)", c);
   int c0 = 0;
@@ -630,19 +735,19 @@ static int text_args_ok(t2l_engine* e, const void* in, const void* out, int n, i
 
 extern "C" int t2l_encode_text_tokens(t2l_engine* e, const float* t5, int n_sentences, int L, float* pooled, void* stream) {
   if (text_args_ok(e, t5, pooled, n_sentences, 1, L)) return 1;
-  CU(cudaSetDevice(e->device));
+  ENTER_STREAM(e, stream);
   return text_tokens(e, t5, n_sentences, L, pooled, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int t2l_encode_text_sentences(t2l_engine* e, const float* pooled, int nq, int S, float* out, void* stream) {
   if (text_args_ok(e, pooled, out, nq, S, 1)) return 1;
-  CU(cudaSetDevice(e->device));
+  ENTER_STREAM(e, stream);
   return text_sentences(e, pooled, nq, S, out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int t2l_encode_text(t2l_engine* e, const float* t5, int nq, int S, int L, float* out, void* stream) {
   if (text_args_ok(e, t5, out, nq, S, L)) return 1;
-  CU(cudaSetDevice(e->device));
+  ENTER_STREAM(e, stream);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n_seq = static_cast<size_t>(nq) * S;
   if (n_seq > e->pooled_cap) {
@@ -660,7 +765,7 @@ extern "C" int t2l_encode_text(t2l_engine* e, const float* t5, int nq, int S, in
 extern "C" int t2l_db_build(t2l_engine* e, const float* D, int64_t n_rows, int64_t row_offset, void* stream) {
   if (!e) return 1;
   if (n_rows < 0 || (n_rows > 0 && !D) || n_rows > 0x7fffff00LL) return fail(e, "db_build: bad argument");
-  CU(cudaSetDevice(e->device));
+  ENTER_STREAM(e, stream);
   if (static_cast<size_t>(n_rows) > e->sw_planes_rows) {
     if (e->db.planes) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->db.planes)); e->db.planes = nullptr; }
     CU(cudaMalloc(&e->db.planes, static_cast<size_t>(n_rows) * 512 * sizeof(__nv_bfloat16) + 1024));
@@ -700,7 +805,7 @@ extern "C" int t2l_search_topk(t2l_engine* e, const float* Q, int nq, int k, int
   if (!Q || !out_idx || !out_score || nq < 0) return fail(e, "search_topk: bad argument");
   if (k < 1 || k > T2L_MAX_TOPK) return fail(e, "search_topk: k must be in 1..%d (use t2l_search_topk_exact beyond)", T2L_MAX_TOPK);
   if (!e->db.D && e->db.n_rows != 0) return fail(e, "search_topk: t2l_db_build has not been called");
-  CU(cudaSetDevice(e->device));
+  ENTER_STREAM(e, stream);
   if (ensure_search_work(e, nq)) return 1;
   CU(search_topk(e->db, e->sw, Q, nq, k, out_idx, out_score, out_n_fallback, static_cast<cudaStream_t>(stream), &e->lc));
   return 0;
@@ -709,7 +814,7 @@ extern "C" int t2l_search_topk(t2l_engine* e, const float* Q, int nq, int k, int
 extern "C" int t2l_search_topk_exact(t2l_engine* e, const float* Q, int nq, int k, int64_t* out_idx, double* out_score, void* stream) {
   if (!e) return 1;
   if (!Q || !out_idx || !out_score || nq < 0 || k < 1 || k > 16) return fail(e, "search_topk_exact: bad argument (k in 1..16)");
-  CU(cudaSetDevice(e->device));
+  ENTER_STREAM(e, stream);
   CU(search_topk_exact(e->db, Q, nq, k, out_idx, out_score, nullptr, static_cast<cudaStream_t>(stream), &e->lc));
   return 0;
 }
@@ -718,8 +823,29 @@ extern "C" int t2l_merge_topk(t2l_engine* e, const int64_t* idx_all, const doubl
                               double* out_score, void* stream) {
   if (!e) return 1;
   if (!idx_all || !score_all || !out_idx || !out_score) return fail(e, "merge_topk: NULL buffer");
-  CU(cudaSetDevice(e->device));
+  ENTER_STREAM(e, stream);
   CU(merge_topk(idx_all, score_all, n_shards, nq, k, out_idx, out_score, static_cast<cudaStream_t>(stream), &e->lc));
+  return 0;
+}
+
+extern "C" int t2l_topk_accuracy(t2l_engine* e, const int64_t* idx, int nq, int k, const int64_t* target_row, const double* query_xy,
+                                 const double* cell_xy, const int32_t* query_scene, const int32_t* cell_scene, const int32_t* top_k_host,
+                                 int n_top, const double* threshs_host, int n_thr, uint8_t* hit, uint8_t* within, double* dists,
+                                 void* stream) {
+  if (!e) return 1;
+  if (!idx || !query_xy || !cell_xy || nq < 0 || k < 1 || n_top < 0 || n_top > 8 || n_thr < 0 || n_thr > 8 || (n_top && !top_k_host) ||
+      (n_thr && !threshs_host) || (within && !n_thr) || ((cell_scene != nullptr) != (query_scene != nullptr)))
+    return fail(e, "topk_accuracy: bad argument (at most 8 k values and 8 thresholds)");
+  TopkAccuracy a{};
+  a.idx = idx; a.nq = nq; a.k = k; a.target_row = target_row; a.query_xy = query_xy; a.cell_xy = cell_xy;
+  a.query_scene = query_scene; a.cell_scene = cell_scene; a.n_top = n_top; a.n_thr = n_thr; a.hit = hit; a.within = within; a.dists = dists;
+  for (int i = 0; i < n_top; ++i) {
+    if (top_k_host[i] < 1 || (i && top_k_host[i] <= top_k_host[i - 1])) return fail(e, "topk_accuracy: top_k must be ascending and >= 1");
+    a.top_k[i] = top_k_host[i];
+  }
+  for (int i = 0; i < n_thr; ++i) a.threshs[i] = threshs_host[i];
+  ENTER_STREAM(e, stream);
+  CU(topk_accuracy(a, static_cast<cudaStream_t>(stream), &e->lc));
   return 0;
 }
 
@@ -729,7 +855,7 @@ extern "C" int t2l_merge_topk(t2l_engine* e, const int64_t* idx_all, const doubl
 extern "C" int t2l_debug_linear(t2l_engine* e, int path, const float* A, int lda, const float* Wt, int ldw, const float* bias, float* C, int ldc,
                                 int M, int N, int K, int act, int segmax, void* stream) {
   if (!e) return 1;
-  CU(cudaSetDevice(e->device));
+  ENTER_STREAM(e, stream);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Linear l;
   l.A = A; l.lda = lda; l.W = Wt; l.ldw = ldw; l.bias = bias; l.C = C; l.ldc = ldc; l.M = M; l.N = N; l.K = K; l.act = act;
@@ -750,7 +876,7 @@ extern "C" int t2l_debug_linear(t2l_engine* e, int path, const float* A, int lda
 extern "C" int t2l_debug_linear_f16(t2l_engine* e, const void* A, int lda, const void* Wt, int ldw, const float* bias, void* C, int ldc,
                                     int M, int N, int K, int act, int out_half, void* stream) {
   if (!e) return 1;
-  CU(cudaSetDevice(e->device));
+  ENTER_STREAM(e, stream);
   Linear l;
   l.A = static_cast<const float*>(A); l.lda = lda; l.W = static_cast<const float*>(Wt); l.ldw = ldw; l.bias = bias;
   l.C = static_cast<float*>(C); l.ldc = ldc; l.M = M; l.N = N; l.K = K; l.act = act; l.half_ops = 1; l.out_half = out_half;

@@ -243,6 +243,17 @@ T2L_DEVICE float sqdist_nofma(float ax, float ay, float az, float bx, float by, 
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// The other possibility for the third-party kernels the reference calls (torch-cluster 1.6.0 `dist += tmp * tmp`, built by
+// nvcc with its default -fmad=true): the same sum contracted into fused multiply-adds.  Which of the two the authors' wheel
+// executed cannot be checked here, so it is a named switch in the oracle (pyg_ops.DIST_FMA)
+// and in the engine (T2L_DIST_FMA=1); the default stays the unfused form.
+template <bool kFma>
+T2L_DEVICE float sqdist(float ax, float ay, float az, float bx, float by, float bz) {
+  if (!kFma) return sqdist_nofma(ax, ay, az, bx, by, bz);
+  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
 T2L_DEVICE float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -9,7 +9,7 @@ namespace t2l {
 
 // One warp per object.  Level L has P points held in registers, P/32 per lane, point j owned by
 // lane j % 32 at register j / 32 (so register order == index order inside a lane).
-template <int P>
+template <int P, bool kFma>
 __device__ __forceinline__ void fps_level(const float* __restrict__ pos_s /*smem [P*3]*/, int lane,
                                           uint8_t* __restrict__ idx_out /*[P/2]*/, float* __restrict__ cpos_s /*smem [(P/2)*3]*/,
                                           float* __restrict__ cpos_out /*[(P/2)*3]*/) {
@@ -35,7 +35,7 @@ __device__ __forceinline__ void fps_level(const float* __restrict__ pos_s /*smem
     int best_j = 0;
 #pragma unroll
     for (int t = 0; t < R; ++t) {
-      dist[t] = fminf(dist[t], sqdist_nofma(px[t], py[t], pz[t], cx, cy, cz));
+      dist[t] = fminf(dist[t], sqdist<kFma>(px[t], py[t], pz[t], cx, cy, cz));
       if (dist[t] > best) { best = dist[t]; best_j = t * 32 + lane; }  // strict: first max within the lane
     }
     // distances are >= +0, so their bit patterns order as unsigned integers
@@ -48,6 +48,7 @@ __device__ __forceinline__ void fps_level(const float* __restrict__ pos_s /*smem
 
 constexpr int kFpsWarps = 4;
 
+template <bool kFma>
 __global__ void __launch_bounds__(kFpsWarps * 32) fps_kernel(const float* __restrict__ pts, int n_obj, Geometry g) {
   __shared__ float s_pos[kFpsWarps][kPoints * 3];
   __shared__ float s_c1[kFpsWarps][128 * 3];
@@ -61,22 +62,23 @@ __global__ void __launch_bounds__(kFpsWarps * 32) fps_kernel(const float* __rest
     s_pos[w][j * 3 + 0] = p[j * 6 + 0]; s_pos[w][j * 3 + 1] = p[j * 6 + 1]; s_pos[w][j * 3 + 2] = p[j * 6 + 2];
   }
   __syncwarp();
-  fps_level<256>(s_pos[w], lane, g.fps1 + o * 128, s_c1[w], g.cpos1 + o * 128 * 3);
-  fps_level<128>(s_c1[w], lane, g.fps2 + o * 64, s_c2[w], g.cpos2 + o * 64 * 3);
-  fps_level<64>(s_c2[w], lane, g.fps3 + o * 32, s_c3[w], g.cpos3 + o * 32 * 3);
+  fps_level<256, kFma>(s_pos[w], lane, g.fps1 + o * 128, s_c1[w], g.cpos1 + o * 128 * 3);
+  fps_level<128, kFma>(s_c1[w], lane, g.fps2 + o * 64, s_c2[w], g.cpos2 + o * 64 * 3);
+  fps_level<64, kFma>(s_c2[w], lane, g.fps3 + o * 32, s_c3[w], g.cpos3 + o * 32 * 3);
 }
 
-cudaError_t fps_all_levels(const float* pts, int n_obj, const Geometry& g, cudaStream_t st, Launches* lc) {
+cudaError_t fps_all_levels(const float* pts, int n_obj, const Geometry& g, bool dist_fma, cudaStream_t st, Launches* lc) {
   if (n_obj <= 0) return cudaSuccess;
   if (lc) lc->n++;
-  fps_kernel<<<(n_obj + kFpsWarps - 1) / kFpsWarps, kFpsWarps * 32, 0, st>>>(pts, n_obj, g);
+  if (dist_fma) fps_kernel<true><<<(n_obj + kFpsWarps - 1) / kFpsWarps, kFpsWarps * 32, 0, st>>>(pts, n_obj, g);
+  else fps_kernel<false><<<(n_obj + kFpsWarps - 1) / kFpsWarps, kFpsWarps * 32, 0, st>>>(pts, n_obj, g);
   return cudaGetLastError();
 }
 
 // Ball query: one warp per centroid scans its object's dense points in ascending index, 32 at
 // a time, and keeps the first 32 with d < r*r (strict).  r*r is the double product rounded to
 // fp32, as torch-cluster passes it.
-template <int P, int M>
+template <int P, int M, bool kFma>
 __device__ __forceinline__ void ball_level(const float* __restrict__ dense_s /*smem [P*3]*/, const float* __restrict__ cpos /*gmem [M*3]*/,
                                            float r2, int warp, int n_warps, int lane, uint8_t* __restrict__ nbr /*[M*32]*/,
                                            uint8_t* __restrict__ cnt /*[M]*/) {
@@ -85,7 +87,7 @@ __device__ __forceinline__ void ball_level(const float* __restrict__ dense_s /*s
     int base = 0;
     for (int t = 0; t < P / 32 && base < kMaxNbr; ++t) {
       const int j = t * 32 + lane;
-      const float d = sqdist_nofma(dense_s[j * 3 + 0], dense_s[j * 3 + 1], dense_s[j * 3 + 2], cx, cy, cz);
+      const float d = sqdist<kFma>(dense_s[j * 3 + 0], dense_s[j * 3 + 1], dense_s[j * 3 + 2], cx, cy, cz);
       const bool in = d < r2;
       const uint32_t ballot = __ballot_sync(0xffffffffu, in);
       const int rank = base + __popc(ballot & ((1u << lane) - 1u));
@@ -96,6 +98,7 @@ __device__ __forceinline__ void ball_level(const float* __restrict__ dense_s /*s
   }
 }
 
+template <bool kFma>
 __global__ void __launch_bounds__(256) ball_kernel(const float* __restrict__ pts, int n_obj, Geometry g, float r2_1, float r2_2, float r2_3) {
   __shared__ float s_d[kPoints * 3];
   const long o = blockIdx.x;
@@ -105,23 +108,24 @@ __global__ void __launch_bounds__(256) ball_kernel(const float* __restrict__ pts
     s_d[j * 3 + 0] = p[j * 6 + 0]; s_d[j * 3 + 1] = p[j * 6 + 1]; s_d[j * 3 + 2] = p[j * 6 + 2];
   }
   __syncthreads();
-  ball_level<256, 128>(s_d, g.cpos1 + o * 128 * 3, r2_1, warp, 8, lane, g.nbr1 + o * 128 * 32, g.cnt1 + o * 128);
+  ball_level<256, 128, kFma>(s_d, g.cpos1 + o * 128 * 3, r2_1, warp, 8, lane, g.nbr1 + o * 128 * 32, g.cnt1 + o * 128);
   __syncthreads();
   for (int j = threadIdx.x; j < 128 * 3; j += blockDim.x) s_d[j] = g.cpos1[o * 128 * 3 + j];
   __syncthreads();
-  ball_level<128, 64>(s_d, g.cpos2 + o * 64 * 3, r2_2, warp, 8, lane, g.nbr2 + o * 64 * 32, g.cnt2 + o * 64);
+  ball_level<128, 64, kFma>(s_d, g.cpos2 + o * 64 * 3, r2_2, warp, 8, lane, g.nbr2 + o * 64 * 32, g.cnt2 + o * 64);
   __syncthreads();
   for (int j = threadIdx.x; j < 64 * 3; j += blockDim.x) s_d[j] = g.cpos2[o * 64 * 3 + j];
   __syncthreads();
-  ball_level<64, 32>(s_d, g.cpos3 + o * 32 * 3, r2_3, warp, 8, lane, g.nbr3 + o * 32 * 32, g.cnt3 + o * 32);
+  ball_level<64, 32, kFma>(s_d, g.cpos3 + o * 32 * 3, r2_3, warp, 8, lane, g.nbr3 + o * 32 * 32, g.cnt3 + o * 32);
 }
 
-cudaError_t ball_query_all_levels(const float* pts, int n_obj, const Geometry& g, cudaStream_t st, Launches* lc) {
+cudaError_t ball_query_all_levels(const float* pts, int n_obj, const Geometry& g, bool dist_fma, cudaStream_t st, Launches* lc) {
   if (n_obj <= 0) return cudaSuccess;
   if (lc) lc->n++;
   // radii of pointnet2.py:57-59; r*r in double then rounded to fp32
   const float r1 = static_cast<float>(0.2 * 0.2), r2 = static_cast<float>(0.3 * 0.3), r3 = static_cast<float>(0.4 * 0.4);
-  ball_kernel<<<n_obj, 256, 0, st>>>(pts, n_obj, g, r1, r2, r3);
+  if (dist_fma) ball_kernel<true><<<n_obj, 256, 0, st>>>(pts, n_obj, g, r1, r2, r3);
+  else ball_kernel<false><<<n_obj, 256, 0, st>>>(pts, n_obj, g, r1, r2, r3);
   return cudaGetLastError();
 }
 

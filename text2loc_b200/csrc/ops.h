@@ -52,8 +52,9 @@ struct Geometry {           // per object, all levels
   uint8_t* nbr1; uint8_t* nbr2; uint8_t* nbr3;   // [n,128,32] [n,64,32] [n,32,32]
   uint8_t* cnt1; uint8_t* cnt2; uint8_t* cnt3;   // [n,128] [n,64] [n,32]
 };
-cudaError_t fps_all_levels(const float* pts, int n_obj, const Geometry& g, cudaStream_t st, Launches* lc);
-cudaError_t ball_query_all_levels(const float* pts, int n_obj, const Geometry& g, cudaStream_t st, Launches* lc);
+// dist_fma: evaluate squared distances with fused multiply-adds (common.cuh::sqdist) instead of one rounding per operation
+cudaError_t fps_all_levels(const float* pts, int n_obj, const Geometry& g, bool dist_fma, cudaStream_t st, Launches* lc);
+cudaError_t ball_query_all_levels(const float* pts, int n_obj, const Geometry& g, bool dist_fma, cudaStream_t st, Launches* lc);
 
 // ---- pointnet.cu --------------------------------------------------------------------------
 // x0[n*256, 4] = rgb (padded to 4 floats) from pts
@@ -105,6 +106,19 @@ struct SaObj {
   int n_obj, P, M;
 };
 cudaError_t sa_obj(const SaObj& a, cudaStream_t st, Launches* lc);
+// Second generation (sa_obj2.cu): W2 resident in tensor memory (TS-mode MMAs), self-loop edges folded in as one extra
+// tile per object (no side tensor), SA1 tiles paired.  Needs the self-loop source of every object.
+struct SaObj2 {
+  const __half* Px16; int C1; int C2;    // Px16 = fp16 (W1x x_j + b1)
+  const float* dense_pos; int dense_stride; const float* cpos;
+  const uint8_t* nbr; const uint8_t* cnt;
+  const int32_t* loop_src_obj; const int32_t* loop_half;  // [n] source object / half of its dense points
+  const float* Wp;                       // [C1,4]
+  const __half* W2h; const float* b2;    // [C2, C1] fp16, [C2]
+  float* out;                            // [n*M, C2]
+  int n_obj, P, M;
+};
+cudaError_t sa_obj2(const SaObj2& a, cudaStream_t st, Launches* lc);
 // Hself[o*M+m, :] only (the re-added self-loop edge of every centroid)
 cudaError_t self_edge_rows(const EdgeGather& a, cudaStream_t st, Launches* lc);
 // GA input: A[n*32, 260] = [x3 (256) | cpos3 (3) | 0]
@@ -178,5 +192,23 @@ cudaError_t search_topk_exact(const SearchDb& db, const float* Q, int nq, int k,
                               const int32_t* only_flagged, cudaStream_t st, Launches* lc);
 cudaError_t merge_topk(const int64_t* idx_all, const double* score_all, int n_shards, int nq, int k, int64_t* out_idx,
                        double* out_score, cudaStream_t st, Launches* lc);
+
+
+// ---- bookkeeping.cu -----------------------------------------------------------------------
+// Per-query accuracy rows of eval_epoch / run_coarse (training/coarse.py:131-150, evaluation/utils.py:31-54).
+struct TopkAccuracy {
+  const int64_t* idx; int nq, k;    // [nq, k] retrieved database rows, best first (-1 = empty slot)
+  const int64_t* target_row;        // [nq] database row of the query's own cell (-1: not in the database) or null
+  const double* query_xy;           // [nq, 2] pose_w[0:2]
+  const double* cell_xy;            // [N, 2] position credited to each database row (cell centre / predicted in-cell position)
+  const int32_t* query_scene;       // [nq] scene code or null
+  const int32_t* cell_scene;        // [N] scene code or null (null: no cross-scene masking)
+  int32_t top_k[8]; int n_top;      // ascending list of k values (by value: the launch carries them)
+  double threshs[8]; int n_thr;     // distance thresholds
+  uint8_t* hit;                     // [nq, n_top] or null
+  uint8_t* within;                  // [nq, n_top, n_thr] or null: min(dists[0:k]) <= thresh
+  double* dists;                    // [nq, k] or null
+};
+cudaError_t topk_accuracy(const TopkAccuracy& a, cudaStream_t st, Launches* lc);
 
 }  // namespace t2l

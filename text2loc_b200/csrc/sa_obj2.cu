@@ -1,0 +1,495 @@
+// Object-resident fused PointConv layer, second generation (models/pointcloud/pointnet2.py:25-37; PyG PointConv with
+// add_self_loops=True), fp16 operands, fp32 accumulation:
+//
+//   out[i] = max( max over the <=32 ball-query neighbours j of  relu(W2 . relu(Px[j] + W1p.(pos_j - pos_i)) + b2),
+//                 the same expression for the re-added self-loop edge (dense point with the centroid's per-cell index) )
+//
+// What changed against sa_obj.cu (profiles/r01: shared-memory-bandwidth bound -- an SS-mode 128x128x16 UMMA alone reads
+// 128 B/clk of operands, the gather warps' LDS/STS come on top; tensor pipe 9 / 19 / 33 % active):
+//   * W2 is the M-side operand of the transposed product D^T[channel, edge] = W2 . A^T and never changes, so it now lives
+//     in TENSOR MEMORY (written once per CTA with tcgen05.st, lane = channel, one 32-bit column per pair of K elements) and
+//     the MMAs run in TS mode: `tcgen05.mma [d], [a_tmem], b_desc`.  Only the gathered edge tile is read from shared memory:
+//     64 B/clk instead of 128, and the 128 KB of shared memory W2 occupied for SA3 become ring slots and a second object
+//     buffer.
+//   * The self-loop edge of every centroid is folded in: its source rows (a contiguous half of ANOTHER object's Px block)
+//     arrive with the object's own block, form one extra tile per object whose columns are centroids instead of edges,
+//     and its post-ReLU result waits in a thread-private column of shared memory until the centroid's neighbour tile is
+//     reduced.  The separate self-edge gather kernel, the side GEMM and the [n*M, C2] side tensor (96 KB per object written
+//     and read back through HBM) are gone.
+//   * SA1 (C1 = 32, C2 = 64) filled half of every 128-byte operand row, half of the accumulator lanes and two of the four
+//     epilogue warps.  Its tiles are now PAIRED: one item carries the 32 channels of two different edge groups side by side
+//     (K = 64) and W2 sits in tensor memory as a block-diagonal [[W2, 0], [0, W2]], so lanes 0..63 of the accumulator
+//     are group A's channels and lanes 64..127 group B's: half as many tiles, barriers and fences per object.
+//   * For SA3 the two 128-channel halves of a tile go to two accumulators one after the other (half outer, K inner): the
+//     epilogue of half 0 overlaps the MMAs of half 1; the edge items stay in the ring until half 1 has read them.
+//
+// Warp roles (512 threads): 0 = bulk-copy producer (one block of seven copies per object), 1 = MMA issuer, 2 = TMEM
+// allocator, 4..7 = W2 upload, then epilogue (one TMEM lane quadrant each), 8..15 = gather (two groups of four warps).
+// Pipelines: object buffers full/empty (producer <-> gather), A ring full/empty (gather <-> MMA), accumulators
+// full/empty (MMA <-> epilogue).
+#include "ops.h"
+#include "umma_gemm.cuh"
+
+namespace t2l {
+
+struct SaObj2Params {
+  const __half* Px16;         // [n*P, C1] fp16 (W1x x_j + b1)
+  const float* dense_pos;     // [n*P, POS_STRIDE] xyz first
+  const float* cpos;          // [n*M, 3]
+  const uint8_t* nbr;         // [n*M, 32]
+  const uint8_t* cnt;         // [n*M]
+  const int32_t* loop_src;    // [n] object whose dense points feed this object's self loops
+  const int32_t* loop_half;   // [n] which half (0 / 1) of that object's dense points
+  const float* Wp;            // [C1, 4] position part of the first Linear
+  const __half* W2h;          // [C2, C1] fp16
+  const float* b2;            // [C2]
+  float* out;                 // [n*M, C2]
+  int n_obj;
+};
+
+template <int C1_, int C2_, int P_, int M_, int POS_STRIDE_, bool PAIR_>
+struct Sa2Cfg {
+  static constexpr int C1 = C1_, C2 = C2_, P = P_, M = M_, POS_STRIDE = POS_STRIDE_;
+  static constexpr bool PAIR = PAIR_;
+  static constexpr int KC = PAIR ? 2 * C1 : C1;       // K extent of a tile's MMAs (halfs): two 32-channel groups side by side when paired
+  static constexpr int KB = KC / 64;                   // 128-byte-row items per tile
+  static constexpr int MH = C2 > 128 ? C2 / 128 : 1;   // 128-channel halves of W2
+  static constexpr int TILE_CEN = PAIR ? 8 : 4;        // centroids per tile (32 edge slots each)
+  static constexpr int TPO = M / TILE_CEN;             // neighbour tiles per object (+ 1 self-loop tile)
+  static constexpr int SELF_COLS = PAIR ? M / 2 : M;   // live columns of the self-loop tile (one per centroid; two lane groups when paired)
+  static constexpr int A_BYTES = 128 * 128;
+  static constexpr int PX_BYTES = P * C1 * 2;
+  static constexpr int POS_BYTES = P * POS_STRIDE * 4;
+  static constexpr int CPOS_BYTES = M * 12;
+  static constexpr int NBR_BYTES = M * 32;
+  static constexpr int CNT_BYTES = M;
+  static constexpr int SPX_BYTES = M * C1 * 2;         // self-loop source rows: half of the source object's Px block
+  static constexpr int SPOS_BYTES = M * POS_STRIDE * 4;
+  static constexpr int OBJ_BYTES = PX_BYTES + POS_BYTES + CPOS_BYTES + NBR_BYTES + CNT_BYTES + SPX_BYTES + SPOS_BYTES;
+  static constexpr int NOBJ = 2;
+  static constexpr int SIDE_BYTES = M * C2 * 4;        // post-ReLU self-loop results, [centroid][channel]
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TABLE_BYTES = C1 * 12;          // w1p as channel pairs: x2[C1/2] | y2[C1/2] | z2[C1/2]
+  static constexpr int FIXED = 1024 + NOBJ * OBJ_BYTES + SIDE_BYTES + BAR_BYTES + TABLE_BYTES;
+  static constexpr int FIT = (227 * 1024 - FIXED) / A_BYTES;
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
+  static constexpr int W_COLS = MH * (KC / 2);         // tensor-memory columns of W2 (two K elements per 32-bit column)
+  static constexpr int NACC = MH == 2 ? 2 : 3;
+  static constexpr int ACC_COL0 = 512 - NACC * 128;
+  static constexpr uint32_t IDESC = umma_idesc(0u, 128, 128);  // f16 x f16 -> f32, M = 128 channels (lanes), N = 128 edge rows
+  static constexpr int SMEM = FIXED + STAGES * A_BYTES;
+  static_assert(PX_BYTES % 16 == 0 && POS_BYTES % 16 == 0 && CPOS_BYTES % 16 == 0 && NBR_BYTES % 16 == 0 && CNT_BYTES % 16 == 0 &&
+                    SPX_BYTES % 16 == 0 && SPOS_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+  static_assert(W_COLS <= ACC_COL0, "W2 and the accumulators share the 512 tensor-memory columns");
+  static_assert((2 * STAGES + 2 * NACC + 2 * NOBJ) * 8 + 4 <= BAR_BYTES, "barrier block too small");
+  static_assert(STAGES >= KB + 1 || MH == 1, "half-outer MMA order keeps a whole tile in the ring");
+  static_assert(STAGES >= 3, "ring too shallow");
+  static_assert(PAIR ? (C1 == 32 && C2 == 64) : (C1 % 64 == 0 && C2 % 128 == 0), "shape not covered");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+constexpr int kSa2Threads = 512;
+
+T2L_DEVICE void bulk_load2(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T: the M-side operand is read from tensor memory (lane = row, 32-bit column = two K elements)
+T2L_DEVICE void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// registers -> TMEM: this warp's 32 lanes x 32 consecutive columns (thread t = lane t of the warp's quadrant)
+T2L_DEVICE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0],"
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16,"
+      " %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+        "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+        "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+T2L_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// Packed fp32 pairs stay in 64-bit registers from the shared-memory load to the fp16 pack (sm_100 packed fp32 pipe).
+T2L_DEVICE uint64_t s2_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+T2L_DEVICE uint64_t s2_dup2(float x) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(x));
+  return d;
+}
+T2L_DEVICE uint64_t s2_half2_to_f32x2(uint32_t h2) {
+  uint64_t d;
+  asm("{\n\t.reg .f16 l, h;\n\t.reg .f32 a, b;\n\t"
+      "mov.b32 {l, h}, %1;\n\t"
+      "cvt.f32.f16 a, l;\n\tcvt.f32.f16 b, h;\n\t"
+      "mov.b64 %0, {a, b};\n\t}"
+      : "=l"(d) : "r"(h2));
+  return d;
+}
+// (lo, hi) fp32 pair -> packed fp16x2 with ReLU, round-to-nearest, saturating at 65504
+T2L_DEVICE uint32_t s2_relu_pack_half2(uint64_t v) {
+  uint32_t r;
+  asm("{\n\t.reg .f32 a, b;\n\tmov.b64 {a, b}, %1;\n\tcvt.rn.relu.satfinite.f16x2.f32 %0, b, a;\n\t}" : "=r"(r) : "l"(v));
+  return r;
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Params p) {
+  constexpr int C1 = Cfg::C1, C2 = Cfg::C2, P = Cfg::P, M = Cfg::M, PS = Cfg::POS_STRIDE;
+  constexpr bool PAIR = Cfg::PAIR;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* stage_base = smem;  // A ring, 1024-aligned (128-byte swizzle atoms)
+  uint8_t* obj_base = stage_base + Cfg::STAGES * Cfg::A_BYTES;
+  float* side_s = reinterpret_cast<float*>(obj_base + Cfg::NOBJ * Cfg::OBJ_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(side_s) + Cfg::SIDE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + Cfg::NACC;
+  uint64_t* obj_full = tmem_empty + Cfg::NACC;
+  uint64_t* obj_empty = obj_full + Cfg::NOBJ;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(obj_empty + Cfg::NOBJ);
+  float* table = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + Cfg::BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 4);  // one arrive per warp of the gather group that built the item
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < Cfg::NACC; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    for (int i = 0; i < Cfg::NOBJ; ++i) {
+      mbar_init(&obj_full[i], 1);
+      mbar_init(&obj_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, 512);
+  for (int c = threadIdx.x; c < C1; c += kSa2Threads) {  // b1 is already folded into Px
+    table[c] = p.Wp[c * 4 + 0];
+    table[C1 + c] = p.Wp[c * 4 + 1];
+    table[2 * C1 + c] = p.Wp[c * 4 + 2];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // ---- W2 -> tensor memory (epilogue warps: warp % 4 is the lane quadrant a warp may touch) ----
+  if (warp >= 4 && warp < 8) {
+    const int ew = warp - 4;
+    const int L = ew * 32 + lane;  // TMEM lane = output channel (mod 128)
+#pragma unroll 1
+    for (int h = 0; h < Cfg::MH; ++h) {
+#pragma unroll 1
+      for (int q = 0; q < Cfg::KC / 64; ++q) {  // 32 columns = 64 K elements per store
+        uint32_t r[32];
+        if (PAIR) {
+          // block-diagonal [[W2, 0], [0, W2]]: lanes 0..63 multiply K elements 0..31 (edge group A), lanes 64..127 elements 32..63
+          const uint4* src = reinterpret_cast<const uint4*>(p.W2h + static_cast<long>(L & 63) * C1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 w = __ldg(src + i);
+            const bool lo = L < 64;
+            r[4 * i + 0] = lo ? w.x : 0u; r[4 * i + 1] = lo ? w.y : 0u; r[4 * i + 2] = lo ? w.z : 0u; r[4 * i + 3] = lo ? w.w : 0u;
+            r[16 + 4 * i + 0] = lo ? 0u : w.x; r[16 + 4 * i + 1] = lo ? 0u : w.y; r[16 + 4 * i + 2] = lo ? 0u : w.z; r[16 + 4 * i + 3] = lo ? 0u : w.w;
+          }
+        } else {
+          const uint4* src = reinterpret_cast<const uint4*>(p.W2h + static_cast<long>(h * 128 + L) * C1 + q * 64);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint4 w = __ldg(src + i);
+            r[4 * i + 0] = w.x; r[4 * i + 1] = w.y; r[4 * i + 2] = w.z; r[4 * i + 3] = w.w;
+          }
+        }
+        tmem_st_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + h * (Cfg::KC / 2) + q * 32, r);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // contiguous run of whole objects per CTA
+  const int o0 = static_cast<int>(static_cast<long>(p.n_obj) * blockIdx.x / gridDim.x);
+  const int o1 = static_cast<int>(static_cast<long>(p.n_obj) * (blockIdx.x + 1) / gridDim.x);
+  constexpr int kTilesPerObj = Cfg::TPO + 1;  // tile 0 of an object = its self-loop edges
+
+  if (warp == 0) {
+    // ================= producer: seven bulk copies per object onto one barrier =================
+    for (int o = o0, n = 0; o < o1; ++o, ++n) {
+      const int buf = n % Cfg::NOBJ;
+      const long src = static_cast<long>(__ldg(p.loop_src + o)) * P + __ldg(p.loop_half + o) * M;  // first dense point of the self-loop sources
+      mbar_wait(&obj_empty[buf], (((n / Cfg::NOBJ) & 1) ^ 1));
+      if (elect_one()) {
+        uint8_t* dst = obj_base + buf * Cfg::OBJ_BYTES;
+        mbar_arrive_expect_tx(&obj_full[buf], Cfg::OBJ_BYTES);
+        bulk_load2(dst, p.Px16 + static_cast<long>(o) * P * C1, Cfg::PX_BYTES, &obj_full[buf]);
+        dst += Cfg::PX_BYTES;
+        bulk_load2(dst, p.dense_pos + static_cast<long>(o) * P * PS, Cfg::POS_BYTES, &obj_full[buf]);
+        dst += Cfg::POS_BYTES;
+        bulk_load2(dst, p.cpos + static_cast<long>(o) * M * 3, Cfg::CPOS_BYTES, &obj_full[buf]);
+        dst += Cfg::CPOS_BYTES;
+        bulk_load2(dst, p.nbr + static_cast<long>(o) * M * 32, Cfg::NBR_BYTES, &obj_full[buf]);
+        dst += Cfg::NBR_BYTES;
+        bulk_load2(dst, p.cnt + static_cast<long>(o) * M, Cfg::CNT_BYTES, &obj_full[buf]);
+        dst += Cfg::CNT_BYTES;
+        bulk_load2(dst, p.Px16 + src * C1, Cfg::SPX_BYTES, &obj_full[buf]);
+        dst += Cfg::SPX_BYTES;
+        bulk_load2(dst, p.dense_pos + src * PS, Cfg::SPOS_BYTES, &obj_full[buf]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    long u0 = 0;  // first ring item of the current tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const long n_tiles = static_cast<long>(o1 - o0) * kTilesPerObj;
+    for (long tile = 0; tile < n_tiles; ++tile, u0 += Cfg::KB) {
+#pragma unroll 1
+      for (int h = 0; h < Cfg::MH; ++h) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + Cfg::ACC_COL0 + acc * 128;
+#pragma unroll 1
+        for (int kb = 0; kb < Cfg::KB; ++kb) {
+          const long u = u0 + kb;
+          const int stage = static_cast<int>(u % Cfg::STAGES);
+          if (h == 0) {  // the items stay resident for the later halves
+            mbar_wait(&full_bar[stage], static_cast<uint32_t>(u / Cfg::STAGES) & 1);
+            tc_fence_after();
+          }
+          if (elect_one()) {  // see umma_gemm.cuh: keeps UTCHMMA/UTCBAR straight-line
+            const uint64_t edesc = umma_desc_sw128(stage_base + stage * Cfg::A_BYTES);  // edge tile: the N-side operand
+            const uint32_t w_addr = tmem_base + h * (Cfg::KC / 2) + kb * 32;            // 64 K elements = 32 columns per item
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ts(d_addr, w_addr + 8 * k, edesc + 2 * k, Cfg::IDESC, (kb | k) != 0);
+            if (h == Cfg::MH - 1) tc_commit(&empty_bar[stage]);
+            if (kb == Cfg::KB - 1) tc_commit(&tmem_full[acc]);
+          }
+          __syncwarp();
+        }
+        if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================= epilogue =================
+    const int ew = warp - 4;  // TMEM lane quadrant
+    const int set = PAIR ? (ew >> 1) : 0;                 // paired tiles: lanes 64..127 belong to the second edge group
+    const int ch_lo = PAIR ? ((ew & 1) * 32 + lane) : (ew * 32 + lane);  // this thread's channel inside a 128-channel half
+    float bias[Cfg::MH];
+#pragma unroll
+    for (int h = 0; h < Cfg::MH; ++h) bias[h] = __ldg(p.b2 + h * 128 + ch_lo);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int o = o0; o < o1; ++o) {
+      float* out_o = p.out + static_cast<long>(o) * M * C2;
+#pragma unroll 1
+      for (int t = 0; t < kTilesPerObj; ++t) {
+#pragma unroll 1
+        for (int h = 0; h < Cfg::MH; ++h) {
+          const int ch = h * 128 + ch_lo;
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + Cfg::ACC_COL0 + acc * 128;
+          float v[2][32];
+          tmem_ld_32x32(t_addr, v[0]);
+          if (t == 0) {
+            // self-loop tile: column e = centroid e (+ 64 for the second lane group of a paired tile); park relu(. + b2)
+            constexpr int kChunks = Cfg::SELF_COLS / 32;
+#pragma unroll
+            for (int q = 0; q < kChunks; ++q) {
+              tmem_ld_wait(v[q & 1]);
+              if (q + 1 < kChunks) tmem_ld_32x32(t_addr + (q + 1) * 32, v[(q + 1) & 1]);
+              float* dst = side_s + (set * Cfg::SELF_COLS + q * 32) * C2 + ch;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) dst[j * C2] = fmaxf(v[q & 1][j] + bias[h], 0.f);
+            }
+          } else {
+            const int cen0 = PAIR ? (2 * (t - 1) + set) * 4 : (t - 1) * 4;  // first centroid of this lane group's tile
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // chunk q = centroid cen0 + q: this thread's channel, its 32 edge slots
+              tmem_ld_wait(v[q & 1]);
+              if (q + 1 < 4) tmem_ld_32x32(t_addr + (q + 1) * 32, v[(q + 1) & 1]);
+              const float* x = v[q & 1];
+              float m[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) m[i] = fmaxf(fmaxf(x[4 * i], x[4 * i + 1]), fmaxf(x[4 * i + 2], x[4 * i + 3]));
+              const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+              // bias and ReLU commute with the max over edges (per-channel constant, monotonic rounding)
+              const float keep = fmaxf(fmaxf(mx + bias[h], 0.f), side_s[(cen0 + q) * C2 + ch]);
+              out_o[(cen0 + q) * C2 + ch] = round_tf32(keep);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ================= gather: A items from the resident object block =================
+    // Two groups of four warps.  Where a tile has <= 2 items the groups alternate TILES (one proxy fence per tile),
+    // else they alternate items.  Thread t of a group owns 16-byte chunk `sub` of rows rb, rb + 16, ...: the eight lanes
+    // of a quarter-warp cover one 128-byte operand row (two 64-byte Px rows when paired).
+    constexpr bool kTileMode = Cfg::KB <= 2;
+    const int group = (warp - 8) >> 2;
+    const int t = threadIdx.x & 127;
+    const int sub = t & 7, rb = t >> 3;
+    const int set = PAIR ? (sub >> 2) : 0;
+    const int px_chunk = (PAIR ? (sub & 3) : sub) * 16;  // byte offset of my 8 channels inside a 64-channel slice of a Px row
+    const ulonglong2* tab2 = reinterpret_cast<const ulonglong2*>(table);  // two channel pairs per 16-byte load
+    long u = 0;     // ring item counter of this CTA
+    long tile = 0;  // tile counter of this CTA (self-loop tiles included)
+    for (int o = o0, n = 0; o < o1; ++o, ++n) {
+      const int buf = n % Cfg::NOBJ;
+      const uint8_t* ob = obj_base + buf * Cfg::OBJ_BYTES;
+      const uint8_t* px_s = ob;
+      const float* pos_s = reinterpret_cast<const float*>(ob + Cfg::PX_BYTES);
+      const float* cpos_s = reinterpret_cast<const float*>(ob + Cfg::PX_BYTES + Cfg::POS_BYTES);
+      const uint8_t* nbr_s = ob + Cfg::PX_BYTES + Cfg::POS_BYTES + Cfg::CPOS_BYTES;
+      const uint8_t* cnt_s = nbr_s + Cfg::NBR_BYTES;
+      const uint8_t* spx_s = cnt_s + Cfg::CNT_BYTES;
+      const float* spos_s = reinterpret_cast<const float*>(spx_s + Cfg::SPX_BYTES);
+      mbar_wait(&obj_full[buf], (n / Cfg::NOBJ) & 1);
+#pragma unroll 1
+      for (int tt = 0; tt < kTilesPerObj; ++tt, ++tile) {
+        if (kTileMode && (tile & 1) != group) { u += Cfg::KB; continue; }
+        const bool self = tt == 0;
+        // rows of a self-loop tile beyond its live columns are never read back: they are not built
+        const int n_rows = self ? Cfg::SELF_COLS / 16 : 8;
+        const uint8_t* src_base = self ? spx_s : px_s;
+        int src_off[8];
+        uint64_t dx[8], dy[8], dz[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = rb + 16 * i;
+          int j, cen;
+          const float* pj;
+          if (self) {
+            cen = (r & (Cfg::SELF_COLS - 1)) + set * Cfg::SELF_COLS;  // row e of the tile = self-loop edge of centroid e
+            j = cen;
+            pj = spos_s + j * PS;
+          } else {
+            cen = (PAIR ? (2 * (tt - 1) + set) * 4 : (tt - 1) * 4) + (r >> 5);
+            const int sl = r & 31;
+            j = nbr_s[cen * 32 + (sl < cnt_s[cen] ? sl : 0)];  // empty slots replicate slot 0: the max is unchanged
+            pj = pos_s + j * PS;
+          }
+          src_off[i] = j * (C1 * 2) + px_chunk;
+          dx[i] = s2_dup2(pj[0] - cpos_s[cen * 3 + 0]);  // pos_j - pos_i: exact fp32 subtraction, as the reference's message()
+          dy[i] = s2_dup2(pj[1] - cpos_s[cen * 3 + 1]);
+          dz[i] = s2_dup2(pj[2] - cpos_s[cen * 3 + 2]);
+        }
+        const long u_tile = u;
+#pragma unroll 1
+        for (int kb = 0; kb < Cfg::KB; ++kb, ++u) {
+          if (!kTileMode && (u & 1) != group) continue;
+          const int stage = static_cast<int>(u % Cfg::STAGES);
+          const uint32_t use = static_cast<uint32_t>(u / Cfg::STAGES);
+          uint4 raw[8];  // all Px reads of the item in flight before anything waits
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < n_rows) raw[i] = *reinterpret_cast<const uint4*>(src_base + src_off[i] + (PAIR ? 0 : kb * 128));
+          // w1p of my 8 channels as pairs: (x, y, z) x 4 pairs
+          const int pair0 = (PAIR ? (sub & 3) * 8 : kb * 64 + sub * 8) >> 2;  // index in ulonglong2 units (2 pairs each)
+          const ulonglong2 wx01 = tab2[pair0], wx23 = tab2[pair0 + 1];
+          const ulonglong2 wy01 = tab2[C1 / 4 + pair0], wy23 = tab2[C1 / 4 + pair0 + 1];
+          const ulonglong2 wz01 = tab2[C1 / 2 + pair0], wz23 = tab2[C1 / 2 + pair0 + 1];
+          const uint64_t wx[4] = {wx01.x, wx01.y, wx23.x, wx23.y}, wy[4] = {wy01.x, wy01.y, wy23.x, wy23.y},
+                         wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
+          mbar_wait(&empty_bar[stage], (use & 1) ^ 1);
+          uint8_t* abase = stage_base + stage * Cfg::A_BYTES;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < n_rows) {
+              const int r = rb + 16 * i;
+              const uint32_t rw[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+              uint32_t packed[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {  // channels 2q, 2q+1:  Px (+ b1) + w1p . (pos_j - pos_i)
+                uint64_t v = s2_half2_to_f32x2(rw[q]);
+                v = s2_fma2(wx[q], dx[i], v);
+                v = s2_fma2(wy[q], dy[i], v);
+                v = s2_fma2(wz[q], dz[i], v);
+                packed[q] = s2_relu_pack_half2(v);
+              }
+              // 128B swizzle: 16-byte chunk `sub` of row r lives at chunk position sub ^ (r % 8)
+              *reinterpret_cast<uint4*>(abase + r * 128 + ((sub ^ (r & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+          }
+          if (!kTileMode) {
+            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
+          }
+        }
+        if (kTileMode) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+#pragma unroll
+            for (int kb = 0; kb < Cfg::KB; ++kb) mbar_arrive(&full_bar[(u_tile + kb) % Cfg::STAGES]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&obj_empty[buf]);  // this warp no longer reads the object block
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <class Cfg>
+static cudaError_t launch_sa_obj2(const SaObj2& a, cudaStream_t st) {
+  static bool configured_dev[64] = {};  // the attribute is per device: one flag per device ordinal
+  bool& configured = configured_dev[current_device() & 63];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sa_obj2_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  SaObj2Params p{a.Px16, a.dense_pos, a.cpos, a.nbr, a.cnt, a.loop_src_obj, a.loop_half, a.Wp, a.W2h, a.b2, a.out, a.n_obj};
+  const int grid = a.n_obj < tma_api().num_sms ? a.n_obj : tma_api().num_sms;
+  sa_obj2_kernel<Cfg><<<grid, kSa2Threads, Cfg::SMEM, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t sa_obj2(const SaObj2& a, cudaStream_t st, Launches* lc) {
+  if (a.n_obj <= 0) return cudaSuccess;
+  if (lc) lc->n++;
+  if (a.C1 == 32 && a.C2 == 64 && a.P == 256 && a.M == 128 && a.dense_stride == 6) return launch_sa_obj2<Sa2Cfg<32, 64, 256, 128, 6, true>>(a, st);
+  if (a.C1 == 128 && a.C2 == 128 && a.P == 128 && a.M == 64 && a.dense_stride == 3) return launch_sa_obj2<Sa2Cfg<128, 128, 128, 64, 3, false>>(a, st);
+  if (a.C1 == 256 && a.C2 == 256 && a.P == 64 && a.M == 32 && a.dense_stride == 3) return launch_sa_obj2<Sa2Cfg<256, 256, 64, 32, 3, false>>(a, st);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace t2l

@@ -44,6 +44,9 @@ class Engine:
             raise EngineError(self._lib.t2l_last_error(None).decode())
         self._h = h
         self._db = None  # keeps the database tensor alive (the engine holds a raw pointer to it)
+        self._stage = None  # device staging pair of the host-streaming encode_text
+        self._copy_stream = None
+        self._stage_done = [None, None]
         self.has_weights = False
 
     def __del__(self):
@@ -126,11 +129,18 @@ class Engine:
         t5 = t5.contiguous()
         cq = max(1, self.TOKENS_PER_CHUNK // (n_sent * n_tok))
         rows_per_chunk = cq * n_sent
-        if getattr(self, "_stage", None) is None or self._stage[0].shape[0] < rows_per_chunk or self._stage[0].shape[1] != n_tok:
-            self._stage = [torch.empty((rows_per_chunk, n_tok, T5_DIM), dtype=torch.float32, device=self.device) for _ in range(2)]
-            self._copy_stream = torch.cuda.Stream(self.device)
-            self._stage_done = [None, None]
         cur = torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)  # one copy stream for the engine's lifetime
+        if self._stage is None or self._stage[0].shape[0] < rows_per_chunk or self._stage[0].shape[1] != n_tok:
+            # (Re)allocation happens on the current stream: the caching allocator may hand back blocks that kernels
+            # already queued on this stream still read (the previous staging pair included).  The copy stream must
+            # not write them before that work has finished, and the blocks must not be recycled under the copies.
+            self._stage = [torch.empty((rows_per_chunk, n_tok, T5_DIM), dtype=torch.float32, device=self.device) for _ in range(2)]
+            for t in self._stage:
+                t.record_stream(self._copy_stream)
+            self._copy_stream.wait_stream(cur)
+            self._stage_done = [None, None]
         pooled = torch.empty((nq * n_sent, T5_DIM), dtype=torch.float32, device=self.device)
         for i, q0 in enumerate(range(0, nq, cq)):
             q1 = min(nq, q0 + cq)
@@ -188,6 +198,32 @@ class Engine:
         sc = torch.empty((nq, k), dtype=torch.float64, device=self.device)
         self._check(self._lib.t2l_merge_topk(self._h, _ptr(idx_all), _ptr(score_all), G, nq, k, _ptr(idx), _ptr(sc), self._stream()))
         return idx, sc
+
+    # ---- bookkeeping ----------------------------------------------------------------------
+    def topk_accuracy(self, idx, query_xy, cell_xy, top_k, threshs=(), target_row=None, query_scene=None, cell_scene=None,
+                      want_dists: bool = False):
+        """Per-query accuracy rows (t2l_topk_accuracy): returns (hit u8 [nq, n_top] or None, within u8 [nq, n_top, n_thr] or
+        None, dists f64 [nq, k] or None), all on device."""
+        idx = self._dev(idx, torch.int64)
+        nq, k = idx.shape
+        query_xy = self._dev(query_xy, torch.float64)
+        cell_xy = self._dev(cell_xy, torch.float64)
+        if query_xy.shape != (nq, 2) or cell_xy.dim() != 2 or cell_xy.shape[1] != 2:
+            raise EngineError(f"topk_accuracy: query_xy {tuple(query_xy.shape)} / cell_xy {tuple(cell_xy.shape)}")
+        tk = np.ascontiguousarray(np.asarray(list(top_k), dtype=np.int32))
+        th = np.ascontiguousarray(np.asarray(list(threshs), dtype=np.float64))
+        target_row = self._dev(target_row, torch.int64) if target_row is not None else None
+        query_scene = self._dev(query_scene, torch.int32) if query_scene is not None else None
+        cell_scene = self._dev(cell_scene, torch.int32) if cell_scene is not None else None
+        hit = torch.empty((nq, len(tk)), dtype=torch.uint8, device=self.device) if target_row is not None else None
+        within = torch.empty((nq, len(tk), len(th)), dtype=torch.uint8, device=self.device) if len(th) else None
+        dists = torch.empty((nq, k), dtype=torch.float64, device=self.device) if want_dists else None
+        with torch.cuda.device(self.device):
+            self._check(self._lib.t2l_topk_accuracy(
+                self._h, _ptr(idx), nq, k, _ptr(target_row), _ptr(query_xy), _ptr(cell_xy), _ptr(query_scene), _ptr(cell_scene),
+                tk.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(tk), th.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), len(th),
+                _ptr(hit), _ptr(within), _ptr(dists), self._stream()))
+        return hit, within, dists
 
     # ---- test hooks -------------------------------------------------------------------------
     def debug_linear_f16(self, A, W, bias=None, act=0, out_half=False):

@@ -1,11 +1,15 @@
 """Drop-ins for training/coarse.py::eval_epoch and evaluation/coarse.py::run_coarse.
 
 Same signatures and return types as the reference.  What changes is where the work happens:
-query and cell encodings stay on the GPU, and the per-query float64 GEMV + full argsort of
-training/coarse.py:119-125 becomes one batched t2l_search_topk call whose result is, by
-construction, the fp64 (score desc, row asc) order.  The accuracy bookkeeping
-(training/coarse.py:127-150, evaluation/coarse.py:61-82) is O(nq*k) host work and stays in
-Python, line for line.
+
+* query and cell encodings stay on the GPU;
+* the per-query float64 GEMV + full argsort of training/coarse.py:119-125 is one batched
+  t2l_search_topk call whose result is, by construction, the fp64 (score desc, row asc) order;
+* the accuracy bookkeeping (training/coarse.py:131-150, evaluation/coarse.py:61-82,
+  evaluation/utils.py:31-54) -- per-query Python loops in the reference -- is one
+  t2l_topk_accuracy launch per function over ALL queries.  Cell ids
+  are strings at the API (training/coarse.py:82,128); they are mapped to database rows once, by a
+  sort, and back with one fancy-index.
 """
 from __future__ import annotations
 
@@ -16,16 +20,22 @@ from torch.utils.data import DataLoader
 from . import dataio
 
 
-def calc_sample_accuracies(pose, top_cells, pos_in_cells, top_k, threshs):
-    """evaluation/utils.py:31-54."""
-    pose_w = pose.pose_w
-    assert len(top_cells) == max(top_k) == len(pos_in_cells)
-    pred_w = np.array([top_cells[i].bbox_w[0:2] + pos_in_cells[i, :] * top_cells[i].cell_size for i in range(len(top_cells))])
-    dists = np.linalg.norm(pose_w[0:2] - pred_w, axis=1)
-    pose_scene_name = pose.cell_id.split("_")[0]
-    cell_scene_names = np.array([cell.id.split("_")[0] for cell in top_cells])
-    dists[pose_scene_name != cell_scene_names] = np.inf
-    return {k: {t: np.min(dists[0:k]) <= t for t in threshs} for k in top_k}
+def rows_of_ids(db_ids: np.ndarray, ids: np.ndarray) -> np.ndarray:
+    """Database row of every id in `ids` (any shape), -1 where the id is not in `db_ids`.
+    db_ids are unique (dataloading/kitti360pose/cells.py:149-150)."""
+    order = np.argsort(db_ids, kind="stable")
+    sorted_ids = db_ids[order]
+    flat = np.asarray(ids).reshape(-1)
+    pos = np.clip(np.searchsorted(sorted_ids, flat), 0, len(sorted_ids) - 1)
+    rows = np.where(sorted_ids[pos] == flat, order[pos], -1).astype(np.int64)
+    return rows.reshape(np.shape(ids))
+
+
+def scene_names(ids) -> np.ndarray:
+    """Scene prefix of each id (`id.split("_")[0]`, evaluation/utils.py:45-46);
+    compared by equality there)."""
+    names = np.array([str(i).split("_")[0] for i in ids])
+    return names
 
 
 @torch.no_grad()
@@ -33,81 +43,89 @@ def eval_epoch(model, dataloader, args, return_encodings=False, return_distance=
     """training/coarse.py:63-157.  Returns (accuracies{k}, accuracies_close{k},
     top_retrievals{query_idx: ndarray<U32>[max(top_k)]}) [+ cell_encodings, text_encodings f64]
     [+ dists, scores]."""
-    assert args.ranking_loss != "triplet"
+    assert args.ranking_loss != "triplet"  # training/coarse.py:65
     model.eval()
-    accuracies = {k: [] for k in args.top_k}
-    accuracies_close = {k: [] for k in args.top_k}
-
-    cells_dataset = dataloader.dataset.get_cell_dataset()
+    dataset = dataloader.dataset
+    cells_dataset = dataset.get_cell_dataset()
     cells_dataloader = DataLoader(cells_dataset, batch_size=args.batch_size, collate_fn=dataio.collate_fn, shuffle=False)
-    cells_dict = {cell.id: cell for cell in cells_dataset.cells}
-    cell_size = cells_dataset.cells[0].cell_size
-
-    n_q, n_c, d = len(dataloader.dataset), len(cells_dataset), model.embed_dim
+    n_q, n_c, d = len(dataset), len(cells_dataset), model.embed_dim
+    assert n_c == len(dataset.all_cells)  # training/coarse.py:122 (`len(scores) == len(all_cells)`)
     dev = model.device
-    cell_enc_dev = torch.zeros((n_c, d), dtype=torch.float32, device=dev)
-    text_enc_dev = torch.zeros((n_q, d), dtype=torch.float32, device=dev)
-    db_cell_ids = np.zeros(n_c, dtype="<U32")
-    query_cell_ids = np.zeros(n_q, dtype="<U32")
-    query_poses_w = np.array([pose.pose_w[0:2] for pose in dataloader.dataset.all_poses])
-
-    # Encode the query side (same traversal order as the reference: queries first, then cells)
-    index_offset = 0
-    for batch in dataloader:
-        text_enc = model.encode_text(batch["texts"])
-        bs = len(text_enc)
-        text_enc_dev[index_offset:index_offset + bs] = text_enc
-        query_cell_ids[index_offset:index_offset + bs] = np.array(batch["cell_ids"])
-        index_offset += bs
-
-    # Encode the database side
-    index_offset = 0
-    for batch in cells_dataloader:
-        cell_enc = model.encode_objects(batch["objects"], batch["object_points"])
-        bs = len(cell_enc)
-        cell_enc_dev[index_offset:index_offset + bs] = cell_enc
-        db_cell_ids[index_offset:index_offset + bs] = np.array(batch["cell_ids"])
-        index_offset += bs
-
-    # Search: scores = D @ q in float64, order high -> low, first max(top_k)  (:119-125)
-    k_max = int(np.max(args.top_k))
-    assert n_c == len(dataloader.dataset.all_cells)
     engine = model.engine
-    engine.db_build(cell_enc_dev)
-    idx_dev, score_dev, _ = engine.search_topk(text_enc_dev, min(k_max, n_c))
-    sorted_idx = idx_dev.cpu().numpy()
-    sorted_scores = score_dev.cpu().numpy()
 
-    top_retrievals = {}
-    dists_list, scores_list = [], []
-    for query_idx in range(n_q):
-        retrieved_cell_ids = db_cell_ids[sorted_idx[query_idx]]
-        target_cell_id = query_cell_ids[query_idx]
-        for k in args.top_k:
-            accuracies[k].append(target_cell_id in retrieved_cell_ids[0:k])
-        top_retrievals[query_idx] = retrieved_cell_ids
-        # Close-by accuracy
-        target_pose_w = query_poses_w[query_idx]
-        retrieved_cell_poses = [cells_dict[cell_id].get_center()[0:2] for cell_id in retrieved_cell_ids]
-        dists = np.linalg.norm(target_pose_w - retrieved_cell_poses, axis=1)
-        if return_distance:
-            dists_list.append(dists[0:max(args.top_k)])
-            scores_list.append(sorted_scores[query_idx])
-        for k in args.top_k:
-            accuracies_close[k].append(np.any(dists[0:k] <= cell_size / 2))
+    # ---- encode: queries first, then cells (the reference's traversal order, :91-113), rows stay on the GPU
+    text_enc = torch.zeros((n_q, d), dtype=torch.float32, device=dev)
+    cell_enc = torch.zeros((n_c, d), dtype=torch.float32, device=dev)
+    query_cell_ids, db_cell_ids = [], []
+    off = 0
+    for batch in dataloader:
+        enc = model.encode_text(batch["texts"])
+        text_enc[off:off + len(enc)] = enc
+        query_cell_ids.extend(batch["cell_ids"])
+        off += len(enc)
+    off = 0
+    for batch in cells_dataloader:
+        enc = model.encode_objects(batch["objects"], batch["object_points"])
+        cell_enc[off:off + len(enc)] = enc
+        db_cell_ids.extend(batch["cell_ids"])
+        off += len(enc)
+    query_cell_ids = np.array(query_cell_ids, dtype="<U32")
+    db_cell_ids = np.array(db_cell_ids, dtype="<U32")
 
-    for k in args.top_k:
-        accuracies[k] = np.mean(accuracies[k])
-        accuracies_close[k] = np.mean(accuracies_close[k])
+    # ---- search (:119-125)
+    k_max = min(int(np.max(args.top_k)), n_c)
+    engine.db_build(cell_enc)
+    idx_dev, score_dev, _ = engine.search_topk(text_enc, k_max)
+
+    # ---- bookkeeping for every query at once (:127-150)
+    top_k = sorted(int(k) for k in args.top_k)
+    cell_size = cells_dataset.cells[0].cell_size
+    cell_centres = np.array([cell.get_center()[0:2] for cell in cells_dataset.cells], dtype=np.float64)  # database row order
+    query_xy = np.array([pose.pose_w[0:2] for pose in dataset.all_poses], dtype=np.float64)
+    hit, close, dists = engine.topk_accuracy(
+        idx_dev, query_xy, cell_centres, top_k, threshs=[cell_size / 2], target_row=rows_of_ids(db_cell_ids, query_cell_ids),
+        want_dists=return_distance)
+    hit_rate = hit.to(torch.float64).mean(dim=0).cpu().numpy()
+    close_rate = close[:, :, 0].to(torch.float64).mean(dim=0).cpu().numpy()
+    accuracies = {k: hit_rate[top_k.index(int(k))] for k in args.top_k}
+    accuracies_close = {k: close_rate[top_k.index(int(k))] for k in args.top_k}
+    retrieved_ids = db_cell_ids[idx_dev.cpu().numpy()]  # [n_q, k_max] strings, best first (:128)
+    top_retrievals = dict(enumerate(retrieved_ids))
 
     if return_encodings or return_distance:
-        cell_encodings = cell_enc_dev.cpu().numpy().astype(np.float64)  # f32 values in f64 buffers, as :81,84
-        text_encodings = text_enc_dev.cpu().numpy().astype(np.float64)
+        cell_encodings = cell_enc.cpu().numpy().astype(np.float64)  # f32 values in f64 buffers, as :81,84
+        text_encodings = text_enc.cpu().numpy().astype(np.float64)
     if return_encodings:
         return accuracies, accuracies_close, top_retrievals, cell_encodings, text_encodings
     elif return_distance:
-        return accuracies, accuracies_close, top_retrievals, cell_encodings, text_encodings, np.stack(dists_list), np.stack(scores_list)
+        return accuracies, accuracies_close, top_retrievals, cell_encodings, text_encodings, dists.cpu().numpy(), score_dev.cpu().numpy()
     return accuracies, accuracies_close, top_retrievals
+
+
+def localisation_accuracies(engine, poses, all_cells, retrievals, pos_in_cells, top_k, threshs):
+    """evaluation/utils.py:31-54 (calc_sample_accuracies) for all samples in one launch.
+
+    retrievals [n, k] cell-id strings; pos_in_cells [n, k, 2] predicted position inside each retrieved
+    cell as a fraction of the cell size.  Returns {k: {t: mean accuracy}}."""
+    retrievals = np.asarray(retrievals)
+    n, k = retrievals.shape
+    assert k == max(top_k) == pos_in_cells.shape[1]  # evaluation/utils.py:33
+    all_ids = np.array([cell.id for cell in all_cells], dtype="<U32")
+    rows = rows_of_ids(all_ids, retrievals)
+    assert (rows >= 0).all(), "retrieved an id that is not in dataset.all_cells"
+    origin = np.array([cell.bbox_w[0:2] for cell in all_cells], dtype=np.float64)
+    size = np.array([cell.cell_size for cell in all_cells], dtype=np.float64)
+    # the credited position depends on (sample, slot), not only on the cell: one pseudo-row per retrieved slot
+    pred_w = origin[rows] + np.asarray(pos_in_cells, dtype=np.float64) * size[rows][..., None]  # :37-42
+    _, codes = np.unique(np.concatenate([scene_names(all_ids), scene_names([p.cell_id for p in poses])]), return_inverse=True)
+    cell_scene, pose_scene = codes[:len(all_ids)], codes[len(all_ids):]
+    top_k = sorted(int(x) for x in top_k)
+    _, within, _ = engine.topk_accuracy(
+        np.arange(n * k, dtype=np.int64).reshape(n, k), np.array([p.pose_w[0:2] for p in poses], dtype=np.float64),
+        pred_w.reshape(n * k, 2), top_k, threshs=list(threshs), query_scene=pose_scene.astype(np.int32),
+        cell_scene=cell_scene[rows].reshape(-1).astype(np.int32))
+    rate = within.to(torch.float64).mean(dim=0).cpu().numpy()
+    return {kk: {t: rate[top_k.index(int(kk)), j] for j, t in enumerate(threshs)} for kk in top_k}
 
 
 @torch.no_grad()
@@ -115,7 +133,6 @@ def run_coarse(model, dataloader, args, verbose: bool = True):
     """evaluation/coarse.py:40-84 / evaluation/pipeline.py:40-87: text-to-cell retrieval ->
     (retrievals: list of ndarray<U32>[max(top_k)], best first; accuracies {k: {thresh: float}})."""
     model.eval()
-    all_cells_dict = {cell.id: cell for cell in dataloader.dataset.all_cells}
     retrieval_accuracies, retrieval_accuracies_close, retrievals = eval_epoch(model, dataloader, args)
     retrievals = [retrievals[idx] for idx in range(len(retrievals))]  # Dict -> list
     if verbose:
@@ -123,18 +140,9 @@ def run_coarse(model, dataloader, args, verbose: bool = True):
         print(retrieval_accuracies)
         print("Retrieval Accs Close:")
         print(retrieval_accuracies_close)
-    assert len(retrievals) == len(dataloader.dataset.all_poses)
-
-    accuracies = {k: {t: [] for t in args.threshs} for k in args.top_k}
-    for i_sample in range(len(retrievals)):
-        pose = dataloader.dataset.all_poses[i_sample]
-        top_cells = [all_cells_dict[cell_id] for cell_id in retrievals[i_sample]]
-        pos_in_cells = 0.5 * np.ones((len(top_cells), 2))  # Predict cell-centers
-        accs = calc_sample_accuracies(pose, top_cells, pos_in_cells, args.top_k, args.threshs)
-        for k in args.top_k:
-            for t in args.threshs:
-                accuracies[k][t].append(accs[k][t])
-    for k in args.top_k:
-        for t in args.threshs:
-            accuracies[k][t] = np.mean(accuracies[k][t])
-    return retrievals, accuracies
+    dataset = dataloader.dataset
+    assert len(retrievals) == len(dataset.all_poses)  # evaluation/coarse.py:66
+    pos_in_cells = np.full((len(retrievals), len(retrievals[0]), 2), 0.5)  # predict cell centres (:74)
+    accuracies = localisation_accuracies(model.engine, dataset.all_poses, dataset.all_cells, np.stack(retrievals), pos_in_cells,
+                                         args.top_k, args.threshs)
+    return retrievals, {k: accuracies[int(k)] for k in args.top_k}

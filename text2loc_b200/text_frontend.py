@@ -14,17 +14,31 @@ from typing import List, Tuple
 import torch
 
 _SENT_END = re.compile(r"(?<=[.!?])\s+")
+_WARNED = False
 
 
 def split_sentences(text: str) -> List[str]:
-    """nltk.tokenize.sent_tokenize when nltk (+punkt) is installed, else a regex split that is
-    exact for the reference's templated hints (dataloading/kitti360pose/base.py:60-68)."""
+    """nltk.tokenize.sent_tokenize, as the reference (models/language_encoder.py:110).  Only when nltk itself is not
+    installed does a regex split stand in -- exact for the reference's templated hints
+    (dataloading/kitti360pose/base.py:60-68), announced once because sentence boundaries of free text may differ.
+    An installed nltk without its punkt model raises, with the fix in the message: a silent fallback would change
+    n_sent and with it the embeddings."""
+    global _WARNED
     try:
         from nltk import tokenize
+    except ImportError:
+        if not _WARNED:
+            import warnings
 
-        return tokenize.sent_tokenize(text)
-    except Exception:
+            warnings.warn("nltk is not installed: sentences are split on [.!?] + whitespace, which matches nltk only for "
+                          "templated hint text; install nltk and its punkt model for the reference's behaviour")
+            _WARNED = True
         return [s for s in _SENT_END.split(text.strip()) if s]
+    try:
+        return tokenize.sent_tokenize(text)
+    except LookupError as err:
+        raise LookupError("nltk is installed but its punkt model is missing: run `python -m nltk.downloader punkt` "
+                          "(the reference hard-depends on it, models/language_encoder.py:110)") from err
 
 
 class HFT5Frontend:
