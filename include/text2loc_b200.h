@@ -102,6 +102,21 @@ int t2l_db_build(t2l_engine* e, const float* D, int64_t n_rows, int64_t row_offs
 int t2l_search_topk(t2l_engine* e, const float* Q, int nq, int k, int64_t* out_idx, double* out_score,
                     int32_t* out_n_fallback, void* stream);
 
+/* Streamed databases (BASELINE configs[3]; the reference's encode loop training/coarse.py:105-113 followed by :119-125,
+ * without ever holding the whole database): search the registered shard and fold its top-k into the caller's running
+ * lists IN PLACE.  run_idx device i64 [nq, k] / run_score device f64 [nq, k], initialised by the caller to -1 / -inf.
+ * After the last chunk the running lists equal t2l_search_topk over the concatenated database, bit for bit (same fp64
+ * scores, same (score desc, row asc) order). */
+int t2l_search_topk_accumulate(t2l_engine* e, const float* Q, int nq, int k, int64_t* run_idx, double* run_score,
+                               int32_t* out_n_fallback, void* stream);
+
+/* Bench / test input tooling: counter-based synthetic cells [first_cell, first_cell + n_cells) x obj_per_cell objects x
+ * 256 points, generated on the device (BASELINE configs[3]'s 98 GB of points never exist at once).  Every value is a pure
+ * function of (seed, global object index): any chunking gives the same bytes; oracle/synthgen.py restates it in numpy.
+ *   pts device f32 [n_cells * obj_per_cell, 256, 6], meta device f32 [n_cells * obj_per_cell, 7] */
+int t2l_synth_cells(t2l_engine* e, uint64_t seed, int64_t first_cell, int n_cells, int obj_per_cell, float* pts, float* meta,
+                    void* stream);
+
 /* Exact fp64 scan only (no tensor-core pass); same contract.  Used for k > T2L_MAX_TOPK. */
 int t2l_search_topk_exact(t2l_engine* e, const float* Q, int nq, int k, int64_t* out_idx, double* out_score, void* stream);
 

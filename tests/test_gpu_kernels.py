@@ -136,8 +136,8 @@ def test_features2_set_abstraction_variants(state_dict, golden, monkeypatch):
     """The set-abstraction layers run object-resident on fp16 operands with W2 in tensor memory and the self-loop edges
     folded in (sa_obj2.cu).  The A/B switches keep their predecessors: T2L_SA_V1=1 = sa_obj.cu (W2 in shared memory, self-loop
     rows through a side GEMM), T2L_SA_TF32=1 = the tf32 kernel that gathers from global memory (sa_fused.cu).  All must
-    meet the tolerance against the reference; the two fp16 variants perform the same arithmetic (same operand roundings,
-    fp32 accumulation in a different order) and must agree far inside it."""
+    meet the tolerance against the reference.  (sa_obj2 also applies the first Linear per point and per centroid in fp16
+    instead of per edge in fp32: other rounding points, same accuracy -- tests/test_oracle.py.)"""
     from text2loc_b200.engine import Engine
 
     g = golden("cells_small.npz")
@@ -157,7 +157,7 @@ def test_features2_set_abstraction_variants(state_dict, golden, monkeypatch):
     a, b = outs["fp16 tmem-resident W2 (default)"], outs["fp16 smem-resident W2"]
     errs["tmem vs smem variant"] = np.abs(a - b).max() / np.abs(b).max()
     print("\nfeatures2 max rel-to-max error:", {k: f"{v:.3e}" for k, v in errs.items()})
-    assert errs["tmem vs smem variant"] < 2e-5
+    assert errs["tmem vs smem variant"] < 1e-3
 
 
 def test_fps_ball_query_fma_switch(state_dict, golden, monkeypatch):

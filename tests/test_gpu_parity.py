@@ -324,6 +324,62 @@ def test_encode_cells_16_objects_per_cell(eng, state_dict):
     assert (rev[::-1] == got).all()
 
 
+# ---- streamed database (BASELINE configs[3]) ------------------------------------------------------------------
+
+def test_synthetic_cell_generator_matches_numpy_restatement(eng):
+    """t2l_synth_cells is a pure function of (seed, global object index): bit-equal to oracle/synthgen.py, and any
+    chunking of the cell range yields the same bytes."""
+    from oracle import synthgen
+
+    pts, meta, ptr = eng.synth_cells(9, 100, 7, 16)
+    wp, wm, wptr = synthgen.synth_cells(9, 100, 7, 16)
+    assert (ptr == wptr).all()
+    assert (pts.cpu().numpy() == wp).all() and (meta.cpu().numpy() == wm).all()
+    a, am, _ = eng.synth_cells(9, 100, 3, 16)
+    b, bm, _ = eng.synth_cells(9, 103, 4, 16)
+    assert torch.equal(torch.cat([a, b]), pts) and torch.equal(torch.cat([am, bm]), meta)
+    assert int((meta[:, 6] < 256).sum()) > 0  # objects that repeat points are present
+    small = int(torch.nonzero(meta[:, 6] < 200)[0])
+    assert len(torch.unique(pts[small, :, 0])) < 200
+
+
+def test_streamed_search_equals_unstreamed_50k_cells(eng, state_dict):
+    """configs[3] shape at 1/20 scale: 50 000 cells x 16 objects generated on the device chunk by chunk, encoded and
+    scored against 1 024 queries with a running top-k; neither the points (4.9 GB) nor the planes of the whole database
+    exist at once.  The result must equal the unstreamed search over the kept embeddings bit for bit, must not depend
+    on the chunking, must equal the fp64 oracle on a sample, and sampled cells must match the oracle encoder."""
+    from oracle import restate, synthgen
+    import synth
+    from text2loc_b200 import streaming
+
+    n_cells, per, k = 50000, 16, 10
+    Q = eng.encode_text(torch.from_numpy(synth.make_t5_features(31, 1024)).cuda(), 6)
+    idx, score, nfb, D = streaming.stream_synthetic(eng, Q, k, seed=5, first_cell=0, n_cells=n_cells, obj_per_cell=per,
+                                                    chunk_cells=1024, keep_embeddings=True)
+    assert D.shape == (n_cells, 256)
+    eng.db_build(D)
+    idx2, score2, _ = eng.search_topk(Q, k)
+    assert torch.equal(idx, idx2) and torch.equal(score, score2)
+    idx3, score3, _ = streaming.stream_synthetic(eng, Q, k, seed=5, first_cell=0, n_cells=n_cells, obj_per_cell=per, chunk_cells=777)
+    assert torch.equal(idx, idx3) and torch.equal(score, score3)
+    # two "ranks" streaming half of the cells each, merged: the 8-GPU layout of configs[3] on one device
+    ia, sa, _ = streaming.stream_synthetic(eng, Q, k, 5, 0, n_cells // 2, per, chunk_cells=1024)
+    ib, sb, _ = streaming.stream_synthetic(eng, Q, k, 5, n_cells // 2, n_cells - n_cells // 2, per, chunk_cells=1024)
+    im, sm = eng.merge_topk(torch.stack([ia, ib]), torch.stack([sa, sb]))
+    assert torch.equal(im, idx) and torch.equal(sm, score)
+    # fp64 oracle on a sample of queries (same embeddings into both)
+    oidx, oscore = restate.search_topk(D.cpu().numpy(), Q[:48].cpu().numpy(), k)
+    assert (idx[:48].cpu().numpy() == oidx).all() and np.abs(score[:48].cpu().numpy() - oscore).max() < 1e-12
+    # encoder parity on generated cells
+    sample = [0, 1023, 1024, 25000, 49999]
+    pts = np.concatenate([synthgen.synth_cells(5, c, 1, per)[0] for c in sample])
+    meta = np.concatenate([synthgen.synth_cells(5, c, 1, per)[1] for c in sample])
+    want = restate.encode_cells(state_dict, pts, meta, np.arange(0, per * len(sample) + 1, per, dtype=np.int32)).numpy()
+    err = row_rel_err(D[sample].cpu().numpy(), want)
+    print(f"\nstreamed 50k cells x 16 objects: top-k == unstreamed == merged halves; sampled cells vs oracle {err:.3e}; second-pass queries {int(nfb)}")
+    assert err < EMB_TOL
+
+
 # ---- drop-in API ---------------------------------------------------------------------------------------
 
 def make_model(state_dict, fake_seed=0):
@@ -466,8 +522,8 @@ def test_topk_accuracy_kernel_matches_reference_loops(eng):
                                           top_k, threshs=[15.0], target_row=evaluation.rows_of_ids(ids, np.array([p.cell_id for p in poses])),
                                           want_dists=True)
     assert (dists.cpu().numpy() == want_d).all()  # same float64 arithmetic as numpy's 2-vector norm
-    assert all(hit[:, i].double().mean().item() == want_acc[kk] for i, kk in enumerate(top_k))
-    assert all(close[:, i, 0].double().mean().item() == want_close[kk] for i, kk in enumerate(top_k))
+    assert all(hit[:, i].sum().item() / n_q == want_acc[kk] for i, kk in enumerate(top_k))
+    assert all(close[:, i, 0].sum().item() / n_q == want_close[kk] for i, kk in enumerate(top_k))
     pos_in = rng.uniform(0, 1, (n_q, k, 2))
     want_loc = restate.localisation_accuracies(poses, cells, ids[idx], pos_in, top_k, threshs)
     got_loc = evaluation.localisation_accuracies(eng, poses, cells, ids[idx], pos_in, top_k, threshs)

@@ -253,3 +253,84 @@ def test_precision_plan_set_abstraction_operand_rounding(state_dict, monkeypatch
     print(f"\nset-abstraction operand rounding, cell embedding error: fp16 {e_f16:.2e}, bf16 {e_bf16:.2e}")
     assert e_f16 < 5e-4
     assert e_bf16 > 3 * e_f16
+
+
+def test_precision_plan_per_point_first_linear(state_dict, monkeypatch):
+    """sa_obj2.cu applies the first Linear of a PointConv once per point and once per centroid (Qx[j] - v[i], both fp16,
+    relative to the object's own origin) instead of once per edge in fp32.  Emulating exactly those rounding points on the
+    CPU keeps the cell embeddings as close to the fp32 oracle as round 1's per-edge form did."""
+    import math
+
+    from oracle.restate import MAX_NUM_NEIGHBORS, ball_query_dense, fps_dense
+    from text2loc_b200 import weights
+
+    fw = {k: torch.from_numpy(v) for k, v in weights.engine_weights(state_dict).items()}
+    r16 = lambda t: t.half().float()
+
+    def tf32(t):
+        return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+    origin = {}
+
+    def make_sa(per_point):
+        def set_abstraction(sd_, prefix, x, pos, loop, ratio, r):
+            lvl = prefix.split(".sa")[1][0]
+            w1x, w1p, b1 = fw[f"sa{lvl}.w1x"], fw[f"sa{lvl}.w1p"], fw[f"sa{lvl}.b1"][0]
+            w2, b2 = fw[f"sa{lvl}.w2"], fw[f"sa{lvl}.b2"][0]
+            loop_src_obj, local_obj = loop
+            n, P, C = x.shape
+            M = int(math.ceil(ratio * P))
+            idx = fps_dense(pos, M)
+            ar = torch.arange(n)[:, None]
+            cpos = pos[ar, idx]
+            nbr = ball_query_dense(pos, cpos, r)
+            valid, g = nbr >= 0, nbr.clamp(min=0)
+            if lvl == "1":
+                origin["o"] = pos[:, 0, :].clone()  # the object's point 0 = centroid 0 of every level
+            o = origin["o"]
+            px32 = (x if lvl == "1" else tf32(x)) @ (w1x if lvl == "1" else tf32(w1x)).T + b1
+            sp = (local_obj % 2)[:, None] * M + torch.arange(M)[None, :]
+            so = loop_src_obj[:, None].expand(n, M)
+            if not per_point:  # round 1: Px fp16, exact fp32 position term per edge, one rounding of the sum
+                px = r16(px32)
+                a = r16(torch.relu(px[ar[:, :, None], g] + (pos[ar[:, :, None], g] - cpos[:, :, None, :]) @ w1p.T))
+                a2 = r16(torch.relu(px[so, sp] + (pos[so, sp] - cpos) @ w1p.T))
+            else:
+                d = pos - o[:, None, :]
+                if lvl == "1":
+                    posterm = d @ w1p.T
+                else:  # tf32 GEMM columns [hi | lo] against [W1p | W1p]
+                    dh = tf32(d)
+                    posterm = dh @ tf32(w1p).T + tf32(d - dh) @ tf32(w1p).T
+                qx = r16(px32 + posterm)
+                v = r16((cpos - o[:, None, :]) @ w1p.T)
+                a = torch.relu(r16(qx[ar[:, :, None], g] - v[:, :, None, :]))  # fma.rn.relu.f16x2(1, Qx, -v)
+                vs = r16((cpos - o[so[:, 0]][:, None, :]) @ w1p.T)  # self loops: relative to the SOURCE object's origin
+                a2 = torch.relu(r16(qx[so, sp] - vs))
+            h = tf32(torch.relu(a @ r16(w2).T + b2))
+            h = torch.where(valid[..., None], h, torch.full_like(h, float("-inf"))).max(dim=2)[0]
+            return torch.maximum(h, tf32(torch.relu(a2 @ r16(w2).T + b2))), cpos, idx, nbr
+        return set_abstraction
+
+    real_mlp, real_sa = restate.mlp, restate.set_abstraction
+
+    def mlp(sd_, prefix, x, n_layers, last_relu=True):
+        if ".ga.mlp" in prefix:
+            g1 = r16(torch.relu(r16(x) @ r16(fw["ga.w1"]).T + fw["ga.b1"][0]))
+            return tf32(torch.relu(g1 @ r16(fw["ga.w2"]).T + fw["ga.b2"][0]))
+        return real_mlp(sd_, prefix, x, n_layers, last_relu)
+
+    cells = synth.make_cell_objects(21, 6, [3, 8, 1, 5, 12, 2], max_raw=400)
+    pts, meta, ptr = synth.pack_cells(cells, 21)
+    want = restate.encode_cells(state_dict, pts, meta, ptr).numpy()
+    errs = {}
+    monkeypatch.setattr(restate, "mlp", mlp)
+    for name, per_point in (("per edge (round 1)", False), ("per point + per centroid", True)):
+        monkeypatch.setattr(restate, "set_abstraction", make_sa(per_point))
+        got = restate.encode_cells(state_dict, pts, meta, ptr).numpy()
+        errs[name] = float((np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)).max())
+    monkeypatch.setattr(restate, "mlp", real_mlp)
+    monkeypatch.setattr(restate, "set_abstraction", real_sa)
+    print("\nfirst-Linear formulation, cell embedding error:", {k: f"{v:.2e}" for k, v in errs.items()})
+    assert errs["per point + per centroid"] < 3e-4
+    assert errs["per point + per centroid"] < 2 * errs["per edge (round 1)"] + 5e-5

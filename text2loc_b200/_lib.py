@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libtext2loc_b200.so")
-SOURCES = ["api.cu", "linear.cu", "geometry.cu", "pointnet.cu", "sa_fused.cu", "sa_obj.cu", "sa_obj2.cu", "rowops.cu", "search.cu", "bookkeeping.cu"]
+SOURCES = ["api.cu", "linear.cu", "geometry.cu", "pointnet.cu", "sa_fused.cu", "sa_obj.cu", "sa_obj2.cu", "rowops.cu", "search.cu", "bookkeeping.cu", "synthgen.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 # every symbol include/text2loc_b200.h declares: (restype, argtypes)
@@ -35,6 +35,8 @@ SIGNATURES = {
     "t2l_encode_text_sentences": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "t2l_db_build": (c_int, [_P, _P, c_int64, c_int64, _P]),
     "t2l_search_topk": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),
+    "t2l_search_topk_accumulate": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),
+    "t2l_synth_cells": (c_int, [_P, ctypes.c_uint64, c_int64, c_int, c_int, _P, _P, _P]),
     "t2l_search_topk_exact": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "t2l_merge_topk": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "t2l_topk_accuracy": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P, POINTER(c_int32), c_int, POINTER(c_double), c_int, _P, _P, _P, _P]),

@@ -82,6 +82,20 @@ struct t2l_engine {
   cudaEvent_t order_ev = nullptr;
   cudaStream_t last_stream = nullptr;
   bool order_recorded = false;
+  // Which candidate pass the search runs first.  The single fp16 pass is a third of the tensor work but its error bound is
+  // ~6x wider; when most queries of a call fail its proof (tightly clustered databases) the three-pass bf16 product is the
+  // cheaper FIRST pass.  The count of the previous call is read back asynchronously (pinned word + event, never waited
+  // for) and steers the next call; the returned top-k is identical either way.  T2L_SEARCH_FIRST=fp16|bf16x3 pins it.
+  int search_first = 0;        // 0 adaptive, 1 always fp16, 2 always bf16x3
+  bool bf16_first_now = false;
+  int bf16_first_calls = 0;
+  int32_t* fail_host = nullptr;
+  int64_t* acc_idx = nullptr;  // per-chunk lists of t2l_search_topk_accumulate
+  double* acc_score = nullptr;
+  int acc_cap = 0;
+  cudaEvent_t fail_ev = nullptr;
+  bool fail_pending = false;
+  int fail_nq = 0;
 };
 
 namespace {
@@ -179,7 +193,10 @@ extern "C" int t2l_create(int device, t2l_engine** out) {
   if (const char* v = getenv("T2L_SA_V1")) e->obj_sa2 = !(v[0] == '1');
   if (const char* v = getenv("T2L_DIST_FMA")) e->dist_fma = v[0] == '1';
   if (const char* v = getenv("T2L_OBJ_CHUNK")) { const int n = atoi(v); if (n >= 64 && n <= 65536) e->obj_chunk = n; }
-  if (cudaMalloc(&e->db.max_norm, sizeof(float)) != cudaSuccess ||
+  if (const char* v = getenv("T2L_SEARCH_FIRST")) e->search_first = v[0] == 'f' ? 1 : (v[0] == 'b' ? 2 : 0);
+  if (cudaMalloc(&e->db.max_norm, sizeof(float)) != cudaSuccess || cudaMalloc(&e->db.scale, sizeof(float)) != cudaSuccess ||
+      cudaMallocHost(reinterpret_cast<void**>(&e->fail_host), sizeof(int32_t)) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->fail_ev, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->order_ev, cudaEventDisableTiming) != cudaSuccess) {
     delete e;
     return fail(nullptr, "t2l_create: cudaMalloc / cudaEventCreate failed");
@@ -189,7 +206,7 @@ extern "C" int t2l_create(int device, t2l_engine** out) {
 }
 
 static void free_search_work(t2l_engine* e) {
-  cudaFree(e->sw.q_planes); cudaFree(e->sw.q_norm); cudaFree(e->sw.cand_score); cudaFree(e->sw.cand_idx);
+  cudaFree(e->sw.q_planes); cudaFree(e->sw.q16); cudaFree(e->sw.q_scale); cudaFree(e->sw.q_norm); cudaFree(e->sw.cand_score); cudaFree(e->sw.cand_idx);
   cudaFree(e->sw.cand_thr); cudaFree(e->sw.flags); cudaFree(e->sw.n_fail); cudaFree(e->sw.fail_ids); cudaFree(e->sw.fail_thr);
   cudaFree(e->sw.q2_planes); cudaFree(e->sw.cand2_idx); cudaFree(e->sw.cand2_cnt);
   e->sw = SearchWork{};
@@ -204,6 +221,12 @@ extern "C" void t2l_destroy(t2l_engine* e) {
   cudaFree(e->pooled);
   for (auto& hs : e->stage) { if (hs.ptr) cudaFreeHost(hs.ptr); if (hs.ev) cudaEventDestroy(hs.ev); }
   if (e->order_ev) cudaEventDestroy(e->order_ev);
+  if (e->fail_ev) cudaEventDestroy(e->fail_ev);
+  if (e->fail_host) cudaFreeHost(e->fail_host);
+  cudaFree(e->db.plane16);
+  cudaFree(e->db.scale);
+  cudaFree(e->acc_idx);
+  cudaFree(e->acc_score);
   cudaFree(e->db.planes);
   cudaFree(e->db.max_norm);
   free_search_work(e);
@@ -216,7 +239,7 @@ extern "C" void t2l_destroy(t2l_engine* e) {
 static bool is_tf32_operand(const std::string& n) {
   // weights consumed by the tcgen05 tf32 GEMMs: pre-rounded once (round-to-nearest) so the tensor
   // core's own truncation of the B operand is exact
-  static const char* pre[] = {"sa1.w2", "sa2.w1x", "sa2.w2", "sa3.w1x", "sa3.w2", "ga.w1", "ga.w2", "lin1.w", "lin2.w",
+  static const char* pre[] = {"sa1.w2", "sa2.w1x", "sa2.w1q", "sa2.w2", "sa3.w1x", "sa3.w1q", "sa3.w2", "ga.w1", "ga.w2", "lin1.w", "lin2.w",
                               "mlp_pointnet.w", "merge.w", "txt_intra.in_w", "txt_intra.out_w", "txt_intra.l1_w", "txt_intra.l2_w"};
   for (const char* p : pre) if (n == p) return true;
   return false;
@@ -249,6 +272,16 @@ extern "C" int t2l_set_weight(t2l_engine* e, const char* name, const float* data
   Weight& w = e->w[name];
   if (w.dev) { CU(cudaFree(w.dev)); w.dev = nullptr; }
   if (w.dev16) { CU(cudaFree(w.dev16)); w.dev16 = nullptr; }
+  const std::string nm(name);
+  if (nm.size() > 4 && nm.compare(nm.size() - 4, 4, ".w1p") == 0) {
+    // sa_obj2.cu forms v = W1p . (pos_i - o) in fp16 next to Qx (|Qx| <= 32752): with in-cell position differences of at most
+    // 4 units (cell-normalised coordinates lie in [0, 1], NormalizeScale'd ones in (-1, 1)) |v| must stay below 32752 as well
+    for (int r = 0; r < rows; ++r) {
+      double l1 = 0;
+      for (int c = 0; c < cols; ++c) l1 += fabs(static_cast<double>(data[static_cast<size_t>(r) * cols + c]));
+      if (!(4.0 * l1 <= 32752.0)) return fail(e, "t2l_set_weight: '%s' row %d is too large for the fp16 set-abstraction path", name, r);
+    }
+  }
   const bool split3 = is_split3_operand(name);
   if (split3 && (cols % 32)) return fail(e, "t2l_set_weight: '%s' needs cols %% 32 == 0", name);
   w.rows = rows; w.cols = cols; w.ld = split3 ? 2 * cols : ((cols + 3) & ~3);
@@ -306,6 +339,7 @@ static std::vector<ShapeSpec> expected_shapes(bool fine) {
     const std::string p = "sa" + std::to_string(i + 1);
     v.push_back({p + ".w1x", sa[i][1], sa[i][0]}); v.push_back({p + ".w1p", sa[i][1], 3}); v.push_back({p + ".b1", 1, sa[i][1]});
     v.push_back({p + ".w2", sa[i][2], sa[i][1]});  v.push_back({p + ".b2", 1, sa[i][2]});
+    if (i > 0) v.push_back({p + ".w1q", sa[i][1], sa[i][0] + 6});  // [W1x | W1p | W1p]: the per-point Linear incl. its position part
   }
   v.push_back({"ga.w1", 512, 259}); v.push_back({"ga.b1", 1, 512}); v.push_back({"ga.w2", 1024, 512}); v.push_back({"ga.b2", 1, 1024});
   v.push_back({"lin1.w", 512, 1024}); v.push_back({"lin1.b", 1, 512}); v.push_back({"lin2.w", 256, 512}); v.push_back({"lin2.b", 1, 256});
@@ -358,12 +392,13 @@ static const Weight& W(t2l_engine* e, const std::string& n) { return e->w.at(n);
 // y = act(x W^T + b) helper
 static cudaError_t lin(t2l_engine* e, bool umma, const float* A, long lda, int M, const std::string& wname, const std::string& bname,
                        float* C, long ldc, int act, cudaStream_t st, const float* residual = nullptr, long ldr = 0, int round_out = 0,
-                       int segmax = 0, const float* side = nullptr, long lds = 0, int out_half = 0) {
+                       int segmax = 0, const float* side = nullptr, long lds = 0, int out_half = 0, float half_max = 65504.f) {
   const Weight& w = W(e, wname);
   Linear l;
   l.A = A; l.lda = lda; l.W = w.dev; l.ldw = w.ld; l.bias = bname.empty() ? nullptr : W(e, bname).dev;
   l.C = C; l.ldc = ldc; l.M = M; l.N = w.rows; l.K = w.cols; l.act = act;
   l.residual = residual; l.ldr = ldr; l.round_out = round_out; l.segmax = segmax; l.side = side; l.lds = lds; l.out_half = out_half;
+  l.half_max = half_max;
   return umma ? linear_umma(l, st, &e->lc) : linear_simt(l, st, &e->lc);
 }
 
@@ -515,20 +550,43 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
   float* H = obj_mode ? nullptr : a.get<float>(N * 32 * 32 * 256);  // edge rows / edge records of the A/B paths (1 MB / object)
   float* Hs = need_side ? a.get<float>(N * 64 * 128) : nullptr;     // self-loop rows (n*128*32, n*64*128, n*32*256)
   float* S = need_side ? a.get<float>(N * 64 * 128) : nullptr;      // second-layer output of the self-loop rows
-  float* x1 = a.get<float>(N * 128 * 64);
-  float* x2 = a.get<float>(N * 64 * 128);
+  // sa_obj2: rows of x1 / x2 carry 8 extra columns (tf32 hi | lo of pos - o) for the next level's per-point Linear
+  const bool sa2 = obj_mode && e->obj_sa2;
+  const int ldx1 = sa2 ? 72 : 64, ldx2 = sa2 ? 136 : 128;
+  float* x1 = a.get<float>(N * 128 * ldx1);
+  float* x2 = a.get<float>(N * 64 * ldx2);
   float* x3 = a.get<float>(N * 32 * 256);
   if (!obj_mode) CU(extract_rgb(p, n, x0, st, &e->lc));  // the object-resident path reads rgb straight from pts (sa1_px16)
 
-  struct Level { const char* name; int C1, C2, P, M; const float* x; long ldx; const float* dense; int dstride; const float* cpos;
-                 const uint8_t* nbr; const uint8_t* cnt; float* Px; float* xout; bool px_umma; };
+  struct Level { const char* name; int C1, C2, P, M; float* x; long ldx; const float* dense; int dstride; const float* cpos;
+                 const uint8_t* nbr; const uint8_t* cnt; float* Px; float* xout; int ldo; bool px_umma; };
   Level lv[3] = {
-      {"sa1", 32, 64, 256, 128, x0, 4, p, 6, g.cpos1, g.nbr1, g.cnt1, px, x1, false},
-      {"sa2", 128, 128, 128, 64, x1, 64, g.cpos1, 3, g.cpos2, g.nbr2, g.cnt2, px23, x2, true},
-      {"sa3", 256, 256, 64, 32, x2, 128, g.cpos2, 3, g.cpos3, g.nbr3, g.cnt3, px23, x3, true},
+      {"sa1", 32, 64, 256, 128, x0, 4, p, 6, g.cpos1, g.nbr1, g.cnt1, px, x1, ldx1, false},
+      {"sa2", 128, 128, 128, 64, x1, ldx1, g.cpos1, 3, g.cpos2, g.nbr2, g.cnt2, px23, x2, ldx2, true},
+      {"sa3", 256, 256, 64, 32, x2, ldx2, g.cpos2, 3, g.cpos3, g.nbr3, g.cnt3, px23, x3, 256, true},
   };
   for (const Level& L : lv) {
     const std::string nm = L.name;
+    if (sa2) {
+      // Qx = W1x x + b1 + W1p (pos - o) per point (fp16, |.| <= 32752), then the fused layer (sa_obj2.cu)
+      if (W(e, nm + ".w1p").ld != 4) return fail(e, "internal: w1p pitch");
+      __half* Qx = reinterpret_cast<__half*>(L.Px);
+      if (!L.px_umma) {
+        if (W(e, nm + ".w1x").ld != 4 || L.C1 != 32) return fail(e, "internal: sa1.w1x shape");
+        CU(sa1_qx16(p, n, W(e, nm + ".w1x").dev, W(e, nm + ".w1p").dev, W(e, nm + ".b1").dev, Qx, st, &e->lc));
+      } else {
+        const int c_in = W(e, nm + ".w1x").cols;
+        CU(append_pos_cols(L.dense, n, L.P, L.x, static_cast<int>(L.ldx), c_in, st, &e->lc));
+        CU(lin(e, true, L.x, L.ldx, n * L.P, nm + ".w1q", nm + ".b1", L.Px, L.C1, 0, st, nullptr, 0, 0, 0, nullptr, 0, /*out_half=*/1, kQxMax));
+      }
+      SaObj2 so;
+      so.Qx16 = Qx; so.C1 = L.C1; so.C2 = L.C2; so.cpos = L.cpos; so.nbr = L.nbr; so.cnt = L.cnt; so.loop_src_obj = loop_src;
+      so.loop_half = loop_half; so.Wp = W(e, nm + ".w1p").dev; so.W2h = W(e, nm + ".w2").dev16; so.b2 = W(e, nm + ".b2").dev;
+      so.out = L.xout; so.ldo = L.ldo; so.n_obj = n; so.P = L.P; so.M = L.M;
+      if (!so.W2h) return fail(e, "internal: no fp16 copy of %s.w2", L.name);
+      CU(sa_obj2(so, st, &e->lc));
+      continue;
+    }
     // per-point half of the first Linear (no bias; b1 is added with the position term per edge); fp16 for the
     // object-resident kernel (the buffer is reused as __half [n*P, C1])
     const bool obj = e->fused_sa && e->obj_sa;
@@ -544,14 +602,7 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
     eg.loop_src_obj = loop_src; eg.loop_half = loop_half; eg.Wp = W(e, nm + ".w1p").dev; eg.b1 = W(e, nm + ".b1").dev;
     eg.n_obj = n; eg.P = L.P; eg.M = L.M; eg.H = H; eg.Hself = Hs;
     if (W(e, nm + ".w1p").ld != 4) return fail(e, "internal: w1p pitch");
-    if (obj && e->obj_sa2) {
-      SaObj2 so;
-      so.Px16 = reinterpret_cast<const __half*>(L.Px); so.C1 = L.C1; so.C2 = L.C2; so.dense_pos = L.dense; so.dense_stride = L.dstride;
-      so.cpos = L.cpos; so.nbr = L.nbr; so.cnt = L.cnt; so.loop_src_obj = loop_src; so.loop_half = loop_half; so.Wp = eg.Wp;
-      so.W2h = W(e, nm + ".w2").dev16; so.b2 = W(e, nm + ".b2").dev; so.out = L.xout; so.n_obj = n; so.P = L.P; so.M = L.M;
-      if (!so.W2h) return fail(e, "internal: no fp16 copy of %s.w2", L.name);
-      CU(sa_obj2(so, st, &e->lc));
-    } else if (obj) {
+    if (obj) {
       eg.Px16 = reinterpret_cast<const __half*>(L.Px);
       eg.Hself16 = reinterpret_cast<__half*>(Hs);  // the self-loop rows go through the same fp16 second layer as the other edges
       CU(self_edge_rows(eg, st, &e->lc));
@@ -767,8 +818,9 @@ extern "C" int t2l_db_build(t2l_engine* e, const float* D, int64_t n_rows, int64
   if (n_rows < 0 || (n_rows > 0 && !D) || n_rows > 0x7fffff00LL) return fail(e, "db_build: bad argument");
   ENTER_STREAM(e, stream);
   if (static_cast<size_t>(n_rows) > e->sw_planes_rows) {
-    if (e->db.planes) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->db.planes)); e->db.planes = nullptr; }
+    if (e->db.planes) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->db.planes)); CU(cudaFree(e->db.plane16)); e->db.planes = nullptr; e->db.plane16 = nullptr; }
     CU(cudaMalloc(&e->db.planes, static_cast<size_t>(n_rows) * 512 * sizeof(__nv_bfloat16) + 1024));
+    CU(cudaMalloc(&e->db.plane16, static_cast<size_t>(n_rows) * 256 * sizeof(__half) + 1024));
     e->sw_planes_rows = static_cast<size_t>(n_rows);
   }
   e->db.D = D; e->db.n_rows = n_rows; e->db.row_offset = row_offset;
@@ -783,6 +835,8 @@ static int ensure_search_work(t2l_engine* e, int nq) {
   const size_t cap = static_cast<size_t>(nq) + 128;
   const int sc = 16;
   CU(cudaMalloc(&e->sw.q_planes, cap * 512 * sizeof(__nv_bfloat16)));
+  CU(cudaMalloc(&e->sw.q16, cap * 256 * sizeof(__half)));
+  CU(cudaMalloc(&e->sw.q_scale, cap * sizeof(float)));
   CU(cudaMalloc(&e->sw.q_norm, cap * sizeof(float)));
   CU(cudaMalloc(&e->sw.cand_score, cap * sc * 16 * sizeof(float)));
   CU(cudaMalloc(&e->sw.cand_idx, cap * sc * 16 * sizeof(int32_t)));
@@ -807,7 +861,58 @@ extern "C" int t2l_search_topk(t2l_engine* e, const float* Q, int nq, int k, int
   if (!e->db.D && e->db.n_rows != 0) return fail(e, "search_topk: t2l_db_build has not been called");
   ENTER_STREAM(e, stream);
   if (ensure_search_work(e, nq)) return 1;
-  CU(search_topk(e->db, e->sw, Q, nq, k, out_idx, out_score, out_n_fallback, static_cast<cudaStream_t>(stream), &e->lc));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  CU(cudaStreamIsCapturing(st, &cap));
+  const bool capturing = cap != cudaStreamCaptureStatusNone;  // (a captured call keeps the mode it was captured with)
+  if (e->search_first == 0 && !capturing) {
+    if (e->fail_pending) {
+      const cudaError_t q = cudaEventQuery(e->fail_ev);
+      if (q == cudaSuccess) {
+        e->fail_pending = false;
+        if (e->fail_nq >= 64 && *e->fail_host > 0.30 * e->fail_nq) { e->bf16_first_now = true; e->bf16_first_calls = 0; }
+      } else {
+        (void)cudaGetLastError();  // cudaErrorNotReady is not an error; keep it out of the launch checks
+      }
+    }
+    if (e->bf16_first_now && ++e->bf16_first_calls > 16) e->bf16_first_now = false;  // probe the fp16 pass again now and then
+  }
+  const bool bf16_first = e->search_first == 2 || (e->search_first == 0 && e->bf16_first_now);
+  CU(search_topk(e->db, e->sw, Q, nq, k, out_idx, out_score, out_n_fallback, bf16_first, st, &e->lc));
+  if (e->search_first == 0 && !capturing && !bf16_first && !e->fail_pending && nq > 0 && e->db.n_rows > 0) {
+    CU(cudaMemcpyAsync(e->fail_host, e->sw.n_fail, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(e->fail_ev, st));
+    e->fail_pending = true;
+    e->fail_nq = nq;
+  }
+  return 0;
+}
+
+// Search the registered shard and fold its top-k into the caller's running lists (streamed databases: encode a chunk,
+// db_build it with its row offset, accumulate).
+extern "C" int t2l_search_topk_accumulate(t2l_engine* e, const float* Q, int nq, int k, int64_t* run_idx, double* run_score,
+                                          int32_t* out_n_fallback, void* stream) {
+  if (!e) return 1;
+  if (!run_idx || !run_score) return fail(e, "search_topk_accumulate: NULL running list");
+  if (nq > e->acc_cap) {
+    ENTER(e);
+    if (e->acc_idx) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->acc_idx)); CU(cudaFree(e->acc_score)); e->acc_idx = nullptr; e->acc_score = nullptr; }
+    CU(cudaMalloc(&e->acc_idx, (static_cast<size_t>(nq) + 128) * T2L_MAX_TOPK * sizeof(int64_t)));
+    CU(cudaMalloc(&e->acc_score, (static_cast<size_t>(nq) + 128) * T2L_MAX_TOPK * sizeof(double)));
+    e->acc_cap = nq + 128;
+  }
+  if (t2l_search_topk(e, Q, nq, k, e->acc_idx, e->acc_score, out_n_fallback, stream)) return 1;
+  ENTER_STREAM(e, stream);
+  CU(merge_running_topk(run_idx, run_score, e->acc_idx, e->acc_score, nq, k, static_cast<cudaStream_t>(stream), &e->lc));
+  return 0;
+}
+
+extern "C" int t2l_synth_cells(t2l_engine* e, uint64_t seed, int64_t first_cell, int n_cells, int obj_per_cell, float* pts, float* meta,
+                               void* stream) {
+  if (!e) return 1;
+  if (!pts || !meta || n_cells < 0 || obj_per_cell < 1 || first_cell < 0) return fail(e, "synth_cells: bad argument");
+  ENTER_STREAM(e, stream);
+  CU(synth_cells(seed, first_cell * obj_per_cell, static_cast<long>(n_cells) * obj_per_cell, pts, meta, static_cast<cudaStream_t>(stream), &e->lc));
   return 0;
 }
 

@@ -43,6 +43,7 @@ struct StoreParams {
   int act;
   int round_out;
   int out_half;  // C is __half [M, ldc]: the consumer is an fp16 tensor-core GEMM (same 11-bit significand as tf32)
+  float half_max = kHalfMax;  // fp16 stores saturate at +-half_max
 };
 
 template <bool kHalfOut, bool kResidual>
@@ -106,8 +107,8 @@ struct StoreEpiT {
         for (int q = 0; q < 4; ++q) {
           float x = o[2 * q], y = o[2 * q + 1];
           if (p.act == kActRelu) { x = fmaxf(x, 0.f); y = fmaxf(y, 0.f); }
-          x = fminf(fmaxf(x, -kHalfMax), kHalfMax);
-          y = fminf(fmaxf(y, -kHalfMax), kHalfMax);
+          x = fminf(fmaxf(x, -p.half_max), p.half_max);
+          y = fminf(fmaxf(y, -p.half_max), p.half_max);
           const __half2 hh = __floats2half2_rn(x, y);
           w[q] = *reinterpret_cast<const uint32_t*>(&hh);
         }

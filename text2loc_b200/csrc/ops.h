@@ -31,7 +31,8 @@ struct Linear {
   int passes = 1;             // 3: A and W are [hi | lo] tf32 planes of logical width K (row pitch >= 2K):
                               //    hi*hi + lo*hi + hi*lo in one accumulator, fp32-level accuracy on the tensor cores
   int half_ops = 0;           // A and W point at __half data (lda, ldw in elements): tcgen05 kind::f16, fp32 accumulate
-  int out_half = 0;           // C points at __half data (ldc in elements); values saturate at +-65504
+  int out_half = 0;           // C points at __half data (ldc in elements); values saturate at +-half_max
+  float half_max = 65504.f;
 };
 // tf32 tensor-core path: needs K-major operands with 16-byte aligned rows (lda, ldw % 4 == 0),
 // N % 32 == 0.  K tails are zero-filled by TMA.
@@ -61,6 +62,11 @@ cudaError_t ball_query_all_levels(const float* pts, int n_obj, const Geometry& g
 cudaError_t extract_rgb(const float* pts, int n_obj, float* x0, cudaStream_t st, Launches* lc);
 // Px16[n*256, 32] = fp16(W1x . rgb + b1) for SA1 (w1x [32, ld 4]) straight from pts
 cudaError_t sa1_px16(const float* pts, int n_obj, const float* w1x, const float* b1, __half* px16, cudaStream_t st, Launches* lc);
+// sa_obj2.cu's per-point operand of SA1: Qx16[n*256, 32] = fp16(W1x . rgb + b1 + W1p . (pos - o)), o = the object's point 0
+constexpr float kQxMax = 32752.f;  // Qx and v are bounded by half of fp16's range, so Qx - v never overflows
+cudaError_t sa1_qx16(const float* pts, int n_obj, const float* w1x, const float* w1p, const float* b1, __half* qx16, cudaStream_t st, Launches* lc);
+// columns C .. C+7 of x [n*P, ldx] = tf32 hi | lo split of (pos_r - pos of the object's row 0) | 0 0  (pos [n*P, 3])
+cudaError_t append_pos_cols(const float* pos, int n_obj, int P, float* x, int ldx, int C, cudaStream_t st, Launches* lc);
 // First-layer edge activations of one PointConv:
 //   H[(o*M+m)*32 + s, :] = relu(Px[src_point] + Wp * (pos_src - cpos[o,m]) + b1)   s < 32 neighbour slots
 //   Hself[o*M+m, :]      = same for the re-added self-loop edge (dense point with the centroid's
@@ -109,13 +115,13 @@ cudaError_t sa_obj(const SaObj& a, cudaStream_t st, Launches* lc);
 // Second generation (sa_obj2.cu): W2 resident in tensor memory (TS-mode MMAs), self-loop edges folded in as one extra
 // tile per object (no side tensor), SA1 tiles paired.  Needs the self-loop source of every object.
 struct SaObj2 {
-  const __half* Px16; int C1; int C2;    // Px16 = fp16 (W1x x_j + b1)
-  const float* dense_pos; int dense_stride; const float* cpos;
+  const __half* Qx16; int C1; int C2;    // Qx16 = fp16 (W1x x_j + b1 + W1p (pos_j - o)), o = the object's point 0; |.| <= 32752
+  const float* cpos;                     // [n*M, 3]
   const uint8_t* nbr; const uint8_t* cnt;
   const int32_t* loop_src_obj; const int32_t* loop_half;  // [n] source object / half of its dense points
   const float* Wp;                       // [C1,4]
   const __half* W2h; const float* b2;    // [C2, C1] fp16, [C2]
-  float* out;                            // [n*M, C2]
+  float* out; int ldo;                   // [n*M, ldo], ldo >= C2
   int n_obj, P, M;
 };
 cudaError_t sa_obj2(const SaObj2& a, cudaStream_t st, Launches* lc);
@@ -165,11 +171,15 @@ cudaError_t add_rows(const float* a, const float* b, float* y, long n, cudaStrea
 struct SearchDb {
   const float* D = nullptr;        // caller's fp32 rows [N, 256]
   __nv_bfloat16* planes = nullptr; // [N, 512]  hi | lo
+  __half* plane16 = nullptr;       // [N, 256]  fp16(d * 2^-ex): rows scaled so that the largest norm lies in [0.5, 1)
   float* max_norm = nullptr;       // [1] max row norm (device)
+  float* scale = nullptr;          // [1] 2^ex, undoes the scaling of plane16 (device)
   int64_t n_rows = 0, row_offset = 0;
 };
 struct SearchWork {
   __nv_bfloat16* q_planes;  // [nq_cap, 512]
+  __half* q16;              // [nq_cap, 256] fp16 rows, each scaled by its own power of two
+  float* q_scale;           // [nq_cap] 2^ex per query
   float* q_norm;            // [nq_cap]
   float* cand_score;        // [nq_cap, splits_cap, 16]
   int32_t* cand_idx;        // [nq_cap, splits_cap, 16]
@@ -186,12 +196,21 @@ struct SearchWork {
 };
 constexpr int kPass2Cap = 256;  // candidates per failed query in the second pass (all splits together)
 cudaError_t search_prepare_db(const SearchDb& db, cudaStream_t st, Launches* lc);
+// first_pass_bf16x3: rank the candidates with the three-pass bf16 hi|lo product instead of the single fp16 pass (better when
+// most score gaps are below the fp16 bound); the result is the same either way
 cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q, int nq, int k, int64_t* out_idx,
-                        double* out_score, int32_t* out_n_fallback, cudaStream_t st, Launches* lc);
+                        double* out_score, int32_t* out_n_fallback, bool first_pass_bf16x3, cudaStream_t st, Launches* lc);
 cudaError_t search_topk_exact(const SearchDb& db, const float* Q, int nq, int k, int64_t* out_idx, double* out_score,
                               const int32_t* only_flagged, cudaStream_t st, Launches* lc);
 cudaError_t merge_topk(const int64_t* idx_all, const double* score_all, int n_shards, int nq, int k, int64_t* out_idx,
                        double* out_score, cudaStream_t st, Launches* lc);
+// run := top-k of (run, new) by (score desc, row asc), in place; empty slots carry idx -1
+cudaError_t merge_running_topk(int64_t* run_idx, double* run_score, const int64_t* new_idx, const double* new_score, int nq, int k,
+                               cudaStream_t st, Launches* lc);
+
+// ---- synthgen.cu ------------------------------------------------------------------------------
+// counter-based synthetic objects [first_obj, first_obj + n_obj): pts [n_obj, 256, 6], meta [n_obj, 7]
+cudaError_t synth_cells(uint64_t seed, long first_obj, long n_obj, float* pts, float* meta, cudaStream_t st, Launches* lc);
 
 
 // ---- bookkeeping.cu -----------------------------------------------------------------------

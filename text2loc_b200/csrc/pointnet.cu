@@ -64,6 +64,74 @@ cudaError_t sa1_px16(const float* pts, int n_obj, const float* w1x, const float*
   return cudaGetLastError();
 }
 
+// SA1's per-point half of the first Linear for sa_obj2.cu: Qx[i, :] = fp16(W1x . rgb_i + b1 + W1p . (pos_i - o)), o = the
+// object's point 0, clamped to +-32752 so that Qx - v stays finite in fp16.  One thread per (point, 8 channels).
+__global__ void __launch_bounds__(256) qx1_kernel(const float* __restrict__ pts, long n_pts, const float* __restrict__ w1x /*[32, ld 4]*/,
+                                                  const float* __restrict__ w1p /*[32, ld 4]*/, const float* __restrict__ b1,
+                                                  __half* __restrict__ qx16) {
+  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long i = idx >> 2;
+  const int q = static_cast<int>(idx & 3);
+  if (i >= n_pts) return;
+  const float* pi = pts + i * 6;
+  const float* po = pts + (i / kPoints) * kPoints * 6;  // the object's point 0
+  const float r = pi[3], g = pi[4], b = pi[5];
+  const float dx = pi[0] - po[0], dy = pi[1] - po[1], dz = pi[2] - po[2];
+  uint32_t out[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = q * 8 + p * 2 + e;
+      const float4 w = __ldg(reinterpret_cast<const float4*>(w1x + c * 4));
+      const float4 wp = __ldg(reinterpret_cast<const float4*>(w1p + c * 4));
+      float acc = fmaf(r, w.x, 0.f);
+      acc = fmaf(g, w.y, acc);
+      acc = fmaf(b, w.z, acc);
+      acc += __ldg(b1 + c);
+      acc = fmaf(wp.x, dx, acc);
+      acc = fmaf(wp.y, dy, acc);
+      acc = fmaf(wp.z, dz, acc);
+      v[e] = fminf(fmaxf(acc, -kQxMax), kQxMax);
+    }
+    const __half2 h = __floats2half2_rn(v[0], v[1]);
+    out[p] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(qx16 + i * 32 + q * 8) = make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+cudaError_t sa1_qx16(const float* pts, int n_obj, const float* w1x, const float* w1p, const float* b1, __half* qx16, cudaStream_t st, Launches* lc) {
+  const long n = static_cast<long>(n_obj) * kPoints;
+  if (n <= 0) return cudaSuccess;
+  if (lc) lc->n++;
+  qx1_kernel<<<static_cast<unsigned>((n * 4 + 255) / 256), 256, 0, st>>>(pts, n, w1x, w1p, b1, qx16);
+  return cudaGetLastError();
+}
+
+// Position columns of the per-point Linear of levels 2 and 3: row r of x [n*P, ldx] (the previous level's output, C
+// feature columns) gets columns C .. C+7 = [hi(d) | lo(d) | 0 0], d = pos_r - o (o = the object's row 0), hi/lo the tf32
+// split (hi + lo = d up to 2^-22 |d|), so that the tf32 GEMM against [W1x | W1p | W1p] adds W1p . d at fp32 accuracy.
+__global__ void __launch_bounds__(256) pos_cols_kernel(const float* __restrict__ pos /*[n*P, 3]*/, long rows, int P, float* __restrict__ x, int ldx, int C) {
+  const long r = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const long r0 = (r / P) * P;
+  const float dx = pos[r * 3 + 0] - pos[r0 * 3 + 0], dy = pos[r * 3 + 1] - pos[r0 * 3 + 1], dz = pos[r * 3 + 2] - pos[r0 * 3 + 2];
+  const float hx = round_tf32(dx), hy = round_tf32(dy), hz = round_tf32(dz);
+  float4* dst = reinterpret_cast<float4*>(x + r * ldx + C);
+  dst[0] = make_float4(hx, hy, hz, round_tf32(dx - hx));
+  dst[1] = make_float4(round_tf32(dy - hy), round_tf32(dz - hz), 0.f, 0.f);
+}
+
+cudaError_t append_pos_cols(const float* pos, int n_obj, int P, float* x, int ldx, int C, cudaStream_t st, Launches* lc) {
+  const long rows = static_cast<long>(n_obj) * P;
+  if (rows <= 0) return cudaSuccess;
+  if ((C & 3) || (ldx & 3) || ldx < C + 8) return cudaErrorInvalidValue;
+  if (lc) lc->n++;
+  pos_cols_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, st>>>(pos, rows, P, x, ldx, C);
+  return cudaGetLastError();
+}
+
 // One warp per centroid; lane l owns channels l, l+32, ... (coalesced row reads and writes).
 // The 33 edge rows are independent, so they are processed four at a time with all gathers
 // (4 x (position + C1/32 feature loads)) issued before the first use: the v1 kernel walked the

@@ -4,6 +4,16 @@
 //   out[i] = max( max over the <=32 ball-query neighbours j of  relu(W2 . relu(Px[j] + W1p.(pos_j - pos_i)) + b2),
 //                 the same expression for the re-added self-loop edge (dense point with the centroid's per-cell index) )
 //
+// The first Linear is applied once per POINT and once per CENTROID instead of once per edge:
+//   Px[j] + W1p.(pos_j - pos_i) = Qx[j] - v[i],   Qx[j] = W1x x_j + b1 + W1p.(pos_j - o),   v[i] = W1p.(pos_i - o)
+// with o the object's own origin (its point 0 = centroid 0 of every level, so |pos - o| stays of the size of the ball
+// radii and nothing cancels).  Qx arrives as fp16 (one rounding of the fp32 sum, in the producing kernel), v is formed here in
+// fp32 and rounded to fp16, and an edge element is ONE instruction: fma.rn.relu.f16x2(1, Qx, -v) -- a single rounding of the
+// difference, then ReLU -- for two channels.  (Round 1 converted Px to fp32, added three packed FMAs per channel pair and
+// converted back: 6 instructions per pair, ~250 per 128 x 64 item and thread; ncu showed the gather warps, not shared memory,
+// as the limiter: all three levels took ~1 300 cycles per item, MMAs or not.)  CPU emulation of these rounding points against
+// the reference: cell embeddings 9.8e-5 (round 1's points: 9.3e-5), tests/test_oracle.py.
+//
 // What changed against sa_obj.cu (profiles/r01: shared-memory-bandwidth bound -- an SS-mode 128x128x16 UMMA alone reads
 // 128 B/clk of operands, the gather warps' LDS/STS come on top; tensor pipe 9 / 19 / 33 % active):
 //   * W2 is the M-side operand of the transposed product D^T[channel, edge] = W2 . A^T and never changes, so it now lives
@@ -23,7 +33,7 @@
 //   * For SA3 the two 128-channel halves of a tile go to two accumulators one after the other (half outer, K inner): the
 //     epilogue of half 0 overlaps the MMAs of half 1; the edge items stay in the ring until half 1 has read them.
 //
-// Warp roles (512 threads): 0 = bulk-copy producer (one block of seven copies per object), 1 = MMA issuer, 2 = TMEM
+// Warp roles (512 threads): 0 = bulk-copy producer (one block of six copies per object), 1 = MMA issuer, 2 = TMEM
 // allocator, 4..7 = W2 upload, then epilogue (one TMEM lane quadrant each), 8..15 = gather (two groups of four warps).
 // Pipelines: object buffers full/empty (producer <-> gather), A ring full/empty (gather <-> MMA), accumulators
 // full/empty (MMA <-> epilogue).
@@ -33,9 +43,8 @@
 namespace t2l {
 
 struct SaObj2Params {
-  const __half* Px16;         // [n*P, C1] fp16 (W1x x_j + b1)
-  const float* dense_pos;     // [n*P, POS_STRIDE] xyz first
-  const float* cpos;          // [n*M, 3]
+  const __half* Qx16;         // [n*P, C1] fp16 (W1x x_j + b1 + W1p (pos_j - o)), |.| <= 32752
+  const float* cpos;          // [n*M, 3]  (centroid 0 of an object is its origin o)
   const uint8_t* nbr;         // [n*M, 32]
   const uint8_t* cnt;         // [n*M]
   const int32_t* loop_src;    // [n] object whose dense points feed this object's self loops
@@ -43,13 +52,14 @@ struct SaObj2Params {
   const float* Wp;            // [C1, 4] position part of the first Linear
   const __half* W2h;          // [C2, C1] fp16
   const float* b2;            // [C2]
-  float* out;                 // [n*M, C2]
+  float* out;                 // [n*M, ldo]
+  int ldo;                    // row pitch of out (>= C2: the next level appends position columns)
   int n_obj;
 };
 
-template <int C1_, int C2_, int P_, int M_, int POS_STRIDE_, bool PAIR_>
+template <int C1_, int C2_, int P_, int M_, bool PAIR_>
 struct Sa2Cfg {
-  static constexpr int C1 = C1_, C2 = C2_, P = P_, M = M_, POS_STRIDE = POS_STRIDE_;
+  static constexpr int C1 = C1_, C2 = C2_, P = P_, M = M_;
   static constexpr bool PAIR = PAIR_;
   static constexpr int KC = PAIR ? 2 * C1 : C1;       // K extent of a tile's MMAs (halfs): two 32-channel groups side by side when paired
   static constexpr int KB = KC / 64;                   // 128-byte-row items per tile
@@ -59,13 +69,12 @@ struct Sa2Cfg {
   static constexpr int SELF_COLS = PAIR ? M / 2 : M;   // live columns of the self-loop tile (one per centroid; two lane groups when paired)
   static constexpr int A_BYTES = 128 * 128;
   static constexpr int PX_BYTES = P * C1 * 2;
-  static constexpr int POS_BYTES = P * POS_STRIDE * 4;
   static constexpr int CPOS_BYTES = M * 12;
   static constexpr int NBR_BYTES = M * 32;
   static constexpr int CNT_BYTES = M;
-  static constexpr int SPX_BYTES = M * C1 * 2;         // self-loop source rows: half of the source object's Px block
-  static constexpr int SPOS_BYTES = M * POS_STRIDE * 4;
-  static constexpr int OBJ_BYTES = PX_BYTES + POS_BYTES + CPOS_BYTES + NBR_BYTES + CNT_BYTES + SPX_BYTES + SPOS_BYTES;
+  static constexpr int SPX_BYTES = M * C1 * 2;         // self-loop source rows: half of the source object's Qx block
+  static constexpr int SORG_BYTES = 16;                // origin of the source object (its centroid 0)
+  static constexpr int OBJ_BYTES = PX_BYTES + CPOS_BYTES + NBR_BYTES + CNT_BYTES + SPX_BYTES + SORG_BYTES;
   static constexpr int NOBJ = 2;
   static constexpr int SIDE_BYTES = M * C2 * 4;        // post-ReLU self-loop results, [centroid][channel]
   static constexpr int BAR_BYTES = 256;
@@ -78,8 +87,8 @@ struct Sa2Cfg {
   static constexpr int ACC_COL0 = 512 - NACC * 128;
   static constexpr uint32_t IDESC = umma_idesc(0u, 128, 128);  // f16 x f16 -> f32, M = 128 channels (lanes), N = 128 edge rows
   static constexpr int SMEM = FIXED + STAGES * A_BYTES;
-  static_assert(PX_BYTES % 16 == 0 && POS_BYTES % 16 == 0 && CPOS_BYTES % 16 == 0 && NBR_BYTES % 16 == 0 && CNT_BYTES % 16 == 0 &&
-                    SPX_BYTES % 16 == 0 && SPOS_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+  static_assert(PX_BYTES % 16 == 0 && CPOS_BYTES % 16 == 0 && NBR_BYTES % 16 == 0 && CNT_BYTES % 16 == 0 && SPX_BYTES % 16 == 0,
+                "bulk copies move multiples of 16 bytes");
   static_assert(W_COLS <= ACC_COL0, "W2 and the accumulators share the 512 tensor-memory columns");
   static_assert((2 * STAGES + 2 * NACC + 2 * NOBJ) * 8 + 4 <= BAR_BYTES, "barrier block too small");
   static_assert(STAGES >= KB + 1 || MH == 1, "half-outer MMA order keeps a whole tile in the ring");
@@ -120,36 +129,22 @@ T2L_DEVICE void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
 }
 T2L_DEVICE void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// Packed fp32 pairs stay in 64-bit registers from the shared-memory load to the fp16 pack (sm_100 packed fp32 pipe).
-T2L_DEVICE uint64_t s2_fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+// relu(q - v) for two channels: one fused multiply-add in fp16 (1 * q + (-v), single rounding), then ReLU
+T2L_DEVICE uint32_t s2_sub_relu_h2(uint32_t q, uint32_t neg_v) {
+  uint32_t d;
+  asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(0x3C003C00u), "r"(q), "r"(neg_v));
   return d;
 }
-T2L_DEVICE uint64_t s2_dup2(float x) {
-  uint64_t d;
-  asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(x));
-  return d;
-}
-T2L_DEVICE uint64_t s2_half2_to_f32x2(uint32_t h2) {
-  uint64_t d;
-  asm("{\n\t.reg .f16 l, h;\n\t.reg .f32 a, b;\n\t"
-      "mov.b32 {l, h}, %1;\n\t"
-      "cvt.f32.f16 a, l;\n\tcvt.f32.f16 b, h;\n\t"
-      "mov.b64 %0, {a, b};\n\t}"
-      : "=l"(d) : "r"(h2));
-  return d;
-}
-// (lo, hi) fp32 pair -> packed fp16x2 with ReLU, round-to-nearest, saturating at 65504
-T2L_DEVICE uint32_t s2_relu_pack_half2(uint64_t v) {
+// (lo, hi) fp32 pair -> packed fp16x2, round-to-nearest, saturating at 65504
+T2L_DEVICE uint32_t s2_pack_half2(float lo, float hi) {
   uint32_t r;
-  asm("{\n\t.reg .f32 a, b;\n\tmov.b64 {a, b}, %1;\n\tcvt.rn.relu.satfinite.f16x2.f32 %0, b, a;\n\t}" : "=r"(r) : "l"(v));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 
 template <class Cfg>
 __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Params p) {
-  constexpr int C1 = Cfg::C1, C2 = Cfg::C2, P = Cfg::P, M = Cfg::M, PS = Cfg::POS_STRIDE;
+  constexpr int C1 = Cfg::C1, C2 = Cfg::C2, P = Cfg::P, M = Cfg::M;
   constexpr bool PAIR = Cfg::PAIR;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -236,27 +231,26 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
   constexpr int kTilesPerObj = Cfg::TPO + 1;  // tile 0 of an object = its self-loop edges
 
   if (warp == 0) {
-    // ================= producer: seven bulk copies per object onto one barrier =================
+    // ================= producer: six bulk copies per object onto one barrier =================
     for (int o = o0, n = 0; o < o1; ++o, ++n) {
       const int buf = n % Cfg::NOBJ;
-      const long src = static_cast<long>(__ldg(p.loop_src + o)) * P + __ldg(p.loop_half + o) * M;  // first dense point of the self-loop sources
+      const int src_obj = __ldg(p.loop_src + o);
+      const long src = static_cast<long>(src_obj) * P + __ldg(p.loop_half + o) * M;  // first dense point of the self-loop sources
       mbar_wait(&obj_empty[buf], (((n / Cfg::NOBJ) & 1) ^ 1));
       if (elect_one()) {
         uint8_t* dst = obj_base + buf * Cfg::OBJ_BYTES;
         mbar_arrive_expect_tx(&obj_full[buf], Cfg::OBJ_BYTES);
-        bulk_load2(dst, p.Px16 + static_cast<long>(o) * P * C1, Cfg::PX_BYTES, &obj_full[buf]);
+        bulk_load2(dst, p.Qx16 + static_cast<long>(o) * P * C1, Cfg::PX_BYTES, &obj_full[buf]);
         dst += Cfg::PX_BYTES;
-        bulk_load2(dst, p.dense_pos + static_cast<long>(o) * P * PS, Cfg::POS_BYTES, &obj_full[buf]);
-        dst += Cfg::POS_BYTES;
         bulk_load2(dst, p.cpos + static_cast<long>(o) * M * 3, Cfg::CPOS_BYTES, &obj_full[buf]);
         dst += Cfg::CPOS_BYTES;
         bulk_load2(dst, p.nbr + static_cast<long>(o) * M * 32, Cfg::NBR_BYTES, &obj_full[buf]);
         dst += Cfg::NBR_BYTES;
         bulk_load2(dst, p.cnt + static_cast<long>(o) * M, Cfg::CNT_BYTES, &obj_full[buf]);
         dst += Cfg::CNT_BYTES;
-        bulk_load2(dst, p.Px16 + src * C1, Cfg::SPX_BYTES, &obj_full[buf]);
+        bulk_load2(dst, p.Qx16 + src * C1, Cfg::SPX_BYTES, &obj_full[buf]);
         dst += Cfg::SPX_BYTES;
-        bulk_load2(dst, p.dense_pos + src * PS, Cfg::SPOS_BYTES, &obj_full[buf]);
+        bulk_load2(dst, p.cpos + static_cast<long>(src_obj) * M * 3, Cfg::SORG_BYTES, &obj_full[buf]);  // centroid 0 of the source object
       }
       __syncwarp();
     }
@@ -304,7 +298,7 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int o = o0; o < o1; ++o) {
-      float* out_o = p.out + static_cast<long>(o) * M * C2;
+      float* out_o = p.out + static_cast<long>(o) * M * p.ldo;
 #pragma unroll 1
       for (int t = 0; t < kTilesPerObj; ++t) {
 #pragma unroll 1
@@ -316,15 +310,20 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
           float v[2][32];
           tmem_ld_32x32(t_addr, v[0]);
           if (t == 0) {
-            // self-loop tile: column e = centroid e (+ 64 for the second lane group of a paired tile); park relu(. + b2)
+            // self-loop tile: column e = one centroid's self-loop edge; park relu(. + b2) until that centroid's neighbour tile is reduced
             constexpr int kChunks = Cfg::SELF_COLS / 32;
 #pragma unroll
             for (int q = 0; q < kChunks; ++q) {
               tmem_ld_wait(v[q & 1]);
               if (q + 1 < kChunks) tmem_ld_32x32(t_addr + (q + 1) * 32, v[(q + 1) & 1]);
-              float* dst = side_s + (set * Cfg::SELF_COLS + q * 32) * C2 + ch;
+              // Paired tiles: lane group `set` reduces centroids 8 m + 4 set + (0..3) in the neighbour tiles, so its self-loop
+              // columns must be exactly those centroids -- the parked value is then read back by the thread that wrote it.
 #pragma unroll
-              for (int j = 0; j < 32; ++j) dst[j * C2] = fmaxf(v[q & 1][j] + bias[h], 0.f);
+              for (int j = 0; j < 32; ++j) {
+                const int e = q * 32 + j;
+                const int cen = PAIR ? 8 * (e >> 2) + 4 * set + (e & 3) : e;
+                side_s[cen * C2 + ch] = fmaxf(v[q & 1][j] + bias[h], 0.f);
+              }
             }
           } else {
             const int cen0 = PAIR ? (2 * (t - 1) + set) * 4 : (t - 1) * 4;  // first centroid of this lane group's tile
@@ -339,7 +338,7 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
               const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
               // bias and ReLU commute with the max over edges (per-channel constant, monotonic rounding)
               const float keep = fmaxf(fmaxf(mx + bias[h], 0.f), side_s[(cen0 + q) * C2 + ch]);
-              out_o[(cen0 + q) * C2 + ch] = round_tf32(keep);
+              out_o[(cen0 + q) * p.ldo + ch] = round_tf32(keep);
             }
           }
           tc_fence_before();
@@ -352,98 +351,115 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
   } else if (warp >= 8) {
     // ================= gather: A items from the resident object block =================
     // Two groups of four warps.  Where a tile has <= 2 items the groups alternate TILES (one proxy fence per tile),
-    // else they alternate items.  Thread t of a group owns 16-byte chunk `sub` of rows rb, rb + 16, ...: the eight lanes
-    // of a quarter-warp cover one 128-byte operand row (two 64-byte Px rows when paired).
+    // else they alternate items.  Thread t of a group owns 16-byte chunk `sub` (8 channels) of eight rows of ONE centroid:
+    // rows cq*32 + (rb & 3) + 4 i, so -v (the centroid's half of the first Linear) is formed once per item and reused
+    // by all eight rows.  The eight lanes of a quarter-warp cover one 128-byte operand row (two 64-byte Qx rows when
+    // paired): the Qx reads and the swizzled A writes are conflict-free.
     constexpr bool kTileMode = Cfg::KB <= 2;
     const int group = (warp - 8) >> 2;
     const int t = threadIdx.x & 127;
     const int sub = t & 7, rb = t >> 3;
+    const int cq = rb >> 2, r0 = cq * 32 + (rb & 3);     // my rows: r0 + 4 i
     const int set = PAIR ? (sub >> 2) : 0;
-    const int px_chunk = (PAIR ? (sub & 3) : sub) * 16;  // byte offset of my 8 channels inside a 64-channel slice of a Px row
-    const ulonglong2* tab2 = reinterpret_cast<const ulonglong2*>(table);  // two channel pairs per 16-byte load
+    const int ch0 = (PAIR ? (sub & 3) : sub) * 8;         // my 8 channels inside a 64-channel slice of a Qx row
+    const ulonglong2* tab2 = reinterpret_cast<const ulonglong2*>(table);  // (wx | wy | wz) of two channel pairs per 16-byte load
+    // -v for my 8 channels: W1p . (o' - pos_i), fp32, rounded once to fp16 (saturating)
+    auto neg_v8 = [&](int c0, float ex, float ey, float ez, uint32_t (&nv)[4]) {
+      const int pair0 = c0 >> 2;  // index in ulonglong2 units (2 channel pairs each)
+      const ulonglong2 wx01 = tab2[pair0], wx23 = tab2[pair0 + 1];
+      const ulonglong2 wy01 = tab2[C1 / 4 + pair0], wy23 = tab2[C1 / 4 + pair0 + 1];
+      const ulonglong2 wz01 = tab2[C1 / 2 + pair0], wz23 = tab2[C1 / 2 + pair0 + 1];
+      const uint64_t wx[4] = {wx01.x, wx01.y, wx23.x, wx23.y}, wy[4] = {wy01.x, wy01.y, wy23.x, wy23.y},
+                     wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 x2 = *reinterpret_cast<const float2*>(&wx[q]), y2 = *reinterpret_cast<const float2*>(&wy[q]),
+                     z2 = *reinterpret_cast<const float2*>(&wz[q]);
+        const float lo = fmaf(z2.x, ez, fmaf(y2.x, ey, x2.x * ex)), hi = fmaf(z2.y, ez, fmaf(y2.y, ey, x2.y * ex));
+        nv[q] = s2_pack_half2(lo, hi);
+      }
+    };
     long u = 0;     // ring item counter of this CTA
     long tile = 0;  // tile counter of this CTA (self-loop tiles included)
     for (int o = o0, n = 0; o < o1; ++o, ++n) {
       const int buf = n % Cfg::NOBJ;
       const uint8_t* ob = obj_base + buf * Cfg::OBJ_BYTES;
       const uint8_t* px_s = ob;
-      const float* pos_s = reinterpret_cast<const float*>(ob + Cfg::PX_BYTES);
-      const float* cpos_s = reinterpret_cast<const float*>(ob + Cfg::PX_BYTES + Cfg::POS_BYTES);
-      const uint8_t* nbr_s = ob + Cfg::PX_BYTES + Cfg::POS_BYTES + Cfg::CPOS_BYTES;
+      const float* cpos_s = reinterpret_cast<const float*>(ob + Cfg::PX_BYTES);
+      const uint8_t* nbr_s = ob + Cfg::PX_BYTES + Cfg::CPOS_BYTES;
       const uint8_t* cnt_s = nbr_s + Cfg::NBR_BYTES;
       const uint8_t* spx_s = cnt_s + Cfg::CNT_BYTES;
-      const float* spos_s = reinterpret_cast<const float*>(spx_s + Cfg::SPX_BYTES);
+      const float* sorg_s = reinterpret_cast<const float*>(spx_s + Cfg::SPX_BYTES);
       mbar_wait(&obj_full[buf], (n / Cfg::NOBJ) & 1);
 #pragma unroll 1
       for (int tt = 0; tt < kTilesPerObj; ++tt, ++tile) {
         if (kTileMode && (tile & 1) != group) { u += Cfg::KB; continue; }
-        const bool self = tt == 0;
-        // rows of a self-loop tile beyond its live columns are never read back: they are not built
-        const int n_rows = self ? Cfg::SELF_COLS / 16 : 8;
-        const uint8_t* src_base = self ? spx_s : px_s;
-        int src_off[8];
-        uint64_t dx[8], dy[8], dz[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = rb + 16 * i;
-          int j, cen;
-          const float* pj;
-          if (self) {
-            cen = (r & (Cfg::SELF_COLS - 1)) + set * Cfg::SELF_COLS;  // row e of the tile = self-loop edge of centroid e
-            j = cen;
-            pj = spos_s + j * PS;
-          } else {
-            cen = (PAIR ? (2 * (tt - 1) + set) * 4 : (tt - 1) * 4) + (r >> 5);
-            const int sl = r & 31;
-            j = nbr_s[cen * 32 + (sl < cnt_s[cen] ? sl : 0)];  // empty slots replicate slot 0: the max is unchanged
-            pj = pos_s + j * PS;
-          }
-          src_off[i] = j * (C1 * 2) + px_chunk;
-          dx[i] = s2_dup2(pj[0] - cpos_s[cen * 3 + 0]);  // pos_j - pos_i: exact fp32 subtraction, as the reference's message()
-          dy[i] = s2_dup2(pj[1] - cpos_s[cen * 3 + 1]);
-          dz[i] = s2_dup2(pj[2] - cpos_s[cen * 3 + 2]);
-        }
         const long u_tile = u;
+        if (tt == 0) {
+          // ---- self-loop tile: row e = the self-loop edge of centroid e (source row e of the other object's half block);
+          // every row has its own centroid, so -v is formed per row.  Only the tile's live rows are built.
+          const bool live = r0 < Cfg::SELF_COLS;  // my centroid quarter lies inside the live rows (warp-uniform per quarter-warp group)
+          const float ox = sorg_s[0], oy = sorg_s[1], oz = sorg_s[2];  // origin of the SOURCE object: its Qx rows are relative to it
 #pragma unroll 1
-        for (int kb = 0; kb < Cfg::KB; ++kb, ++u) {
-          if (!kTileMode && (u & 1) != group) continue;
-          const int stage = static_cast<int>(u % Cfg::STAGES);
-          const uint32_t use = static_cast<uint32_t>(u / Cfg::STAGES);
-          uint4 raw[8];  // all Px reads of the item in flight before anything waits
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < n_rows) raw[i] = *reinterpret_cast<const uint4*>(src_base + src_off[i] + (PAIR ? 0 : kb * 128));
-          // w1p of my 8 channels as pairs: (x, y, z) x 4 pairs
-          const int pair0 = (PAIR ? (sub & 3) * 8 : kb * 64 + sub * 8) >> 2;  // index in ulonglong2 units (2 pairs each)
-          const ulonglong2 wx01 = tab2[pair0], wx23 = tab2[pair0 + 1];
-          const ulonglong2 wy01 = tab2[C1 / 4 + pair0], wy23 = tab2[C1 / 4 + pair0 + 1];
-          const ulonglong2 wz01 = tab2[C1 / 2 + pair0], wz23 = tab2[C1 / 2 + pair0 + 1];
-          const uint64_t wx[4] = {wx01.x, wx01.y, wx23.x, wx23.y}, wy[4] = {wy01.x, wy01.y, wy23.x, wy23.y},
-                         wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
-          mbar_wait(&empty_bar[stage], (use & 1) ^ 1);
-          uint8_t* abase = stage_base + stage * Cfg::A_BYTES;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (i < n_rows) {
-              const int r = rb + 16 * i;
-              const uint32_t rw[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
-              uint32_t packed[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {  // channels 2q, 2q+1:  Px (+ b1) + w1p . (pos_j - pos_i)
-                uint64_t v = s2_half2_to_f32x2(rw[q]);
-                v = s2_fma2(wx[q], dx[i], v);
-                v = s2_fma2(wy[q], dy[i], v);
-                v = s2_fma2(wz[q], dz[i], v);
-                packed[q] = s2_relu_pack_half2(v);
+          for (int kb = 0; kb < Cfg::KB; ++kb, ++u) {
+            if (!kTileMode && (u & 1) != group) continue;
+            const int stage = static_cast<int>(u % Cfg::STAGES);
+            mbar_wait(&empty_bar[stage], (static_cast<uint32_t>(u / Cfg::STAGES) & 1) ^ 1);
+            uint8_t* abase = stage_base + stage * Cfg::A_BYTES;
+            if (live) {
+#pragma unroll 2
+              for (int i = 0; i < 8; ++i) {
+                const int r = r0 + 4 * i;
+                const int cen = PAIR ? 8 * (r >> 2) + 4 * set + (r & 3) : r;  // same centroid split between the lane groups as the neighbour tiles
+                const uint4 raw = *reinterpret_cast<const uint4*>(spx_s + cen * (C1 * 2) + (PAIR ? 0 : kb * 128) + ch0 * 2);
+                uint32_t nv[4];
+                neg_v8((PAIR ? 0 : kb * 64) + ch0, ox - cpos_s[cen * 3 + 0], oy - cpos_s[cen * 3 + 1], oz - cpos_s[cen * 3 + 2], nv);
+                *reinterpret_cast<uint4*>(abase + r * 128 + ((sub ^ (r & 7)) << 4)) =
+                    make_uint4(s2_sub_relu_h2(raw.x, nv[0]), s2_sub_relu_h2(raw.y, nv[1]), s2_sub_relu_h2(raw.z, nv[2]), s2_sub_relu_h2(raw.w, nv[3]));
               }
-              // 128B swizzle: 16-byte chunk `sub` of row r lives at chunk position sub ^ (r % 8)
-              *reinterpret_cast<uint4*>(abase + r * 128 + ((sub ^ (r & 7)) << 4)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            }
+            if (!kTileMode) {
+              fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&full_bar[stage]);
             }
           }
-          if (!kTileMode) {
-            fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core's async proxy
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full_bar[stage]);
+        } else {
+          // ---- neighbour tile: my eight rows are edge slots (rb & 3) + 4 i of centroid cen
+          const int cen = (PAIR ? (2 * (tt - 1) + set) * 4 : (tt - 1) * 4) + cq;
+          const int cnt = cnt_s[cen];
+          int src_off[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int sl = (rb & 3) + 4 * i;
+            const int j = nbr_s[cen * 32 + (sl < cnt ? sl : 0)];  // empty slots replicate slot 0: the max is unchanged
+            src_off[i] = j * (C1 * 2) + ch0 * 2;
+          }
+          const float ex = cpos_s[0] - cpos_s[cen * 3 + 0], ey = cpos_s[1] - cpos_s[cen * 3 + 1], ez = cpos_s[2] - cpos_s[cen * 3 + 2];  // o - pos_i
+#pragma unroll 1
+          for (int kb = 0; kb < Cfg::KB; ++kb, ++u) {
+            if (!kTileMode && (u & 1) != group) continue;
+            const int stage = static_cast<int>(u % Cfg::STAGES);
+            uint4 raw[8];  // all Qx reads of the item in flight before anything waits
+#pragma unroll
+            for (int i = 0; i < 8; ++i) raw[i] = *reinterpret_cast<const uint4*>(px_s + src_off[i] + (PAIR ? 0 : kb * 128));
+            uint32_t nv[4];
+            neg_v8((PAIR ? 0 : kb * 64) + ch0, ex, ey, ez, nv);
+            mbar_wait(&empty_bar[stage], (static_cast<uint32_t>(u / Cfg::STAGES) & 1) ^ 1);
+            uint8_t* abase = stage_base + stage * Cfg::A_BYTES;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = r0 + 4 * i;
+              // 128B swizzle: 16-byte chunk `sub` of row r lives at chunk position sub ^ (r % 8)
+              *reinterpret_cast<uint4*>(abase + r * 128 + ((sub ^ (r & 7)) << 4)) =
+                  make_uint4(s2_sub_relu_h2(raw[i].x, nv[0]), s2_sub_relu_h2(raw[i].y, nv[1]), s2_sub_relu_h2(raw[i].z, nv[2]),
+                             s2_sub_relu_h2(raw[i].w, nv[3]));
+            }
+            if (!kTileMode) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&full_bar[stage]);
+            }
           }
         }
         if (kTileMode) {
@@ -477,7 +493,7 @@ static cudaError_t launch_sa_obj2(const SaObj2& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  SaObj2Params p{a.Px16, a.dense_pos, a.cpos, a.nbr, a.cnt, a.loop_src_obj, a.loop_half, a.Wp, a.W2h, a.b2, a.out, a.n_obj};
+  SaObj2Params p{a.Qx16, a.cpos, a.nbr, a.cnt, a.loop_src_obj, a.loop_half, a.Wp, a.W2h, a.b2, a.out, a.ldo, a.n_obj};
   const int grid = a.n_obj < tma_api().num_sms ? a.n_obj : tma_api().num_sms;
   sa_obj2_kernel<Cfg><<<grid, kSa2Threads, Cfg::SMEM, st>>>(p);
   return cudaGetLastError();
@@ -486,9 +502,10 @@ static cudaError_t launch_sa_obj2(const SaObj2& a, cudaStream_t st) {
 cudaError_t sa_obj2(const SaObj2& a, cudaStream_t st, Launches* lc) {
   if (a.n_obj <= 0) return cudaSuccess;
   if (lc) lc->n++;
-  if (a.C1 == 32 && a.C2 == 64 && a.P == 256 && a.M == 128 && a.dense_stride == 6) return launch_sa_obj2<Sa2Cfg<32, 64, 256, 128, 6, true>>(a, st);
-  if (a.C1 == 128 && a.C2 == 128 && a.P == 128 && a.M == 64 && a.dense_stride == 3) return launch_sa_obj2<Sa2Cfg<128, 128, 128, 64, 3, false>>(a, st);
-  if (a.C1 == 256 && a.C2 == 256 && a.P == 64 && a.M == 32 && a.dense_stride == 3) return launch_sa_obj2<Sa2Cfg<256, 256, 64, 32, 3, false>>(a, st);
+  if (a.ldo < a.C2) return cudaErrorInvalidValue;
+  if (a.C1 == 32 && a.C2 == 64 && a.P == 256 && a.M == 128) return launch_sa_obj2<Sa2Cfg<32, 64, 256, 128, true>>(a, st);
+  if (a.C1 == 128 && a.C2 == 128 && a.P == 128 && a.M == 64) return launch_sa_obj2<Sa2Cfg<128, 128, 128, 64, false>>(a, st);
+  if (a.C1 == 256 && a.C2 == 256 && a.P == 64 && a.M == 32) return launch_sa_obj2<Sa2Cfg<256, 256, 64, 32, false>>(a, st);
   return cudaErrorInvalidValue;
 }
 

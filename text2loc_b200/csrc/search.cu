@@ -1,10 +1,14 @@
 // Query x database cosine-similarity top-k (training/coarse.py:119-125).
 //
 // The reference scores in float64 on the host, one GEMV + full argsort per query.  Here:
-//   1. candidate pass on the tensor cores: Q and D are split once into bf16 hi|lo planes and the
-//      product hi*hi + hi*lo + lo*hi (three K=256 passes into one fp32 TMEM accumulator,
-//      umma_gemm.cuh) approximates q.d to ~1e-5; the epilogue keeps, per query row and per
-//      database split, the 16 best approximate scores and the threshold below which it dropped;
+//   1. candidate pass on the tensor cores, ONE K=256 pass over fp16 copies of Q and D (rows scaled by exact powers of two
+//      into fp16's normal range): |approx - q.d| <= kEps16 * ||q|| * max||d||, a rigorous worst-case bound (derivation at
+//      kEps16).  The epilogue keeps, per query row and per database split, the 16 best approximate scores and the threshold
+//      below which it dropped.  Exactness never depended on the precision of this pass -- steps 2-4 establish it -- so the
+//      bf16 hi|lo three-pass product (hi*hi + hi*lo + lo*hi, |err| <= kEpsRel ...) that round 1 used for the candidates is
+//      now the SECOND pass only; it is still the better first pass for tightly clustered databases (score gaps below
+//      2 kEps16), so the engine falls back to it when most queries of the previous call failed the fp16 proof
+//      (search_topk's `first_pass_bf16x3`; api.cu decides);
 //   2. exact re-rank: fp64 dot products of the fp32 originals for those candidates, ordered by
 //      (score desc, row asc);
 //   3. proof: if every split's drop threshold + error bound is below the k-th exact score, no
@@ -22,9 +26,19 @@ namespace t2l {
 constexpr int kCand = 16;         // candidates kept per (query, split)
 constexpr int kMaxSplits = 16;
 constexpr int kMaxK = 12;
-// |approx - exact| <= kEpsRel * ||q|| * max||d||: 3 * 2^-18 from the dropped lo*lo term and
-// the two bf16 residuals, plus fp32 accumulation of 768 products, with a 2x safety factor.
-constexpr float kEpsRel = 2.5e-4f;
+// bf16 hi|lo three-pass product: x = hi + lo + r with |r| <= 2^-16 |x| (two roundings at u = 2^-8).  The dropped terms
+// lo*lo, r_q*d, q*r_d sum to <= 3 * 2^-16 |q_i||d_i| per element, <= 4.6e-5 ||q|| ||d|| per dot product (Cauchy-Schwarz);
+// the 768 products are exact in fp32 (8 x 8 significand bits) and their fp32 accumulation, worst case with truncating
+// adds, costs <= 768 * 2^-23 = 9.2e-5 of sum|terms|.  Total 1.37e-4, used with a 1.15x margin.
+constexpr float kEpsRel = 1.6e-4f;
+// fp16 single pass on rows scaled by exact powers of two so that ||q~||, max||d~|| lie in [0.5, 1): fl(x) = x (1 + delta) with
+// |delta| <= u = 2^-11 in the normal range, absolute error <= 2^-25 below it.  Per element
+//   |q~ d~ - fl(q~) fl(d~)| <= (2u + u^2) |q~||d~| + 2^-25 (|q~| + |d~|) + ...,
+// summed over 256 elements: <= (2^-10 + 2^-22) ||q~|| ||d~|| + 2^-25 (||q~||_1 + ||d~||_1) <= 9.77e-4 ||q~|| ||d~|| + 1e-6
+// (||x||_1 <= 16 ||x||_2); the 256 products are exact in fp32 (11 x 11 bits), truncating fp32 accumulation adds
+// <= 256 * 2^-23 = 3.1e-5 of sum|terms| <= ||q~|| ||d~||.  With ||q~|| max||d~|| >= 1/4 the absolute 1e-6 is <= 4e-6 relative:
+// total <= 1.012e-3 ||q|| max||d|| after undoing the (exact) scaling.
+constexpr float kEps16 = 1.05e-3f;
 
 // ---- fp32 rows -> bf16 hi | lo planes (+ row norms) ---------------------------------------------
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, long rows, __nv_bfloat16* __restrict__ planes,
@@ -52,11 +66,45 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restri
   }
 }
 
+// ---- fp32 rows -> fp16 rows scaled by a power of two ------------------------------------------------
+// scale = 2^-ex with ex from frexp(norm): norm * scale lies in [0.5, 1) (1 for an all-zero operand), so every element is
+// <= 1 in magnitude and the scaling itself is exact.  kPerRow: each row by its own norm (queries); else all rows by
+// *ref_norm (the database's largest row norm).  scale_out receives 2^ex, the factor that undoes the scaling.
+template <bool kPerRow>
+__global__ void __launch_bounds__(256) scaled_half_rows_kernel(const float* __restrict__ x, long rows, const float* __restrict__ ref_norm,
+                                                               __half* __restrict__ out, float* __restrict__ scale_out) {
+  const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xr = reinterpret_cast<const float4*>(x + r * kEmbed);
+  const float4 a = xr[2 * lane], b = xr[2 * lane + 1];  // 8 consecutive elements per lane
+  float norm;
+  if (kPerRow) {
+    float ss = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+    norm = sqrtf(warp_sum(ss)) * 1.000001f;  // the fp32 sum may round down: never let the scaled norm exceed 1
+  } else {
+    norm = ref_norm[0] * 1.000001f;
+  }
+  int ex = 0;
+  if (norm > 0.f && norm < INFINITY) frexpf(norm, &ex);
+  const float sc = ldexpf(1.f, -ex);
+  if (lane == 0 && (kPerRow || r == 0)) scale_out[kPerRow ? r : 0] = ldexpf(1.f, ex);
+  const __half2 h0 = __floats2half2_rn(a.x * sc, a.y * sc), h1 = __floats2half2_rn(a.z * sc, a.w * sc),
+                h2 = __floats2half2_rn(b.x * sc, b.y * sc), h3 = __floats2half2_rn(b.z * sc, b.w * sc);
+  uint4 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+  u.z = *reinterpret_cast<const uint32_t*>(&h2); u.w = *reinterpret_cast<const uint32_t*>(&h3);
+  reinterpret_cast<uint4*>(out + r * kEmbed)[lane] = u;
+}
+
 cudaError_t search_prepare_db(const SearchDb& db, cudaStream_t st, Launches* lc) {
   cudaError_t e = cudaMemsetAsync(db.max_norm, 0, sizeof(float), st);
   if (e != cudaSuccess || db.n_rows <= 0) return e;
-  if (lc) lc->n++;
-  split_planes_kernel<<<static_cast<unsigned>((db.n_rows + 7) / 8), 256, 0, st>>>(db.D, db.n_rows, db.planes, nullptr, db.max_norm);
+  if (lc) lc->n += 2;
+  const unsigned grid = static_cast<unsigned>((db.n_rows + 7) / 8);
+  split_planes_kernel<<<grid, 256, 0, st>>>(db.D, db.n_rows, db.planes, nullptr, db.max_norm);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  scaled_half_rows_kernel<false><<<grid, 256, 0, st>>>(db.D, db.n_rows, db.max_norm, db.plane16, db.scale);
   return cudaGetLastError();
 }
 
@@ -180,7 +228,9 @@ constexpr int kRerankWarps = 4;
 
 __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const float* __restrict__ Q, const float* __restrict__ D, const float* __restrict__ cand_score,
                                                                    const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_thr,
-                                                                   const float* __restrict__ q_norm, const float* __restrict__ max_norm, int nq, int n_splits,
+                                                                   const float* __restrict__ q_norm, const float* __restrict__ max_norm,
+                                                                   const float* __restrict__ q_scale, const float* __restrict__ db_scale, float eps_cand,
+                                                                   int nq, int n_splits,
                                                                    int k, long row_offset, int64_t* __restrict__ out_idx, double* __restrict__ out_score,
                                                                    int32_t* __restrict__ flags, int32_t* __restrict__ n_fail, int32_t* __restrict__ fail_ids,
                                                                    float* __restrict__ fail_thr) {
@@ -204,11 +254,13 @@ __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const float* 
   // proof: every dropped row has approx <= thr_s, hence exact <= thr_s + eps; it cannot enter
   // (or tie into) the top-k if thr_s + eps < k-th exact score.
   const double kth = s_osc[w][k - 1];
-  const float eps = kEpsRel * q_norm[q] * max_norm[0];
+  const float qn = q_norm[q] * 1.000001f, dn = max_norm[0] * 1.000001f;  // fp32 norms may be rounded down
+  const double eps = static_cast<double>(eps_cand) * qn * dn;            // error bound of the candidate pass that ran
+  const double unscale = q_scale ? static_cast<double>(q_scale[q]) * static_cast<double>(db_scale[0]) : 1.0;  // exact powers of two
   bool fail = false;
   for (int s = lane; s < n_splits; s += 32) {
     const float thr = cand_thr[static_cast<long>(q) * n_splits + s];
-    if (thr != -INFINITY && !(static_cast<double>(thr) + static_cast<double>(eps) < kth)) fail = true;
+    if (thr != -INFINITY && !(static_cast<double>(thr) * unscale + eps < kth)) fail = true;
   }
   fail = __any_sync(0xffffffffu, fail);
   if (lane < k) {
@@ -221,7 +273,8 @@ __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const float* 
     if (fail) {  // queue for the second pass: rows with approx >= kth - eps are the only possible top-k members
       const int slot = atomicAdd(n_fail, 1);
       fail_ids[slot] = q;
-      fail_thr[slot] = __double2float_rd(kth - static_cast<double>(eps));
+      // the second pass is always the bf16 hi|lo product on unscaled rows: its own bound applies
+      fail_thr[slot] = __double2float_rd(kth - static_cast<double>(kEpsRel) * qn * dn);
     }
   }
 }
@@ -368,7 +421,7 @@ cudaError_t search_topk_exact(const SearchDb& db, const float* Q, int nq, int k,
 
 // ---- the search ----------------------------------------------------------------------------------------
 cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q, int nq, int k, int64_t* out_idx,
-                        double* out_score, int32_t* out_n_fallback, cudaStream_t st, Launches* lc) {
+                        double* out_score, int32_t* out_n_fallback, bool first_pass_bf16x3, cudaStream_t st, Launches* lc) {
   if (nq <= 0) return cudaSuccess;
   if (k < 1 || k > kMaxK || nq > w.nq_cap) return cudaErrorInvalidValue;
   cudaError_t e;
@@ -376,15 +429,20 @@ cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q,
   if (out_n_fallback && (e = cudaMemsetAsync(out_n_fallback, 0, sizeof(int32_t), st)) != cudaSuccess) return e;
   if (db.n_rows <= 0) return search_topk_exact(db, Q, nq, k, out_idx, out_score, nullptr, st, lc);
 
-  using Cfg = GemmCfg<256, true, 2>;  // CTA pairs: 256 queries x 256 database rows per tile
+  using Cfg = GemmCfg<256, kOpBf16, 2>;   // CTA pairs: 256 queries x 256 database rows per tile
+  using Cfg16 = GemmCfg<256, kOpF16, 2>;  // same tile on the fp16 rows
   constexpr int kTileM = Cfg::BLOCK_M * Cfg::CTA_GROUP;
-  if (lc) lc->n += 3;
+  if (lc) lc->n += 4;
   split_planes_kernel<<<(nq + 7) / 8, 256, 0, st>>>(Q, nq, w.q_planes, w.q_norm, nullptr);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (!first_pass_bf16x3) {
+    scaled_half_rows_kernel<true><<<(nq + 7) / 8, 256, 0, st>>>(Q, nq, nullptr, w.q16, w.q_scale);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
 
   CUtensorMap ta, tb;
-  if (make_operand_map(&ta, w.q_planes, true, nq, 2 * kEmbed, 2 * kEmbed, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
-  if (make_operand_map(&tb, db.planes, true, db.n_rows, 2 * kEmbed, 2 * kEmbed, Cfg::LOAD_N)) return cudaErrorInvalidValue;
+  if (make_operand_map(&ta, w.q_planes, kOpBf16, nq, 2 * kEmbed, 2 * kEmbed, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
+  if (make_operand_map(&tb, db.planes, kOpBf16, db.n_rows, 2 * kEmbed, 2 * kEmbed, Cfg::LOAD_N)) return cudaErrorInvalidValue;
   GemmShape s;
   s.M = nq;
   s.N = static_cast<int>(db.n_rows);
@@ -406,11 +464,22 @@ cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q,
   s.ks.a_off[1] = 0;      s.ks.b_off[1] = kEmbed;  // hi * lo
   s.ks.a_off[2] = kEmbed; s.ks.b_off[2] = 0;       // lo * hi
   TopKEpi::Params ep{w.cand_score, w.cand_idx, w.cand_thr, nq, s.N, n_splits};
-  if ((e = launch_umma_gemm<Cfg, TopKEpi>(ta, tb, s, ep, st)) != cudaSuccess) return e;
+  if (first_pass_bf16x3) {
+    if ((e = launch_umma_gemm<Cfg, TopKEpi>(ta, tb, s, ep, st)) != cudaSuccess) return e;
+  } else {
+    CUtensorMap ta16, tb16;
+    if (make_operand_map(&ta16, w.q16, kOpF16, nq, kEmbed, kEmbed, Cfg16::BLOCK_M)) return cudaErrorInvalidValue;
+    if (make_operand_map(&tb16, db.plane16, kOpF16, db.n_rows, kEmbed, kEmbed, Cfg16::LOAD_N)) return cudaErrorInvalidValue;
+    GemmShape s16 = s;
+    s16.ks.n_pass = 1;
+    s16.ks.kb_per_pass = kEmbed / Cfg16::BLOCK_K;
+    s16.ks.a_off[0] = 0; s16.ks.b_off[0] = 0;
+    if ((e = launch_umma_gemm<Cfg16, TopKEpi>(ta16, tb16, s16, ep, st)) != cudaSuccess) return e;
+  }
 
   rerank_kernel<<<(nq + kRerankWarps - 1) / kRerankWarps, kRerankWarps * 32, 0, st>>>(
-      Q, db.D, w.cand_score, w.cand_idx, w.cand_thr, w.q_norm, db.max_norm, nq, n_splits, k, db.row_offset, out_idx, out_score, w.flags,
-      w.n_fail, w.fail_ids, w.fail_thr);
+      Q, db.D, w.cand_score, w.cand_idx, w.cand_thr, w.q_norm, db.max_norm, first_pass_bf16x3 ? nullptr : w.q_scale, db.scale,
+      first_pass_bf16x3 ? kEpsRel : kEps16, nq, n_splits, k, db.row_offset, out_idx, out_score, w.flags, w.n_fail, w.fail_ids, w.fail_thr);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
 
   // ---- second pass over the queries whose proof failed (count lives on the device: no host sync; the GEMM
@@ -419,7 +488,7 @@ cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q,
   gather_fail_planes_kernel<<<(nq + 7) / 8, 256, 0, st>>>(w.q_planes, w.fail_ids, w.n_fail, w.q2_planes, w.cand2_cnt);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   CUtensorMap ta2;
-  if (make_operand_map(&ta2, w.q2_planes, true, nq, 2 * kEmbed, 2 * kEmbed, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
+  if (make_operand_map(&ta2, w.q2_planes, kOpBf16, nq, 2 * kEmbed, 2 * kEmbed, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
   GemmShape s2 = s;
   s2.m_rows_dev = w.n_fail;
   CollectEpi::Params ep2{w.fail_thr, w.n_fail, w.cand2_idx, w.cand2_cnt, s.N};
@@ -455,6 +524,39 @@ __global__ void __launch_bounds__(128) merge_kernel(const int64_t* __restrict__ 
     out_idx[static_cast<long>(q) * k + lane] = s_oix[w][lane];
     out_score[static_cast<long>(q) * k + lane] = s_osc[w][lane];
   }
+}
+
+// ---- running top-k of a streamed database (one warp per query): merge a chunk's list into the running list, in place ----
+__global__ void __launch_bounds__(128) merge_running_kernel(int64_t* __restrict__ run_idx, double* __restrict__ run_score, const int64_t* __restrict__ new_idx,
+                                                            const double* __restrict__ new_score, int nq, int k) {
+  __shared__ double s_sc[4][2 * kCand];
+  __shared__ long s_ix[4][2 * kCand];
+  __shared__ double s_osc[4][kCand];
+  __shared__ long s_oix[4][kCand];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + w;
+  if (q >= nq) return;
+  for (int c = lane; c < 2 * k; c += 32) {
+    const bool from_new = c >= k;
+    const long src = static_cast<long>(q) * k + (from_new ? c - k : c);
+    s_sc[w][c] = from_new ? new_score[src] : run_score[src];
+    s_ix[w][c] = from_new ? new_idx[src] : run_idx[src];
+  }
+  __syncwarp();
+  warp_select_topk(s_sc[w], s_ix[w], 2 * k, k, lane, s_osc[w], s_oix[w]);
+  if (lane < k) {
+    run_idx[static_cast<long>(q) * k + lane] = s_oix[w][lane];
+    run_score[static_cast<long>(q) * k + lane] = s_osc[w][lane];
+  }
+}
+
+cudaError_t merge_running_topk(int64_t* run_idx, double* run_score, const int64_t* new_idx, const double* new_score, int nq, int k,
+                               cudaStream_t st, Launches* lc) {
+  if (nq <= 0) return cudaSuccess;
+  if (k < 1 || k > kCand) return cudaErrorInvalidValue;
+  if (lc) lc->n++;
+  merge_running_kernel<<<(nq + 3) / 4, 128, 0, st>>>(run_idx, run_score, new_idx, new_score, nq, k);
+  return cudaGetLastError();
 }
 
 cudaError_t merge_topk(const int64_t* idx_all, const double* score_all, int n_shards, int nq, int k, int64_t* out_idx,

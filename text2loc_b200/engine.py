@@ -189,6 +189,34 @@ class Engine:
             self._check(self._lib.t2l_search_topk(self._h, _ptr(Q), nq, k, _ptr(idx), _ptr(sc), _ptr(nfb), self._stream()))
         return idx, sc, nfb
 
+    def search_topk_accumulate(self, Q, k: int, run_idx: torch.Tensor, run_score: torch.Tensor):
+        """Fold the top-k of the registered shard into the running lists (in place); returns n_fallback [1]."""
+        if self._db is None:
+            raise EngineError("search_topk_accumulate: call db_build first")
+        Q = self._dev(Q, torch.float32)
+        nq = Q.shape[0]
+        if (run_idx.shape != (nq, k) or run_score.shape != (nq, k) or run_idx.dtype != torch.int64 or run_score.dtype != torch.float64
+                or not run_idx.is_contiguous() or not run_score.is_contiguous() or run_idx.device != self.device):
+            raise EngineError("search_topk_accumulate: running lists must be contiguous int64 / float64 [nq, k] on the engine's device")
+        nfb = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._check(self._lib.t2l_search_topk_accumulate(self._h, _ptr(Q), nq, k, _ptr(run_idx), _ptr(run_score), _ptr(nfb), self._stream()))
+        return nfb
+
+    def new_running_topk(self, nq: int, k: int):
+        """Empty running lists for search_topk_accumulate: idx -1, score -inf."""
+        return (torch.full((nq, k), -1, dtype=torch.int64, device=self.device),
+                torch.full((nq, k), float("-inf"), dtype=torch.float64, device=self.device))
+
+    def synth_cells(self, seed: int, first_cell: int, n_cells: int, obj_per_cell: int, out=None):
+        """Counter-based synthetic cells on the device -> (pts [n,256,6], meta [n,7], cell_ptr np.int32 [n_cells+1])."""
+        n = n_cells * obj_per_cell
+        if out is None:
+            out = (torch.empty((n, NUM_POINTS, 6), dtype=torch.float32, device=self.device),
+                   torch.empty((n, 7), dtype=torch.float32, device=self.device))
+        pts, meta = out[0][:n], out[1][:n]
+        self._check(self._lib.t2l_synth_cells(self._h, int(seed), int(first_cell), n_cells, obj_per_cell, _ptr(pts), _ptr(meta), self._stream()))
+        return pts, meta, (np.arange(n_cells + 1, dtype=np.int64) * obj_per_cell).astype(np.int32)
+
     def merge_topk(self, idx_all, score_all):
         """[G,nq,k] per-shard lists -> global (idx, score) [nq,k]."""
         idx_all = self._dev(idx_all, torch.int64)

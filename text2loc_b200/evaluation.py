@@ -85,8 +85,9 @@ def eval_epoch(model, dataloader, args, return_encodings=False, return_distance=
     hit, close, dists = engine.topk_accuracy(
         idx_dev, query_xy, cell_centres, top_k, threshs=[cell_size / 2], target_row=rows_of_ids(db_cell_ids, query_cell_ids),
         want_dists=return_distance)
-    hit_rate = hit.to(torch.float64).mean(dim=0).cpu().numpy()
-    close_rate = close[:, :, 0].to(torch.float64).mean(dim=0).cpu().numpy()
+    # count / n in float64, which is what np.mean of the reference's per-query boolean lists evaluates to
+    hit_rate = hit.sum(dim=0, dtype=torch.int64).cpu().numpy() / n_q
+    close_rate = close[:, :, 0].sum(dim=0, dtype=torch.int64).cpu().numpy() / n_q
     accuracies = {k: hit_rate[top_k.index(int(k))] for k in args.top_k}
     accuracies_close = {k: close_rate[top_k.index(int(k))] for k in args.top_k}
     retrieved_ids = db_cell_ids[idx_dev.cpu().numpy()]  # [n_q, k_max] strings, best first (:128)
@@ -124,7 +125,7 @@ def localisation_accuracies(engine, poses, all_cells, retrievals, pos_in_cells, 
         np.arange(n * k, dtype=np.int64).reshape(n, k), np.array([p.pose_w[0:2] for p in poses], dtype=np.float64),
         pred_w.reshape(n * k, 2), top_k, threshs=list(threshs), query_scene=pose_scene.astype(np.int32),
         cell_scene=cell_scene[rows].reshape(-1).astype(np.int32))
-    rate = within.to(torch.float64).mean(dim=0).cpu().numpy()
+    rate = within.sum(dim=0, dtype=torch.int64).cpu().numpy() / n
     return {kk: {t: rate[top_k.index(int(kk)), j] for j, t in enumerate(threshs)} for kk in top_k}
 
 

@@ -63,6 +63,10 @@ def engine_weights(sd: dict) -> dict:
         assert w1.shape[1] == c_in + 3
         out[f"sa{i}.w1x"], out[f"sa{i}.w1p"], out[f"sa{i}.b1"] = w1[:, :c_in], w1[:, c_in:], b1
         out[f"sa{i}.w2"], out[f"sa{i}.b2"] = w2, b2
+        if i > 1:
+            # per-point form of the first Linear: W1 [x_j | pos_j - pos_i] + b = (W1x x_j + W1p (pos_j - o) + b) - W1p (pos_i - o);
+            # the position columns come twice because the engine feeds pos_j - o as a tf32 hi | lo pair (csrc/pointnet.cu)
+            out[f"sa{i}.w1q"] = np.concatenate([w1[:, :c_in], w1[:, c_in:], w1[:, c_in:]], axis=1)
     out["ga.w1"], out["ga.b1"] = fold_linear_bn(sd, f"{pn}.ga.mlp.0")
     out["ga.w2"], out["ga.b2"] = fold_linear_bn(sd, f"{pn}.ga.mlp.1")
     for n in ("lin1", "lin2"):
