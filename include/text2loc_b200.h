@@ -87,6 +87,28 @@ int t2l_encode_text(t2l_engine* e, const float* t5, int n_queries, int n_sent, i
 int t2l_encode_text_tokens(t2l_engine* e, const float* t5, int n_sentences, int n_tok, float* pooled, void* stream);
 int t2l_encode_text_sentences(t2l_engine* e, const float* pooled, int n_queries, int n_sent, float* out, void* stream);
 
+/* ---- fine stage: CrossMatch.forward (models/cross_matcher.py:83-129; evaluation/pipeline.py:113-116 calls it once per query) ----
+ * An engine serves the fine stage when the weights set on it are CrossMatch's (text2loc_b200/weights.py detects the state
+ * dict by its offset MLP): ObjectEncoder and LanguageEncoder(is_fine) at d = T2L_FINE_DIM, two cascaded pairs of
+ * TransformerDecoderLayers, the offset MLP.  The coarse entry points then fail, and vice versa.
+ *
+ * t2l_fine_offsets = CrossMatch.forward for a batch of (cell, description) pairs, every cell padded / cut to the same number of
+ * objects (pad_size):  pts / meta / cell_ptr_host as t2l_encode_cells;  t5 device f32 [n_cells * n_hints, n_tok, 1024] = T5
+ * states of each pair's hint sentences;  offsets device f32 [n_cells, 2].
+ * The three stages are exposed separately so that a caller can encode every database cell's objects ONCE and match many
+ * (query, cell) pairs against them (run_fine batched over queries):
+ *   t2l_fine_encode_objects  -> obj_emb device f32 [n_objects, 128]   F.normalize(ObjectEncoder(...)) (:98-108)
+ *   t2l_fine_encode_hints    -> hints device f32 [n_sentences, 128]   LanguageEncoder(is_fine) after T5 (language_encoder.py:130-140)
+ *   t2l_fine_match           pair p uses the n_obj rows of cell pair_cell[p] and the n_hints rows of query pair_query[p]
+ *                            (device i32 [n_pairs]; NULL = identity) -> offsets [n_pairs, 2] (:113-127) */
+int t2l_fine_offsets(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr_host, int n_cells, const float* t5,
+                     int n_hints, int n_tok, float* offsets, void* stream);
+int t2l_fine_encode_objects(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr_host, int n_cells,
+                            float* obj_emb, void* stream);
+int t2l_fine_encode_hints(t2l_engine* e, const float* t5, int n_sentences, int n_tok, float* hints, void* stream);
+int t2l_fine_match(t2l_engine* e, const float* obj_emb, const int32_t* pair_cell, const float* hints, const int32_t* pair_query,
+                   int n_pairs, int n_obj, int n_hints, float* offsets, void* stream);
+
 /* Database side of eval_epoch's search loop (training/coarse.py:81-84,105-113): registers this
  * rank's shard of cell embeddings.  D device f32 [n_rows, 256]; the engine keeps a reference to D
  * (it must stay alive and unchanged) and builds its bf16 hi/lo operand planes.  row_offset is

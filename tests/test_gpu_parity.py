@@ -380,6 +380,130 @@ def test_streamed_search_equals_unstreamed_50k_cells(eng, state_dict):
     assert err < EMB_TOL
 
 
+# ---- fine stage (BASELINE configs[4]) -------------------------------------------------
+
+FINE_TOL = 1e-3  # relative to the largest offset component, as for embeddings / similarities
+
+
+@pytest.fixture(scope="module")
+def fine_sd():
+    import synth
+
+    return synth.make_fine_state_dict(0)
+
+
+@pytest.fixture(scope="module")
+def fine_eng(fine_sd):
+    from text2loc_b200.engine import Engine
+
+    e = Engine("cuda:0")
+    e.load_state_dict(fine_sd)
+    return e
+
+
+def test_fine_offsets_golden(fine_eng, golden):
+    """t2l_fine_offsets against the reference's own CrossMatch.forward (models/cross_matcher.py:83-129) on 5 cells padded to
+    16 objects x 6 hints (tests/golden/fine_small.npz)."""
+    from oracle import fake_t5
+
+    g = golden("fine_small.npz")
+    feat, n_hints = fake_t5.FakeFrontend(int(g["fake_t5_seed"]))([str(t) for t in g["texts"]])
+    got = fine_eng.fine_offsets(g["pts"], g["meta"], g["cell_ptr"], feat, n_hints).cpu().numpy()
+    err = np.abs(got - g["offsets"]).max() / np.abs(g["offsets"]).max()
+    print(f"\nfine offsets vs the reference's CrossMatch.forward: max error {err:.3e} of the largest component")
+    assert got.shape == (5, 2) and err < FINE_TOL
+    # the three stages on their own compose to the same result (what the batched run_fine uses)
+    obj = fine_eng.fine_encode_objects(g["pts"], g["meta"], g["cell_ptr"])
+    assert float((obj.norm(dim=1) - 1).abs().max()) < 1e-5
+    hints = fine_eng.fine_encode_hints(feat)
+    staged = fine_eng.fine_match(obj, None, hints, None, 16, n_hints).cpu().numpy()
+    assert np.abs(staged - got).max() < 1e-6
+    # pairs that re-use cells and queries: pair (cell 3, query 1) differs from both diagonal pairs and equals the oracle
+    from oracle import restate
+
+    mixed = fine_eng.fine_match(obj, np.array([3, 0], np.int32), hints, np.array([1, 4], np.int32), 16, n_hints).cpu().numpy()
+    import synth
+
+    sd = synth.make_fine_state_dict(int(g["weight_seed"]))
+    t5 = feat.view(5, n_hints, feat.shape[1], 1024)
+    pts, meta = torch.from_numpy(g["pts"]).view(5, 16, 256, 6), torch.from_numpy(g["meta"]).view(5, 16, 7)
+    want = restate.fine_offsets(sd, torch.cat([pts[3], pts[0]]), torch.cat([meta[3], meta[0]]), np.array([0, 16, 32]),
+                                torch.cat([t5[1], t5[4]]), n_hints).numpy()
+    assert np.abs(mixed - want).max() / np.abs(want).max() < FINE_TOL
+
+
+def test_fine_dropin_crossmatch_and_engine_guards(fine_sd, state_dict, golden):
+    from oracle import fake_t5, reference_run
+    from oracle.make_golden import fine_case
+    from text2loc_b200 import CrossMatch
+    from text2loc_b200.engine import Engine, EngineError
+
+    g = golden("fine_small.npz")
+    args = reference_run.fine_args()
+    model = CrossMatch(["c"] * 22, ["k"] * 8, args, text_frontend=fake_t5.FakeFrontend(int(g["fake_t5_seed"])))
+    model.load_state_dict({k: torch.as_tensor(np.asarray(v)) for k, v in fine_sd.items()}, strict=False)
+    assert model.embed_dim == 128 and model.eval() is model and model.get_device() == model.device
+    cells, batches, texts = fine_case()  # the raw objects / point batches / descriptions the golden was made from
+    out = model(cells, texts, batches)
+    assert out.shape == (5, 2) and out.is_cuda
+    assert np.abs(out.cpu().numpy() - g["offsets"]).max() / np.abs(g["offsets"]).max() < FINE_TOL
+    # a fine engine refuses the coarse entry points and vice versa; wrong-sized checkpoints are rejected
+    with pytest.raises(EngineError, match="fine-stage"):
+        model.engine.encode_cells(g["pts"], g["meta"], g["cell_ptr"])
+    coarse = Engine("cuda:0")
+    coarse.load_state_dict(state_dict)
+    with pytest.raises(EngineError, match="coarse model"):
+        coarse.fine_encode_hints(torch.zeros(6, 12, 1024))
+    bad = dict(fine_sd)
+    bad["mlp_offsets.0.weight"] = np.asarray(bad["mlp_offsets.0.weight"])[:, :64]
+    with pytest.raises(EngineError, match="size mismatch"):
+        Engine("cuda:0").load_state_dict(bad)
+
+
+def test_run_fine_batched_equals_per_pair_oracle(fine_sd):
+    """The drop-in run_fine encodes every distinct retrieved cell once and matches all query x cell pairs in one batch.
+    Replaying its (seeded) padding / point sampling in the test, every pair's offsets must equal the oracle's
+    CrossMatch restatement on that pair, and the accuracies must equal the reference's calc_sample_accuracies loop."""
+    from oracle import fake_t5, reference_run, restate
+    import synth
+    from text2loc_b200 import CrossMatch, dataio, evaluation
+
+    args = reference_run.fine_args(top_k=[1, 3], threshs=[5, 10, 15])
+    ds = synth.SynthCoarseDataset(seed=4, n_cells=12, n_poses=7, n_obj=[3, 16, 20, 1, 8, 5, 16, 2, 9, 30, 4, 6], max_raw=300)
+    loader = DataLoader(ds, batch_size=4, collate_fn=dataio.collate_fn, shuffle=False)
+    rng = np.random.default_rng(2)
+    ids = np.array([c.id for c in ds.all_cells])
+    retrievals = np.stack([ids[rng.permutation(12)[:3]] for _ in range(7)])
+    frontend = fake_t5.FakeFrontend(0)
+    model = CrossMatch([], [], args, text_frontend=frontend)
+    model.load_state_dict({k: torch.as_tensor(np.asarray(v)) for k, v in fine_sd.items()}, strict=False)
+    transform = dataio.FixedPoints(256)
+    np.random.seed(77)
+    acc, offsets = evaluation.run_fine(model, retrievals, loader, args, transform, return_offsets=True)
+    assert offsets.shape == (7, 3, 2)
+    # replay: distinct retrieved cells in ascending row order, padded then sampled, exactly as run_fine does
+    rows = evaluation.rows_of_ids(ids, retrievals)
+    used = np.unique(rows)
+    np.random.seed(77)
+    objects = [evaluation._padded_objects(ds.all_cells[int(r)], args.pad_size) for r in used]
+    points = [dataio.batch_object_points(o, transform) for o in objects]
+    pts, meta, _ = dataio.pack_cells(objects, points)
+    pts, meta = pts.view(len(used), 16, 256, 6), meta.view(len(used), 16, 7)
+    slot = {int(r): i for i, r in enumerate(used)}
+    feats, n_hints = frontend([p.text for p in ds.all_poses])
+    feats = feats.view(7, n_hints, feats.shape[1], 1024)
+    worst = 0.0
+    for q in range(7):
+        sel = [slot[int(r)] for r in rows[q]]
+        want = restate.fine_offsets(fine_sd, pts[sel].reshape(-1, 256, 6), meta[sel].reshape(-1, 7), np.arange(0, 16 * 3 + 1, 16),
+                                    feats[q].repeat(3, 1, 1), n_hints).numpy()
+        worst = max(worst, float(np.abs(offsets[q] - want).max() / np.abs(want).max()))
+    print(f"\nrun_fine: 21 query x cell pairs over {len(used)} distinct cells, worst offset error vs oracle {worst:.3e}")
+    assert worst < FINE_TOL
+    want_acc = restate.localisation_accuracies(ds.all_poses, ds.all_cells, retrievals, offsets, args.top_k, args.threshs)
+    assert all(acc[k][t] == want_acc[k][t] for k in args.top_k for t in args.threshs)
+
+
 # ---- drop-in API ---------------------------------------------------------------------------------------
 
 def make_model(state_dict, fake_seed=0):

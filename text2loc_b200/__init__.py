@@ -6,7 +6,7 @@ Importing the package is cheap and works without a GPU (synthetic data, weight f
 packing).  Anything that computes goes through the CUDA extension and raises if it is missing.
 """
 
-__all__ = ["CellRetrievalNetwork", "Engine", "EngineError", "eval_epoch", "run_coarse"]
+__all__ = ["CellRetrievalNetwork", "CrossMatch", "Engine", "EngineError", "eval_epoch", "run_coarse", "run_fine"]
 
 
 def __getattr__(name):
@@ -14,11 +14,15 @@ def __getattr__(name):
         from .cell_retrieval import CellRetrievalNetwork
 
         return CellRetrievalNetwork
+    if name == "CrossMatch":
+        from .cross_matcher import CrossMatch
+
+        return CrossMatch
     if name in ("Engine", "EngineError"):
         from . import engine
 
         return getattr(engine, name)
-    if name in ("eval_epoch", "run_coarse"):
+    if name in ("eval_epoch", "run_coarse", "run_fine"):
         from . import evaluation
 
         return getattr(evaluation, name)

@@ -33,6 +33,10 @@ SIGNATURES = {
     "t2l_encode_text": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "t2l_encode_text_tokens": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "t2l_encode_text_sentences": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "t2l_fine_offsets": (c_int, [_P, _P, _P, POINTER(c_int32), c_int, _P, c_int, c_int, _P, _P]),
+    "t2l_fine_encode_objects": (c_int, [_P, _P, _P, POINTER(c_int32), c_int, _P, _P]),
+    "t2l_fine_encode_hints": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "t2l_fine_match": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P]),
     "t2l_db_build": (c_int, [_P, _P, c_int64, c_int64, _P]),
     "t2l_search_topk": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),
     "t2l_search_topk_accumulate": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),

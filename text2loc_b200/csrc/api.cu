@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/text2loc_b200.h"
@@ -90,6 +91,8 @@ struct t2l_engine {
   bool bf16_first_now = false;
   int bf16_first_calls = 0;
   int32_t* fail_host = nullptr;
+  float* fine_buf = nullptr;   // object encodings | hint encodings between the stages of t2l_fine_offsets
+  size_t fine_cap = 0;
   int64_t* acc_idx = nullptr;  // per-chunk lists of t2l_search_topk_accumulate
   double* acc_score = nullptr;
   int acc_cap = 0;
@@ -227,6 +230,7 @@ extern "C" void t2l_destroy(t2l_engine* e) {
   cudaFree(e->db.scale);
   cudaFree(e->acc_idx);
   cudaFree(e->acc_score);
+  cudaFree(e->fine_buf);
   cudaFree(e->db.planes);
   cudaFree(e->db.max_norm);
   free_search_work(e);
@@ -252,8 +256,8 @@ static bool is_f16_operand(const std::string& n) {
 
 static bool is_split3_operand(const std::string& n) {
   // weights of the fp32-accurate tensor-core layers: stored as [hi | lo] tf32 planes
-  static const char* pre[] = {"obj_attn0", "obj_attn1", "txt_inter"};
-  static const char* parts[] = {".in_w", ".out_w", ".l1_w", ".l2_w"};
+  static const char* pre[] = {"obj_attn0", "obj_attn1", "txt_inter", "cross_objects0", "cross_objects1", "cross_hints0", "cross_hints1"};
+  static const char* parts[] = {".in_w", ".out_w", ".l1_w", ".l2_w", ".ca_q_w", ".ca_kv_w", ".ca_out_w"};
   for (const char* p : pre) for (const char* q : parts) if (n == std::string(p) + q) return true;
   return n == "txt_mlp.w";
 }
@@ -361,8 +365,9 @@ static std::vector<ShapeSpec> expected_shapes(bool fine) {
       for (int i = 0; i < 2; ++i) {
         const std::string p = std::string(side_name) + std::to_string(i);
         attn_shapes(v, p, d, 4 * d);  // self-attention block + FFN + norm1 / norm2 (norm2 follows the cross-attention)
-        v.push_back({p + ".ca_in_w", 3 * d, d}); v.push_back({p + ".ca_in_b", 1, 3 * d});
-        v.push_back({p + ".ca_out_w", d, d});    v.push_back({p + ".ca_out_b", 1, d});
+        v.push_back({p + ".ca_q_w", d, d});       v.push_back({p + ".ca_q_b", 1, d});       // multihead_attn.in_proj rows [0, d)
+        v.push_back({p + ".ca_kv_w", 2 * d, d});  v.push_back({p + ".ca_kv_b", 1, 2 * d});  // rows [d, 3d): keys | values of the memory
+        v.push_back({p + ".ca_out_w", d, d});     v.push_back({p + ".ca_out_b", 1, d});
         v.push_back({p + ".n3_w", 1, d}); v.push_back({p + ".n3_b", 1, d});
       }
     v.push_back({"offs.w1", d / 2, d}); v.push_back({"offs.b1", 1, d / 2}); v.push_back({"offs.w2", 2, d / 2}); v.push_back({"offs.b2", 1, 2});
@@ -498,8 +503,9 @@ static size_t obj_chunk_bytes(size_t n, size_t cells, bool obj_mode) {
   return n * (obj_mode ? size_t(440000) : (size_t(1) << 21) + 700000) + cells * size_t(28) * 256 * 4 * 32 + (size_t(1) << 20);
 }
 
+// obj_emb_out != nullptr: stop after the object encoder and write its normalised rows [n_objects, d] (fine stage)
 static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr, int c0, int c1, float* out,
-                        const ObjDebug* dbg, cudaStream_t st) {
+                        const ObjDebug* dbg, cudaStream_t st, float* obj_emb_out = nullptr) {
   const int o0 = cell_ptr[c0], o1 = cell_ptr[c1];
   const int n = o1 - o0, B = c1 - c0;
   if (ensure_arena(e, obj_chunk_bytes(n, B, e->fused_sa && e->obj_sa))) return 1;
@@ -662,26 +668,32 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
     if (!out) return 0;
   }
 
-  // ObjectEncoder.forward (object_encoder.py:98-149): four normalised 256-d features -> mlp_merge
-  float* cat = a.get<float>(N * 1024);
-  float* t256 = a.get<float>(N * 256);
-  float* t64 = a.get<float>(N * 64);
-  float* numf = a.get<float>(N);
-  float* emb = a.get<float>(N * 256);
+  // ObjectEncoder.forward (object_encoder.py:98-149): four normalised d-dim features -> mlp_merge (d = 256 coarse, 128 fine)
+  const int d = e->fine ? T2L_FINE_DIM : T2L_EMBED_DIM;
+  float* cat = a.get<float>(N * 4 * d);
+  float* td = a.get<float>(N * d);
+  float* emb = a.get<float>(N * d);
   const float* m = meta + static_cast<size_t>(o0) * 7;
-  CU(lin(e, true, f2, 256, n, "mlp_pointnet.w", "mlp_pointnet.b", t256, 256, 1, st));
-  CU(l2_normalize_rows(t256, 256, cat + 0, 1024, n, 256, st, &e->lc));
+  CU(lin(e, true, f2, 256, n, "mlp_pointnet.w", "mlp_pointnet.b", td, d, 1, st));
+  CU(l2_normalize_rows(td, d, cat + 0, 4L * d, n, d, st, &e->lc));
   {
     if (W(e, "color.w1").ld != 4 || W(e, "pos.w1").ld != 4 || W(e, "num.w1").ld != 4 || W(e, "color.w2").ld != 64 || W(e, "pos.w2").ld != 64 ||
-        W(e, "num.w2").ld != 64 || W(e, "color.w2").rows != 256)
+        W(e, "num.w2").ld != 64 || W(e, "color.w2").rows != d)
       return fail(e, "internal: side encoder weight shapes");
     const float* w1[3] = {W(e, "color.w1").dev, W(e, "pos.w1").dev, W(e, "num.w1").dev};
     const float* b1[3] = {W(e, "color.b1").dev, W(e, "pos.b1").dev, W(e, "num.b1").dev};
     const float* w2[3] = {W(e, "color.w2").dev, W(e, "pos.w2").dev, W(e, "num.w2").dev};
     const float* b2[3] = {W(e, "color.b2").dev, W(e, "pos.b2").dev, W(e, "num.b2").dev};
-    CU(side_encoders(m, n, w1, b1, w2, b2, cat, st, &e->lc));
+    CU(side_encoders(m, n, w1, b1, w2, b2, cat, d, st, &e->lc));
   }
-  CU(lin(e, true, cat, 1024, n, "merge.w", "merge.b", emb, 256, 1, st));
+  CU(lin(e, true, cat, 4L * d, n, "merge.w", "merge.b", emb, d, 1, st));
+
+  if (obj_emb_out) {
+    // fine stage (models/cross_matcher.py:98-108): the per-object encodings, L2-normalised, are the result
+    CU(l2_normalize_rows(emb, d, obj_emb_out + static_cast<size_t>(o0) * d, d, n, d, st, &e->lc));
+    if (a.overflow) return fail(e, "internal: workspace arena too small for %d objects", n);
+    return 0;
+  }
 
   // intra-cell attention (cell_retrieval.py:85-108); fp32 throughout: these two layers amplify
   // operand rounding the most (precision table)
@@ -700,10 +712,12 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
 }
 
 static int encode_cells_impl(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr, int n_cells, float* out,
-                             const ObjDebug* dbg, cudaStream_t st) {
+                             const ObjDebug* dbg, cudaStream_t st, float* obj_emb_out = nullptr) {
   if (!e) return 1;
   if (!e->finalized) return fail(e, "weights not finalized");
   if (n_cells < 0 || !cell_ptr || cell_ptr[0] != 0) return fail(e, "encode_cells: bad cell_ptr");
+  if (e->fine && !obj_emb_out && !dbg) return fail(e, "encode_cells: this engine holds the fine-stage model (CrossMatch); use t2l_fine_*");
+  if (!e->fine && obj_emb_out) return fail(e, "fine_encode_objects: this engine holds the coarse model; load a CrossMatch state dict");
   ENTER_STREAM(e, st);
   for (int c = 0; c < n_cells; ++c)
     if (cell_ptr[c + 1] <= cell_ptr[c]) return fail(e, "encode_cells: cell %d has no objects (the reference asserts >= 1, cells.py:202)", c);
@@ -711,7 +725,7 @@ static int encode_cells_impl(t2l_engine* e, const float* pts, const float* meta,
   while (c0 < n_cells) {
     int c1 = c0 + 1;
     while (c1 < n_cells && cell_ptr[c1 + 1] - cell_ptr[c0] <= e->obj_chunk) ++c1;
-    if (encode_chunk(e, pts, meta, cell_ptr, c0, c1, out, dbg, st)) return 1;
+    if (encode_chunk(e, pts, meta, cell_ptr, c0, c1, out, dbg, st, obj_emb_out)) return 1;
     c0 = c1;
   }
   return 0;
@@ -780,6 +794,7 @@ static int text_sentences(t2l_engine* e, const float* pooled, int nq, int S, flo
 static int text_args_ok(t2l_engine* e, const void* in, const void* out, int n, int S, int L) {
   if (!e) return 1;
   if (!e->finalized) return fail(e, "weights not finalized");
+  if (e->fine) return fail(e, "encode_text: this engine holds the fine-stage model (CrossMatch); use t2l_fine_*");
   if (!in || !out || n < 0 || S < 1 || S > 32 || L < 1 || L > 32) return fail(e, "encode_text: bad argument (n_sent, n_tok must be in 1..32)");
   return 0;
 }
@@ -808,6 +823,149 @@ extern "C" int t2l_encode_text(t2l_engine* e, const float* t5, int nq, int S, in
   }
   if (text_tokens(e, t5, static_cast<int>(n_seq), L, e->pooled, st)) return 1;
   return text_sentences(e, e->pooled, nq, S, out, st);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// fine stage: CrossMatch.forward (models/cross_matcher.py:83-129), SURVEY.md section 8f row 1 / BASELINE configs[4]
+// ---------------------------------------------------------------------------------------------
+// One post-norm nn.TransformerDecoderLayer (ReLU, eps 1e-5, eval, no masks; cross_matcher.py:66-72) on packed rows:
+//   x = LN1(t + SelfAttn(t));  x = LN2(x + CrossAttn(x, mem));  x = LN3(x + FFN(x))
+// T [n_seq * St, d], Mem [n_seq * Sm, d] -> Tout [n_seq * St, d].  All projections are three-pass split products (fp32 accuracy).
+static int decoder_layer(t2l_engine* e, const std::string& pfx, const float* T, int St, const float* Mem, int Sm, float* Tout, int n_seq, int d,
+                         cudaStream_t st) {
+  const int rt = n_seq * St, rm = n_seq * Sm;
+  Arena& a = e->arena;
+  const size_t mark = a.off;
+  float* qkv = a.get<float>(static_cast<size_t>(rt) * 3 * d);
+  float* att = a.get<float>(static_cast<size_t>(rt) * d);
+  float* y = a.get<float>(static_cast<size_t>(rt) * d);
+  float* x1 = a.get<float>(static_cast<size_t>(rt) * d);
+  float* q2 = a.get<float>(static_cast<size_t>(rt) * d);
+  float* kv2 = a.get<float>(static_cast<size_t>(rm) * 2 * d);
+  float* x2 = a.get<float>(static_cast<size_t>(rt) * d);
+  float* h = a.get<float>(static_cast<size_t>(rt) * 4 * d);
+  CU(lin3(e, T, d, rt, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st));
+  CU(mha_small(qkv, att, n_seq, St, d, 4, st, &e->lc));
+  CU(lin3(e, att, d, rt, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, T, d));
+  CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rt, d, st, &e->lc));
+  CU(lin3(e, x1, d, rt, pfx + ".ca_q_w", pfx + ".ca_q_b", q2, d, 0, st));
+  CU(lin3(e, Mem, d, rm, pfx + ".ca_kv_w", pfx + ".ca_kv_b", kv2, 2L * d, 0, st));
+  CU(mha_cross_small(q2, d, kv2, kv2 + d, 2L * d, att, n_seq, St, Sm, d, 4, st, &e->lc));
+  CU(lin3(e, att, d, rt, pfx + ".ca_out_w", pfx + ".ca_out_b", y, d, 0, st, x1, d));
+  CU(layer_norm_rows(y, x2, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, rt, d, st, &e->lc));
+  CU(lin3(e, x2, d, rt, pfx + ".l1_w", pfx + ".l1_b", h, 4L * d, 1, st));
+  CU(lin3(e, h, 4 * d, rt, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x2, d));
+  CU(layer_norm_rows(y, Tout, W(e, pfx + ".n3_w").dev, W(e, pfx + ".n3_b").dev, rt, d, st, &e->lc));
+  a.off = mark;  // Tout lives outside the scratch of this layer
+  return 0;
+}
+
+static int fine_args_ok(t2l_engine* e) {
+  if (!e) return 1;
+  if (!e->finalized) return fail(e, "weights not finalized");
+  if (!e->fine) return fail(e, "this engine holds the coarse model; the fine stage needs a CrossMatch state dict");
+  return 0;
+}
+
+extern "C" int t2l_fine_encode_objects(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr_host, int n_cells,
+                                       float* obj_emb, void* stream) {
+  if (fine_args_ok(e)) return 1;
+  if (!pts || !meta || !obj_emb) return fail(e, "fine_encode_objects: NULL buffer");
+  if (reinterpret_cast<uintptr_t>(pts) & 15) return fail(e, "fine_encode_objects: pts must be 16-byte aligned");
+  return encode_cells_impl(e, pts, meta, cell_ptr_host, n_cells, nullptr, nullptr, static_cast<cudaStream_t>(stream), obj_emb);
+}
+
+// LanguageEncoder(is_fine=True) after T5 (models/language_encoder.py:130-140): token layer, max over tokens, inter_mlp
+static int fine_hints_impl(t2l_engine* e, const float* t5, int n_sent, int L, float* hints, cudaStream_t st) {
+  const int d = T2L_FINE_DIM;
+  if (n_sent == 0) return 0;
+  if (static_cast<size_t>(n_sent) > e->pooled_cap) {
+    if (e->pooled) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->pooled)); e->pooled = nullptr; }
+    CU(cudaMalloc(&e->pooled, (static_cast<size_t>(n_sent) + 1024) * T2L_T5_DIM * sizeof(float)));
+    e->pooled_cap = static_cast<size_t>(n_sent) + 1024;
+  }
+  if (text_tokens(e, t5, n_sent, L, e->pooled, st)) return 1;
+  if (ensure_arena(e, static_cast<size_t>(n_sent) * 2 * T2L_T5_DIM * 4 + (size_t(1) << 22))) return 1;
+  CU(lin3(e, e->pooled, T2L_T5_DIM, n_sent, "txt_mlp.w", "txt_mlp.b", hints, d, 0, st));
+  if (e->arena.overflow) return fail(e, "internal: workspace arena too small for %d hint sentences", n_sent);
+  return 0;
+}
+
+extern "C" int t2l_fine_encode_hints(t2l_engine* e, const float* t5, int n_sentences, int n_tok, float* hints, void* stream) {
+  if (fine_args_ok(e)) return 1;
+  if (!t5 || !hints || n_sentences < 0 || n_tok < 1 || n_tok > 32) return fail(e, "fine_encode_hints: bad argument (n_tok in 1..32)");
+  ENTER_STREAM(e, stream);
+  return fine_hints_impl(e, t5, n_sentences, n_tok, hints, static_cast<cudaStream_t>(stream));
+}
+
+static int fine_match_impl(t2l_engine* e, const float* obj_emb, const int32_t* pair_cell, const float* hints, const int32_t* pair_query, int n_pairs,
+                           int n_obj, int n_hints, float* offsets, cudaStream_t st) {
+  const int d = T2L_FINE_DIM;
+  const int chunk = 4096;  // pairs per pass (~300 KB of scratch each)
+  for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
+    const int np = n_pairs - p0 < chunk ? n_pairs - p0 : chunk;
+    if (ensure_arena(e, static_cast<size_t>(np) * (static_cast<size_t>(n_obj) + n_hints) * d * 4 * 40 + (size_t(1) << 22))) return 1;
+    Arena& a = e->arena;
+    float* d0 = a.get<float>(static_cast<size_t>(np) * n_obj * d);
+    float* d0b = a.get<float>(static_cast<size_t>(np) * n_obj * d);
+    float* d1 = a.get<float>(static_cast<size_t>(np) * n_hints * d);
+    float* d1b = a.get<float>(static_cast<size_t>(np) * n_hints * d);
+    float* hmax = a.get<float>(static_cast<size_t>(np) * d);
+    float* h64 = a.get<float>(static_cast<size_t>(np) * (d / 2));
+    // desc0 / desc1 of every pair: rows of the cell's (already normalised) objects, rows of the query's hints (:105-111)
+    CU(gather_row_groups(obj_emb, pair_cell ? pair_cell + p0 : nullptr, p0, np, n_obj, d, d0, st, &e->lc));
+    CU(gather_row_groups(hints, pair_query ? pair_query + p0 : nullptr, p0, np, n_hints, d, d1, st, &e->lc));
+    // cascaded cross-attention (:113-115): objects attend to hints, then hints to the updated objects, twice
+    float *o_in = d0, *o_out = d0b, *h_in = d1, *h_out = d1b;
+    for (int i = 0; i < 2; ++i) {
+      if (decoder_layer(e, "cross_objects" + std::to_string(i), o_in, n_obj, h_in, n_hints, o_out, np, d, st)) return 1;
+      if (decoder_layer(e, "cross_hints" + std::to_string(i), h_in, n_hints, o_out, n_obj, h_out, np, d, st)) return 1;
+      std::swap(o_in, o_out);
+      std::swap(h_in, h_out);
+    }
+    CU(max_over_rows(h_in, hmax, np, n_hints, d, st, &e->lc));  // desc1.max(dim=0) (:126)
+    // mlp_offsets = Linear(d, d/2) + ReLU + Linear(d/2, 2) (:17-36, :127), exact fp32
+    CU(lin(e, false, hmax, d, np, "offs.w1", "offs.b1", h64, d / 2, 1, st));
+    CU(lin(e, false, h64, d / 2, np, "offs.w2", "offs.b2", offsets + static_cast<size_t>(p0) * 2, 2, 0, st));
+    if (a.overflow) return fail(e, "internal: workspace arena too small for %d pairs", np);
+  }
+  return 0;
+}
+
+extern "C" int t2l_fine_match(t2l_engine* e, const float* obj_emb, const int32_t* pair_cell, const float* hints, const int32_t* pair_query,
+                              int n_pairs, int n_obj, int n_hints, float* offsets, void* stream) {
+  if (fine_args_ok(e)) return 1;
+  if (!obj_emb || !hints || !offsets || n_pairs < 0 || n_obj < 1 || n_obj > 32 || n_hints < 1 || n_hints > 32)
+    return fail(e, "fine_match: bad argument (objects per cell and hints per query in 1..32)");
+  ENTER_STREAM(e, stream);
+  return fine_match_impl(e, obj_emb, pair_cell, hints, pair_query, n_pairs, n_obj, n_hints, offsets, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int t2l_fine_offsets(t2l_engine* e, const float* pts, const float* meta, const int32_t* cell_ptr_host, int n_cells, const float* t5,
+                                int n_hints, int n_tok, float* offsets, void* stream) {
+  if (fine_args_ok(e)) return 1;
+  if (!pts || !meta || !cell_ptr_host || !t5 || !offsets || n_cells < 0 || n_hints < 1 || n_hints > 32 || n_tok < 1 || n_tok > 32)
+    return fail(e, "fine_offsets: bad argument");
+  if (n_cells == 0) return 0;
+  const int n_obj = cell_ptr_host[1] - cell_ptr_host[0];
+  for (int c = 0; c < n_cells; ++c)
+    if (cell_ptr_host[c + 1] - cell_ptr_host[c] != n_obj)
+      return fail(e, "fine_offsets: every cell must hold the same number of (padded) objects (pad_size, dataloading/kitti360pose/eval.py:147-160)");
+  if (n_obj < 1 || n_obj > 32) return fail(e, "fine_offsets: objects per cell must be in 1..32");
+  const int d = T2L_FINE_DIM;
+  const size_t need = static_cast<size_t>(n_cells) * (static_cast<size_t>(n_obj) + n_hints) * d;
+  if (need > e->fine_cap) {
+    ENTER(e);
+    if (e->fine_buf) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->fine_buf)); e->fine_buf = nullptr; }
+    CU(cudaMalloc(&e->fine_buf, (need + 4096) * sizeof(float)));
+    e->fine_cap = need + 4096;
+  }
+  float* obj_emb = e->fine_buf;
+  float* hints = e->fine_buf + static_cast<size_t>(n_cells) * n_obj * d;
+  if (t2l_fine_encode_objects(e, pts, meta, cell_ptr_host, n_cells, obj_emb, stream)) return 1;
+  if (t2l_fine_encode_hints(e, t5, n_cells * n_hints, n_tok, hints, stream)) return 1;
+  return t2l_fine_match(e, obj_emb, nullptr, hints, nullptr, n_cells, n_obj, n_hints, offsets, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -144,6 +144,9 @@ cudaError_t to_half_rows(const float* x, __half* y, long n, cudaStream_t st, Lau
 // Unmasked multi-head self attention on packed QKV rows [n_seq*S, 3d] (q | k | v), head h uses
 // columns [h*hd, (h+1)*hd); out [n_seq*S, d].  softmax(q k^T / sqrt(hd)) v, fp32.
 cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out = 0);
+// Cross attention with the same core: q [n_seq*Sq, ldq], k / v [n_seq*Sk, ldkv] -> out [n_seq*Sq, d]; Sk <= 32, head dim 32 / 64 / 256
+cudaError_t mha_cross_small(const float* q, long ldq, const float* k, const float* v, long ldkv, float* out, int n_seq, int Sq, int Sk, int d,
+                            int n_heads, cudaStream_t st, Launches* lc, int round_out = 0);
 // Same contract for d = 1024, 4 heads of 256 (the token layer): warp-level mma.sync tf32 tiles.
 // round_out: 0 fp32, 1 fp32 rounded to tf32, 2 `out` is __half [rows, 1024].
 // half_in: qkv is __half [rows, 3072].
@@ -158,11 +161,13 @@ cudaError_t max_over_rows(const float* x, float* y, int groups, int S, int d, cu
 cudaError_t scatter_objects(const float* emb, const int32_t* cell_ptr_dev, int n_cells, float* X, cudaStream_t st, Launches* lc);
 // meta[:, 6] -> (cnt - mean) / std  (object_encoder.py:141-143)
 cudaError_t num_feature(const float* meta, int n_obj, float* out, cudaStream_t st, Launches* lc);
-// cat[:, 256:1024] = [normalize(color_enc(mean rgb)) | normalize(pos_enc(centre)) | normalize(num_enc((count-mean)/std))]
+// cat[:, d:4d] = [normalize(color_enc(mean rgb)) | normalize(pos_enc(centre)) | normalize(num_enc((count-mean)/std))], d = 256 or 128
 // from meta [n, 7]; w1[i] [64, ld 4], b1[i] [64], w2[i] [256, 64], b2[i] [256] for i = colour, position, count
 // (models/object_encoder.py:122-145)
 cudaError_t side_encoders(const float* meta, int n_obj, const float* const* w1, const float* const* b1, const float* const* w2, const float* const* b2,
-                          float* cat, cudaStream_t st, Launches* lc);
+                          float* cat, int d, cudaStream_t st, Launches* lc);
+// dst[p * G + g, :] = src[(idx ? idx[p] : p0 + p) * G + g, :] for p < n_groups, g < G (rows of d floats)
+cudaError_t gather_row_groups(const float* src, const int32_t* idx, int p0, int n_groups, int G, int d, float* dst, cudaStream_t st, Launches* lc);
 // y = a + b (elementwise)
 cudaError_t add_rows(const float* a, const float* b, float* y, long n, cudaStream_t st, Launches* lc);
 // text: [S, nq] row order helpers are not needed: rows are kept query-major (q*S + s)

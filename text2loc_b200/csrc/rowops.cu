@@ -103,6 +103,7 @@ cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const floa
   if (lc) lc->n++;
   const unsigned grid = (rows + 7) / 8;
   if (d == 256) layer_norm_kernel<256><<<grid, 256, 0, st>>>(x, y, w, b, rows, y_half);
+  else if (d == 128) layer_norm_kernel<128><<<grid, 256, 0, st>>>(x, y, w, b, rows, y_half);
   else if (d == 1024) layer_norm_kernel<1024><<<grid, 256, 0, st>>>(x, y, w, b, rows, y_half);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
@@ -115,9 +116,12 @@ cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const floa
 // so the L2 latency of one group hides behind the arithmetic of the previous one.  No mask:
 // padded slots/tokens attend like real ones, exactly as the reference
 // (cell_retrieval.py:101-103, language_encoder.py:130-131).
+// Generalised to cross attention (nn.TransformerDecoderLayer.multihead_attn, models/cross_matcher.py:113-115): queries come from
+// q [n_seq * Sq, ldq], keys and values from k / v [n_seq * Sk, ldkv]; self attention passes the three slices of one packed buffer.
 template <int HD>
-__global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict__ qkv, float* __restrict__ out, long n_rows_total, int S, int d,
-                                                        int n_heads, float scale, int round_out) {
+__global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict__ qp, long ldq, const float* __restrict__ kp, const float* __restrict__ vp,
+                                                        long ldkv, float* __restrict__ out, long n_rows_total, int Sq, int S, int d, int n_heads,
+                                                        float scale, int round_out) {
   constexpr int R = HD / 32;
   constexpr int U = 4;
   // 32-bit index math: the 64-bit runtime divisions this replaced cost more instructions than the attention itself
@@ -125,12 +129,12 @@ __global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict_
   const int lane = threadIdx.x & 31;
   if (wid >= static_cast<unsigned>(n_rows_total) * static_cast<unsigned>(n_heads)) return;
   const int h = static_cast<int>(wid % static_cast<unsigned>(n_heads));
-  const long row = wid / static_cast<unsigned>(n_heads);  // seq * S + i
-  const long seq0 = static_cast<long>((static_cast<unsigned>(row) / static_cast<unsigned>(S)) * static_cast<unsigned>(S));
-  const long ld = 3L * d;
-  const float* q = qkv + row * ld + h * HD;
-  const float* kbase = qkv + seq0 * ld + d + h * HD + lane;
-  const float* vbase = qkv + seq0 * ld + 2 * d + h * HD + lane;
+  const long row = wid / static_cast<unsigned>(n_heads);  // seq * Sq + i
+  const long seq0 = static_cast<long>((static_cast<unsigned>(row) / static_cast<unsigned>(Sq)) * static_cast<unsigned>(S));  // first key row
+  const long ld = ldkv;
+  const float* q = qp + row * ldq + h * HD;
+  const float* kbase = kp + seq0 * ld + h * HD + lane;
+  const float* vbase = vp + seq0 * ld + h * HD + lane;
   float qv[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) qv[r] = q[r * 32 + lane];
@@ -178,19 +182,25 @@ __global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict_
   for (int r = 0; r < R; ++r) o[r * 32 + lane] = round_out ? round_tf32(acc[r]) : acc[r];
 }
 
-cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out) {
+cudaError_t mha_cross_small(const float* q, long ldq, const float* k, const float* v, long ldkv, float* out, int n_seq, int Sq, int Sk, int d,
+                            int n_heads, cudaStream_t st, Launches* lc, int round_out) {
   if (n_seq <= 0) return cudaSuccess;
-  if (S > 32 || S < 1) return cudaErrorInvalidValue;
+  if (Sk > 32 || Sk < 1 || Sq < 1) return cudaErrorInvalidValue;
   if (lc) lc->n++;
-  const long rows = static_cast<long>(n_seq) * S;
+  const long rows = static_cast<long>(n_seq) * Sq;
   const int hd = d / n_heads;
   if (rows * n_heads >= (1L << 31)) return cudaErrorInvalidValue;
   const unsigned grid = static_cast<unsigned>((rows * n_heads + 7) / 8);
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
-  if (hd == 64) mha_small_kernel<64><<<grid, 256, 0, st>>>(qkv, out, rows, S, d, n_heads, scale, round_out);
-  else if (hd == 256) mha_small_kernel<256><<<grid, 256, 0, st>>>(qkv, out, rows, S, d, n_heads, scale, round_out);
+  if (hd == 64) mha_small_kernel<64><<<grid, 256, 0, st>>>(q, ldq, k, v, ldkv, out, rows, Sq, Sk, d, n_heads, scale, round_out);
+  else if (hd == 32) mha_small_kernel<32><<<grid, 256, 0, st>>>(q, ldq, k, v, ldkv, out, rows, Sq, Sk, d, n_heads, scale, round_out);
+  else if (hd == 256) mha_small_kernel<256><<<grid, 256, 0, st>>>(q, ldq, k, v, ldkv, out, rows, Sq, Sk, d, n_heads, scale, round_out);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
+}
+
+cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out) {
+  return mha_cross_small(qkv, 3L * d, qkv + d, qkv + 2 * d, 3L * d, out, n_seq, S, S, d, n_heads, st, lc, round_out);
 }
 
 // ---- tensor-core attention core for the token layer (head_dim 256) ---------------------------------
@@ -523,10 +533,12 @@ struct SideEncoders {
   const float* w1[3]; const float* b1[3]; const float* w2[3]; const float* b2[3];  // w1 [64, ld 4], w2 [256, 64]
 };
 
-__global__ void __launch_bounds__(256) side_encoders_kernel(const float* __restrict__ meta, int n, SideEncoders w, float* __restrict__ cat) {
+template <int D>  // embedding dim = threads per block: 256 (coarse) or 128 (fine stage)
+__global__ void __launch_bounds__(D) side_encoders_kernel(const float* __restrict__ meta, int n, SideEncoders w, float* __restrict__ cat) {
   constexpr int OB = 8;
+  constexpr int OPP = D / 64;  // objects whose 64 hidden units one pass of the block computes
   __shared__ float hid[OB][64];
-  __shared__ float red[8][OB];
+  __shared__ float red[D / 32][OB];
   const int c = threadIdx.x, lane = c & 31, wp = c >> 5;
   const float mean = static_cast<float>(1826.6844940968194), std_ = static_cast<float>(2516.8905096993817);
   for (int enc = 0; enc < 3; ++enc) {
@@ -542,8 +554,8 @@ __global__ void __launch_bounds__(256) side_encoders_kernel(const float* __restr
     const float b1h = __ldg(w.b1[enc] + h);
     for (int o0 = blockIdx.x * OB; o0 < n; o0 += gridDim.x * OB) {
 #pragma unroll
-      for (int pass = 0; pass < OB / 4; ++pass) {  // 256 threads = 4 objects x 64 hidden units per pass
-        const int ol = pass * 4 + (c >> 6), o = o0 + ol;
+      for (int pass = 0; pass < OB / OPP; ++pass) {  // D threads = OPP objects x 64 hidden units per pass
+        const int ol = pass * OPP + (c >> 6), o = o0 + ol;
         float x = 0.f;
         if (o < n) {
           const float* m = meta + static_cast<long>(o) * 7;
@@ -578,9 +590,9 @@ __global__ void __launch_bounds__(256) side_encoders_kernel(const float* __restr
         if (o0 + ol >= n) break;
         float ss = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) ss += red[q][ol];
+        for (int q = 0; q < D / 32; ++q) ss += red[q][ol];
         const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize
-        cat[static_cast<long>(o0 + ol) * 1024 + 256 * (enc + 1) + c] = acc[ol] * inv;
+        cat[static_cast<long>(o0 + ol) * (4 * D) + D * (enc + 1) + c] = acc[ol] * inv;
       }
       __syncthreads();
     }
@@ -588,14 +600,40 @@ __global__ void __launch_bounds__(256) side_encoders_kernel(const float* __restr
 }
 
 cudaError_t side_encoders(const float* meta, int n_obj, const float* const* w1, const float* const* b1, const float* const* w2, const float* const* b2,
-                          float* cat, cudaStream_t st, Launches* lc) {
+                          float* cat, int d, cudaStream_t st, Launches* lc) {
   if (n_obj <= 0) return cudaSuccess;
   if (lc) lc->n++;
   SideEncoders w;
   for (int i = 0; i < 3; ++i) { w.w1[i] = w1[i]; w.b1[i] = b1[i]; w.w2[i] = w2[i]; w.b2[i] = b2[i]; }
   const int batches = (n_obj + 7) / 8;
   const int grid = batches < 296 ? batches : 296;
-  side_encoders_kernel<<<grid, 256, 0, st>>>(meta, n_obj, w, cat);
+  if (d == 256) side_encoders_kernel<256><<<grid, 256, 0, st>>>(meta, n_obj, w, cat);
+  else if (d == 128) side_encoders_kernel<128><<<grid, 128, 0, st>>>(meta, n_obj, w, cat);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// dst[(p * G + g), :] = src[(idx ? idx[p] : p0 + p) * G + g, :]: the G rows of group idx[p] for every pair p (fine stage: the
+// objects of the pair's cell, the hints of the pair's query)
+__global__ void gather_row_groups_kernel(const float4* __restrict__ src, const int32_t* __restrict__ idx, int p0, long n_rows, int G, int d4,
+                                         float4* __restrict__ dst) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_rows * d4) return;
+  const long row = i / d4;
+  const int c = static_cast<int>(i - row * d4);
+  const long p = row / G;
+  const int g = static_cast<int>(row - p * G);
+  const long s = (idx ? static_cast<long>(idx[p]) : p0 + p) * G + g;
+  dst[i] = src[s * d4 + c];
+}
+
+cudaError_t gather_row_groups(const float* src, const int32_t* idx, int p0, int n_groups, int G, int d, float* dst, cudaStream_t st, Launches* lc) {
+  if (n_groups <= 0) return cudaSuccess;
+  if (d % 4) return cudaErrorInvalidValue;
+  if (lc) lc->n++;
+  const long n = static_cast<long>(n_groups) * G * (d / 4);
+  gather_row_groups_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), idx, p0, static_cast<long>(n_groups) * G, G,
+                                                                                 d / 4, reinterpret_cast<float4*>(dst));
   return cudaGetLastError();
 }
 

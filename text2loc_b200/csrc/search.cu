@@ -152,10 +152,18 @@ struct TopKEpi {
       for (int i = 0; i < 32; ++i) v[i] = (col0 + i < p.n_db) ? v[i] : -INFINITY;
     }
     const float thr = ls[kCand - 1];
+    // The common case once the list has warmed up: nothing in the chunk beats the list minimum.  One max tree (3-input
+    // FMNMX) decides that in ~16 instructions; the per-element mask (3 instructions each) is only built behind it.  With a
+    // single K = 256 pass per tile the epilogue has as many cycles as the MMAs take (2 048 per 128 x 256 tile, and draining
+    // the accumulator from tensor memory at 64 B/clk already uses all of them), so this test is the epilogue's budget.
+    float m8[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
+    const float vmax = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+    if (!(vmax > thr)) return;
     uint32_t mask = 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) mask |= (v[i] > thr) ? (1u << i) : 0u;
-    if (mask == 0) return;  // the common case once the list has warmed up
     // rare path: park the 32 scores in shared memory so ONE copy of the insertion chain can walk the
     // set bits with a dynamic index (32 unrolled copies thrashed the instruction cache: 3x slower)
 #pragma unroll
@@ -489,8 +497,16 @@ cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q,
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   CUtensorMap ta2;
   if (make_operand_map(&ta2, w.q2_planes, kOpBf16, nq, 2 * kEmbed, 2 * kEmbed, Cfg::BLOCK_M)) return cudaErrorInvalidValue;
+  // Few queries fail, so the second pass has few query tiles: it is split along the DATABASE instead (the collecting
+  // epilogue keeps no per-split state), enough units for every CTA pair even when a single 256-query tile is live.
   GemmShape s2 = s;
   s2.m_rows_dev = w.n_fail;
+  {
+    int splits2 = tma_api().num_sms / Cfg::CTA_GROUP;
+    if (splits2 > s.n_tiles) splits2 = s.n_tiles;
+    s2.tiles_per_split = (s.n_tiles + splits2 - 1) / splits2;
+    s2.n_splits = (s.n_tiles + s2.tiles_per_split - 1) / s2.tiles_per_split;
+  }
   CollectEpi::Params ep2{w.fail_thr, w.n_fail, w.cand2_idx, w.cand2_cnt, s.N};
   if ((e = launch_umma_gemm<Cfg, CollectEpi>(ta2, tb, s2, ep2, st)) != cudaSuccess) return e;
   rerank2_kernel<<<(nq + kRerankWarps - 1) / kRerankWarps, kRerankWarps * 32, 0, st>>>(

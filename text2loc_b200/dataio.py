@@ -75,6 +75,22 @@ class Compose:
         return data
 
 
+class PaddingObject:
+    """Object3d.create_padding() (datapreparation/kitti360pose/imports.py:74-83): eight near-zero points, black, label "pad"."""
+
+    def __init__(self):
+        self.id = self.instance_id = -1
+        self.xyz = np.random.rand(8, 3) * 0.001
+        self.rgb = np.zeros((8, 3))
+        self.label = "pad"
+
+    def get_color_rgb(self):
+        return np.mean(self.rgb, axis=0)
+
+    def get_center(self):
+        return np.mean(self.xyz, axis=0)
+
+
 def batch_object_points(objects, transform) -> PointsBatch:
     """One point batch for the objects of a single cell (utils.py:134-146, default branch)."""
     data_list = [

@@ -164,6 +164,46 @@ class Engine:
         nq = t5.shape[0] // n_sent
         self._check(self._lib.t2l_encode_text(self._h, _ptr(t5), nq, n_sent, t5.shape[1], _ptr(out), self._stream()))
 
+    # ---- fine stage -----------------------------------------------------------------------
+    FINE_DIM = 128
+
+    def fine_offsets(self, pts, meta, cell_ptr, t5, n_hints: int) -> torch.Tensor:
+        """CrossMatch.forward on packed inputs: one (cell, description) pair per cell -> offsets [n_cells, 2]."""
+        pts, meta = self._dev(pts, torch.float32), self._dev(meta, torch.float32)
+        t5 = self._dev(t5, torch.float32)
+        cp = np.ascontiguousarray(np.asarray(cell_ptr.cpu() if torch.is_tensor(cell_ptr) else cell_ptr), dtype=np.int32)
+        n_cells = len(cp) - 1
+        if t5.dim() != 3 or t5.shape[0] != n_cells * n_hints or t5.shape[2] != T5_DIM or cp[-1] != pts.shape[0]:
+            raise EngineError(f"fine_offsets: t5 {tuple(t5.shape)} for {n_cells} cells x {n_hints} hints, pts {tuple(pts.shape)}")
+        out = torch.empty((n_cells, 2), dtype=torch.float32, device=self.device)
+        self._check(self._lib.t2l_fine_offsets(self._h, _ptr(pts), _ptr(meta), cp.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), n_cells,
+                                               _ptr(t5), n_hints, t5.shape[1], _ptr(out), self._stream()))
+        return out
+
+    def fine_encode_objects(self, pts, meta, cell_ptr) -> torch.Tensor:
+        pts, meta = self._dev(pts, torch.float32), self._dev(meta, torch.float32)
+        cp = np.ascontiguousarray(np.asarray(cell_ptr.cpu() if torch.is_tensor(cell_ptr) else cell_ptr), dtype=np.int32)
+        out = torch.empty((pts.shape[0], self.FINE_DIM), dtype=torch.float32, device=self.device)
+        self._check(self._lib.t2l_fine_encode_objects(self._h, _ptr(pts), _ptr(meta), cp.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                                      len(cp) - 1, _ptr(out), self._stream()))
+        return out
+
+    def fine_encode_hints(self, t5) -> torch.Tensor:
+        t5 = self._dev(t5, torch.float32)
+        out = torch.empty((t5.shape[0], self.FINE_DIM), dtype=torch.float32, device=self.device)
+        self._check(self._lib.t2l_fine_encode_hints(self._h, _ptr(t5), t5.shape[0], t5.shape[1], _ptr(out), self._stream()))
+        return out
+
+    def fine_match(self, obj_emb, pair_cell, hints, pair_query, n_obj: int, n_hints: int) -> torch.Tensor:
+        obj_emb, hints = self._dev(obj_emb, torch.float32), self._dev(hints, torch.float32)
+        pair_cell = self._dev(pair_cell, torch.int32) if pair_cell is not None else None
+        pair_query = self._dev(pair_query, torch.int32) if pair_query is not None else None
+        n_pairs = len(pair_cell) if pair_cell is not None else (len(pair_query) if pair_query is not None else obj_emb.shape[0] // n_obj)
+        out = torch.empty((n_pairs, 2), dtype=torch.float32, device=self.device)
+        self._check(self._lib.t2l_fine_match(self._h, _ptr(obj_emb), _ptr(pair_cell), _ptr(hints), _ptr(pair_query), n_pairs, n_obj, n_hints,
+                                             _ptr(out), self._stream()))
+        return out
+
     # ---- search ---------------------------------------------------------------------------
     def db_build(self, D, row_offset: int = 0):
         D = self._dev(D, torch.float32)

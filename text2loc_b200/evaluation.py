@@ -147,3 +147,73 @@ def run_coarse(model, dataloader, args, verbose: bool = True):
     accuracies = localisation_accuracies(model.engine, dataset.all_poses, dataset.all_cells, np.stack(retrievals), pos_in_cells,
                                          args.top_k, args.threshs)
     return retrievals, {k: accuracies[int(k)] for k in args.top_k}
+
+
+def _hint_text(pose) -> str:
+    """The description run_fine feeds the model (dataloading/kitti360pose/eval.py:162-164, base.py:60-68)."""
+    if hasattr(pose, "descriptions"):
+        return " ".join(f"The pose is {d.direction} of a {d.object_color_text} {d.object_label}." for d in pose.descriptions)
+    return pose.text
+
+
+def _padded_objects(cell, pad_size: int):
+    """Cut / pad a cell's object list to pad_size (dataloading/kitti360pose/eval.py:147-160); padding objects are 8 near-zero
+    points, black (datapreparation/kitti360pose/imports.py:74-83), created by the objects' own class when it knows how."""
+    objects = list(cell.objects)[:pad_size]
+    maker = getattr(type(objects[0]), "create_padding", None) if objects else None
+    while len(objects) < pad_size:
+        objects.append(maker() if maker else dataio.PaddingObject())
+    return objects
+
+
+@torch.no_grad()
+def run_fine(model, retrievals, dataloader, args, transform_fine, return_offsets: bool = False):
+    """evaluation/pipeline.py:91-204: offsets of every query against each of its max(top_k) retrieved cells, then the
+    thresholded localisation accuracy at the predicted in-cell positions -> {k: {thresh: accuracy}}.
+
+    The reference calls the model once per query on max(top_k) re-padded, re-sampled copies of the retrieved cells
+    (a Python loop over queries, "using a dataloader does not make it much faster").  Here the object branch does not
+    depend on the query, so every DISTINCT retrieved cell is padded, sampled and encoded once
+    (t2l_fine_encode_objects), every query's hints once (t2l_fine_encode_hints), and all query x cell pairs go through
+    the cross-attention stack in one batched call (t2l_fine_match)."""
+    model.eval()
+    dataset = dataloader.dataset
+    poses, all_cells = dataset.all_poses, dataset.all_cells
+    retrievals = np.asarray(retrievals)
+    n_q, k = retrievals.shape
+    assert n_q == len(poses) and k == max(args.top_k)  # dataloading/kitti360pose/eval.py:133-134
+    engine = model.engine
+    pad = args.pad_size
+    all_ids = np.array([cell.id for cell in all_cells], dtype="<U32")
+    rows = rows_of_ids(all_ids, retrievals)  # [n_q, k] rows of all_cells
+    assert (rows >= 0).all()
+    used, pair_cell = np.unique(rows.reshape(-1), return_inverse=True)  # distinct retrieved cells, pair -> its slot
+
+    # ---- object branch, once per distinct cell, in batches
+    obj_emb = torch.empty((len(used) * pad, engine.FINE_DIM), dtype=torch.float32, device=engine.device)
+    batch = max(1, 4096 // pad)
+    for b0 in range(0, len(used), batch):
+        cells = [all_cells[int(r)] for r in used[b0:b0 + batch]]
+        objects = [_padded_objects(c, pad) for c in cells]
+        points = [dataio.batch_object_points(o, transform_fine) for o in objects]
+        pts, meta, cell_ptr = dataio.pack_cells(objects, points)
+        obj_emb[b0 * pad:(b0 + len(cells)) * pad] = engine.fine_encode_objects(pts, meta, cell_ptr)
+
+    # ---- textual branch, once per query
+    frontend = model.frontend()
+    hints, n_hints = [], None
+    qb = 256
+    for q0 in range(0, n_q, qb):
+        feats, nh = frontend([_hint_text(p) for p in poses[q0:q0 + qb]])
+        assert n_hints in (None, nh), "every description must have the same number of hints (language_encoder.py:114)"
+        n_hints = nh
+        hints.append(engine.fine_encode_hints(feats))
+    hints = torch.cat(hints)
+
+    # ---- all query x retrieved-cell pairs
+    pair_query = np.repeat(np.arange(n_q, dtype=np.int32), k)
+    offsets = engine.fine_match(obj_emb, pair_cell.astype(np.int32), hints, pair_query, pad, n_hints).view(n_q, k, 2)
+    offsets_np = offsets.cpu().numpy().astype(np.float64)
+    acc = localisation_accuracies(engine, poses, all_cells, retrievals, offsets_np, args.top_k, args.threshs)
+    acc = {kk: acc[int(kk)] for kk in args.top_k}
+    return (acc, offsets_np) if return_offsets else acc

@@ -53,9 +53,29 @@ def _attn(out, sd, src, dst):
     out[dst + ".n2_b"] = f("norm2.bias")
 
 
+def _decoder(out, sd, src, dst):
+    """nn.TransformerDecoderLayer keys (models/cross_matcher.py:66-72) -> engine names.  The packed in_proj of the cross
+    attention is split by rows: queries come from the target sequence, keys | values from the memory."""
+    _attn(out, sd, src, dst)  # self_attn.*, linear1/2, norm1, norm2 (norm2 follows the cross attention)
+    f = lambda k: _np(sd[f"{src}.{k}"]).astype(np.float32)
+    w, b = f("multihead_attn.in_proj_weight"), f("multihead_attn.in_proj_bias")
+    d = w.shape[1]
+    out[dst + ".ca_q_w"], out[dst + ".ca_q_b"] = w[:d], b[:d]
+    out[dst + ".ca_kv_w"], out[dst + ".ca_kv_b"] = w[d:], b[d:]
+    out[dst + ".ca_out_w"], out[dst + ".ca_out_b"] = f("multihead_attn.out_proj.weight"), f("multihead_attn.out_proj.bias")
+    out[dst + ".n3_w"], out[dst + ".n3_b"] = f("norm3.weight"), f("norm3.bias")
+
+
+def is_fine_state_dict(sd: dict) -> bool:
+    """CrossMatch.state_dict() (models/cross_matcher.py:39-78) carries the offset MLP; CellRetrievalNetwork's does not."""
+    return "mlp_offsets.0.weight" in sd
+
+
 def engine_weights(sd: dict) -> dict:
-    """name -> float32 2-D array (biases and norm vectors as [1, n])."""
+    """name -> float32 2-D array (biases and norm vectors as [1, n]).  Accepts the coarse model's state dict
+    (CellRetrievalNetwork) or the fine stage's (CrossMatch)."""
     out = {}
+    fine = is_fine_state_dict(sd)
     pn = "object_encoder.pointnet"
     for i, c_in in ((1, 3), (2, 64), (3, 128)):
         w1, b1 = fold_linear_bn(sd, f"{pn}.sa{i}.point_conv.local_nn.0")
@@ -77,11 +97,21 @@ def engine_weights(sd: dict) -> dict:
         out[dst + ".w1"], out[dst + ".b1"] = fold_linear_bn(sd, f"{oe}.{src}.0")
         out[dst + ".w2"], out[dst + ".b2"] = fold_linear_bn(sd, f"{oe}.{src}.1")
     out["merge.w"], out["merge.b"] = fold_linear_bn(sd, f"{oe}.mlp_merge.0")
-    _attn(out, sd, "obj_inter_module.0", "obj_attn0")
-    _attn(out, sd, "obj_inter_module.1", "obj_attn1")
     _attn(out, sd, "language_encoder.intra_module.0", "txt_intra")
-    _attn(out, sd, "language_encoder.inter_module.0", "txt_inter")
     out["txt_mlp.w"], out["txt_mlp.b"] = fold_linear_bn(sd, "language_encoder.inter_mlp.0")
+    if fine:
+        n_layers = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("cross_hints."))
+        if n_layers != 2 or not any(k.startswith("cross_objects.1.") for k in sd):
+            raise ValueError("the B200 fine stage is built for fine_num_decoder_layers = 2 (evaluation/args.py default)")
+        for i in range(2):
+            _decoder(out, sd, f"cross_objects.{i}", f"cross_objects{i}")
+            _decoder(out, sd, f"cross_hints.{i}", f"cross_hints{i}")
+        out["offs.w1"], out["offs.b1"] = _np(sd["mlp_offsets.0.weight"]), _np(sd["mlp_offsets.0.bias"])
+        out["offs.w2"], out["offs.b2"] = _np(sd["mlp_offsets.2.weight"]), _np(sd["mlp_offsets.2.bias"])
+    else:
+        _attn(out, sd, "obj_inter_module.0", "obj_attn0")
+        _attn(out, sd, "obj_inter_module.1", "obj_attn1")
+        _attn(out, sd, "language_encoder.inter_module.0", "txt_inter")
     return {k: np.ascontiguousarray(np.atleast_2d(np.asarray(v, dtype=np.float32))) for k, v in out.items()}
 
 
