@@ -132,34 +132,6 @@ def test_features2_within_tolerance(eng, state_dict, golden):
     assert rel < 1e-3
 
 
-def test_features2_set_abstraction_variants(state_dict, golden, monkeypatch):
-    """The set-abstraction layers run object-resident on fp16 operands with W2 in tensor memory and the self-loop edges
-    folded in (sa_obj2.cu).  The A/B switches keep their predecessors: T2L_SA_V1=1 = sa_obj.cu (W2 in shared memory, self-loop
-    rows through a side GEMM), T2L_SA_TF32=1 = the tf32 kernel that gathers from global memory (sa_fused.cu).  All must
-    meet the tolerance against the reference.  (sa_obj2 also applies the first Linear per point and per centroid in fp16
-    instead of per edge in fp32: other rounding points, same accuracy -- tests/test_oracle.py.)"""
-    from text2loc_b200.engine import Engine
-
-    g = golden("cells_small.npz")
-    errs, outs = {}, {}
-    for name, env in (("fp16 tmem-resident W2 (default)", {}), ("fp16 smem-resident W2", {"T2L_SA_V1": "1"}),
-                      ("tf32 global gather", {"T2L_SA_TF32": "1"})):
-        for k in ("T2L_SA_V1", "T2L_SA_TF32"):
-            monkeypatch.delenv(k, raising=False)
-        for k, v in env.items():
-            monkeypatch.setenv(k, v)
-        e = Engine("cuda:0")
-        e.load_state_dict(state_dict)
-        got = e.encode_objects_debug(torch.from_numpy(g["pts"]), g["cell_ptr"])["features2"].cpu().numpy()
-        errs[name] = np.abs(got - g["features2"]).max() / np.abs(g["features2"]).max()
-        outs[name] = got
-        assert errs[name] < 1e-3, name
-    a, b = outs["fp16 tmem-resident W2 (default)"], outs["fp16 smem-resident W2"]
-    errs["tmem vs smem variant"] = np.abs(a - b).max() / np.abs(b).max()
-    print("\nfeatures2 max rel-to-max error:", {k: f"{v:.3e}" for k, v in errs.items()})
-    assert errs["tmem vs smem variant"] < 1e-3
-
-
 def test_fps_ball_query_fma_switch(state_dict, golden, monkeypatch):
     """T2L_DIST_FMA=1 / pyg_ops.DIST_FMA evaluate squared distances with fused multiply-adds (what nvcc's default
     contraction would make of torch-cluster's `dist += tmp * tmp`): engine and oracle must still agree bit for bit."""
@@ -186,7 +158,7 @@ def test_fps_ball_query_fma_switch(state_dict, golden, monkeypatch):
 
 def test_sa_empty_neighbour_slots(state_dict):
     """Objects whose points are far apart leave most of the 32 neighbour slots empty (down to the centroid alone): the
-    object-resident kernel replicates slot 0 there, the oracle masks the slots; the max must agree."""
+    fused kernel (sa_obj2.cu) replicates slot 0 there, the oracle masks the slots; the max must agree."""
     from oracle import restate
     import synth
     from text2loc_b200.engine import Engine

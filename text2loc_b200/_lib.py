@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libtext2loc_b200.so")
-SOURCES = ["api.cu", "linear.cu", "geometry.cu", "pointnet.cu", "sa_fused.cu", "sa_obj.cu", "sa_obj2.cu", "rowops.cu", "search.cu", "bookkeeping.cu", "synthgen.cu"]
+SOURCES = ["api.cu", "linear.cu", "geometry.cu", "pointnet.cu", "sa_obj2.cu", "rowops.cu", "search.cu", "bookkeeping.cu", "synthgen.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 # every symbol include/text2loc_b200.h declares: (restype, argtypes)

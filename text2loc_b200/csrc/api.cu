@@ -64,9 +64,6 @@ struct t2l_engine {
   size_t sw_planes_rows = 0;
   int obj_chunk = 16384;     // objects per encode chunk (cell-aligned); 2048 -> 4096 -> 8192 -> 16384 is +9 % / +5 % / +4 % cells/s (fuller
                              // grids for the small kernels), ~48 GB of workspace (T2L_OBJ_CHUNK to change)
-  bool fused_sa = true;      // sa_fused.cu; false = v1 edge_gather -> H -> SegMax GEMM (kept for A/B checks, T2L_UNFUSED_SA=1)
-  bool obj_sa = true;        // sa_obj.cu (object-resident, fp16 operands); T2L_SA_TF32=1 selects sa_fused.cu (tf32, global gathers)
-  bool obj_sa2 = true;       // sa_obj2.cu: W2 in tensor memory, self-loop edges folded in, paired SA1 tiles; T2L_SA_V1=1 selects sa_obj.cu
   bool dist_fma = false;     // FPS / ball-query distances with FMA contraction (T2L_DIST_FMA=1; oracle: pyg_ops.DIST_FMA)
   int tok_chunk = 32768;     // tokens per text chunk (sentence-aligned)
   bool text_f16 = true;      // token layer on fp16 operands (same 11-bit significand as tf32, twice the MMA rate, half the
@@ -190,10 +187,7 @@ extern "C" int t2l_create(int device, t2l_engine** out) {
   g_tma.num_sms = prop.multiProcessorCount;
   e = new t2l_engine();
   e->device = device;
-  if (const char* v = getenv("T2L_UNFUSED_SA")) e->fused_sa = !(v[0] == '1');
   if (const char* v = getenv("T2L_TEXT_TF32")) e->text_f16 = !(v[0] == '1');
-  if (const char* v = getenv("T2L_SA_TF32")) e->obj_sa = !(v[0] == '1');
-  if (const char* v = getenv("T2L_SA_V1")) e->obj_sa2 = !(v[0] == '1');
   if (const char* v = getenv("T2L_DIST_FMA")) e->dist_fma = v[0] == '1';
   if (const char* v = getenv("T2L_OBJ_CHUNK")) { const int n = atoi(v); if (n >= 64 && n <= 65536) e->obj_chunk = n; }
   if (const char* v = getenv("T2L_SEARCH_FIRST")) e->search_first = v[0] == 'f' ? 1 : (v[0] == 'b' ? 2 : 0);
@@ -496,11 +490,11 @@ struct ObjDebug {
           *cnt2 = nullptr, *cnt3 = nullptr;
 };
 
-static size_t obj_chunk_bytes(size_t n, size_t cells, bool obj_mode) {
-  // upper bound of everything encode_chunk carves from the arena.  Object-resident path: ~381 KB per object (geometry 10 KB,
-  // Px 96 KB, self-loop rows 64 KB when they exist, x1..x3 96 KB, GA 97 KB, tails 13 KB); the A/B paths add the 1 MB / object
-  // edge tensor.  Per cell: the two attention layers' buffers (~0.6 MB).  A too-small estimate fails the call (Arena::overflow).
-  return n * (obj_mode ? size_t(440000) : (size_t(1) << 21) + 700000) + cells * size_t(28) * 256 * 4 * 32 + (size_t(1) << 20);
+static size_t obj_chunk_bytes(size_t n, size_t cells) {
+  // upper bound of everything encode_chunk carves from the arena: ~330 KB per object (geometry 10 KB, Qx 96 KB, x1..x3 105 KB,
+  // GA 99 KB, tails 14 KB) and, per cell, the two attention layers' buffers (~0.6 MB).  A too-small estimate fails the call
+  // (Arena::overflow), it never hands out memory out of bounds.
+  return n * size_t(400000) + cells * size_t(28) * 256 * 4 * 32 + (size_t(1) << 20);
 }
 
 // obj_emb_out != nullptr: stop after the object encoder and write its normalised rows [n_objects, d] (fine stage)
@@ -508,7 +502,7 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
                         const ObjDebug* dbg, cudaStream_t st, float* obj_emb_out = nullptr) {
   const int o0 = cell_ptr[c0], o1 = cell_ptr[c1];
   const int n = o1 - o0, B = c1 - c0;
-  if (ensure_arena(e, obj_chunk_bytes(n, B, e->fused_sa && e->obj_sa))) return 1;
+  if (ensure_arena(e, obj_chunk_bytes(n, B))) return 1;
   Arena& a = e->arena;
   const float* p = pts + static_cast<size_t>(o0) * kPoints * 6;
 
@@ -548,113 +542,52 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
   CU(fps_all_levels(p, n, g, e->dist_fma, st, &e->lc));
   CU(ball_query_all_levels(p, n, g, e->dist_fma, st, &e->lc));
 
-  float* x0 = a.get<float>(N * 256 * 4);
-  float* px = a.get<float>(N * 256 * 32);      // max over levels: 256*32 = 128*128/2 ... sized below
-  float* px23 = a.get<float>(N * 128 * 128);   // Px of levels 2 and 3 (n*128*128 == n*64*256)
-  const bool obj_mode = e->fused_sa && e->obj_sa;
-  const bool need_side = !(obj_mode && e->obj_sa2);  // sa_obj2 folds the self-loop edges in: no side tensors
-  float* H = obj_mode ? nullptr : a.get<float>(N * 32 * 32 * 256);  // edge rows / edge records of the A/B paths (1 MB / object)
-  float* Hs = need_side ? a.get<float>(N * 64 * 128) : nullptr;     // self-loop rows (n*128*32, n*64*128, n*32*256)
-  float* S = need_side ? a.get<float>(N * 64 * 128) : nullptr;      // second-layer output of the self-loop rows
-  // sa_obj2: rows of x1 / x2 carry 8 extra columns (tf32 hi | lo of pos - o) for the next level's per-point Linear
-  const bool sa2 = obj_mode && e->obj_sa2;
-  const int ldx1 = sa2 ? 72 : 64, ldx2 = sa2 ? 136 : 128;
+  // Set abstraction x3 (pointnet2.py:25-37).  Per level: Qx = W1x x + b1 + W1p (pos - o) per point (fp16, |.| <= 32752), then
+  // the fused gather / second Linear / max kernel (sa_obj2.cu).  Rows of x1 / x2 carry 8 extra columns (tf32 hi | lo of
+  // pos - o) so that the next level's per-point Linear is ONE tf32 GEMM against [W1x | W1p | W1p].
+  __half* qx1 = a.get<__half>(N * 256 * 32);
+  __half* qx23 = a.get<__half>(N * 128 * 128);  // levels 2 and 3 (n*128*128 == n*64*256)
+  constexpr int ldx1 = 72, ldx2 = 136;
   float* x1 = a.get<float>(N * 128 * ldx1);
   float* x2 = a.get<float>(N * 64 * ldx2);
   float* x3 = a.get<float>(N * 32 * 256);
-  if (!obj_mode) CU(extract_rgb(p, n, x0, st, &e->lc));  // the object-resident path reads rgb straight from pts (sa1_px16)
-
-  struct Level { const char* name; int C1, C2, P, M; float* x; long ldx; const float* dense; int dstride; const float* cpos;
-                 const uint8_t* nbr; const uint8_t* cnt; float* Px; float* xout; int ldo; bool px_umma; };
+  struct Level { const char* name; int C1, C2, P, M; float* x; int ldx; const float* dense; const float* cpos;
+                 const uint8_t* nbr; const uint8_t* cnt; __half* Qx; float* xout; int ldo; };
   Level lv[3] = {
-      {"sa1", 32, 64, 256, 128, x0, 4, p, 6, g.cpos1, g.nbr1, g.cnt1, px, x1, ldx1, false},
-      {"sa2", 128, 128, 128, 64, x1, ldx1, g.cpos1, 3, g.cpos2, g.nbr2, g.cnt2, px23, x2, ldx2, true},
-      {"sa3", 256, 256, 64, 32, x2, ldx2, g.cpos2, 3, g.cpos3, g.nbr3, g.cnt3, px23, x3, 256, true},
+      {"sa1", 32, 64, 256, 128, nullptr, 0, nullptr, g.cpos1, g.nbr1, g.cnt1, qx1, x1, ldx1},
+      {"sa2", 128, 128, 128, 64, x1, ldx1, g.cpos1, g.cpos2, g.nbr2, g.cnt2, qx23, x2, ldx2},
+      {"sa3", 256, 256, 64, 32, x2, ldx2, g.cpos2, g.cpos3, g.nbr3, g.cnt3, qx23, x3, 256},
   };
   for (const Level& L : lv) {
     const std::string nm = L.name;
-    if (sa2) {
-      // Qx = W1x x + b1 + W1p (pos - o) per point (fp16, |.| <= 32752), then the fused layer (sa_obj2.cu)
-      if (W(e, nm + ".w1p").ld != 4) return fail(e, "internal: w1p pitch");
-      __half* Qx = reinterpret_cast<__half*>(L.Px);
-      if (!L.px_umma) {
-        if (W(e, nm + ".w1x").ld != 4 || L.C1 != 32) return fail(e, "internal: sa1.w1x shape");
-        CU(sa1_qx16(p, n, W(e, nm + ".w1x").dev, W(e, nm + ".w1p").dev, W(e, nm + ".b1").dev, Qx, st, &e->lc));
-      } else {
-        const int c_in = W(e, nm + ".w1x").cols;
-        CU(append_pos_cols(L.dense, n, L.P, L.x, static_cast<int>(L.ldx), c_in, st, &e->lc));
-        CU(lin(e, true, L.x, L.ldx, n * L.P, nm + ".w1q", nm + ".b1", L.Px, L.C1, 0, st, nullptr, 0, 0, 0, nullptr, 0, /*out_half=*/1, kQxMax));
-      }
-      SaObj2 so;
-      so.Qx16 = Qx; so.C1 = L.C1; so.C2 = L.C2; so.cpos = L.cpos; so.nbr = L.nbr; so.cnt = L.cnt; so.loop_src_obj = loop_src;
-      so.loop_half = loop_half; so.Wp = W(e, nm + ".w1p").dev; so.W2h = W(e, nm + ".w2").dev16; so.b2 = W(e, nm + ".b2").dev;
-      so.out = L.xout; so.ldo = L.ldo; so.n_obj = n; so.P = L.P; so.M = L.M;
-      if (!so.W2h) return fail(e, "internal: no fp16 copy of %s.w2", L.name);
-      CU(sa_obj2(so, st, &e->lc));
-      continue;
-    }
-    // per-point half of the first Linear (no bias; b1 is added with the position term per edge); fp16 for the
-    // object-resident kernel (the buffer is reused as __half [n*P, C1])
-    const bool obj = e->fused_sa && e->obj_sa;
-    // (there b1 is folded into Px as well: one add less per edge element)
-    if (obj && !L.px_umma) {
-      if (W(e, nm + ".w1x").ld != 4 || L.C1 != 32) return fail(e, "internal: sa1.w1x shape");
-      CU(sa1_px16(p, n, W(e, nm + ".w1x").dev, W(e, nm + ".b1").dev, reinterpret_cast<__half*>(L.Px), st, &e->lc));
-    } else {
-      CU(lin(e, L.px_umma, L.x, L.ldx, n * L.P, nm + ".w1x", obj ? nm + ".b1" : "", L.Px, L.C1, 0, st, nullptr, 0, 0, 0, nullptr, 0, obj ? 1 : 0));
-    }
-    EdgeGather eg;
-    eg.Px = L.Px; eg.C1 = L.C1; eg.dense_pos = L.dense; eg.dense_stride = L.dstride; eg.cpos = L.cpos; eg.nbr = L.nbr; eg.cnt = L.cnt;
-    eg.loop_src_obj = loop_src; eg.loop_half = loop_half; eg.Wp = W(e, nm + ".w1p").dev; eg.b1 = W(e, nm + ".b1").dev;
-    eg.n_obj = n; eg.P = L.P; eg.M = L.M; eg.H = H; eg.Hself = Hs;
     if (W(e, nm + ".w1p").ld != 4) return fail(e, "internal: w1p pitch");
-    if (obj) {
-      eg.Px16 = reinterpret_cast<const __half*>(L.Px);
-      eg.Hself16 = reinterpret_cast<__half*>(Hs);  // the self-loop rows go through the same fp16 second layer as the other edges
-      CU(self_edge_rows(eg, st, &e->lc));
-      CU(lin_h(e, eg.Hself16, L.C1, n * L.M, nm + ".w2", nm + ".b2", S, L.C2, 1, 0, st));
-      SaObj so;
-      so.Px16 = eg.Px16; so.C1 = L.C1; so.C2 = L.C2; so.dense_pos = L.dense; so.dense_stride = L.dstride; so.cpos = L.cpos;
-      so.nbr = L.nbr; so.cnt = L.cnt; so.Wp = eg.Wp; so.b1 = eg.b1; so.W2h = W(e, nm + ".w2").dev16; so.b2 = W(e, nm + ".b2").dev;
-      so.side = S; so.out = L.xout; so.n_obj = n; so.P = L.P; so.M = L.M;
-      if (!so.W2h) return fail(e, "internal: no fp16 copy of %s.w2", L.name);
-      CU(sa_obj(so, st, &e->lc));
-    } else if (e->fused_sa) {
-      // self-loop edges: one row per centroid through the same MLP -> side input of the fused kernel
-      CU(self_edge_rows(eg, st, &e->lc));
-      CU(lin(e, true, Hs, L.C1, n * L.M, nm + ".w2", nm + ".b2", S, L.C2, 1, st));
-      // gather + edge MLP + max over each centroid's 32 slots in one kernel (A operand built in smem)
-      SaFused sf;
-      sf.Px = L.Px; sf.C1 = L.C1; sf.C2 = L.C2; sf.dense_pos = L.dense; sf.dense_stride = L.dstride; sf.cpos = L.cpos;
-      sf.nbr = L.nbr; sf.cnt = L.cnt; sf.loop_src_obj = loop_src; sf.loop_half = loop_half; sf.Wp = eg.Wp; sf.b1 = eg.b1;
-      sf.W2 = W(e, nm + ".w2").dev; sf.ldw2 = W(e, nm + ".w2").ld; sf.b2 = W(e, nm + ".b2").dev; sf.side = S; sf.out = L.xout;
-      sf.n_obj = n; sf.P = L.P; sf.M = L.M; sf.rec = reinterpret_cast<float4*>(H);  // H is free on the fused path
-      CU(sa_fused(sf, st, &e->lc));
+    if (!L.x) {  // level 1 reads rgb and xyz straight from pts (K = 3 + 3: exact fp32 SIMT)
+      if (W(e, nm + ".w1x").ld != 4) return fail(e, "internal: sa1.w1x pitch");
+      CU(sa1_qx16(p, n, W(e, nm + ".w1x").dev, W(e, nm + ".w1p").dev, W(e, nm + ".b1").dev, L.Qx, st, &e->lc));
     } else {
-      CU(edge_gather(eg, st, &e->lc));
-      // second Linear + ReLU; max over each centroid's 32 slots in the GEMM epilogue, joined with the self-loop row
-      CU(lin(e, true, Hs, L.C1, n * L.M, nm + ".w2", nm + ".b2", S, L.C2, 1, st));
-      CU(lin(e, true, H, L.C1, n * L.M * 32, nm + ".w2", nm + ".b2", L.xout, L.C2, 1, st, nullptr, 0, /*round_out=*/1, /*segmax=*/1, S, L.C2));
+      const int c_in = W(e, nm + ".w1x").cols;
+      CU(append_pos_cols(L.dense, n, L.P, L.x, L.ldx, c_in, st, &e->lc));
+      CU(lin(e, true, L.x, L.ldx, n * L.P, nm + ".w1q", nm + ".b1", reinterpret_cast<float*>(L.Qx), L.C1, 0, st, nullptr, 0, 0, 0, nullptr, 0,
+             /*out_half=*/1, kQxMax));
     }
+    SaObj2 so;
+    so.Qx16 = L.Qx; so.C1 = L.C1; so.C2 = L.C2; so.cpos = L.cpos; so.nbr = L.nbr; so.cnt = L.cnt; so.loop_src_obj = loop_src;
+    so.loop_half = loop_half; so.Wp = W(e, nm + ".w1p").dev; so.W2h = W(e, nm + ".w2").dev16; so.b2 = W(e, nm + ".b2").dev;
+    so.out = L.xout; so.ldo = L.ldo; so.n_obj = n; so.P = L.P; so.M = L.M;
+    if (!so.W2h) return fail(e, "internal: no fp16 copy of %s.w2", L.name);
+    CU(sa_obj2(so, st, &e->lc));
   }
 
-  // GlobalAbstraction: mlp([x | pos]) then max over the object's 32 points (pointnet2.py:45-49)
-  float* gaA = a.get<float>(N * 32 * 260);
-  float* g1 = a.get<float>(N * 32 * 512);
+  // GlobalAbstraction: mlp([x | pos]) then max over the object's 32 points (pointnet2.py:45-49), fp16 operands like the
+  // set-abstraction layers
+  __half* gaA16 = a.get<__half>(N * 32 * 264);
+  __half* g1h = a.get<__half>(N * 32 * 512);
   float* f0 = a.get<float>(N * 1024);
   float* f1 = a.get<float>(N * 512);
   float* f2 = a.get<float>(N * 256);
-  if (obj_mode) {  // fp16 operands like the set-abstraction layers (x3 and the centroid positions were tf32-rounded operands before)
-    __half* gaA16 = reinterpret_cast<__half*>(gaA);  // [n*32, 264]
-    __half* g1h = reinterpret_cast<__half*>(g1);     // [n*32, 512]
-    CU(ga_concat_half(x3, g.cpos3, n, gaA16, st, &e->lc));
-    CU(lin_h(e, gaA16, 264, n * 32, "ga.w1", "ga.b1", g1h, 512, 1, /*out_half=*/1, st));
-    CU(lin_h(e, g1h, 512, n * 32, "ga.w2", "ga.b2", f0, 1024, 1, 0, st, nullptr, 0, /*segmax=*/1));
-  } else {
-    CU(ga_concat(x3, g.cpos3, n, gaA, st, &e->lc));
-    CU(lin(e, true, gaA, 260, n * 32, "ga.w1", "ga.b1", g1, 512, 1, st, nullptr, 0, 1));
-    CU(lin(e, true, g1, 512, n * 32, "ga.w2", "ga.b2", f0, 1024, 1, st, nullptr, 0, 1, 1));
-  }
+  CU(ga_concat_half(x3, g.cpos3, n, gaA16, st, &e->lc));
+  CU(lin_h(e, gaA16, 264, n * 32, "ga.w1", "ga.b1", g1h, 512, 1, /*out_half=*/1, st));
+  CU(lin_h(e, g1h, 512, n * 32, "ga.w2", "ga.b2", f0, 1024, 1, 0, st, nullptr, 0, /*segmax=*/1));
   CU(lin(e, true, f0, 1024, n, "lin1.w", "lin1.b", f1, 512, 1, st, nullptr, 0, 1));  // relu(lin1) (:89)
   CU(lin(e, true, f1, 512, n, "lin2.w", "lin2.b", f2, 256, 1, st, nullptr, 0, 1));   // relu(lin2) = features2 (:90)
 

@@ -51,13 +51,15 @@ struct StoreEpiT {
   using Params = StoreParams;
   static constexpr int kStageBytes = 32 * 128;  // one 32 x 32 fp32 block per epilogue warp
   static constexpr int kSmemBytes = kEpiBiasSmem + 4 * kStageBytes;
+  static constexpr bool kCompactLoop = false;
+  static constexpr int kSets = 1;
   const Params& p;
   float* s_bias;
   uint8_t* stage;
   int ew, lane, block_n;
   int bias_col0 = -1;  // column slice currently staged in s_bias (tiles of one N column share it)
   float4 res[8];       // residual of the chunk about to be processed (coalesced layout: row 4 j + lane / 8, chunk lane % 8)
-  __device__ StoreEpiT(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_)
+  __device__ StoreEpiT(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_, int)
       : p(p_), s_bias(reinterpret_cast<float*>(smem) + ew_ * 256), stage(smem + kEpiBiasSmem + ew_ * kStageBytes), ew(ew_), lane(lane_),
         block_n(block_n_) {}
   __device__ void begin_unit(int, int) {}
@@ -170,12 +172,14 @@ struct SegMaxEpi {
     int round_out;
   };
   static constexpr int kSmemBytes = kEpiBiasSmem;
+  static constexpr bool kCompactLoop = false;
+  static constexpr int kSets = 1;
   const Params& p;
   float* s_bias;
   int ew, lane, block_n;
   float side_v[8];  // this lane's side value for each 32-column chunk of the tile
   int bias_col0 = -1;
-  __device__ SegMaxEpi(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_)
+  __device__ SegMaxEpi(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_, int)
       : p(p_), s_bias(reinterpret_cast<float*>(smem) + ew_ * 256), ew(ew_), lane(lane_), block_n(block_n_) {}
   __device__ void prefetch_unit(int, int) {}
   __device__ void begin_unit(int, int) {}

@@ -58,62 +58,14 @@ cudaError_t fps_all_levels(const float* pts, int n_obj, const Geometry& g, bool 
 cudaError_t ball_query_all_levels(const float* pts, int n_obj, const Geometry& g, bool dist_fma, cudaStream_t st, Launches* lc);
 
 // ---- pointnet.cu --------------------------------------------------------------------------
-// x0[n*256, 4] = rgb (padded to 4 floats) from pts
-cudaError_t extract_rgb(const float* pts, int n_obj, float* x0, cudaStream_t st, Launches* lc);
-// Px16[n*256, 32] = fp16(W1x . rgb + b1) for SA1 (w1x [32, ld 4]) straight from pts
-cudaError_t sa1_px16(const float* pts, int n_obj, const float* w1x, const float* b1, __half* px16, cudaStream_t st, Launches* lc);
 // sa_obj2.cu's per-point operand of SA1: Qx16[n*256, 32] = fp16(W1x . rgb + b1 + W1p . (pos - o)), o = the object's point 0
 constexpr float kQxMax = 32752.f;  // Qx and v are bounded by half of fp16's range, so Qx - v never overflows
 cudaError_t sa1_qx16(const float* pts, int n_obj, const float* w1x, const float* w1p, const float* b1, __half* qx16, cudaStream_t st, Launches* lc);
 // columns C .. C+7 of x [n*P, ldx] = tf32 hi | lo split of (pos_r - pos of the object's row 0) | 0 0  (pos [n*P, 3])
 cudaError_t append_pos_cols(const float* pos, int n_obj, int P, float* x, int ldx, int C, cudaStream_t st, Launches* lc);
-// First-layer edge activations of one PointConv:
-//   H[(o*M+m)*32 + s, :] = relu(Px[src_point] + Wp * (pos_src - cpos[o,m]) + b1)   s < 32 neighbour slots
-//   Hself[o*M+m, :]      = same for the re-added self-loop edge (dense point with the centroid's
-//                          per-cell global index); empty neighbour slots replicate it.
-// dense positions: level 1 reads pts (stride 6), levels 2/3 read the previous level's cpos.
-struct EdgeGather {
-  const float* Px; int C1;            // [n*P, C1] per dense point
-  const __half* Px16 = nullptr;       // fp16 Px WITH b1 folded in (object-resident path): read instead of Px by self_edge_rows
-  const float* dense_pos; int dense_stride;  // [n*P, stride] xyz first
-  const float* cpos;                  // [n*M, 3]
-  const uint8_t* nbr; const uint8_t* cnt;
-  const int32_t* loop_src_obj;        // [n] flat object index feeding this object's self loops
-  const int32_t* loop_half;           // [n] 0/1: which half of that object's dense points
-  const float* Wp;                    // [C1, 3] folded, row pitch 4
-  const float* b1;                    // [C1] folded
-  int n_obj, P, M;
-  float* H; float* Hself;
-  __half* Hself16 = nullptr;          // self_edge_rows writes fp16 rows here instead of Hself (operand of an fp16 side GEMM)
-};
-cudaError_t edge_gather(const EdgeGather& a, cudaStream_t st, Launches* lc);
-// Fused PointConv layer (sa_fused.cu): gathers, first-layer edge activations, second Linear on the
-// tensor cores and the per-centroid max in ONE kernel; `side` [n*M, C2] carries the self-loop edges.
-struct SaFused {
-  const float* Px; int C1; int C2;
-  const float* dense_pos; int dense_stride; const float* cpos;
-  const uint8_t* nbr; const uint8_t* cnt; const int32_t* loop_src_obj; const int32_t* loop_half;
-  const float* Wp; const float* b1;      // [C1,4], [C1]
-  const float* W2; long ldw2; const float* b2;  // [C2, C1] tf32-rounded, [C2]
-  const float* side; float* out;         // [n*M, C2]
-  float4* rec;                           // scratch [n*M*32]: per-edge (Px row offset, pos_j - pos_i)
-  int n_obj, P, M;
-};
-cudaError_t sa_fused(const SaFused& a, cudaStream_t st, Launches* lc);
-// Object-resident variant on fp16 operands (sa_obj.cu): Px as fp16 [n*P, C1], W2 as fp16 [C2, C1]; the edges are
-// taken straight from the ball-query lists and positions (no per-edge records).
-struct SaObj {
-  const __half* Px16; int C1; int C2;    // Px16 = fp16 (W1x x_j + b1)
-  const float* dense_pos; int dense_stride; const float* cpos;
-  const uint8_t* nbr; const uint8_t* cnt;
-  const float* Wp; const float* b1;      // [C1,4], [C1]
-  const __half* W2h; const float* b2;    // [C2, C1] fp16, [C2]
-  const float* side; float* out;         // [n*M, C2]
-  int n_obj, P, M;
-};
-cudaError_t sa_obj(const SaObj& a, cudaStream_t st, Launches* lc);
-// Second generation (sa_obj2.cu): W2 resident in tensor memory (TS-mode MMAs), self-loop edges folded in as one extra
-// tile per object (no side tensor), SA1 tiles paired.  Needs the self-loop source of every object.
+// Fused PointConv layer (sa_obj2.cu): gather, first-layer edge activations, second Linear on the tensor cores and the per-centroid
+// max in ONE kernel.  W2 resident in tensor memory (TS-mode MMAs), self-loop edges folded in as one extra tile per object, SA1
+// tiles paired.  Needs the self-loop source of every object.
 struct SaObj2 {
   const __half* Qx16; int C1; int C2;    // Qx16 = fp16 (W1x x_j + b1 + W1p (pos_j - o)), o = the object's point 0; |.| <= 32752
   const float* cpos;                     // [n*M, 3]
@@ -125,11 +77,7 @@ struct SaObj2 {
   int n_obj, P, M;
 };
 cudaError_t sa_obj2(const SaObj2& a, cudaStream_t st, Launches* lc);
-// Hself[o*M+m, :] only (the re-added self-loop edge of every centroid)
-cudaError_t self_edge_rows(const EdgeGather& a, cudaStream_t st, Launches* lc);
-// GA input: A[n*32, 260] = [x3 (256) | cpos3 (3) | 0]
-cudaError_t ga_concat(const float* x3, const float* cpos3, int n_obj, float* A, cudaStream_t st, Launches* lc);
-// the same as fp16 rows of 264 halfs (K padded to a 16-byte multiple)
+// GA input as fp16 rows of 264 halfs: A16[n*32, 264] = [x3 (256) | cpos3 (3) | 0 x 5] (K padded to a 16-byte multiple)
 cudaError_t ga_concat_half(const float* x3, const float* cpos3, int n_obj, __half* A, cudaStream_t st, Launches* lc);
 
 // ---- rowops.cu ----------------------------------------------------------------------------

@@ -15,8 +15,9 @@
 // planes give the error-compensated split product hi*hi + hi*lo + lo*hi in one accumulator.
 //
 // The epilogue is a policy class (see gemm_epilogues.cuh, search.cu):
-//   struct Epi { struct Params; static constexpr int kSmemBytes;
-//     __device__ Epi(const Params&, uint8_t* smem, int epi_warp, int lane, int block_n);
+//   struct Epi { struct Params; static constexpr int kSmemBytes; static constexpr bool kCompactLoop;  // (see the drain loop)
+//     static constexpr int kSets;   // epilogue warp sets (1, or 2 with kCompactLoop)
+//     __device__ Epi(const Params&, uint8_t* smem, int epi_warp, int lane, int block_n, int set);
 //     __device__ void prefetch_unit(int m_tile, int col0);   // the unit this CTA will process AFTER the current one (L2 prefetch hook)
 //     __device__ void begin_unit(int m_tile, int split);
 //     __device__ void begin_tile(int m_tile, int n_tile, int col0);   // BEFORE the accumulator is waited for: issue global loads here
@@ -78,8 +79,11 @@ struct GemmCfg {
 
 constexpr int kGemmThreads = 256;
 
+// Epi::kSets epilogue warp sets of four warps each (warps 4..7, 8..11): with two sets every SM sub-partition hosts two epilogue
+// warps, which interleave the 32-column chunks of a tile between them (an epilogue that is latency-bound in a single warp --
+// the top-k list maintenance -- then keeps pace with single-pass K = 256 tiles).
 template <class Cfg, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(128 + 128 * Epi::kSets, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const GemmShape shape, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -112,7 +116,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4 * Cfg::CTA_GROUP);  // one arrive per epilogue warp (of both CTAs, on the leader's barrier)
+      mbar_init(&tmem_empty[i], 4 * Cfg::CTA_GROUP * Epi::kSets);  // one arrive per epilogue warp (of both CTAs, on the leader's barrier)
     }
     fence_barrier_init();
   }
@@ -220,8 +224,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may read
-    Epi epi(ep, epi_smem, ew, lane, Cfg::BLOCK_N);
+    const int ew = (warp - 4) & 3;   // == warp % 4: the TMEM lane quadrant this warp may read
+    const int set = (warp - 4) >> 2;  // epilogue warp set: handles chunks set, set + kSets, ...
+    Epi epi(ep, epi_smem, ew, lane, Cfg::BLOCK_N, set);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int u = cta; u < n_units; u += n_cta) {
@@ -241,12 +246,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * Cfg::BLOCK_N;
         // software-pipelined drain: the TMEM load of chunk c+1 is in flight while chunk c is processed
         float v[2][32];
-        tmem_ld_32x32(t_addr, v[0]);
+        if constexpr (!Epi::kCompactLoop) tmem_ld_32x32(t_addr, v[0]);
+        if constexpr (Epi::kCompactLoop) {
+          // two inlined copies of chunk() instead of BLOCK_N / 32: an epilogue whose chunk() is hundreds of instructions long
+          // (the top-k list maintenance) would otherwise not fit the instruction cache (measured: 2.3x slower unrolled 8x)
+          constexpr int NC = Cfg::BLOCK_N / 32, ST = Epi::kSets;
+          static_assert(NC % (2 * ST) == 0, "chunks must split evenly over the epilogue sets, two per iteration");
+          tmem_ld_32x32(t_addr + set * 32, v[0]);
+#pragma unroll 1
+          for (int c = set; c < NC; c += 2 * ST) {
+            tmem_ld_wait(v[0]);
+            tmem_ld_32x32(t_addr + (c + ST) * 32, v[1]);
+            epi.chunk(m_tile, nt, c, nt * Cfg::BLOCK_N + c * 32, v[0]);
+            tmem_ld_wait(v[1]);
+            if (c + 2 * ST < NC) tmem_ld_32x32(t_addr + (c + 2 * ST) * 32, v[0]);
+            epi.chunk(m_tile, nt, c + ST, nt * Cfg::BLOCK_N + (c + ST) * 32, v[1]);
+          }
+        } else {
 #pragma unroll
-        for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
-          tmem_ld_wait(v[c & 1]);
-          if (c + 1 < Cfg::BLOCK_N / 32) tmem_ld_32x32(t_addr + (c + 1) * 32, v[(c + 1) & 1]);
-          epi.chunk(m_tile, nt, c, nt * Cfg::BLOCK_N + c * 32, v[c & 1]);
+          for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
+            tmem_ld_wait(v[c & 1]);
+            if (c + 1 < Cfg::BLOCK_N / 32) tmem_ld_32x32(t_addr + (c + 1) * 32, v[(c + 1) & 1]);
+            epi.chunk(m_tile, nt, c, nt * Cfg::BLOCK_N + c * 32, v[c & 1]);
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -322,7 +344,7 @@ cudaError_t launch_umma_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, c
   const int n_sched = n_units < slots ? n_units : slots;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(n_sched * Cfg::CTA_GROUP);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(128 + 128 * Epi::kSets);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
