@@ -109,17 +109,20 @@ cudaError_t search_prepare_db(const SearchDb& db, cudaStream_t st, Launches* lc)
 }
 
 // ---- candidate epilogue -------------------------------------------------------------------------
-// Each epilogue thread owns one query row and keeps its 16 best approximate scores of the current split in REGISTERS as a
-// descending sorted list.  Everything the thread ever dropped is <= the final list minimum, which is what the re-rank
-// proof needs.
+// Each epilogue thread owns one query row (and one of the two column sets, below) and keeps its 16 best approximate scores
+// of the current split in REGISTERS as a descending sorted list; inserting is a branch-free 16-step compare-exchange chain
+// taken only when a score beats the list minimum (the drop threshold).  Everything the thread ever dropped is therefore <=
+// the final minimum, which is what the re-rank proof needs.
 //
-// A warp executes an instruction whenever ANY of its 32 rows needs it, so the costly part -- the 16-step compare-exchange
-// chain that sinks a new score into the list -- must not run per hit.  Scores that beat the (possibly stale) list minimum
-// are parked in a small per-thread buffer in shared memory (a few instructions), and the buffers of all 32 rows are
-// drained TOGETHER once per tile: one pass of the chain inserts one parked score of every row that has one.  Early tiles,
-// where every row takes ~16/t new entries per tile, cost ~max-over-rows chains per tile instead of one per hit
-// (round 1: a chain per hit, ~10 hits per 32-column chunk and warp while the lists warm up -- with a single K = 256 pass
-// per tile the epilogue, not the MMAs, set the pace: 2.9 ms of epilogue behind 1.0 ms of MMAs at 32 768 x 100 000).
+// With a single K = 256 pass per tile the epilogue has only as many cycles as the MMAs take (2 048 per 128 x 256 tile, and
+// draining the accumulator from tensor memory at 64 B/clk already uses all of them), and one warp per SM sub-partition --
+// latency-bound on its dependent compare chains -- needed ~3x that (measured: 2.9 ms of epilogue behind 1.0 ms of MMAs at
+// 32 768 x 100 000).  Hence: (1) TWO epilogue warp sets (warps 4..7 take the even 32-column chunks of a tile, warps 8..11 the
+// odd ones; every row then has two lists per split, 32 candidates); (2) a 3-input max tree (~16 instructions) decides the
+// common "nothing in this chunk beats the minimum" case before any per-element work; (3) two inlined copies of chunk() instead
+// of eight (instruction cache).  Measured: 1.92 ms for the whole search at 32 768 x 100 000 (3.5 ms with the three-pass
+// candidates of round 1).  A variant that parked hits in shared memory and inserted them once per tile for all 32 rows
+// together was slower (2.7 ms): its per-chunk parking code outweighed the chains it saved.
 struct TopKEpi {
   struct Params {
     float* cand_score;  // [nq, n_lists, kCand]     n_lists = n_splits * kSets: one list per (database split, column set)
@@ -127,28 +130,22 @@ struct TopKEpi {
     float* cand_thr;    // [nq, n_lists]            -inf = nothing was dropped
     int nq, n_db, n_splits;
   };
-  static constexpr int kPend = 8;                                   // parked scores per row between drains
-  static constexpr int kSets = 2;                                   // two epilogue warps per row: even / odd 32-column chunks
-  static constexpr int kSmemBytes = kSets * kPend * 128 * (4 + 4);  // score + row index per slot, thread and set
+  static constexpr int kSets = 2;                          // two epilogue warps per row: even / odd 32-column chunks
+  static constexpr int kSmemBytes = kSets * 32 * 128 * 4;  // one 32-float column per epilogue thread (candidate staging)
   static constexpr bool kCompactLoop = true;
   const Params& p;
-  float* s_ps;
-  int* s_pi;
+  float* s_v;
   int t;  // 0..127: row inside this CTA's 128-row tile
   int set;
-  int last_chunk;
   float ls[kCand];
   int li[kCand];
-  int cnt;
   bool active;
 
-  __device__ TopKEpi(const Params& p_, uint8_t* smem, int ew, int lane, int block_n, int set_)
-      : p(p_), s_ps(reinterpret_cast<float*>(smem + set_ * kPend * 128 * 8)), s_pi(reinterpret_cast<int*>(smem + set_ * kPend * 128 * 8 + kPend * 128 * 4)),
-        t(ew * 32 + lane), set(set_), last_chunk(block_n / 32 - kSets + set_), cnt(0), active(false) {}
+  __device__ TopKEpi(const Params& p_, uint8_t* smem, int ew, int lane, int, int set_)
+      : p(p_), s_v(reinterpret_cast<float*>(smem) + set_ * 32 * 128), t(ew * 32 + lane), set(set_), active(false) {}
   __device__ void prefetch_unit(int, int) {}
   __device__ void begin_unit(int m_tile, int) {
     active = (m_tile * 128 + t) < p.nq;
-    cnt = 0;
 #pragma unroll
     for (int i = 0; i < kCand; ++i) { ls[i] = active ? -INFINITY : INFINITY; li[i] = -1; }
   }
@@ -162,58 +159,32 @@ struct TopKEpi {
       ls[i] = s_keep; li[i] = i_keep; x = s_next; xi = i_next;
     }
   }
-  // one chain pass per round: every row with a parked score inserts its next one
-  __device__ __forceinline__ void drain() {
-    for (int j = 0; j < cnt; ++j) {
-      const float x = s_ps[j * 128 + t];
-      if (x > ls[kCand - 1]) insert(x, s_pi[j * 128 + t]);
-    }
-    cnt = 0;
-  }
-  __device__ void chunk(int, int, int c, int col0, float (&v)[32]) {
+  __device__ void chunk(int, int, int, int col0, float (&v)[32]) {
     if (col0 + 32 > p.n_db) {  // database tail: zero-filled rows must not compete
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = (col0 + i < p.n_db) ? v[i] : -INFINITY;
     }
-    float thr = ls[kCand - 1];
-    // The common case once the lists have warmed up: nothing in the chunk beats the list minimum.  One max tree (3-input
-    // FMNMX) decides that in ~16 instructions.
+    const float thr = ls[kCand - 1];
     float m8[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
     const float vmax = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
-    if (vmax > thr) {
-      uint32_t done = 0;  // elements of this chunk already parked
-      for (;;) {
-        bool left = false;
+    if (!(vmax > thr)) return;  // the common case once the list has warmed up
+    // rare path: park the 32 scores in shared memory so ONE copy of the insertion chain can walk the
+    // set bits with a dynamic index (32 unrolled copies thrashed the instruction cache: 3x slower)
+    uint32_t mask = 0;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (m8[g] > thr) {
+    for (int i = 0; i < 32; ++i) mask |= (v[i] > thr) ? (1u << i) : 0u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int i = 4 * g + j;
-              if (v[i] > thr && !((done >> i) & 1u)) {
-                if (cnt < kPend) {
-                  s_ps[cnt * 128 + t] = v[i];
-                  s_pi[cnt * 128 + t] = col0 + i;
-                  ++cnt;
-                  done |= 1u << i;
-                } else {
-                  left = true;
-                }
-              }
-            }
-          }
-        }
-        if (!left) break;
-        drain();  // buffer full (the first tiles of a split): make room, raise the bar, park the rest
-        thr = ls[kCand - 1];
-      }
+    for (int i = 0; i < 32; ++i) s_v[i * 128 + t] = v[i];
+    while (mask) {
+      const int i = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const float x = s_v[i * 128 + t];
+      if (x > ls[kCand - 1]) insert(x, col0 + i);
     }
-    if (c == last_chunk && cnt) drain();  // once per tile
   }
   __device__ void end_unit(int m_tile, int split) {
-    if (cnt) drain();
     if (!active) return;
     const long row = static_cast<long>(m_tile) * 128 + t;
     const long list = row * (p.n_splits * kSets) + split * kSets + set;
