@@ -86,6 +86,10 @@ int t2l_encode_text(t2l_engine* e, const float* t5, int n_queries, int n_sent, i
  *              (inter_mlp, inter_module with `x += layer(x)`, max over sentences, normalise, :137-148) */
 int t2l_encode_text_tokens(t2l_engine* e, const float* t5, int n_sentences, int n_tok, float* pooled, void* stream);
 int t2l_encode_text_sentences(t2l_engine* e, const float* pooled, int n_queries, int n_sent, float* out, void* stream);
+/* Token stage on T5 states delivered as fp16 (device, raw 16-bit words, [n_sentences, n_tok, 1024], 16-byte aligned): half the
+ * bytes to ship and no conversion kernel.  The token layer computes on fp16 operand copies either way; here the residual of
+ * its out-projection is read from the fp16 input as well. */
+int t2l_encode_text_tokens_f16(t2l_engine* e, const void* t5_half, int n_sentences, int n_tok, float* pooled, void* stream);
 
 /* ---- fine stage: CrossMatch.forward (models/cross_matcher.py:83-129; evaluation/pipeline.py:113-116 calls it once per query) ----
  * An engine serves the fine stage when the weights set on it are CrossMatch's (text2loc_b200/weights.py detects the state
@@ -147,6 +151,11 @@ int t2l_search_topk_exact(t2l_engine* e, const float* Q, int nq, int k, int64_t*
  *   same (score desc, index asc) order, independent of the number of shards. */
 int t2l_merge_topk(t2l_engine* e, const int64_t* idx_all, const double* score_all, int n_shards, int nq, int k,
                    int64_t* out_idx, double* out_score, void* stream);
+
+/* The same merge on PACKED per-shard results: shard g contributes one contiguous block of 2 * nq * k 8-byte words,
+ * [idx i64 [nq, k] | score f64 [nq, k]], i.e. what a single all-gather of each rank's (idx, score) pair delivers. */
+int t2l_merge_topk_packed(t2l_engine* e, const void* packed_all, int n_shards, int nq, int k, int64_t* out_idx, double* out_score,
+                          void* stream);
 
 /* Accuracy bookkeeping of eval_epoch / run_coarse for a whole query batch (training/coarse.py:131-150: top-k hit and
  * close-by accuracy; evaluation/utils.py:31-54: calc_sample_accuracies).  For every query q and every k in top_k:

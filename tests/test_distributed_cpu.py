@@ -43,6 +43,25 @@ def _worker(rank, world, port, q):
     mine = torch.full((3, 4), float(rank))
     g = t2ld.all_gather_rows(mine).reshape(-1, 4)
     ok = ok and g.shape == (3 * world, 4) and bool((g[:3] == 0).all() and (g[3:6] == 1).all())
+    # the production exchange: ONE all-gather of the packed (idx | score bits) buffer, merged in place -- sharded_search with the
+    # numpy oracle behind the engine's two calls
+    class OracleEngine:
+        def search_topk(self, Qt, k, out=None):
+            i, s_ = restate.search_topk(D[lo:hi], Qt.numpy(), k)
+            out[0].copy_(torch.from_numpy(i + lo))
+            out[1].copy_(torch.from_numpy(s_))
+            return out[0], out[1], torch.zeros(1, dtype=torch.int32)
+
+        def merge_topk_packed(self, gathered, nq, k):
+            assert gathered.shape == (world, 2, nq, k) and gathered.dtype == torch.int64
+            i, s_ = t2ld.merge_topk_host(gathered[:, 0].numpy(), gathered[:, 1].contiguous().view(torch.float64).numpy(), k)
+            return torch.from_numpy(i), torch.from_numpy(s_)
+
+    Qs = torch.from_numpy(Q)
+    per = (len(Q) + world - 1) // world  # queries split by rank (padded to equal shares), gathered inside sharded_search
+    Qpad = torch.cat([Qs, Qs[:per * world - len(Q)]])
+    pidx, psc, _ = t2ld.sharded_search(OracleEngine(), Qpad[rank * per:(rank + 1) * per], 10, queries_are_sharded=True)
+    ok = ok and bool((pidx[:len(Q)].numpy() == oidx).all() and np.array_equal(psc[:len(Q)].numpy(), osc))
     q.put((rank, ok, (lo, hi)))
     dist.destroy_process_group()
 

@@ -130,6 +130,28 @@ def test_encode_text_host_streaming_equals_device(eng):
     assert torch.equal(a, b) and torch.equal(c, b)
 
 
+def test_encode_text_fp16_features(eng, state_dict, golden):
+    """T5 states delivered as float16 (t2l_encode_text_tokens_f16), from device memory and streamed from pinned host memory:
+    same embeddings as the fp32 entry within the tolerance against the REFERENCE (fp32 features), both ways bit-equal."""
+    from oracle import fake_t5
+
+    g = golden("text_small.npz")
+    feat, n_sent = fake_t5.FakeFrontend(int(g["fake_t5_seed"]))([str(t) for t in g["texts"]])
+    got = eng.encode_text(feat.half().cuda(), n_sent).cpu().numpy()
+    err = row_rel_err(got, g["text_emb"])
+    print(f"\ntext embedding error with fp16 T5 features: {err:.3e}")
+    assert err < EMB_TOL
+    import synth
+
+    t5 = torch.from_numpy(synth.make_t5_features(78, 1000, 6, 12)).half()
+    a = eng.encode_text(t5.cuda(), 6)
+    b = eng.encode_text(t5.pin_memory(), 6)
+    assert torch.equal(a, b)
+    ref32 = eng.encode_text(t5.float().cuda(), 6)  # the same (fp16-representable) values through the fp32 entry
+    assert float((a - ref32).norm(dim=1).max()) < 2e-3  # only the residual operand's width differs... and it is exact here
+    assert torch.equal(a, ref32) or float((a - ref32).abs().max()) < 1e-4
+
+
 # ---- search ----------------------------------------------------------------------------------------
 
 @pytest.mark.parametrize("n,nq,k", [(3000, 64, 10), (20000, 1000, 10), (257, 130, 5), (100000, 512, 10), (1000, 1, 1), (5000, 300, 12)])

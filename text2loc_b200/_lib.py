@@ -32,6 +32,7 @@ SIGNATURES = {
     "t2l_encode_objects_debug": (c_int, [_P, _P, POINTER(c_int32), c_int] + [_P] * 10 + [_P]),
     "t2l_encode_text": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "t2l_encode_text_tokens": (c_int, [_P, _P, c_int, c_int, _P, _P]),
+    "t2l_encode_text_tokens_f16": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "t2l_encode_text_sentences": (c_int, [_P, _P, c_int, c_int, _P, _P]),
     "t2l_fine_offsets": (c_int, [_P, _P, _P, POINTER(c_int32), c_int, _P, c_int, c_int, _P, _P]),
     "t2l_fine_encode_objects": (c_int, [_P, _P, _P, POINTER(c_int32), c_int, _P, _P]),
@@ -43,6 +44,7 @@ SIGNATURES = {
     "t2l_synth_cells": (c_int, [_P, ctypes.c_uint64, c_int64, c_int, c_int, _P, _P, _P]),
     "t2l_search_topk_exact": (c_int, [_P, _P, c_int, c_int, _P, _P, _P]),
     "t2l_merge_topk": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "t2l_merge_topk_packed": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
     "t2l_topk_accuracy": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P, POINTER(c_int32), c_int, POINTER(c_double), c_int, _P, _P, _P, _P]),
     "t2l_launch_count": (c_int64, [_P]),
     "t2l_debug_linear": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),

@@ -417,14 +417,15 @@ static cudaError_t lin3(t2l_engine* e, const float* A, long lda, int M, const st
 
 // y = act(x W^T + b) with fp16 operands (A and the weight's fp16 copy), fp32 accumulate; C is fp32 or fp16 (out_half).
 static cudaError_t lin_h(t2l_engine* e, const __half* A, long lda, int M, const std::string& wname, const std::string& bname, void* C,
-                         long ldc, int act, int out_half, cudaStream_t st, const float* residual = nullptr, long ldr = 0, int segmax = 0) {
+                         long ldc, int act, int out_half, cudaStream_t st, const float* residual = nullptr, long ldr = 0, int segmax = 0,
+                         int residual_half = 0) {
   const Weight& w = W(e, wname);
   if (!w.dev16) return cudaErrorInvalidValue;
   Linear l;
   l.A = reinterpret_cast<const float*>(A); l.lda = lda; l.W = reinterpret_cast<const float*>(w.dev16); l.ldw = w.ld16;
   l.bias = bname.empty() ? nullptr : W(e, bname).dev;
   l.C = static_cast<float*>(C); l.ldc = ldc; l.M = M; l.N = w.rows; l.K = w.cols; l.act = act; l.residual = residual; l.ldr = ldr;
-  l.half_ops = 1; l.out_half = out_half; l.segmax = segmax; l.round_out = segmax ? 1 : 0;
+  l.half_ops = 1; l.out_half = out_half; l.segmax = segmax; l.round_out = segmax ? 1 : 0; l.residual_half = residual_half;
   return linear_umma(l, st, &e->lc);
 }
 
@@ -434,8 +435,10 @@ static cudaError_t lin_h(t2l_engine* e, const __half* A, long lda, int M, const 
 // operand rounding the most, DESIGN.md precision table).
 // pooled_out != nullptr: the layer's output is only needed max-pooled over each sequence (token layer): norm2 and the max
 // are one kernel and Xout is not written.
+// x_is_half: X points at __half rows (fp16 T5 states): they are the first GEMM's A operand as they are and the residual of the
+// out-projection is read from them (no fp32 copy of the input exists).
 static int encoder_layer(t2l_engine* e, const std::string& pfx, bool fast, const float* X, float* Xout, int n_seq, int S, int d, int ffn,
-                         cudaStream_t st, float* pooled_out = nullptr) {
+                         cudaStream_t st, float* pooled_out = nullptr, bool x_is_half = false) {
   const int rows = n_seq * S;
   Arena& a = e->arena;
   float* qkv = a.get<float>(static_cast<size_t>(rows) * 3 * d);
@@ -446,17 +449,23 @@ static int encoder_layer(t2l_engine* e, const std::string& pfx, bool fast, const
   if (fast && e->text_f16 && d == 1024) {
     // fp16 operands, fp32 accumulation and fp32 residual/LayerNorm stream: x -> fp16 once, the attention core and
     // LayerNorm1 emit the fp16 A operands of the next GEMMs, the FFN hidden activations exist only in fp16
-    __half* xh = a.get<__half>(static_cast<size_t>(rows) * d);
+    const __half* xh = reinterpret_cast<const __half*>(X);
     __half* atth = reinterpret_cast<__half*>(att);
     __half* x1h = a.get<__half>(static_cast<size_t>(rows) * d);
     __half* hh = reinterpret_cast<__half*>(h);
-    CU(to_half_rows(X, xh, static_cast<long>(rows) * d, st, &e->lc));
+    if (!x_is_half) {
+      __half* xc = a.get<__half>(static_cast<size_t>(rows) * d);
+      CU(to_half_rows(X, xc, static_cast<long>(rows) * d, st, &e->lc));
+      xh = xc;
+    }
     CU(lin_h(e, xh, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, /*out_half=*/1, st));
     CU(mha_tc256(qkv, att, n_seq, S, st, &e->lc, /*round_out=*/2, /*half_in=*/1));
-    CU(lin_h(e, atth, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, 0, st, X, d));
+    CU(lin_h(e, atth, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, 0, st, X, d, 0, x_is_half ? 1 : 0));
     CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc, x1h));
     CU(lin_h(e, x1h, d, rows, pfx + ".l1_w", pfx + ".l1_b", hh, ffn, 1, 1, st));
     CU(lin_h(e, hh, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, 0, st, x1, d));
+  } else if (x_is_half) {
+    return fail(e, "internal: fp16 input needs the fp16 token layer");
   } else if (fast) {
     CU(lin(e, true, X, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st));
     if (d == 1024) CU(mha_tc256(qkv, att, n_seq, S, st, &e->lc, /*round_out=*/1));
@@ -685,7 +694,7 @@ extern "C" int t2l_encode_objects_debug(t2l_engine* e, const float* pts, const i
 // ---------------------------------------------------------------------------------------------
 // Token level: intra_module (one encoder layer over the tokens of each sentence, no key-padding mask,
 // language_encoder.py:130-131) then max over tokens (:133).  pooled [n_seq, 1024].
-static int text_tokens(t2l_engine* e, const float* t5, int n_seq, int L, float* pooled, cudaStream_t st) {
+static int text_tokens(t2l_engine* e, const float* t5, int n_seq, int L, float* pooled, cudaStream_t st, bool t5_is_half = false) {
   const int d = T2L_T5_DIM;
   int sc = e->tok_chunk / L;  // sentences per chunk
   if (sc < 1) sc = 1;
@@ -696,8 +705,9 @@ static int text_tokens(t2l_engine* e, const float* t5, int n_seq, int L, float* 
   for (int s0 = 0; s0 < n_seq; s0 += sc) {
     const int ns = (n_seq - s0 < sc) ? n_seq - s0 : sc;
     a.off = 0;
-    const float* X = t5 + static_cast<size_t>(s0) * L * d;
-    if (encoder_layer(e, "txt_intra", true, X, nullptr, ns, L, d, 4 * d, st, pooled + static_cast<size_t>(s0) * d)) return 1;
+    const float* X = t5_is_half ? reinterpret_cast<const float*>(reinterpret_cast<const __half*>(t5) + static_cast<size_t>(s0) * L * d)
+                                : t5 + static_cast<size_t>(s0) * L * d;
+    if (encoder_layer(e, "txt_intra", true, X, nullptr, ns, L, d, 4 * d, st, pooled + static_cast<size_t>(s0) * d, t5_is_half)) return 1;
   }
   if (a.overflow) return fail(e, "internal: workspace arena too small for %d sentences", n_seq);
   return 0;
@@ -736,6 +746,17 @@ extern "C" int t2l_encode_text_tokens(t2l_engine* e, const float* t5, int n_sent
   if (text_args_ok(e, t5, pooled, n_sentences, 1, L)) return 1;
   ENTER_STREAM(e, stream);
   return text_tokens(e, t5, n_sentences, L, pooled, static_cast<cudaStream_t>(stream));
+}
+
+// The same with the T5 states delivered as fp16 (raw 16-bit words): half the bytes over PCIe / from HBM and no conversion
+// kernel.  The token layer already runs on fp16 copies of its operands; here the out-projection's residual is read from the
+// fp16 input too (one more 11-bit rounding on that operand).  Needs the fp16 token layer (the default).
+extern "C" int t2l_encode_text_tokens_f16(t2l_engine* e, const void* t5_half, int n_sentences, int L, float* pooled, void* stream) {
+  if (text_args_ok(e, t5_half, pooled, n_sentences, 1, L)) return 1;
+  if (!e->text_f16) return fail(e, "encode_text_tokens_f16: T2L_TEXT_TF32=1 selects the tf32 token layer, which takes fp32 input");
+  if (reinterpret_cast<uintptr_t>(t5_half) & 15) return fail(e, "encode_text_tokens_f16: input must be 16-byte aligned");
+  ENTER_STREAM(e, stream);
+  return text_tokens(e, static_cast<const float*>(t5_half), n_sentences, L, pooled, static_cast<cudaStream_t>(stream), true);
 }
 
 extern "C" int t2l_encode_text_sentences(t2l_engine* e, const float* pooled, int nq, int S, float* out, void* stream) {
@@ -1020,7 +1041,20 @@ extern "C" int t2l_merge_topk(t2l_engine* e, const int64_t* idx_all, const doubl
   if (!e) return 1;
   if (!idx_all || !score_all || !out_idx || !out_score) return fail(e, "merge_topk: NULL buffer");
   ENTER_STREAM(e, stream);
-  CU(merge_topk(idx_all, score_all, n_shards, nq, k, out_idx, out_score, static_cast<cudaStream_t>(stream), &e->lc));
+  CU(merge_topk(idx_all, score_all, static_cast<long>(nq) * k, n_shards, nq, k, out_idx, out_score, static_cast<cudaStream_t>(stream), &e->lc));
+  return 0;
+}
+
+// The same for PACKED per-shard results: shard g contributes one block of 2 * nq * k 8-byte words, [idx i64 [nq, k] | score f64
+// [nq, k]] -- what ONE all-gather of a rank's (idx, score) pair delivers (text2loc_b200/distributed.py).
+extern "C" int t2l_merge_topk_packed(t2l_engine* e, const void* packed_all, int n_shards, int nq, int k, int64_t* out_idx, double* out_score,
+                                     void* stream) {
+  if (!e) return 1;
+  if (!packed_all || !out_idx || !out_score) return fail(e, "merge_topk_packed: NULL buffer");
+  ENTER_STREAM(e, stream);
+  const int64_t* idx0 = static_cast<const int64_t*>(packed_all);
+  const double* sc0 = reinterpret_cast<const double*>(idx0 + static_cast<long>(nq) * k);
+  CU(merge_topk(idx0, sc0, 2L * nq * k, n_shards, nq, k, out_idx, out_score, static_cast<cudaStream_t>(stream), &e->lc));
   return 0;
 }
 

@@ -44,6 +44,7 @@ struct StoreParams {
   int round_out;
   int out_half;  // C is __half [M, ldc]: the consumer is an fp16 tensor-core GEMM (same 11-bit significand as tf32)
   float half_max = kHalfMax;  // fp16 stores saturate at +-half_max
+  int res_half = 0;           // residual points at __half data [M, ldr] (the token layer fed with fp16 T5 states)
 };
 
 template <bool kHalfOut, bool kResidual>
@@ -69,16 +70,25 @@ struct StoreEpiT {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const long row = row0 + 4 * j + rr;
-      res[j] = (row < p.M && col0 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col0) + ch)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!(row < p.M && col0 < p.N)) {
+        res[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else if (p.res_half) {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.residual) + row * p.ldr + col0) + ch);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        res[j] = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        res[j] = __ldg(reinterpret_cast<const float4*>(p.residual + row * p.ldr + col0) + ch);
+      }
     }
   }
   __device__ void prefetch_unit(int m_tile, int col0) {
     if (!kResidual) return;
     const long row = static_cast<long>(m_tile) * 128 + ew * 32 + lane;
     if (row < p.M && col0 < p.N) {
-      const int bytes = min(block_n, p.N - col0) * 4;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.residual + row * p.ldr + col0), "r"(bytes) : "memory");
+      const int esz = p.res_half ? 2 : 4;
+      const int bytes = min(block_n, p.N - col0) * esz;
+      const char* src = reinterpret_cast<const char*>(p.residual) + (row * p.ldr + col0) * esz;
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
     }
   }
   __device__ void begin_tile(int m_tile, int, int col0) {

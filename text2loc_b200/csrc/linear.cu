@@ -57,7 +57,7 @@ cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
     return wide ? run_umma<256, 1, SegMaxEpi>(l, ep, st) : run_umma<128, 1, SegMaxEpi>(l, ep, st);
   }
   if (l.out_half && l.residual) return cudaErrorInvalidValue;
-  StoreParams ep{l.C, l.ldc, l.bias, l.residual, l.ldr, l.M, l.N, l.act, l.round_out, l.out_half, l.half_max};
+  StoreParams ep{l.C, l.ldc, l.bias, l.residual, l.ldr, l.M, l.N, l.act, l.round_out, l.out_half, l.half_max, l.residual_half};
   if (l.half_ops) {  // fp16 operands (A, W are __half), kind::f16: twice the tf32 rate at the same 11-bit significand
     if (l.out_half) return run_store<StoreEpiT<true, false>, kOpF16>(l, ep, wide, pair, st);
     if (l.residual) return run_store<StoreEpiT<false, true>, kOpF16>(l, ep, wide, pair, st);
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(Linear l) {
       float x = acc[i][j];
       if (l.bias) x += l.bias[c];
       if (l.act == 1) x = fmaxf(x, 0.f);
-      if (l.residual) x += l.residual[r * l.ldr + c];
+      if (l.residual) x += l.residual_half ? __half2float(reinterpret_cast<const __half*>(l.residual)[r * l.ldr + c]) : l.residual[r * l.ldr + c];
       if (l.out_half) { reinterpret_cast<__half*>(l.C)[r * l.ldc + c] = __float2half_rn(fminf(fmaxf(x, -l.half_max), l.half_max)); continue; }
       if (l.round_out) x = round_tf32(x);
       l.C[r * l.ldc + c] = x;

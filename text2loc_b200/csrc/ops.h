@@ -25,6 +25,7 @@ struct Linear {
   int M, N, K;
   int act = 0;                // 0 none, 1 relu
   const float* residual = nullptr; long ldr = 0;  // added after act (store mode only)
+  int residual_half = 0;      // residual points at __half data (ldr in elements)
   int segmax = 0;             // max over 32-row groups after relu
   const float* side = nullptr; long lds = 0;      // segmax: elementwise max with side[g, :]
   int round_out = 0;          // round stored values to tf32 (rna)
@@ -155,7 +156,8 @@ cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q,
                         double* out_score, int32_t* out_n_fallback, bool first_pass_bf16x3, cudaStream_t st, Launches* lc);
 cudaError_t search_topk_exact(const SearchDb& db, const float* Q, int nq, int k, int64_t* out_idx, double* out_score,
                               const int32_t* only_flagged, cudaStream_t st, Launches* lc);
-cudaError_t merge_topk(const int64_t* idx_all, const double* score_all, int n_shards, int nq, int k, int64_t* out_idx,
+// shard g's lists start at idx_all + g * shard_stride / score_all + g * shard_stride (elements)
+cudaError_t merge_topk(const int64_t* idx_all, const double* score_all, long shard_stride, int n_shards, int nq, int k, int64_t* out_idx,
                        double* out_score, cudaStream_t st, Launches* lc);
 // run := top-k of (run, new) by (score desc, row asc), in place; empty slots carry idx -1
 cudaError_t merge_running_topk(int64_t* run_idx, double* run_score, const int64_t* new_idx, const double* new_score, int nq, int k,

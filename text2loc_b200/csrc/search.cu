@@ -530,8 +530,8 @@ cudaError_t search_topk(const SearchDb& db, const SearchWork& w, const float* Q,
 }
 
 // ---- merge of per-shard lists (one warp per query) -----------------------------------------------------
-__global__ void __launch_bounds__(128) merge_kernel(const int64_t* __restrict__ idx_all, const double* __restrict__ score_all, int n_shards, int nq, int k,
-                                                    int64_t* __restrict__ out_idx, double* __restrict__ out_score) {
+__global__ void __launch_bounds__(128) merge_kernel(const int64_t* __restrict__ idx_all, const double* __restrict__ score_all, long shard_stride,
+                                                    int n_shards, int nq, int k, int64_t* __restrict__ out_idx, double* __restrict__ out_score) {
   __shared__ double s_sc[4][kMaxSplits * kCand];
   __shared__ long s_ix[4][kMaxSplits * kCand];
   __shared__ double s_osc[4][kCand];
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(128) merge_kernel(const int64_t* __restrict__ 
   const int C = n_shards * k;
   for (int c = lane; c < C; c += 32) {
     const int g = c / k, j = c % k;
-    const long src = (static_cast<long>(g) * nq + q) * k + j;
+    const long src = g * shard_stride + static_cast<long>(q) * k + j;
     s_sc[w][c] = score_all[src];
     s_ix[w][c] = idx_all[src];
   }
@@ -587,12 +587,12 @@ cudaError_t merge_running_topk(int64_t* run_idx, double* run_score, const int64_
   return cudaGetLastError();
 }
 
-cudaError_t merge_topk(const int64_t* idx_all, const double* score_all, int n_shards, int nq, int k, int64_t* out_idx,
+cudaError_t merge_topk(const int64_t* idx_all, const double* score_all, long shard_stride, int n_shards, int nq, int k, int64_t* out_idx,
                        double* out_score, cudaStream_t st, Launches* lc) {
   if (nq <= 0) return cudaSuccess;
   if (k < 1 || k > kCand || n_shards < 1 || n_shards * k > kMaxSplits * kCand) return cudaErrorInvalidValue;
   if (lc) lc->n++;
-  merge_kernel<<<(nq + 3) / 4, 128, 0, st>>>(idx_all, score_all, n_shards, nq, k, out_idx, out_score);
+  merge_kernel<<<(nq + 3) / 4, 128, 0, st>>>(idx_all, score_all, shard_stride, n_shards, nq, k, out_idx, out_score);
   return cudaGetLastError();
 }
 

@@ -50,21 +50,47 @@ def merge_topk_host(idx_all: np.ndarray, score_all: np.ndarray, k: int):
     return np.take_along_axis(idx, order, 1), np.take_along_axis(sc, order, 1)
 
 
-def sharded_search(engine, Q_local_or_all: torch.Tensor, k: int, queries_are_sharded: bool = False, group=None):
+def sharded_search(engine, Q_local_or_all: torch.Tensor, k: int, queries_are_sharded: bool = False, group=None, timers=None):
     """Search this rank's shard (engine.db_build must hold it, with its row_offset) for ALL queries
     and merge across ranks.  Returns (idx [nq,k], score [nq,k], n_fallback) on every rank.
 
     queries_are_sharded: each rank holds a different slice of the query embeddings (the text head
     was split by queries); they are all-gathered first.
+
+    ONE exchange step joins the results: the rank's (idx, score) pair lives in one packed buffer of 8-byte words
+    ([2, nq, k]: row indices, then the fp64 scores' bits), so a single all-gather moves both, and t2l_merge_topk_packed
+    reads the gathered [G, 2, nq, k] block in place.
+    timers: optional dict of lists; when given, CUDA events bracket each stage and their milliseconds are appended under
+    'allgather_q', 'search', 'allgather_topk', 'merge' (this synchronises the device: measurement passes only).
     """
+    ws = dist.get_world_size(group) if dist.is_initialized() else 1
+    marks = []
+
+    def mark(name):
+        if timers is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
     Q = Q_local_or_all
     if queries_are_sharded:
         Q = all_gather_rows(Q, group).reshape(-1, Q.shape[-1])
-    idx, score, nfb = engine.search_topk(Q, k)
-    ws = dist.get_world_size(group) if dist.is_initialized() else 1
+    mark("allgather_q")
+    nq = Q.shape[0]
     if ws == 1:
-        return idx, score, nfb
-    idx_all = all_gather_rows(idx, group)
-    score_all = all_gather_rows(score, group)
-    idx, score = engine.merge_topk(idx_all, score_all)
+        idx, score, nfb = engine.search_topk(Q, k)
+        mark("search")
+    else:
+        packed = torch.empty((2, nq, k), dtype=torch.int64, device=Q.device)
+        _, _, nfb = engine.search_topk(Q, k, out=(packed[0], packed[1].view(torch.float64)))
+        mark("search")
+        gathered = all_gather_rows(packed, group)  # [G, 2, nq, k]
+        mark("allgather_topk")
+        idx, score = engine.merge_topk_packed(gathered, nq, k)
+        mark("merge")
+    if timers is not None:
+        torch.cuda.synchronize()
+        for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+            timers.setdefault(name, []).append(a.elapsed_time(b))
     return idx, score, nfb

@@ -114,17 +114,27 @@ class Engine:
     TOKENS_PER_CHUNK = 32768  # the engine's internal text chunk (api.cu: tok_chunk)
 
     def encode_text(self, t5, n_sent: int) -> torch.Tensor:
-        """t5 [nq*n_sent, n_tok, 1024] (T5 last_hidden_state) -> unit rows [nq,256] on device.
+        """t5 [nq*n_sent, n_tok, 1024] (T5 last_hidden_state, float32 or float16) -> unit rows [nq,256] on device.
 
+        float16 features take the fp16 entry point (t2l_encode_text_tokens_f16): half the bytes to move, no conversion
+        kernel; the token layer computes on fp16 operand copies either way.
         A HOST tensor (ideally pinned) is streamed: the H2D copy of chunk i+1 runs on a side
         stream while the engine works on chunk i, so PCIe time hides behind compute."""
         t5 = torch.as_tensor(t5)
-        if t5.dim() != 3 or t5.shape[2] != T5_DIM or t5.shape[0] % n_sent or t5.dtype != torch.float32:
-            raise EngineError(f"encode_text: need float32 [nq*{n_sent}, n_tok, 1024], got {t5.dtype} {tuple(t5.shape)}")
+        if t5.dim() != 3 or t5.shape[2] != T5_DIM or t5.shape[0] % n_sent or t5.dtype not in (torch.float32, torch.float16):
+            raise EngineError(f"encode_text: need float32 / float16 [nq*{n_sent}, n_tok, 1024], got {t5.dtype} {tuple(t5.shape)}")
+        half = t5.dtype == torch.float16
+        tokens = self._lib.t2l_encode_text_tokens_f16 if half else self._lib.t2l_encode_text_tokens
         nq, n_tok = t5.shape[0] // n_sent, t5.shape[1]
         out = torch.empty((nq, EMBED_DIM), dtype=torch.float32, device=self.device)
         if t5.is_cuda:
-            self._encode_text_dev(self._dev(t5, torch.float32), n_sent, out)
+            t5 = self._dev(t5, t5.dtype)
+            if not half:
+                self._encode_text_dev(t5, n_sent, out)
+                return out
+            pooled = torch.empty((nq * n_sent, T5_DIM), dtype=torch.float32, device=self.device)
+            self._check(tokens(self._h, _ptr(t5), nq * n_sent, n_tok, _ptr(pooled), self._stream()))
+            self._check(self._lib.t2l_encode_text_sentences(self._h, _ptr(pooled), nq, n_sent, _ptr(out), self._stream()))
             return out
         t5 = t5.contiguous()
         cq = max(1, self.TOKENS_PER_CHUNK // (n_sent * n_tok))
@@ -132,11 +142,12 @@ class Engine:
         cur = torch.cuda.current_stream(self.device)
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)  # one copy stream for the engine's lifetime
-        if self._stage is None or self._stage[0].shape[0] < rows_per_chunk or self._stage[0].shape[1] != n_tok:
+        if (self._stage is None or self._stage[0].shape[0] < rows_per_chunk or self._stage[0].shape[1] != n_tok
+                or self._stage[0].dtype != t5.dtype):
             # (Re)allocation happens on the current stream: the caching allocator may hand back blocks that kernels
             # already queued on this stream still read (the previous staging pair included).  The copy stream must
             # not write them before that work has finished, and the blocks must not be recycled under the copies.
-            self._stage = [torch.empty((rows_per_chunk, n_tok, T5_DIM), dtype=torch.float32, device=self.device) for _ in range(2)]
+            self._stage = [torch.empty((rows_per_chunk, n_tok, T5_DIM), dtype=t5.dtype, device=self.device) for _ in range(2)]
             for t in self._stage:
                 t.record_stream(self._copy_stream)
             self._copy_stream.wait_stream(cur)
@@ -153,7 +164,7 @@ class Engine:
                 copied = torch.cuda.Event()
                 copied.record(self._copy_stream)
             cur.wait_event(copied)
-            self._check(self._lib.t2l_encode_text_tokens(  # token stage of this chunk; sentence stage once at the end
+            self._check(tokens(  # token stage of this chunk; sentence stage once at the end
                 self._h, _ptr(self._stage[b]), n_rows, n_tok, _ptr(pooled[q0 * n_sent:q1 * n_sent]), self._stream()))
             self._stage_done[b] = torch.cuda.Event()
             self._stage_done[b].record(cur)
@@ -212,16 +223,23 @@ class Engine:
         self._db = D
         self._check(self._lib.t2l_db_build(self._h, _ptr(D), D.shape[0], int(row_offset), self._stream()))
 
-    def search_topk(self, Q, k: int, exact: bool = False):
-        """-> (idx int64 [nq,k], score float64 [nq,k], n_fallback int tensor [1]); order (score desc, row asc)."""
+    def search_topk(self, Q, k: int, exact: bool = False, out=None):
+        """-> (idx int64 [nq,k], score float64 [nq,k], n_fallback int tensor [1]); order (score desc, row asc).
+        out: optional pre-allocated (idx, score) pair to write into (e.g. the two halves of one packed buffer)."""
         if self._db is None:
             raise EngineError("search_topk: call db_build first")
         Q = self._dev(Q, torch.float32)
         if Q.dim() != 2 or Q.shape[1] != EMBED_DIM:
             raise EngineError(f"search_topk: queries must be [nq,256], got {tuple(Q.shape)}")
         nq = Q.shape[0]
-        idx = torch.empty((nq, k), dtype=torch.int64, device=self.device)
-        sc = torch.empty((nq, k), dtype=torch.float64, device=self.device)
+        if out is not None:
+            idx, sc = out
+            if (idx.shape != (nq, k) or sc.shape != (nq, k) or idx.dtype != torch.int64 or sc.dtype != torch.float64
+                    or not idx.is_contiguous() or not sc.is_contiguous()):
+                raise EngineError("search_topk: out must be contiguous (int64 [nq,k], float64 [nq,k])")
+        else:
+            idx = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+            sc = torch.empty((nq, k), dtype=torch.float64, device=self.device)
         nfb = torch.zeros(1, dtype=torch.int32, device=self.device)
         if exact or k > MAX_TOPK_FAST:
             self._check(self._lib.t2l_search_topk_exact(self._h, _ptr(Q), nq, k, _ptr(idx), _ptr(sc), self._stream()))
@@ -265,6 +283,16 @@ class Engine:
         idx = torch.empty((nq, k), dtype=torch.int64, device=self.device)
         sc = torch.empty((nq, k), dtype=torch.float64, device=self.device)
         self._check(self._lib.t2l_merge_topk(self._h, _ptr(idx_all), _ptr(score_all), G, nq, k, _ptr(idx), _ptr(sc), self._stream()))
+        return idx, sc
+
+    def merge_topk_packed(self, packed_all: torch.Tensor, nq: int, k: int):
+        """[G, 2, nq, k] int64 words (idx | score bits) gathered from G shards -> global (idx, score) [nq,k]."""
+        G = packed_all.shape[0]
+        if packed_all.dtype != torch.int64 or tuple(packed_all.shape[1:]) != (2, nq, k) or not packed_all.is_contiguous():
+            raise EngineError("merge_topk_packed: need a contiguous int64 [G, 2, nq, k] buffer")
+        idx = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        sc = torch.empty((nq, k), dtype=torch.float64, device=self.device)
+        self._check(self._lib.t2l_merge_topk_packed(self._h, _ptr(packed_all), G, nq, k, _ptr(idx), _ptr(sc), self._stream()))
         return idx, sc
 
     # ---- bookkeeping ----------------------------------------------------------------------
