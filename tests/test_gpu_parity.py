@@ -684,6 +684,33 @@ def test_topk_accuracy_kernel_matches_reference_loops(eng):
     assert (close2[:, 3, 0] == close2[:, 2, 0]).all()
 
 
+def test_eval_epoch_with_packed_database_cache(state_dict, monkeypatch):
+    """model.cache_packed_cells: the database is packed once (vectorised), encoded in one call and
+    re-used by the next evaluation; retrievals are then reproducible across calls and remain the fp64 oracle's on the
+    engine's own embeddings."""
+    from oracle import restate
+    from oracle.make_golden import e2e_dataset
+    from text2loc_b200 import dataio, eval_epoch
+
+    model, args = make_model(state_dict)
+    args.batch_size = 4
+    model.cache_packed_cells = True
+    ds = e2e_dataset()
+    loader = DataLoader(ds, batch_size=4, collate_fn=dataio.collate_fn, shuffle=False)
+    calls = []
+    real = dataio.pack_cell_database
+    monkeypatch.setattr(dataio, "pack_cell_database", lambda *a, **k: calls.append(1) or real(*a, **k))
+    np.random.seed(5)
+    acc1, _, r1, cells1, text1 = eval_epoch(model, loader, args, return_encodings=True)
+    acc2, _, r2 = eval_epoch(model, loader, args)
+    assert len(calls) == 1
+    got = np.stack([r1[i] for i in range(len(ds))])
+    assert (got == np.stack([r2[i] for i in range(len(ds))])).all() and acc1 == acc2
+    assert np.abs(np.linalg.norm(cells1, axis=1) - 1).max() < 1e-5
+    oidx, _ = restate.search_topk(cells1, text1, 10)
+    assert (got == np.array([c.id for c in ds.all_cells])[oidx]).all()
+
+
 def test_dropin_surface(state_dict):
     from text2loc_b200.engine import EngineError
 

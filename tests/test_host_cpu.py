@@ -146,3 +146,46 @@ def test_oracle_bookkeeping_restatement_matches_reference_functions():
     want = ref_calc(pose, top, pos, [1, 3, 5, 10], [5, 10, 15])
     got = restate.calc_sample_accuracies(pose, top, pos, [1, 3, 5, 10], [5, 10, 15])
     assert got == want
+
+
+def test_sentence_cache_frontend_reproduces_the_uncached_front_end():
+    """Each distinct sentence passes the frozen encoder once; batches are assembled from the cache and equal what the
+    uncached front end (the reference's steps, models/language_encoder.py:108-125) produces, pad positions included."""
+    from oracle import fake_t5
+    from oracle.stubs import sent_tokenize
+    from text2loc_b200.text_frontend import SentenceCacheFrontend
+
+    plain = fake_t5.FakeFrontend(0)
+    cached = SentenceCacheFrontend(fake_t5.FakeTokenizer(), fake_t5.FakeT5Encoder(0).eval(), "cpu", cap=16, split=sent_tokenize)
+    a = ["The pose is north of a gray building. The pose is on-top of a dark-green traffic light.",
+         "The pose is east of a red pole. The pose is north of a gray building."]
+    b = ["The pose is west of a beige vending machine. The pose is east of a red pole."]
+    for batch in (a, b, a + b):
+        want, ns = plain(batch)
+        got, ns2 = cached(batch)
+        assert ns == ns2 == 2 and got.shape == want.shape
+        assert torch.equal(got, want)
+    assert cached.encoder_calls == 2 and len(cached.cache) == 4  # the third batch was served from the cache alone
+
+
+def test_pack_cell_database_vectorised_matches_per_object_packing():
+    """meta is the per-object reductions of pack_cells; every sampled point is one of the object's raw points; the
+    NormalizeScale variant centres each sample and scales it into (-1, 1)."""
+    import synth
+    from text2loc_b200 import dataio
+
+    objs = synth.make_cell_objects(3, 5, [2, 9, 1, 4, 30], max_raw=400)
+    cells = [synth.SynthCell(i, "0000", o, 30.0, np.zeros(6)) for i, o in enumerate(objs)]
+    db = dataio.pack_cell_database(cells, rng=np.random.default_rng(0))
+    np.random.seed(0)
+    pts, meta, ptr = dataio.pack_cells(objs, [dataio.batch_object_points(o, dataio.FixedPoints(256)) for o in objs])
+    assert (db.cell_ptr == ptr).all() and db.pts.shape == pts.shape and db.cell_ids == [c.id for c in cells]
+    assert np.abs(db.meta.numpy() - meta.numpy()).max() < 1e-6 and (db.meta[:, 6] == meta[:, 6]).all()
+    flat = [o for c in objs for o in c]
+    for k in (0, 7, 45):
+        raw = np.concatenate([flat[k].xyz, flat[k].rgb], axis=1).astype(np.float32)
+        d = np.abs(db.pts[k].numpy()[:, None, :] - raw[None, :, :]).max(axis=2).min(axis=1)
+        assert d.max() == 0.0
+    ns = dataio.pack_cell_database(cells, normalize_scale=True, rng=np.random.default_rng(0))
+    p = ns.pts[:, :, 0:3].numpy()
+    assert np.abs(p.mean(axis=1)).max() < 1e-5 and abs(np.abs(p).max(axis=(1, 2)).max() - 0.999999) < 1e-5

@@ -48,6 +48,8 @@ class CellRetrievalNetwork:
         self._engine = Engine(device)
         self._frontend = text_frontend
         self.training = False
+        # opt-in: eval_epoch packs the cell database once (vectorised) and re-uses it across evaluations (evaluation.py)
+        self.cache_packed_cells = False
 
     # ---- nn.Module surface the eval drivers touch -----------------------------------------
     def eval(self):

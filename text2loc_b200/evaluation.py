@@ -38,6 +38,22 @@ def scene_names(ids) -> np.ndarray:
     return names
 
 
+def _cached_database(model, cells_dataset):
+    """model.cache_packed_cells = True opts in: the cell database is packed once per (model, dataset) with
+    dataio.pack_cell_database and reused by every later evaluation; otherwise the reference's per-batch traversal runs."""
+    if not getattr(model, "cache_packed_cells", False):
+        return None
+    cache = model.__dict__.setdefault("_packed_cells", {})
+    key = (id(cells_dataset.cells), len(cells_dataset.cells))
+    if key not in cache:
+        names = [type(t).__name__ for t in getattr(cells_dataset.transform, "transforms", [cells_dataset.transform])]
+        if not names or names[0] != "FixedPoints" or any(n not in ("FixedPoints", "NormalizeScale") for n in names):
+            raise ValueError(f"cache_packed_cells supports FixedPoints [+ NormalizeScale] transforms, got {names}")
+        num = getattr(getattr(cells_dataset.transform, "transforms", [cells_dataset.transform])[0], "num", dataio.NUM_POINTS)
+        cache[key] = dataio.pack_cell_database(cells_dataset.cells, num, normalize_scale="NormalizeScale" in names)
+    return cache[key]
+
+
 @torch.no_grad()
 def eval_epoch(model, dataloader, args, return_encodings=False, return_distance=False):
     """training/coarse.py:63-157.  Returns (accuracies{k}, accuracies_close{k},
@@ -63,12 +79,18 @@ def eval_epoch(model, dataloader, args, return_encodings=False, return_distance=
         text_enc[off:off + len(enc)] = enc
         query_cell_ids.extend(batch["cell_ids"])
         off += len(enc)
-    off = 0
-    for batch in cells_dataloader:
-        enc = model.encode_objects(batch["objects"], batch["object_points"])
-        cell_enc[off:off + len(enc)] = enc
-        db_cell_ids.extend(batch["cell_ids"])
-        off += len(enc)
+    packed = _cached_database(model, cells_dataset)
+    if packed is not None:
+        # the database was packed once (vectorised) and is encoded in one engine call
+        cell_enc[:] = model.encode_cells_packed(packed.pts, packed.meta, packed.cell_ptr)
+        db_cell_ids = list(packed.cell_ids)
+    else:
+        off = 0
+        for batch in cells_dataloader:
+            enc = model.encode_objects(batch["objects"], batch["object_points"])
+            cell_enc[off:off + len(enc)] = enc
+            db_cell_ids.extend(batch["cell_ids"])
+            off += len(enc)
     query_cell_ids = np.array(query_cell_ids, dtype="<U32")
     db_cell_ids = np.array(db_cell_ids, dtype="<U32")
 

@@ -41,6 +41,56 @@ def split_sentences(text: str) -> List[str]:
                           "(the reference hard-depends on it, models/language_encoder.py:110)") from err
 
 
+class SentenceCacheFrontend:
+    """Sentence-level cache in front of the frozen encoder.
+
+    The reference pushes every description's sentences through T5-large on every call (models/language_encoder.py:116-125),
+    ~27x the FLOPs of the text head behind it, although the templated hint vocabulary is tiny (direction x colour x class =
+    5 x 8 x 22 sentences, dataloading/kitti360pose/base.py:60-68).  Each distinct sentence is encoded ONCE, padded to `cap`
+    tokens, and its states [cap, 1024] are kept on the device; a batch is assembled by slicing every sentence's states to the
+    batch's longest token count (the reference pads with padding="longest").  This reproduces the uncached output because an
+    encoder with a key-padding mask never lets a position attend to pads: the state at position p -- pad positions included,
+    which the reference feeds UNMASKED into its intra-module -- depends only on the sentence's real
+    tokens and on p (T5's relative position buckets), not on how many pads follow.
+
+    tokenizer(sentences, return_tensors="pt", padding="longest") -> {"input_ids", "attention_mask"};
+    model(input_ids=, attention_mask=).last_hidden_state."""
+
+    def __init__(self, tokenizer, model, device, cap: int = 32, pad_id: int = 0, split=None):
+        self.tokenizer, self.model, self.device, self.cap, self.pad_id = tokenizer, model, device, cap, pad_id
+        self.split = split or split_sentences
+        self.cache = {}  # sentence -> (n_tokens, states [cap, 1024] on device)
+        self.encoder_calls = 0
+
+    @torch.no_grad()
+    def _encode_new(self, sentences: List[str]):
+        tok = self.tokenizer(sentences, return_tensors="pt", padding="longest")
+        ids, mask = tok["input_ids"], tok["attention_mask"]
+        n_tok = mask.sum(dim=1)
+        if ids.shape[1] > self.cap:
+            raise ValueError(f"a sentence has {ids.shape[1]} tokens; raise SentenceCacheFrontend(cap=...) (the engine takes up to 32)")
+        pad = self.cap - ids.shape[1]
+        if pad:
+            ids = torch.cat([ids, torch.full((ids.shape[0], pad), self.pad_id, dtype=ids.dtype)], dim=1)
+            mask = torch.cat([mask, torch.zeros((mask.shape[0], pad), dtype=mask.dtype)], dim=1)
+        out = self.model(input_ids=ids.to(self.device), attention_mask=mask.to(self.device), output_attentions=False).last_hidden_state
+        self.encoder_calls += 1
+        for s, n, h in zip(sentences, n_tok.tolist(), out.float()):
+            self.cache[s] = (int(n), h.contiguous())
+
+    @torch.no_grad()
+    def __call__(self, descriptions: List[str]) -> Tuple[torch.Tensor, int]:
+        sentences: List[str] = []
+        for d in descriptions:
+            sentences.extend(self.split(d))
+        n_sent = len(sentences) // len(descriptions)  # the reference assumes equal counts (:114)
+        new = [s for s in dict.fromkeys(sentences) if s not in self.cache]
+        if new:
+            self._encode_new(new)
+        L = max(self.cache[s][0] for s in sentences)  # padding="longest" over THIS batch
+        return torch.stack([self.cache[s][1][:L] for s in sentences]).contiguous(), n_sent
+
+
 class HFT5Frontend:
     def __init__(self, model_name: str, device):
         from transformers import AutoTokenizer, T5EncoderModel
@@ -48,6 +98,10 @@ class HFT5Frontend:
         self.tokenizer = AutoTokenizer.from_pretrained(model_name)
         self.model = T5EncoderModel.from_pretrained(model_name).to(device).eval()
         self.device = device
+
+    def cached(self, cap: int = 32) -> SentenceCacheFrontend:
+        """The same front end with the sentence-level cache (each distinct sentence goes through T5 once)."""
+        return SentenceCacheFrontend(self.tokenizer, self.model, self.device, cap, pad_id=self.tokenizer.pad_token_id or 0)
 
     @torch.no_grad()
     def __call__(self, descriptions: List[str]) -> Tuple[torch.Tensor, int]:
