@@ -112,42 +112,57 @@ def bind_to_gpu_numa_node(index: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clocks and throttle reasons DURING the timed region (B200_PROFILING.md), sampled through NVML in-process.
 
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    One sampler per job: rank 0 watches every GPU of the run.  (Round 1 forked `nvidia-smi` five times a second from EVERY rank;
+    at 8 ranks those forks and their driver locks sat on the launch path of all eight processes.  NVML is the library
+    nvidia-smi reads the same fields from.)"""
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.stop, self.t = index, [], threading.Event(), None
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
+    def __init__(self, indices, active: bool = True):
+        self.indices = list(indices) if not isinstance(indices, int) else [indices]
+        self.active = active
+        self.rows, self.stop, self.t = [], threading.Event(), None
+        self.nvml = None
 
     def _run(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            self.nvml = pynvml
+        except Exception:
+            return
         while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.2)
+            for h in handles:
+                try:
+                    self.rows.append((self.nvml.nvmlDeviceGetClockInfo(h, self.nvml.NVML_CLOCK_SM),
+                                      self.nvml.nvmlDeviceGetMaxClockInfo(h, self.nvml.NVML_CLOCK_SM),
+                                      int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                except Exception:
+                    pass
+            self.stop.wait(0.1)
 
     def __enter__(self):
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
+        if self.active:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.t.join(timeout=6)
+        if self.t:
+            self.t.join(timeout=6)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for n, bit in self.REASONS if any(r[2] & bit for r in self.rows)]
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_min_mhz": float(sm[0]), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "gpus_sampled": len(self.indices), "source": "NVML (in-process, rank 0)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -354,8 +369,45 @@ def run_engine_arm(args):
         barrier()
         return max_over_ranks(a.elapsed_time(b)) / steps, (eng.launch_count - l0) // steps, out
 
-    with ClockSampler(local_rank) as clocks:
-        ms_step, launches, out = timed(step_resident, args.steps, args.warmup)
+    # ---- optional (--graph): the resident step as ONE CUDA graph: ~105 kernel launches (+ the collectives at N > 1) captured once
+    # after a warm-up and replayed.  Inputs and outputs are static device buffers; the eager step stays the reference the replay
+    # is compared with.
+    graph, graph_out, graph_err = None, None, None
+    if args.graph:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step_resident()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            barrier()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                graph_out = step_resident()
+            graph.replay()
+            torch.cuda.synchronize()
+            eager = step_resident()
+            torch.cuda.synchronize()
+            if not (torch.equal(graph_out[0], eager[0]) and torch.equal(graph_out[1], eager[1])):
+                raise RuntimeError("graph replay and eager step disagree")
+        except Exception as ex:  # capture is an optimisation: report and fall back to the eager step
+            graph, graph_err = None, f"{type(ex).__name__}: {ex}"[:300]
+    ok_all = torch.tensor([1 if graph is not None else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+    if int(ok_all.item()) == 0:
+        graph = None
+
+    def step_graph():
+        graph.replay()
+        return graph_out
+
+    with ClockSampler(range(world), active=rank == 0) as clocks:
+        ms_eager, launches, out = timed(step_resident, args.steps, args.warmup)
+        ms_step = ms_eager
+        if graph is not None:
+            ms_step, _, out = timed(step_graph, args.steps, args.warmup)
         ms_e2e, _, out_e2e = timed(step_e2e, args.steps, args.warmup)
     idx, score, nfb = out
 
@@ -514,15 +566,31 @@ def run_engine_arm(args):
             "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
                     "input": "fp16 T5 states in pinned host memory (t2l_encode_text_tokens_f16), streamed H2D in chunks under the compute; "
                              "top-k (i64 row, f64 score) read back D2H every step"},
+            "cuda_graph": graph is not None, "cuda_graph_error": graph_err, "ms_per_step_eager": ms_eager,
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roof, "roofline_other_kernels": extra, "cpu_baseline": cpu_base,
             "ms_text_head": ms_text, "ms_search": ms_search, "stage_ms": stage_ms, "search_fallbacks": int(nfb),
             "db_encode_cells_per_s": n_db / (enc_ms_max * 1e-3), "db_encode_ms": enc_ms_max, "db_encode_ms_first": enc_ms[0], "db_encode_ms_runs": enc_ms,
             "cold_db_qps": nq / ((ms_step + enc_ms_max) * 1e-3), "topk_matches_fp64_oracle_sample": parity,
             "reference_arm_note": "--impl reference runs the oracle PORT of the reference's Python (kind: port) on the host cores, sampled",
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    graph = graph_out = None
+    finish(world)
+
+
+def finish(world: int):
+    """Leave without the process-group teardown: with a captured NCCL graph alive destroy_process_group() did not return
+    (one N=2 run sat until its timeout); every rank has printed and synchronised by now."""
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def bench_stream(eng, dev, n_cells: int, nq: int, obj_per_cell: int, steps: int, first_cell: int = 0, seed: int = 5):
@@ -615,14 +683,13 @@ def run_extra_workload(args):
     if args.workload == "fine":
         if rank == 0:
             nq = args.queries or 32768
-            with ClockSampler(local_rank) as clocks:
+            with ClockSampler([local_rank]) as clocks:
                 r = bench_fine(dev, n_queries=nq, top_cells=5, n_db_cells=10000)
             print(json.dumps({"metric": "fine-stage queries/sec (CrossMatch offsets for the top-5 retrieved cells of every query)", "value": r["queries_per_s"],
                               "unit": "queries/s", "n_gpus": 1, "higher_is_better": True, "data": "synthetic", "dtype": "f16 token layer + PointNet++, 3xtf32 decoder layers",
                               "config": {"workload": "configs[4]: coarse->fine, top-5 retrieved cells into cross_matcher offset regression, "
-                                                     f"{nq} queries, 1xB200"}, "detail": r, "clocks": clocks.summary()}))
-        if world > 1:
-            dist.destroy_process_group()
+                                                     f"{nq} queries, 1xB200"}, "detail": r, "clocks": clocks.summary()}), flush=True)
+        finish(world)
         return
 
     n_cells = args.cells or 1000000 // world
@@ -642,7 +709,7 @@ def run_extra_workload(args):
         return idx, score, out
 
     step()  # warm-up: arena, planes, NCCL
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(range(world), active=rank == 0) as clocks:
         barrier()
         a, b = ev(), ev()
         a.record()
@@ -674,9 +741,8 @@ def run_extra_workload(args):
                           "streamed_equals_unstreamed_rank_shard": same, "topk_matches_fp64_oracle_sample_rank0_shard": oracle_ok,
                           "second_pass_queries_rank0": int(nfb), "clocks": clocks.summary(),
                           "hbm_note": "per object 6 172 B of generated points are written and read once (never leave the GPU); the stage stays "
-                                      "tensor-bound (~53 kFLOP/B), see roofline_other_kernels.db_encode of the default run"}))
-    if world > 1:
-        dist.destroy_process_group()
+                                      "tensor-bound (~53 kFLOP/B), see roofline_other_kernels.db_encode of the default run"}), flush=True)
+    finish(world)
 
 
 def main():
@@ -685,6 +751,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--graph", action="store_true",
+                    help="also capture the resident step in ONE CUDA graph and report its replay time as `value` (measured: no gain at N=1, "
+                         "1.7 %% at N=2 -- the step is GPU-bound, launches queue ahead -- so the default times the eager step)")
     ap.add_argument("--skip-extras", action="store_true", help="leave out the small configs[3] / configs[4] / configs[0]-CPU extras")
     ap.add_argument("--workload", default="coarse", choices=["coarse", "stream", "fine"],
                     help="coarse = the headline step (default); stream = BASELINE configs[3] at full per-GPU size; fine = configs[4]")

@@ -114,10 +114,14 @@ struct CallScope {
   t2l_engine* e;
   cudaStream_t st;
   bool ok = true;
+  bool capturing = false;  // inside a CUDA graph capture the stream order IS the graph order: no cross-stream events are recorded
   CallScope(t2l_engine* e_, void* stream) : e(e_), st(static_cast<cudaStream_t>(stream)) {
-    if (e->order_recorded && st != e->last_stream) ok = cudaStreamWaitEvent(st, e->order_ev, 0) == cudaSuccess;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess) capturing = cap != cudaStreamCaptureStatusNone;
+    if (!capturing && e->order_recorded && st != e->last_stream) ok = cudaStreamWaitEvent(st, e->order_ev, 0) == cudaSuccess;
   }
   ~CallScope() {
+    if (capturing) return;
     if (cudaEventRecord(e->order_ev, st) == cudaSuccess) { e->last_stream = st; e->order_recorded = true; }
   }
 };
