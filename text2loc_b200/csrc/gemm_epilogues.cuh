@@ -51,18 +51,23 @@ template <bool kHalfOut, bool kResidual>
 struct StoreEpiT {
   using Params = StoreParams;
   static constexpr int kStageBytes = 32 * 128;  // one 32 x 32 fp32 block per epilogue warp
-  static constexpr int kSmemBytes = kEpiBiasSmem + 4 * kStageBytes;
-  static constexpr bool kCompactLoop = false;
-  static constexpr int kSets = 1;
+  // The residual variants (out-proj, FFN2) are bound by how many residual bytes their epilogue keeps in flight -- one chunk
+  // (4 KB) per warp -- not by the MMAs (out-proj: 105 us against a 52 us HBM floor, profiles/r01).  They run TWO epilogue warp
+  // sets (even / odd 32-column chunks), which doubles the loads in flight; their bias then comes straight from L1 (__ldg, a
+  // broadcast) instead of a per-warp shared-memory slice, which keeps the second set's transpose tiles inside the 227 KB.
+  static constexpr int kSets = kResidual ? 2 : 1;
+  static constexpr bool kSmemBias = kSets == 1;
+  static constexpr int kSmemBytes = (kSmemBias ? kEpiBiasSmem : 0) + 4 * kSets * kStageBytes;
+  static constexpr bool kCompactLoop = kSets == 2;  // two inlined chunk() copies keep the 384-thread variant inside its 168 registers
   const Params& p;
   float* s_bias;
   uint8_t* stage;
-  int ew, lane, block_n;
+  int ew, lane, block_n, set;
   int bias_col0 = -1;  // column slice currently staged in s_bias (tiles of one N column share it)
   float4 res[8];       // residual of the chunk about to be processed (coalesced layout: row 4 j + lane / 8, chunk lane % 8)
-  __device__ StoreEpiT(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_, int)
-      : p(p_), s_bias(reinterpret_cast<float*>(smem) + ew_ * 256), stage(smem + kEpiBiasSmem + ew_ * kStageBytes), ew(ew_), lane(lane_),
-        block_n(block_n_) {}
+  __device__ StoreEpiT(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_, int set_)
+      : p(p_), s_bias(reinterpret_cast<float*>(smem) + ew_ * 256), stage(smem + (kSmemBias ? kEpiBiasSmem : 0) + (set_ * 4 + ew_) * kStageBytes),
+        ew(ew_), lane(lane_), block_n(block_n_), set(set_) {}
   __device__ void begin_unit(int, int) {}
   __device__ void end_unit(int, int) {}
   __device__ __forceinline__ void load_res(long row0, int col0) {
@@ -82,7 +87,7 @@ struct StoreEpiT {
     }
   }
   __device__ void prefetch_unit(int m_tile, int col0) {
-    if (!kResidual) return;
+    if (!kResidual || set != 0) return;  // one set pulls the next tile's residual rows into L2 for both
     const long row = static_cast<long>(m_tile) * 128 + ew * 32 + lane;
     if (row < p.M && col0 < p.N) {
       const int esz = p.res_half ? 2 : 4;
@@ -92,8 +97,8 @@ struct StoreEpiT {
     }
   }
   __device__ void begin_tile(int m_tile, int, int col0) {
-    if (kResidual) load_res(static_cast<long>(m_tile) * 128 + ew * 32, col0);  // chunk 0, in flight while the MMAs finish
-    if (col0 == bias_col0) return;
+    if (kResidual) load_res(static_cast<long>(m_tile) * 128 + ew * 32, col0 + set * 32);  // my first chunk, in flight while the MMAs finish
+    if (!kSmemBias || col0 == bias_col0) return;
     bias_col0 = col0;
     __syncwarp();
     for (int i = lane; i < block_n; i += 32) s_bias[i] = (p.bias && col0 + i < p.N) ? __ldg(p.bias + col0 + i) : 0.f;
@@ -103,6 +108,11 @@ struct StoreEpiT {
     const long row0 = static_cast<long>(m_tile) * 128 + ew * 32;
     if (row0 >= p.M || col0 >= p.N) return;  // warp-uniform
     const float4* sb = reinterpret_cast<const float4*>(s_bias + c * 32);
+    const float4* gb = reinterpret_cast<const float4*>(p.bias + col0);  // (only dereferenced when p.bias != nullptr)
+    auto bias4 = [&](int i) -> float4 {  // columns 4 i .. 4 i + 3 of this chunk: the same address in every lane (broadcast)
+      if (kSmemBias) return sb[i];
+      return p.bias ? __ldg(gb + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
     if (kHalfOut) {
       // own row -> 64 bytes = four 16-byte chunks at position i ^ ((row >> 1) & 3)
 #pragma unroll
@@ -110,7 +120,7 @@ struct StoreEpiT {
         float o[8];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const float4 b = sb[2 * i + h];
+          const float4 b = bias4(2 * i + h);
           o[4 * h + 0] = v[8 * i + 4 * h + 0] + b.x; o[4 * h + 1] = v[8 * i + 4 * h + 1] + b.y;
           o[4 * h + 2] = v[8 * i + 4 * h + 2] + b.z; o[4 * h + 3] = v[8 * i + 4 * h + 3] + b.w;
         }
@@ -142,11 +152,11 @@ struct StoreEpiT {
     if (kResidual) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) cur[j] = res[j];
-      if ((c + 1) * 32 < block_n) load_res(row0, col0 + 32);  // next chunk's residual in flight during this one
+      if ((c + kSets) * 32 < block_n) load_res(row0, col0 + 32 * kSets);  // my next chunk's residual in flight during this one
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 b = sb[i];  // same address in every lane: broadcast
+      const float4 b = bias4(i);
       float4 o = make_float4(v[4 * i] + b.x, v[4 * i + 1] + b.y, v[4 * i + 2] + b.z, v[4 * i + 3] + b.w);
       if (p.act == kActRelu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
       *reinterpret_cast<float4*>(stage + lane * 128 + ((i ^ (lane & 7)) << 4)) = o;

@@ -23,7 +23,10 @@
 
 namespace t2l {
 
-constexpr int kCand = 16;         // candidates kept per (query, split)
+constexpr int kCand = 16;         // width of the exact-scan / merge lists (k <= kCand)
+constexpr int kList = 12;         // approximate candidates kept per register list; a query row has 2 lists per database split (24 candidates).
+                                  // Measured at 32 768 x 100 000 / x 12 500: 16 -> 1.92 / 0.62 ms; 8 -> 2.30 / 0.54 ms (a fifth of the queries then fail
+                                  // the proof: one half of the columns often holds 8 of the top ~12)
 constexpr int kMaxSplits = 16;
 constexpr int kMaxK = 12;
 // bf16 hi|lo three-pass product: x = hi + lo + r with |r| <= 2^-16 |x| (two roundings at u = 2^-8).  The dropped terms
@@ -109,8 +112,8 @@ cudaError_t search_prepare_db(const SearchDb& db, cudaStream_t st, Launches* lc)
 }
 
 // ---- candidate epilogue -------------------------------------------------------------------------
-// Each epilogue thread owns one query row (and one of the two column sets, below) and keeps its 16 best approximate scores
-// of the current split in REGISTERS as a descending sorted list; inserting is a branch-free 16-step compare-exchange chain
+// Each epilogue thread owns one query row (and one of the two column sets, below) and keeps its kList = 12 best approximate scores
+// of the current split in REGISTERS as a descending sorted list; inserting is a branch-free 12-step compare-exchange chain
 // taken only when a score beats the list minimum (the drop threshold).  Everything the thread ever dropped is therefore <=
 // the final minimum, which is what the re-rank proof needs.
 //
@@ -118,15 +121,16 @@ cudaError_t search_prepare_db(const SearchDb& db, cudaStream_t st, Launches* lc)
 // draining the accumulator from tensor memory at 64 B/clk already uses all of them), and one warp per SM sub-partition --
 // latency-bound on its dependent compare chains -- needed ~3x that (measured: 2.9 ms of epilogue behind 1.0 ms of MMAs at
 // 32 768 x 100 000).  Hence: (1) TWO epilogue warp sets (warps 4..7 take the even 32-column chunks of a tile, warps 8..11 the
-// odd ones; every row then has two lists per split, 32 candidates); (2) a 3-input max tree (~16 instructions) decides the
+// odd ones; every row then has two lists per split, 2 x 12 = 24 candidates; a shorter list means fewer insertions while it warms
+// up, ~L (1 + ln(n / L)), and a shorter chain per insertion); (2) a 3-input max tree (~16 instructions) decides the
 // common "nothing in this chunk beats the minimum" case before any per-element work; (3) two inlined copies of chunk() instead
 // of eight (instruction cache).  Measured: 1.92 ms for the whole search at 32 768 x 100 000 (3.5 ms with the three-pass
 // candidates of round 1).  A variant that parked hits in shared memory and inserted them once per tile for all 32 rows
 // together was slower (2.7 ms): its per-chunk parking code outweighed the chains it saved.
 struct TopKEpi {
   struct Params {
-    float* cand_score;  // [nq, n_lists, kCand]     n_lists = n_splits * kSets: one list per (database split, column set)
-    int32_t* cand_idx;  // [nq, n_lists, kCand]     -1 = empty
+    float* cand_score;  // [nq, n_lists, kList]     n_lists = n_splits * kSets: one list per (database split, column set)
+    int32_t* cand_idx;  // [nq, n_lists, kList]     -1 = empty
     float* cand_thr;    // [nq, n_lists]            -inf = nothing was dropped
     int nq, n_db, n_splits;
   };
@@ -137,8 +141,8 @@ struct TopKEpi {
   float* s_v;
   int t;  // 0..127: row inside this CTA's 128-row tile
   int set;
-  float ls[kCand];
-  int li[kCand];
+  float ls[kList];
+  int li[kList];
   bool active;
 
   __device__ TopKEpi(const Params& p_, uint8_t* smem, int ew, int lane, int, int set_)
@@ -147,12 +151,12 @@ struct TopKEpi {
   __device__ void begin_unit(int m_tile, int) {
     active = (m_tile * 128 + t) < p.nq;
 #pragma unroll
-    for (int i = 0; i < kCand; ++i) { ls[i] = active ? -INFINITY : INFINITY; li[i] = -1; }
+    for (int i = 0; i < kList; ++i) { ls[i] = active ? -INFINITY : INFINITY; li[i] = -1; }
   }
   __device__ void begin_tile(int, int, int) {}
   __device__ __forceinline__ void insert(float x, int xi) {
 #pragma unroll
-    for (int i = 0; i < kCand; ++i) {  // x sinks through the descending list; the old minimum falls out
+    for (int i = 0; i < kList; ++i) {  // x sinks through the descending list; the old minimum falls out
       const bool gt = x > ls[i];
       const float s_keep = gt ? x : ls[i], s_next = gt ? ls[i] : x;
       const int i_keep = gt ? xi : li[i], i_next = gt ? li[i] : xi;
@@ -164,7 +168,7 @@ struct TopKEpi {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = (col0 + i < p.n_db) ? v[i] : -INFINITY;
     }
-    const float thr = ls[kCand - 1];
+    const float thr = ls[kList - 1];
     float m8[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) m8[i] = fmaxf(fmaxf(v[4 * i], v[4 * i + 1]), fmaxf(v[4 * i + 2], v[4 * i + 3]));
@@ -181,7 +185,7 @@ struct TopKEpi {
       const int i = __ffs(mask) - 1;
       mask &= mask - 1;
       const float x = s_v[i * 128 + t];
-      if (x > ls[kCand - 1]) insert(x, col0 + i);
+      if (x > ls[kList - 1]) insert(x, col0 + i);
     }
   }
   __device__ void end_unit(int m_tile, int split) {
@@ -189,11 +193,11 @@ struct TopKEpi {
     const long row = static_cast<long>(m_tile) * 128 + t;
     const long list = row * (p.n_splits * kSets) + split * kSets + set;
 #pragma unroll
-    for (int i = 0; i < kCand; ++i) {
-      p.cand_score[list * kCand + i] = ls[i];
-      p.cand_idx[list * kCand + i] = li[i];
+    for (int i = 0; i < kList; ++i) {
+      p.cand_score[list * kList + i] = ls[i];
+      p.cand_idx[list * kList + i] = li[i];
     }
-    p.cand_thr[list] = (li[kCand - 1] >= 0) ? ls[kCand - 1] : -INFINITY;  // list not full: nothing was dropped
+    p.cand_thr[list] = (li[kList - 1] >= 0) ? ls[kList - 1] : -INFINITY;  // list not full: nothing was dropped
   }
 };
 
@@ -258,7 +262,7 @@ __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const float* 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * kRerankWarps + w;
   if (q >= nq) return;
-  const int C = n_splits * kCand;
+  const int C = n_splits * kList;
   const float* qr = Q + static_cast<long>(q) * kEmbed;
   for (int c = 0; c < C; ++c) {
     const int idx = cand_idx[static_cast<long>(q) * C + c];  // warp-uniform

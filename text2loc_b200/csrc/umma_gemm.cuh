@@ -246,7 +246,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * Cfg::BLOCK_N;
         // software-pipelined drain: the TMEM load of chunk c+1 is in flight while chunk c is processed
         float v[2][32];
-        if constexpr (!Epi::kCompactLoop) tmem_ld_32x32(t_addr, v[0]);
+        if constexpr (!Epi::kCompactLoop && Epi::kSets == 1) tmem_ld_32x32(t_addr, v[0]);
         if constexpr (Epi::kCompactLoop) {
           // two inlined copies of chunk() instead of BLOCK_N / 32: an epilogue whose chunk() is hundreds of instructions long
           // (the top-k list maintenance) would otherwise not fit the instruction cache (measured: 2.3x slower unrolled 8x)
@@ -263,11 +263,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             epi.chunk(m_tile, nt, c + ST, nt * Cfg::BLOCK_N + (c + ST) * 32, v[1]);
           }
         } else {
+          constexpr int NC = Cfg::BLOCK_N / 32, ST = Epi::kSets;
+          static_assert(NC % ST == 0, "chunks must split evenly over the epilogue sets");
+          if constexpr (ST > 1) tmem_ld_32x32(t_addr + set * 32, v[0]);
 #pragma unroll
-          for (int c = 0; c < Cfg::BLOCK_N / 32; ++c) {
-            tmem_ld_wait(v[c & 1]);
-            if (c + 1 < Cfg::BLOCK_N / 32) tmem_ld_32x32(t_addr + (c + 1) * 32, v[(c + 1) & 1]);
-            epi.chunk(m_tile, nt, c, nt * Cfg::BLOCK_N + c * 32, v[c & 1]);
+          for (int i = 0; i < NC / ST; ++i) {
+            const int c = ST == 1 ? i : set + i * ST;  // compile-time for single-set epilogues (their chunk() folds it into addresses)
+            tmem_ld_wait(v[i & 1]);
+            if (i + 1 < NC / ST) tmem_ld_32x32(t_addr + (c + ST) * 32, v[(i + 1) & 1]);
+            epi.chunk(m_tile, nt, c, nt * Cfg::BLOCK_N + c * 32, v[i & 1]);
           }
         }
         tc_fence_before();
