@@ -53,6 +53,10 @@ int t2l_version(void);
 int t2l_set_weight(t2l_engine* e, const char* name, const float* data_host, int rows, int cols);
 int t2l_finalize_weights(t2l_engine* e);
 
+/* Optional: size the engine's workspace once for the largest calls to come (objects / cells per t2l_encode_cells call,
+ * sentences x tokens per text call, queries per search), so that no later call re-allocates.  Synchronises the device. */
+int t2l_reserve(t2l_engine* e, int max_objects, int max_cells, int max_sentences, int max_tokens_per_sentence, int max_queries);
+
 /* CellRetrievalNetwork.encode_objects (models/cell_retrieval.py:65-110) = PointNet2 features2
  * (models/pointcloud/pointnet2.py:80-90) -> ObjectEncoder.forward (models/object_encoder.py:92-149)
  * -> intra-cell attention, max over slots, L2 normalise.

@@ -28,6 +28,7 @@ SIGNATURES = {
     "t2l_version": (c_int, []),
     "t2l_set_weight": (c_int, [_P, c_char_p, POINTER(c_float), c_int, c_int]),
     "t2l_finalize_weights": (c_int, [_P]),
+    "t2l_reserve": (c_int, [_P, c_int, c_int, c_int, c_int, c_int]),
     "t2l_encode_cells": (c_int, [_P, _P, _P, POINTER(c_int32), c_int, _P, _P]),
     "t2l_encode_objects_debug": (c_int, [_P, _P, POINTER(c_int32), c_int] + [_P] * 10 + [_P]),
     "t2l_encode_text": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),

@@ -929,6 +929,37 @@ extern "C" int t2l_fine_offsets(t2l_engine* e, const float* pts, const float* me
 // ---------------------------------------------------------------------------------------------
 // search
 // ---------------------------------------------------------------------------------------------
+static int ensure_search_work(t2l_engine* e, int nq);
+
+// Size the workspace once for the largest calls to come, so that no later call re-allocates (and synchronises).
+extern "C" int t2l_reserve(t2l_engine* e, int max_objects, int max_cells, int max_sentences, int max_tokens_per_sentence, int max_queries) {
+  if (!e) return 1;
+  if (max_objects < 0 || max_cells < 0 || max_sentences < 0 || max_tokens_per_sentence < 0 || max_queries < 0) return fail(e, "reserve: bad argument");
+  ENTER(e);
+  size_t need = 0;
+  if (max_objects > 0) {
+    const size_t n = static_cast<size_t>(max_objects < e->obj_chunk ? max_objects : e->obj_chunk);
+    need = obj_chunk_bytes(n, static_cast<size_t>(max_cells < static_cast<int>(n) ? max_cells : static_cast<int>(n)));
+  }
+  if (max_sentences > 0 && max_tokens_per_sentence > 0) {
+    int sc = e->tok_chunk / max_tokens_per_sentence;
+    if (sc < 1) sc = 1;
+    if (sc > max_sentences) sc = max_sentences;
+    const size_t t = static_cast<size_t>(sc) * max_tokens_per_sentence * (12 * static_cast<size_t>(T2L_T5_DIM)) * 4 + (size_t(1) << 22);
+    if (t > need) need = t;
+    const size_t s2 = static_cast<size_t>(max_sentences) * (64 * 256) * 4 + (size_t(1) << 22);
+    if (s2 > need) need = s2;
+    if (static_cast<size_t>(max_sentences) > e->pooled_cap) {
+      if (e->pooled) { CU(cudaDeviceSynchronize()); CU(cudaFree(e->pooled)); e->pooled = nullptr; }
+      CU(cudaMalloc(&e->pooled, (static_cast<size_t>(max_sentences) + 1024) * T2L_T5_DIM * sizeof(float)));
+      e->pooled_cap = static_cast<size_t>(max_sentences) + 1024;
+    }
+  }
+  if (need && ensure_arena(e, need)) return 1;
+  if (max_queries > 0 && ensure_search_work(e, max_queries)) return 1;
+  return 0;
+}
+
 extern "C" int t2l_db_build(t2l_engine* e, const float* D, int64_t n_rows, int64_t row_offset, void* stream) {
   if (!e) return 1;
   if (n_rows < 0 || (n_rows > 0 && !D) || n_rows > 0x7fffff00LL) return fail(e, "db_build: bad argument");

@@ -74,11 +74,15 @@ struct Sa2Cfg {
   static constexpr int CNT_BYTES = M;
   static constexpr int SPX_BYTES = M * C1 * 2;         // self-loop source rows: half of the source object's Qx block
   static constexpr int SORG_BYTES = 16;                // origin of the source object (its centroid 0)
-  static constexpr int OBJ_BYTES = PX_BYTES + CPOS_BYTES + NBR_BYTES + CNT_BYTES + SPX_BYTES + SORG_BYTES;
+  // block layout: Qx | self-loop Qx rows | centroids | lists | counts | source origin, padded to a multiple of 128 bytes: the
+  // row blocks then start on 128-byte lines in BOTH buffers, so a quarter-warp's 128-byte row read is one shared-memory
+  // wavefront (ncu: 28 % of the gather's wavefronts were the second halves of rows straddling two lines)
+  static constexpr int OBJ_RAW = PX_BYTES + SPX_BYTES + CPOS_BYTES + NBR_BYTES + CNT_BYTES + SORG_BYTES;
+  static constexpr int OBJ_BYTES = (OBJ_RAW + 127) / 128 * 128;
   static constexpr int NOBJ = 2;
   static constexpr int SIDE_BYTES = M * C2 * 4;        // post-ReLU self-loop results, [centroid][channel]
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TABLE_BYTES = C1 * 12;          // w1p as channel pairs: x2[C1/2] | y2[C1/2] | z2[C1/2]
+  static constexpr int TABLE_BYTES = (C1 < 64 ? 64 : C1) * 12;  // W1p, 768 bytes per 64-channel slice (layout: kernel prologue)
   static constexpr int FIXED = 1024 + NOBJ * OBJ_BYTES + SIDE_BYTES + BAR_BYTES + TABLE_BYTES;
   static constexpr int FIT = (227 * 1024 - FIXED) / A_BYTES;
   static constexpr int STAGES = FIT > 8 ? 8 : FIT;
@@ -179,10 +183,13 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr, 512);
-  for (int c = threadIdx.x; c < C1; c += kSa2Threads) {  // b1 is already folded into Px
-    table[c] = p.Wp[c * 4 + 0];
-    table[C1 + c] = p.Wp[c * 4 + 1];
-    table[2 * C1 + c] = p.Wp[c * 4 + 2];
+  // W1p, laid out for the gather's reads: [64-channel slice][x|y|z][channel half 0|1][8-channel group][4 channels].  The eight
+  // lanes of a quarter-warp (one 8-channel group each) then read 128 contiguous bytes per load -- with channel-major rows
+  // their 32-byte stride made every one of the six loads a 2-way bank conflict (ncu: 13M of the 21M conflict wavefronts).
+  for (int c = threadIdx.x; c < C1; c += kSa2Threads) {
+    const int slice = c >> 6, grp = (c & 63) >> 3, half = (c & 7) >> 2, e = c & 3;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) table[((((slice * 3 + a) * 2 + half) * 8 + grp) << 2) + e] = p.Wp[c * 4 + a];
   }
   tc_fence_before();
   __syncthreads();
@@ -239,17 +246,17 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
       mbar_wait(&obj_empty[buf], (((n / Cfg::NOBJ) & 1) ^ 1));
       if (elect_one()) {
         uint8_t* dst = obj_base + buf * Cfg::OBJ_BYTES;
-        mbar_arrive_expect_tx(&obj_full[buf], Cfg::OBJ_BYTES);
+        mbar_arrive_expect_tx(&obj_full[buf], Cfg::OBJ_RAW);
         bulk_load2(dst, p.Qx16 + static_cast<long>(o) * P * C1, Cfg::PX_BYTES, &obj_full[buf]);
         dst += Cfg::PX_BYTES;
+        bulk_load2(dst, p.Qx16 + src * C1, Cfg::SPX_BYTES, &obj_full[buf]);
+        dst += Cfg::SPX_BYTES;
         bulk_load2(dst, p.cpos + static_cast<long>(o) * M * 3, Cfg::CPOS_BYTES, &obj_full[buf]);
         dst += Cfg::CPOS_BYTES;
         bulk_load2(dst, p.nbr + static_cast<long>(o) * M * 32, Cfg::NBR_BYTES, &obj_full[buf]);
         dst += Cfg::NBR_BYTES;
         bulk_load2(dst, p.cnt + static_cast<long>(o) * M, Cfg::CNT_BYTES, &obj_full[buf]);
         dst += Cfg::CNT_BYTES;
-        bulk_load2(dst, p.Qx16 + src * C1, Cfg::SPX_BYTES, &obj_full[buf]);
-        dst += Cfg::SPX_BYTES;
         bulk_load2(dst, p.cpos + static_cast<long>(src_obj) * M * 3, Cfg::SORG_BYTES, &obj_full[buf]);  // centroid 0 of the source object
       }
       __syncwarp();
@@ -362,13 +369,11 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
     const int cq = rb >> 2, r0 = cq * 32 + (rb & 3);     // my rows: r0 + 4 i
     const int set = PAIR ? (sub >> 2) : 0;
     const int ch0 = (PAIR ? (sub & 3) : sub) * 8;         // my 8 channels inside a 64-channel slice of a Qx row
-    const ulonglong2* tab2 = reinterpret_cast<const ulonglong2*>(table);  // (wx | wy | wz) of two channel pairs per 16-byte load
+    const ulonglong2* tab2 = reinterpret_cast<const ulonglong2*>(table);
     // -v for my 8 channels: W1p . (o' - pos_i), fp32, rounded once to fp16 (saturating)
-    auto neg_v8 = [&](int c0, float ex, float ey, float ez, uint32_t (&nv)[4]) {
-      const int pair0 = c0 >> 2;  // index in ulonglong2 units (2 channel pairs each)
-      const ulonglong2 wx01 = tab2[pair0], wx23 = tab2[pair0 + 1];
-      const ulonglong2 wy01 = tab2[C1 / 4 + pair0], wy23 = tab2[C1 / 4 + pair0 + 1];
-      const ulonglong2 wz01 = tab2[C1 / 2 + pair0], wz23 = tab2[C1 / 2 + pair0 + 1];
+    auto neg_v8 = [&](int slice, float ex, float ey, float ez, uint32_t (&nv)[4]) {
+      const ulonglong2* tb = tab2 + slice * 48 + (PAIR ? (sub & 3) : sub);  // 48 = 3 coordinates x 2 halves x 8 groups
+      const ulonglong2 wx01 = tb[0], wx23 = tb[8], wy01 = tb[16], wy23 = tb[24], wz01 = tb[32], wz23 = tb[40];
       const uint64_t wx[4] = {wx01.x, wx01.y, wx23.x, wx23.y}, wy[4] = {wy01.x, wy01.y, wy23.x, wy23.y},
                      wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
 #pragma unroll
@@ -385,11 +390,11 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
       const int buf = n % Cfg::NOBJ;
       const uint8_t* ob = obj_base + buf * Cfg::OBJ_BYTES;
       const uint8_t* px_s = ob;
-      const float* cpos_s = reinterpret_cast<const float*>(ob + Cfg::PX_BYTES);
-      const uint8_t* nbr_s = ob + Cfg::PX_BYTES + Cfg::CPOS_BYTES;
+      const uint8_t* spx_s = ob + Cfg::PX_BYTES;
+      const float* cpos_s = reinterpret_cast<const float*>(spx_s + Cfg::SPX_BYTES);
+      const uint8_t* nbr_s = reinterpret_cast<const uint8_t*>(cpos_s) + Cfg::CPOS_BYTES;
       const uint8_t* cnt_s = nbr_s + Cfg::NBR_BYTES;
-      const uint8_t* spx_s = cnt_s + Cfg::CNT_BYTES;
-      const float* sorg_s = reinterpret_cast<const float*>(spx_s + Cfg::SPX_BYTES);
+      const float* sorg_s = reinterpret_cast<const float*>(cnt_s + Cfg::CNT_BYTES);
       mbar_wait(&obj_full[buf], (n / Cfg::NOBJ) & 1);
 #pragma unroll 1
       for (int tt = 0; tt < kTilesPerObj; ++tt, ++tile) {
@@ -413,7 +418,7 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
                 const int cen = PAIR ? 8 * (r >> 2) + 4 * set + (r & 3) : r;  // same centroid split between the lane groups as the neighbour tiles
                 const uint4 raw = *reinterpret_cast<const uint4*>(spx_s + cen * (C1 * 2) + (PAIR ? 0 : kb * 128) + ch0 * 2);
                 uint32_t nv[4];
-                neg_v8((PAIR ? 0 : kb * 64) + ch0, ox - cpos_s[cen * 3 + 0], oy - cpos_s[cen * 3 + 1], oz - cpos_s[cen * 3 + 2], nv);
+                neg_v8(PAIR ? 0 : kb, ox - cpos_s[cen * 3 + 0], oy - cpos_s[cen * 3 + 1], oz - cpos_s[cen * 3 + 2], nv);
                 *reinterpret_cast<uint4*>(abase + r * 128 + ((sub ^ (r & 7)) << 4)) =
                     make_uint4(s2_sub_relu_h2(raw.x, nv[0]), s2_sub_relu_h2(raw.y, nv[1]), s2_sub_relu_h2(raw.z, nv[2]), s2_sub_relu_h2(raw.w, nv[3]));
               }
@@ -444,7 +449,7 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
 #pragma unroll
             for (int i = 0; i < 8; ++i) raw[i] = *reinterpret_cast<const uint4*>(px_s + src_off[i] + (PAIR ? 0 : kb * 128));
             uint32_t nv[4];
-            neg_v8((PAIR ? 0 : kb * 64) + ch0, ex, ey, ez, nv);
+            neg_v8(PAIR ? 0 : kb, ex, ey, ez, nv);
             mbar_wait(&empty_bar[stage], (static_cast<uint32_t>(u / Cfg::STAGES) & 1) ^ 1);
             uint8_t* abase = stage_base + stage * Cfg::A_BYTES;
 #pragma unroll

@@ -83,6 +83,10 @@ class Engine:
         self._check(self._lib.t2l_finalize_weights(self._h))
         self.has_weights = True
 
+    def reserve(self, max_objects: int = 0, max_cells: int = 0, max_sentences: int = 0, max_tokens: int = 0, max_queries: int = 0):
+        """Size the workspace up front (t2l_reserve) so that steady-state calls never re-allocate."""
+        self._check(self._lib.t2l_reserve(self._h, max_objects, max_cells, max_sentences, max_tokens, max_queries))
+
     # ---- encoders -------------------------------------------------------------------------
     def encode_cells(self, pts, meta, cell_ptr) -> torch.Tensor:
         """pts [n,256,6], meta [n,7], cell_ptr int32 [B+1] (host) -> unit rows [B,256] on device."""
