@@ -191,6 +191,12 @@ int t2l_debug_linear(t2l_engine* e, int path, const float* A, int lda, const flo
 int t2l_debug_linear_f16(t2l_engine* e, const void* A, int lda, const void* W, int ldw, const float* bias,
                          void* C, int ldc, int M, int N, int K, int act, int out_half, void* stream);
 
+/* Test hook for the fp16 residual stream of the token layer: C = fp16(A W^T + bias + R) with A f16 [M, lda], W f16 [N, ldw],
+ * R f16 [M, ldr], C f16 [M, ldc] (acc + bias + R summed in fp32, one rounding, saturating).  reg_epilogue = 0: residual and
+ * output move by TMA (the product path when M > 128 and N % 256 == 0); != 0: the register-staged epilogue. */
+int t2l_debug_linear_f16_residual(t2l_engine* e, const void* A, int lda, const void* W, int ldw, const float* bias, const void* R,
+                                  int ldr, void* C, int ldc, int M, int N, int K, int reg_epilogue, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,29 @@ def test_umma_gemm_f16_operands(eng, M, N, K):
         assert torch.isfinite(big).all() and big.max().item() == 65504.0
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (300, 1024, 1024), (1000, 512, 264), (32760, 1024, 1024), (777, 1024, 4096), (129, 256, 128),
+                                   (96, 256, 64), (40000, 256, 64)])
+def test_umma_gemm_f16_residual_stream(eng, M, N, K):
+    """Out-projection / FFN2 on the token layer's fp16 residual stream: fp16(A W^T + bias + R), the sum formed in fp32 and
+    rounded once.  The TMA epilogue (residual slabs in, result slabs out, in place in shared memory) and the register-staged
+    one must both equal the fp64 result rounded to fp16 up to fp32 accumulation error -- including ragged M (rows beyond M are
+    zero-filled on the way in and clipped on the way out) and many tiles per CTA (slab barrier phases)."""
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, device="cuda", generator=g).half()
+    W = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).half()
+    R = (3.0 * torch.randn(M, N, device="cuda", generator=g)).half()
+    b = torch.randn(N, device="cuda", generator=g)
+    want = A.double() @ W.double().T + b.double() + R.double()
+    tol = 2e-5 * max(1.0, K / 256) ** 0.5 + 2.0 ** -11 * want.abs().max().item()
+    for reg in (False, True):
+        C = eng.debug_linear_f16_residual(A, W, b, R, reg_epilogue=reg)  # (the hook also checks that rows beyond M stay untouched)
+        err = (C.double() - want).abs().max().item()
+        print(f"\n[f16+residual {M}x{N}x{K} {'registers' if reg else 'tma'}] |C-fp64|={err:.3e} (tol {tol:.3e})")
+        assert C.dtype == torch.float16 and err < tol
+    # the two epilogues round the same fp32 sums: bit-identical
+    assert torch.equal(eng.debug_linear_f16_residual(A, W, b, R, reg_epilogue=False), eng.debug_linear_f16_residual(A, W, b, R, reg_epilogue=True))
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (4224 * 4, 64, 32), (2112 * 3, 128, 128), (1056, 256, 256), (64, 1024, 512)])
 def test_umma_segmax_epilogue(eng, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)

@@ -88,6 +88,24 @@ def test_encode_text_tf32_path_also_within_tolerance(state_dict, golden, monkeyp
     assert err < EMB_TOL
 
 
+def test_encode_text_fp32_stream_variant(eng, state_dict, golden, monkeypatch):
+    """Default: the token layer's residual stream (x + attn, LayerNorm1, x1 + ffn) is carried as fp16 rows; T2L_TEXT_STREAM32=1
+    keeps it in fp32.  Both meet the tolerance against the reference's fp32 modules; the fp32 stream is the closer one."""
+    from oracle import fake_t5
+    from text2loc_b200.engine import Engine
+
+    g = golden("text_small.npz")
+    feat, n_sent = fake_t5.FakeFrontend(int(g["fake_t5_seed"]))([str(t) for t in g["texts"]])
+    err16 = row_rel_err(eng.encode_text(feat, n_sent).cpu().numpy(), g["text_emb"])
+    monkeypatch.setenv("T2L_TEXT_STREAM32", "1")
+    e32 = Engine("cuda:0")
+    e32.load_state_dict(state_dict)
+    err32 = row_rel_err(e32.encode_text(feat, n_sent).cpu().numpy(), g["text_emb"])
+    print(f"\ntext embedding error: fp16 residual stream {err16:.3e}, fp32 residual stream {err32:.3e}")
+    assert err16 < EMB_TOL and err32 < EMB_TOL
+    assert err32 < err16 * 1.05
+
+
 def test_encode_text_feature_magnitudes(eng, state_dict):
     """fp16 operands: features 4x larger / 100x smaller than the synthetic default stay in tolerance (fp16 has the
     range for anything a LayerNorm-ed T5 state can hold); absurd magnitudes saturate at 65504 instead of producing inf."""

@@ -209,6 +209,57 @@ def test_precision_plan_token_layer_operand_rounding(state_dict, monkeypatch):
     assert e_bf16 > 1e-3
 
 
+def test_precision_plan_token_layer_fp16_residual_stream(state_dict, monkeypatch):
+    """The engine's default token layer also carries the residual stream as fp16 rows: fp16 T5 states, q/k/v stored fp16,
+    y = r16(x + attn), x1 = r16(LN(y)), y2 = r16(x1 + ffn), statistics and sums in fp32.  Emulating exactly those rounding
+    points keeps the text embeddings inside the 1e-3 tolerance with a 2x margin (about 1.5x the error of the fp32 stream)."""
+    import math
+
+    import torch.nn.functional as F_
+
+    from oracle.restate import _t
+
+    def r16(t):
+        return t.half().float()
+
+    real_layer = restate.encoder_layer
+
+    def make_layer(stream16):
+        def layer(sd, prefix, x, n_heads):
+            if "intra_module" not in prefix:
+                return real_layer(sd, prefix, x, n_heads)
+            S, B, d = x.shape
+            hd = d // n_heads
+
+            def lin(a, w, b):
+                return F_.linear(r16(a), r16(_t(sd, prefix + w)), _t(sd, prefix + b))
+
+            x = r16(x) if stream16 else x
+            qkv = r16(lin(x, ".self_attn.in_proj_weight", ".self_attn.in_proj_bias"))
+            q, k, v = (t.reshape(S, B, n_heads, hd).permute(1, 2, 0, 3) for t in qkv.split(d, dim=-1))
+            att = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+            o = lin((att @ v).permute(2, 0, 1, 3).reshape(S, B, d), ".self_attn.out_proj.weight", ".self_attn.out_proj.bias")
+            y = r16(x + o) if stream16 else x + o
+            x1 = F_.layer_norm(y, (d,), _t(sd, prefix + ".norm1.weight"), _t(sd, prefix + ".norm1.bias"), 1e-5)
+            x1 = r16(x1) if stream16 else x1
+            f = lin(r16(F_.relu(lin(x1, ".linear1.weight", ".linear1.bias"))), ".linear2.weight", ".linear2.bias")
+            y2 = r16(x1 + f) if stream16 else x1 + f
+            return F_.layer_norm(y2, (d,), _t(sd, prefix + ".norm2.weight"), _t(sd, prefix + ".norm2.bias"), 1e-5)
+        return layer
+
+    t5 = synth.make_t5_features(5, 16, 6, 12)
+    want = restate.encode_text(state_dict, t5, 6).numpy()
+    errs = {}
+    for stream16 in (False, True):
+        monkeypatch.setattr(restate, "encoder_layer", make_layer(stream16))
+        got = restate.encode_text(state_dict, t5, 6).numpy()
+        monkeypatch.setattr(restate, "encoder_layer", real_layer)
+        errs[stream16] = float((np.linalg.norm(got - want, axis=1) / np.linalg.norm(want, axis=1)).max())
+    print(f"\ntoken layer residual stream, text embedding error: fp32 {errs[False]:.2e}, fp16 {errs[True]:.2e}")
+    assert errs[False] < 4e-4
+    assert errs[True] < 6e-4
+
+
 def _emulated_cell_error(state_dict, r16, monkeypatch):
     """Row-relative error of the cell embeddings when the set-abstraction and global-abstraction MLPs use the engine's
     rounding points (sa_obj.cu / GA on fp16 operands): Px = r16(W1x x + b1), edge activation r16(relu(Px + W1p.d)),

@@ -65,9 +65,14 @@ struct t2l_engine {
   int obj_chunk = 16384;     // objects per encode chunk (cell-aligned); 2048 -> 4096 -> 8192 -> 16384 is +9 % / +5 % / +4 % cells/s (fuller
                              // grids for the small kernels), ~48 GB of workspace (T2L_OBJ_CHUNK to change)
   bool dist_fma = false;     // FPS / ball-query distances with FMA contraction (T2L_DIST_FMA=1; oracle: pyg_ops.DIST_FMA)
-  int tok_chunk = 32768;     // tokens per text chunk (sentence-aligned)
+  int tok_chunk = 75776;     // tokens per text chunk (sentence-aligned): 296 row tiles of 256 = whole waves of 74 CTA pairs for all four
+                             // token GEMMs; 32768 -> 75776 is ~5 % on the text head (fewer launch tails), larger gains nothing
+                             // (scripts/tok_chunk_sweep.py); T2L_TOK_CHUNK to change
   bool text_f16 = true;      // token layer on fp16 operands (same 11-bit significand as tf32, twice the MMA rate, half the
                              // operand bytes); T2L_TEXT_TF32=1 selects the tf32 path for A/B checks
+  bool text_stream16 = true; // token layer's residual stream (x + attn, LayerNorm1, x1 + ffn) carried as fp16 rows between the GEMMs and
+                             // the LayerNorms; T2L_TEXT_STREAM32=1 keeps it in fp32 (round 1's layout)
+  bool text_reg_epilogue = false;  // T2L_TEXT_REG_EPI=1: register-staged residual epilogue instead of the TMA one (A/B)
   float* pooled = nullptr;   // [pooled_cap, 1024] max-over-tokens sentence features between the two text stages
   size_t pooled_cap = 0;
   // pinned staging ring for the per-chunk index arrays of encode_cells: a pageable cudaMemcpyAsync larger than 64 KB
@@ -192,7 +197,10 @@ extern "C" int t2l_create(int device, t2l_engine** out) {
   e = new t2l_engine();
   e->device = device;
   if (const char* v = getenv("T2L_TEXT_TF32")) e->text_f16 = !(v[0] == '1');
+  if (const char* v = getenv("T2L_TEXT_STREAM32")) e->text_stream16 = !(v[0] == '1');
+  if (const char* v = getenv("T2L_TEXT_REG_EPI")) e->text_reg_epilogue = v[0] == '1';
   if (const char* v = getenv("T2L_DIST_FMA")) e->dist_fma = v[0] == '1';
+  if (const char* v = getenv("T2L_TOK_CHUNK")) { const int n = atoi(v); if (n >= 256 && n <= (1 << 20)) e->tok_chunk = n; }
   if (const char* v = getenv("T2L_OBJ_CHUNK")) { const int n = atoi(v); if (n >= 64 && n <= 65536) e->obj_chunk = n; }
   if (const char* v = getenv("T2L_SEARCH_FIRST")) e->search_first = v[0] == 'f' ? 1 : (v[0] == 'b' ? 2 : 0);
   if (cudaMalloc(&e->db.max_norm, sizeof(float)) != cudaSuccess || cudaMalloc(&e->db.scale, sizeof(float)) != cudaSuccess ||
@@ -430,6 +438,7 @@ static cudaError_t lin_h(t2l_engine* e, const __half* A, long lda, int M, const 
   l.bias = bname.empty() ? nullptr : W(e, bname).dev;
   l.C = static_cast<float*>(C); l.ldc = ldc; l.M = M; l.N = w.rows; l.K = w.cols; l.act = act; l.residual = residual; l.ldr = ldr;
   l.half_ops = 1; l.out_half = out_half; l.segmax = segmax; l.round_out = segmax ? 1 : 0; l.residual_half = residual_half;
+  l.reg_epilogue = e->text_reg_epilogue ? 1 : 0;
   return linear_umma(l, st, &e->lc);
 }
 
@@ -464,6 +473,18 @@ static int encoder_layer(t2l_engine* e, const std::string& pfx, bool fast, const
     }
     CU(lin_h(e, xh, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, /*out_half=*/1, st));
     CU(mha_tc256(qkv, att, n_seq, S, st, &e->lc, /*round_out=*/2, /*half_in=*/1));
+    if (e->text_stream16 && pooled_out) {
+      // fp16 residual stream: x + attn, LayerNorm1, x1 + ffn exist only as fp16 rows (each sum is formed in fp32 in the GEMM
+      // epilogue and rounded once; LayerNorm statistics in fp32).  Halves the bytes of the two HBM-bound epilogues and of both
+      // LayerNorm kernels (4.0e-4 worst row error against 2.6e-4 with the fp32 stream, tolerance 1e-3).
+      __half* yh = reinterpret_cast<__half*>(y);
+      CU(lin_h(e, atth, d, rows, pfx + ".out_w", pfx + ".out_b", yh, d, 0, 1, st, reinterpret_cast<const float*>(xh), d, 0, 1));
+      CU(layer_norm_half_rows(yh, x1h, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc));
+      CU(lin_h(e, x1h, d, rows, pfx + ".l1_w", pfx + ".l1_b", hh, ffn, 1, 1, st));
+      CU(lin_h(e, hh, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", yh, d, 0, 1, st, reinterpret_cast<const float*>(x1h), d, 0, 1));
+      CU(layer_norm_max_half_rows(yh, pooled_out, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, n_seq, S, d, st, &e->lc));
+      return 0;
+    }
     CU(lin_h(e, atth, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, 0, st, X, d, 0, x_is_half ? 1 : 0));
     CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc, x1h));
     CU(lin_h(e, x1h, d, rows, pfx + ".l1_w", pfx + ".l1_b", hh, ffn, 1, 1, st));
@@ -1145,6 +1166,19 @@ extern "C" int t2l_debug_linear_f16(t2l_engine* e, const void* A, int lda, const
   Linear l;
   l.A = static_cast<const float*>(A); l.lda = lda; l.W = static_cast<const float*>(Wt); l.ldw = ldw; l.bias = bias;
   l.C = static_cast<float*>(C); l.ldc = ldc; l.M = M; l.N = N; l.K = K; l.act = act; l.half_ops = 1; l.out_half = out_half;
+  CU(linear_umma(l, static_cast<cudaStream_t>(stream), &e->lc));
+  return 0;
+}
+
+extern "C" int t2l_debug_linear_f16_residual(t2l_engine* e, const void* A, int lda, const void* Wt, int ldw, const float* bias, const void* R,
+                                             int ldr, void* C, int ldc, int M, int N, int K, int reg_epilogue, void* stream) {
+  if (!e) return 1;
+  if (!A || !Wt || !R || !C) return fail(e, "debug_linear_f16_residual: NULL buffer");
+  ENTER_STREAM(e, stream);
+  Linear l;
+  l.A = static_cast<const float*>(A); l.lda = lda; l.W = static_cast<const float*>(Wt); l.ldw = ldw; l.bias = bias;
+  l.C = static_cast<float*>(C); l.ldc = ldc; l.M = M; l.N = N; l.K = K; l.half_ops = 1; l.out_half = 1;
+  l.residual = static_cast<const float*>(R); l.ldr = ldr; l.residual_half = 1; l.reg_epilogue = reg_epilogue;
   CU(linear_umma(l, static_cast<cudaStream_t>(stream), &e->lc));
   return 0;
 }

@@ -84,6 +84,20 @@ T2L_DEVICE void tma_load_2d(const void* desc, uint64_t* bar, void* smem_dst, int
       : "memory");
 }
 
+// TMA store: a [box] tile in shared memory (layout of the tensor map, e.g. 128-byte swizzle) -> global; elements outside the
+// tensor are not written.  Bulk async-group completion: commit, then wait (.read: the source may be overwritten again).
+T2L_DEVICE void tma_store_2d(const void* desc, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+T2L_DEVICE void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+T2L_DEVICE void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+T2L_DEVICE void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// named barrier over `n_threads` threads (a multiple of 32) of the CTA; id 0 is __syncthreads'
+T2L_DEVICE void named_bar_sync(uint32_t id, uint32_t n_threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
+
 // ---------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ---------------------------------------------------------------------------------------

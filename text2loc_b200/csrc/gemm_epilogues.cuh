@@ -6,6 +6,7 @@
 // ~1.2k cycles per 32-column chunk in long-scoreboard stalls on exactly these loads).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -37,7 +38,7 @@ struct StoreParams {
   float* C;
   long ldc;
   const float* bias;      // [N] or nullptr
-  const float* residual;  // [M, ldr] or nullptr (fp32 output only)
+  const float* residual;  // [M, ldr] or nullptr
   long ldr;
   int M, N;
   int act;
@@ -113,7 +114,7 @@ struct StoreEpiT {
       if (kSmemBias) return sb[i];
       return p.bias ? __ldg(gb + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    if (kHalfOut) {
+    if (kHalfOut && !kResidual) {
       // own row -> 64 bytes = four 16-byte chunks at position i ^ ((row >> 1) & 3)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -167,9 +168,130 @@ struct StoreEpiT {
       const int r = 4 * j + rr;
       float4 o = *reinterpret_cast<const float4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
       if (kResidual) { o.x += cur[j].x; o.y += cur[j].y; o.z += cur[j].z; o.w += cur[j].w; }
+      if (kHalfOut) {  // fp16 residual stream: acc + bias + residual summed in fp32, ONE rounding, 8 lanes x 8 bytes per row slice
+        const __half2 h0 = __floats2half2_rn(fminf(fmaxf(o.x, -p.half_max), p.half_max), fminf(fmaxf(o.y, -p.half_max), p.half_max));
+        const __half2 h1 = __floats2half2_rn(fminf(fmaxf(o.z, -p.half_max), p.half_max), fminf(fmaxf(o.w, -p.half_max), p.half_max));
+        if (row0 + r < p.M)
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.C) + (row0 + r) * p.ldc + col0 + ch * 4) =
+              make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        continue;
+      }
       if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
       if (row0 + r < p.M) *reinterpret_cast<float4*>(p.C + (row0 + r) * p.ldc + col0 + ch * 4) = o;
     }
+    __syncwarp();
+  }
+};
+
+// C[row, col] = fp16(acc + bias[col] + residual[row, col]) with fp16 residual and output rows, both moved by TMA: the token
+// layer's fp16 residual stream (out-projection: x + attn(x); FFN2: x1 + ffn(x1)).
+//
+// The register-staged residual epilogue above is bound by the residual bytes a warp keeps in flight (one 4 KB chunk; out-proj
+// ran at 0.40 of the tensor peak, profiles/r02) and halving the element size halves exactly that.  Here the residual of a
+// tile arrives the way the operands do: 128-row x 64-column slabs (16 KB, 128-byte swizzle) fetched by TMA into shared
+// memory a whole tile ahead and signalled on an mbarrier.  A thread reads the 64 bytes of ITS row from the slab (the swizzle
+// spreads the eight rows of a quarter-warp over all 32 banks), adds accumulator and bias in fp32, rounds once, and writes
+// the result back IN PLACE; when the four warps of a set have finished a slab, one thread stores it with TMA (full lines,
+// rows beyond M clipped by the hardware) and, once the store has read the slab, refills it with the same slab of the NEXT
+// tile.  Two warp sets; set s owns columns [128 s, 128 s + 128) of the tile = two slabs = two buffers.
+struct ResidualTmaParams {
+  CUtensorMap tm_res;  // residual [M, N] fp16, box 64 columns x 128 rows, SWIZZLE_128B
+  CUtensorMap tm_out;  // C [M, N] fp16, same box
+  const float* bias;   // [N] or nullptr
+  int M, N;
+  int act;
+  float half_max;
+};
+
+struct ResidualTmaEpi {
+  using Params = ResidualTmaParams;
+  static constexpr bool kTmaIo = true;
+  static constexpr int kMaxStages = 5;  // operand ring 6 -> 5 stages of 32 KB: room for the four slabs
+  static constexpr int kSets = 2;
+  static constexpr bool kCompactLoop = false;
+  static constexpr int kSlabBytes = 128 * 128;
+  static constexpr int kBarBytes = 64;  // res_full[set][slab]
+  static constexpr int kSmemBytes = 1024 + 4 * kSlabBytes;  // barriers + padding to the 1024-byte swizzle period + slabs
+  const Params& p;
+  uint64_t* res_full;  // this set's two barriers
+  uint8_t* slab;       // this set's two slabs
+  int ew, lane, set;
+  uint32_t tile_seq = 0;  // tiles this CTA has drained: parity of the slab barriers
+  int next_m = -1, next_col0 = 0;
+  static __device__ void init_barriers(uint8_t* smem) {
+    for (int i = 0; i < 4; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem) + i, 1);
+  }
+  __device__ ResidualTmaEpi(const Params& p_, uint8_t* smem, int ew_, int lane_, int, int set_)
+      : p(p_), res_full(reinterpret_cast<uint64_t*>(smem) + 2 * set_), ew(ew_), lane(lane_), set(set_) {
+    uint8_t* base = smem + kBarBytes;
+    base += (1024u - (smem_u32(base) & 1023u)) & 1023u;
+    slab = base + set_ * 2 * kSlabBytes;
+  }
+  __device__ __forceinline__ bool leader() const { return ew == 0 && lane == 0; }
+  __device__ __forceinline__ void load_slab(int j, int m_tile, int col0) {  // leader only
+    mbar_arrive_expect_tx(&res_full[j], kSlabBytes);
+    tma_load_2d(&p.tm_res, &res_full[j], slab + j * kSlabBytes, col0 + (2 * set + j) * 64, m_tile * 128, kEvictFirst);
+  }
+  __device__ void first_unit(int m_tile, int col0) {
+    if (leader()) {
+      tma_prefetch_desc(&p.tm_res);
+      tma_prefetch_desc(&p.tm_out);
+      load_slab(0, m_tile, col0);
+      load_slab(1, m_tile, col0);
+    }
+    __syncwarp();
+  }
+  __device__ void prefetch_unit(int m_tile, int col0) { next_m = m_tile; next_col0 = col0; }
+  __device__ void no_next_unit() { next_m = -1; }
+  __device__ void begin_unit(int, int) {}
+  __device__ void end_unit(int, int) {}
+  __device__ void begin_tile(int, int, int) {}
+  // c runs over this set's four chunks 4 set .. 4 set + 3 in order (EpiTraits::kTmaIo); col0 = first column of chunk c
+  __device__ void chunk(int m_tile, int, int c, int col0, float (&v)[32]) {
+    const int i = c & 3, j = i >> 1, cc = i & 1;
+    uint8_t* buf = slab + j * kSlabBytes;
+    if (cc == 0) mbar_wait(&res_full[j], tile_seq & 1);
+    const int r = ew * 32 + lane;
+    uint8_t* rowp = buf + r * 128;
+    const float4* gb = reinterpret_cast<const float4*>(p.bias + col0);  // (only dereferenced when p.bias != nullptr)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4* slot = reinterpret_cast<uint4*>(rowp + (((cc * 4 + k) ^ (r & 7)) << 4));
+      const uint4 rv = *slot;
+      const float4 b0 = p.bias ? __ldg(gb + 2 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 b1 = p.bias ? __ldg(gb + 2 * k + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 rr = __half22float2(*reinterpret_cast<const __half2*>(&rw[e]));
+        float x = v[8 * k + 2 * e] + bb[2 * e], y = v[8 * k + 2 * e + 1] + bb[2 * e + 1];
+        if (p.act == kActRelu) { x = fmaxf(x, 0.f); y = fmaxf(y, 0.f); }
+        x = fminf(fmaxf(x + rr.x, -p.half_max), p.half_max);
+        y = fminf(fmaxf(y + rr.y, -p.half_max), p.half_max);
+        const __half2 hh = __floats2half2_rn(x, y);
+        o[e] = *reinterpret_cast<const uint32_t*>(&hh);
+      }
+      *slot = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (cc == 1) {
+      fence_proxy_async();              // my writes to the slab -> visible to the TMA store
+      named_bar_sync(1 + set, 128);     // all four warps of the set have finished this slab
+      if (leader()) {
+        tma_store_2d(&p.tm_out, buf, col0 - 32, m_tile * 128);  // this slab = chunks c - 1, c
+        bulk_commit_group();
+        if (next_m >= 0) {
+          bulk_wait_group_read0();      // the store has read the slab: refill it with the next tile's residual
+          load_slab(j, next_m, next_col0);
+        }
+      }
+      __syncwarp();
+      if (i == 3) ++tile_seq;
+    }
+  }
+  __device__ void finish() {
+    if (leader()) bulk_wait_group0();
     __syncwarp();
   }
 };

@@ -31,6 +31,15 @@ static cudaError_t run_umma(const Linear& l, const typename Epi::Params& ep, cud
   return launch_umma_gemm<Cfg, Epi>(ta, tb, s, ep, st);
 }
 
+// fp16 residual stream (out-proj, FFN2 of the token layer): residual and output rows move by TMA (ResidualTmaEpi)
+static cudaError_t run_residual_tma(const Linear& l, cudaStream_t st) {
+  ResidualTmaParams ep;
+  if (make_operand_map(&ep.tm_res, l.residual, kOpF16, l.M, l.N, l.ldr, 128)) return cudaErrorInvalidValue;
+  if (make_operand_map(&ep.tm_out, l.C, kOpF16, l.M, l.N, l.ldc, 128)) return cudaErrorInvalidValue;
+  ep.bias = l.bias; ep.M = l.M; ep.N = l.N; ep.act = l.act; ep.half_max = l.half_max;
+  return run_umma<256, 2, ResidualTmaEpi, kOpF16>(l, ep, st);
+}
+
 template <class Epi, int TYPE>
 static cudaError_t run_store(const Linear& l, const StoreParams& ep, bool wide, bool pair, cudaStream_t st) {
   if (pair) return run_umma<256, 2, Epi, TYPE>(l, ep, st);
@@ -56,9 +65,13 @@ cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
     if (pair) return run_umma<256, 2, SegMaxEpi>(l, ep, st);
     return wide ? run_umma<256, 1, SegMaxEpi>(l, ep, st) : run_umma<128, 1, SegMaxEpi>(l, ep, st);
   }
-  if (l.out_half && l.residual) return cudaErrorInvalidValue;
+  if (l.out_half && l.residual && !l.half_ops) return cudaErrorInvalidValue;
   StoreParams ep{l.C, l.ldc, l.bias, l.residual, l.ldr, l.M, l.N, l.act, l.round_out, l.out_half, l.half_max, l.residual_half};
   if (l.half_ops) {  // fp16 operands (A, W are __half), kind::f16: twice the tf32 rate at the same 11-bit significand
+    if (l.out_half && l.residual) {  // fp16 residual stream
+      if (pair && l.residual_half && !l.reg_epilogue && !(l.ldr % 8) && !(l.ldc % 8)) return run_residual_tma(l, st);
+      return run_store<StoreEpiT<true, true>, kOpF16>(l, ep, wide, pair, st);
+    }
     if (l.out_half) return run_store<StoreEpiT<true, false>, kOpF16>(l, ep, wide, pair, st);
     if (l.residual) return run_store<StoreEpiT<false, true>, kOpF16>(l, ep, wide, pair, st);
     return run_store<StoreEpiT<false, false>, kOpF16>(l, ep, wide, pair, st);

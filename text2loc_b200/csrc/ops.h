@@ -34,6 +34,7 @@ struct Linear {
   int half_ops = 0;           // A and W point at __half data (lda, ldw in elements): tcgen05 kind::f16, fp32 accumulate
   int out_half = 0;           // C points at __half data (ldc in elements); values saturate at +-half_max
   float half_max = 65504.f;
+  int reg_epilogue = 0;       // out_half + residual: force the register-staged epilogue instead of the TMA one (A/B switch)
 };
 // tf32 tensor-core path: needs K-major operands with 16-byte aligned rows (lda, ldw % 4 == 0),
 // N % 32 == 0.  K tails are zero-filled by TMA.
@@ -88,6 +89,8 @@ cudaError_t l2_normalize_rows(const float* x, long ldx, float* y, long ldy, int 
 // (optional y_half: an fp16 copy of the output, the A operand of a following fp16 tensor-core GEMM)
 cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const float* b, int rows, int d, cudaStream_t st, Launches* lc,
                             __half* y_half = nullptr);
+// the same on fp16 rows in and out (d = 1024): the token layer's fp16 residual stream
+cudaError_t layer_norm_half_rows(const __half* x, __half* y, const float* w, const float* b, int rows, int d, cudaStream_t st, Launches* lc);
 // y = fp16(x), saturating at +-65504; n % 4 == 0
 cudaError_t to_half_rows(const float* x, __half* y, long n, cudaStream_t st, Launches* lc);
 // Unmasked multi-head self attention on packed QKV rows [n_seq*S, 3d] (q | k | v), head h uses
@@ -104,6 +107,8 @@ cudaError_t mha_tc256(const void* qkv, float* out, int n_seq, int S, cudaStream_
 // materialising the normalised rows
 cudaError_t layer_norm_max_rows(const float* x, float* y, const float* w, const float* b, int groups, int S, int d, cudaStream_t st,
                                 Launches* lc);
+cudaError_t layer_norm_max_half_rows(const __half* x, float* y, const float* w, const float* b, int groups, int S, int d, cudaStream_t st,
+                                     Launches* lc);
 // y[g, :] = max over the S rows of group g
 cudaError_t max_over_rows(const float* x, float* y, int groups, int S, int d, cudaStream_t st, Launches* lc);
 // X[b, s, :] = normalize(emb[cell_ptr[b]+s]) for s < min(n_b, 28), else 0   (cell_retrieval.py:85-98)

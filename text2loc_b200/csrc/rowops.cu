@@ -109,6 +109,72 @@ cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const floa
   return cudaGetLastError();
 }
 
+// ---- the same on the fp16 residual stream of the token layer: rows in as fp16, out as fp16 only ----------------
+// (the normalised row is the next GEMM's A operand AND its residual; statistics and the affine map in fp32).
+// Lane l holds columns i * 256 + 8 l .. + 7, i = 0..3: 16-byte loads and stores, 512 contiguous bytes per warp instruction.
+__device__ __forceinline__ void unpack_half8(const uint4& u, float (&f)[8]) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&u.z)), d = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+
+// mean and 1/std of one 1024-wide fp16 row spread over a warp (v[i][e] = column i * 256 + 8 lane + e)
+__device__ __forceinline__ void half_row_load(const __half* __restrict__ row, int lane, uint4 (&raw)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) raw[i] = reinterpret_cast<const uint4*>(row)[i * 32 + lane];
+}
+__device__ __forceinline__ void half_row_stats(const uint4 (&raw)[4], float (&v)[4][8], float& mean, float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    unpack_half8(raw[i], v[i]);
+    s += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
+  }
+  mean = warp_sum(s) * (1.f / 1024);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float a = v[i][e] - mean;
+      q = fmaf(a, a, q);
+    }
+  rstd = rsqrtf(warp_sum(q) * (1.f / 1024) + 1e-5f);
+}
+
+__global__ void __launch_bounds__(256) layer_norm_half_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ w,
+                                                              const float* __restrict__ b, int rows) {
+  const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float v[4][8], mean, rstd;
+  uint4 raw[4];
+  half_row_load(x + r * 1024, lane, raw);
+  half_row_stats(raw, v, mean, rstd);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 w0 = reinterpret_cast<const float4*>(w)[i * 64 + lane * 2], w1 = reinterpret_cast<const float4*>(w)[i * 64 + lane * 2 + 1];
+    const float4 b0 = reinterpret_cast<const float4*>(b)[i * 64 + lane * 2], b1 = reinterpret_cast<const float4*>(b)[i * 64 + lane * 2 + 1];
+    const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 h = __floats2half2_rn(sat_half((v[i][2 * e] - mean) * rstd * ww[2 * e] + bb[2 * e]),
+                                          sat_half((v[i][2 * e + 1] - mean) * rstd * ww[2 * e + 1] + bb[2 * e + 1]));
+      o[e] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    reinterpret_cast<uint4*>(y + r * 1024)[i * 32 + lane] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+cudaError_t layer_norm_half_rows(const __half* x, __half* y, const float* w, const float* b, int rows, int d, cudaStream_t st, Launches* lc) {
+  if (rows <= 0) return cudaSuccess;
+  if (d != 1024) return cudaErrorInvalidValue;
+  if (lc) lc->n++;
+  layer_norm_half_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, y, w, b, rows);
+  return cudaGetLastError();
+}
+
 // ---- small-sequence attention core -----------------------------------------------------------
 // One warp per (sequence, head, query row).  S <= 32.  Lanes split the head dimension for the
 // q.k dot products (coalesced row reads, warp-sum), lane j then holds score j for the softmax,
@@ -443,6 +509,66 @@ __global__ void __launch_bounds__(256) layer_norm_max_kernel(const float* __rest
   float4* yr = reinterpret_cast<float4*>(y + g * D);
 #pragma unroll
   for (int i = 0; i < R; ++i) yr[i * 32 + lane] = m[i];
+}
+
+// fp16 rows in (the token layer's fp16 residual stream), fp32 maxima out.  One CTA of four warps per group: warp w takes
+// rows w, w + 4, ... with the next row's loads in flight while the current one is reduced, and the four partial maxima meet in
+// shared memory (one warp per group walked its rows one dependent reduction at a time: 1.8 TB/s, profiles/r02).
+__global__ void __launch_bounds__(128) layer_norm_max_half_kernel(const __half* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
+                                                                  const float* __restrict__ b, int groups, int S) {
+  __shared__ float part[4][1024];
+  const long g = blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float m[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[i][e] = -INFINITY;
+  uint4 raw[4], nxt[4];
+  if (wid < S) half_row_load(x + (g * S + wid) * 1024, lane, raw);
+  for (int s = wid; s < S; s += 4) {
+    if (s + 4 < S) half_row_load(x + (g * S + s + 4) * 1024, lane, nxt);
+    float v[4][8], mean, rstd;
+    half_row_stats(raw, v, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {  // weight and bias from L1 (4 KB each, shared by every row): keeps the kernel at 4+ CTAs per SM
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + i * 64 + lane * 2 + h), b4 = __ldg(reinterpret_cast<const float4*>(b) + i * 64 + lane * 2 + h);
+        m[i][4 * h + 0] = fmaxf(m[i][4 * h + 0], (v[i][4 * h + 0] - mean) * rstd * w4.x + b4.x);
+        m[i][4 * h + 1] = fmaxf(m[i][4 * h + 1], (v[i][4 * h + 1] - mean) * rstd * w4.y + b4.y);
+        m[i][4 * h + 2] = fmaxf(m[i][4 * h + 2], (v[i][4 * h + 2] - mean) * rstd * w4.z + b4.z);
+        m[i][4 * h + 3] = fmaxf(m[i][4 * h + 3], (v[i][4 * h + 3] - mean) * rstd * w4.w + b4.w);
+      }
+      raw[i] = nxt[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    reinterpret_cast<float4*>(part[wid])[i * 64 + lane * 2] = make_float4(m[i][0], m[i][1], m[i][2], m[i][3]);
+    reinterpret_cast<float4*>(part[wid])[i * 64 + lane * 2 + 1] = make_float4(m[i][4], m[i][5], m[i][6], m[i][7]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {  // 128 threads x 2 float4 = 1024 columns
+    const int c4 = i * 128 + threadIdx.x;
+    float4 o = reinterpret_cast<const float4*>(part[0])[c4];
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float4 t = reinterpret_cast<const float4*>(part[k])[c4];
+      o.x = fmaxf(o.x, t.x); o.y = fmaxf(o.y, t.y); o.z = fmaxf(o.z, t.z); o.w = fmaxf(o.w, t.w);
+    }
+    reinterpret_cast<float4*>(y + g * 1024)[c4] = o;
+  }
+}
+
+cudaError_t layer_norm_max_half_rows(const __half* x, float* y, const float* w, const float* b, int groups, int S, int d, cudaStream_t st,
+                                     Launches* lc) {
+  if (groups <= 0) return cudaSuccess;
+  if (d != 1024 || S < 1) return cudaErrorInvalidValue;
+  if (lc) lc->n++;
+  layer_norm_max_half_kernel<<<groups, 128, 0, st>>>(x, y, w, b, groups, S);
+  return cudaGetLastError();
 }
 
 cudaError_t layer_norm_max_rows(const float* x, float* y, const float* w, const float* b, int groups, int S, int d, cudaStream_t st,

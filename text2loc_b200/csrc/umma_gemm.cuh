@@ -27,6 +27,8 @@
 
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace t2l {
@@ -73,11 +75,30 @@ struct GemmCfg {
   static constexpr uint32_t IDESC = umma_idesc(kType == kOpTf32 ? 2u : (kType == kOpBf16 ? 1u : 0u), BLOCK_M * kCtaGroup, BLOCK_N);
   static constexpr bool IS_HALF = kType != kOpTf32;  // 2-byte operands: tcgen05.mma kind::f16
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two >= 32");
-  template <class Epi>
-  static constexpr int smem_bytes() { return 1024 + STAGES * STAGE_BYTES + BAR_BYTES + Epi::kSmemBytes; }
 };
 
 constexpr int kGemmThreads = 256;
+
+// Optional parts of the epilogue interface, detected by the marker `static constexpr bool kTmaIo`: an epilogue that moves its
+// side input and its output with TMA (ResidualTmaEpi, gemm_epilogues.cuh) owns mbarriers in its shared memory
+// (init_barriers), shrinks the operand ring to make room for its slabs (kMaxStages), takes the 32-column chunks of a tile
+// as one contiguous run per warp set, and is told about the first unit, the absence of a next unit, and the end of the loop.
+template <class Epi, class = void>
+struct EpiTraits {
+  static constexpr bool kTmaIo = false;
+  static constexpr int kMaxStages = 64;
+};
+template <class Epi>
+struct EpiTraits<Epi, std::enable_if_t<Epi::kTmaIo>> {
+  static constexpr bool kTmaIo = true;
+  static constexpr int kMaxStages = Epi::kMaxStages;
+};
+template <class Cfg, class Epi>
+struct GemmLayout {
+  static constexpr int STAGES = Cfg::STAGES < EpiTraits<Epi>::kMaxStages ? Cfg::STAGES : EpiTraits<Epi>::kMaxStages;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + Epi::kSmemBytes;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory of the GEMM kernel exceeds 227 KB");
+};
 
 // Epi::kSets epilogue warp sets of four warps each (warps 4..7, 8..11): with two sets every SM sub-partition hosts two epilogue
 // warps, which interleave the 32-column chunks of a tile between them (an epilogue that is latency-bound in a single warp --
@@ -85,18 +106,20 @@ constexpr int kGemmThreads = 256;
 template <class Cfg, class Epi>
 __global__ void __launch_bounds__(128 + 128 * Epi::kSets, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const GemmShape shape, const typename Epi::Params ep) {
+                 const GemmShape shape, const __grid_constant__ typename Epi::Params ep) {
+  constexpr int STAGES = GemmLayout<Cfg, Epi>::STAGES;
+  constexpr bool kTmaIo = EpiTraits<Epi>::kTmaIo;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms; offset arithmetic on the __shared__ array keeps the
   // pointer in the shared address space (integer round trips degrade every access to generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint8_t* epi_smem = smem + Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
+  uint8_t* epi_smem = smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,7 +133,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tma_prefetch_desc(&tm_b);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < Cfg::STAGES; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], Cfg::CTA_GROUP);  // pairs: both producers arrive on the LEADER's barrier
       mbar_init(&empty_bar[i], 1);
     }
@@ -118,6 +141,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 4 * Cfg::CTA_GROUP * Epi::kSets);  // one arrive per epilogue warp (of both CTAs, on the leader's barrier)
     }
+    if constexpr (kTmaIo) Epi::init_barriers(epi_smem);
     fence_barrier_init();
   }
   if (kPair) cluster_sync_all();  // both CTAs resident before the paired TMEM allocation
@@ -167,7 +191,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
               }
             }
             __syncwarp();
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -217,7 +241,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
           }
           __syncwarp();
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -229,6 +253,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     Epi epi(ep, epi_smem, ew, lane, Cfg::BLOCK_N, set);
     int acc = 0;
     uint32_t acc_phase = 0;
+    if constexpr (kTmaIo) {
+      if (cta < n_units)
+        epi.first_unit((cta / shape.n_splits) * Cfg::CTA_GROUP + static_cast<int>(rank), (cta % shape.n_splits) * shape.tiles_per_split * Cfg::BLOCK_N);
+    }
     for (int u = cta; u < n_units; u += n_cta) {
       const int m_tile = (u / shape.n_splits) * Cfg::CTA_GROUP + static_cast<int>(rank);  // this CTA's 128-row tile
       const int split = u % shape.n_splits;
@@ -237,6 +265,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if (u + n_cta < n_units) {
         const int u2 = u + n_cta;
         epi.prefetch_unit((u2 / shape.n_splits) * Cfg::CTA_GROUP + static_cast<int>(rank), (u2 % shape.n_splits) * shape.tiles_per_split * Cfg::BLOCK_N);
+      } else if constexpr (kTmaIo) {
+        epi.no_next_unit();
       }
       epi.begin_unit(m_tile, split);
       for (int nt = nt0; nt < nt1; ++nt) {
@@ -265,12 +295,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         } else {
           constexpr int NC = Cfg::BLOCK_N / 32, ST = Epi::kSets;
           static_assert(NC % ST == 0, "chunks must split evenly over the epilogue sets");
-          if constexpr (ST > 1) tmem_ld_32x32(t_addr + set * 32, v[0]);
+          if constexpr (kTmaIo) tmem_ld_32x32(t_addr + set * (NC / ST) * 32, v[0]);
+          else if constexpr (ST > 1) tmem_ld_32x32(t_addr + set * 32, v[0]);
 #pragma unroll
           for (int i = 0; i < NC / ST; ++i) {
-            const int c = ST == 1 ? i : set + i * ST;  // compile-time for single-set epilogues (their chunk() folds it into addresses)
+            // compile-time for single-set epilogues (their chunk() folds it into addresses); TMA epilogues: one contiguous run per set
+            const int c = ST == 1 ? i : (kTmaIo ? set * (NC / ST) + i : set + i * ST);
             tmem_ld_wait(v[i & 1]);
-            if (i + 1 < NC / ST) tmem_ld_32x32(t_addr + (c + ST) * 32, v[(i + 1) & 1]);
+            if (i + 1 < NC / ST) tmem_ld_32x32(t_addr + (c + (kTmaIo ? 1 : ST)) * 32, v[(i + 1) & 1]);
             epi.chunk(m_tile, nt, c, nt * Cfg::BLOCK_N + c * 32, v[i & 1]);
           }
         }
@@ -284,6 +316,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       epi.end_unit(m_tile, split);
     }
+    if constexpr (kTmaIo) epi.finish();
   }
 
   tc_fence_before();
@@ -334,7 +367,7 @@ inline int current_device() {
 template <class Cfg, class Epi>
 cudaError_t launch_umma_gemm(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const GemmShape& shape,
                              const typename Epi::Params& ep, cudaStream_t stream) {
-  constexpr int smem = Cfg::template smem_bytes<Epi>();
+  constexpr int smem = GemmLayout<Cfg, Epi>::SMEM_BYTES;
   static bool configured_dev[64] = {};  // the attribute is per device: one flag per device ordinal
   bool& configured = configured_dev[current_device() & 63];
   if (!configured) {

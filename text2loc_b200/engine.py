@@ -337,6 +337,19 @@ class Engine:
                                                    int(out_half), self._stream()))
         return C
 
+    def debug_linear_f16_residual(self, A, W, bias, R, reg_epilogue=False):
+        """fp16(A W^T + bias + R): the out-projection / FFN2 of the token layer on its fp16 residual stream."""
+        A, W, R = self._dev(A, torch.float16), self._dev(W, torch.float16), self._dev(R, torch.float16)
+        bias = self._dev(bias, torch.float32) if bias is not None else None
+        M, K = A.shape
+        N = W.shape[0]
+        buf = torch.full((M + 160, N), 7.0, dtype=torch.float16, device=self.device)  # the rows beyond M must stay untouched
+        self._check(self._lib.t2l_debug_linear_f16_residual(self._h, _ptr(A), K, _ptr(W), K, _ptr(bias), _ptr(R), N, _ptr(buf), N, M, N, K,
+                                                            int(reg_epilogue), self._stream()))
+        if not bool((buf[M:] == 7.0).all()):
+            raise RuntimeError("debug_linear_f16_residual: rows beyond M were written")
+        return buf[:M]
+
     def debug_linear(self, A, W, bias=None, act=0, segmax=False, path=1):
         rowmajor = lambda t: t if (t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1) else self._dev(t, torch.float32)
         A, W = rowmajor(A), rowmajor(W)  # row-padded views (stride(0) > K) are passed through as lda / ldw
