@@ -197,6 +197,16 @@ int t2l_debug_linear_f16(t2l_engine* e, const void* A, int lda, const void* W, i
 int t2l_debug_linear_f16_residual(t2l_engine* e, const void* A, int lda, const void* W, int ldw, const float* bias, const void* R,
                                   int ldr, void* C, int ldc, int M, int N, int K, int reg_epilogue, void* stream);
 
+/* Test hook for the small-sequence attention core (intra-cell and sentence-level layers): qkv device f32 [n_seq*S, 3d] packed
+ * (q | k | v), head h = columns [h*d/n_heads, ...), no mask; out device f32 [n_seq*S, d] = softmax(q k^T / sqrt(hd)) v. */
+int t2l_debug_mha(t2l_engine* e, const float* qkv, float* out, int n_seq, int S, int d, int n_heads, void* stream);
+
+/* Test hook for the intra-cell attention core on packed rows without duplicate padding rows: cell b owns rows
+ * row_ptr[b] .. row_ptr[b+1]) = its min(n_b, slots) objects + (if n_b < slots) one row standing for the slots - n_b
+ * zero-padded slots of the reference's [B, slots, d] tensor; n_b = cell_ptr[b+1] - cell_ptr[b].  All pointers device. */
+int t2l_debug_mha_cells(t2l_engine* e, const float* qkv, float* out, int n_cells, const int32_t* row_ptr_dev,
+                        const int32_t* cell_ptr_dev, int slots, int d, int n_heads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

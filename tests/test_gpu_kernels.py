@@ -94,6 +94,47 @@ def test_umma_gemm_f16_residual_stream(eng, M, N, K):
     assert torch.equal(eng.debug_linear_f16_residual(A, W, b, R, reg_epilogue=False), eng.debug_linear_f16_residual(A, W, b, R, reg_epilogue=True))
 
 
+@pytest.mark.parametrize("n_seq,S,d,heads", [(2048, 28, 256, 4), (37, 17, 256, 4), (5, 32, 256, 4), (300, 16, 256, 4), (1000, 6, 256, 4),
+                                             (64, 9, 128, 4), (1, 28, 256, 4)])
+def test_small_attention_core(eng, n_seq, S, d, heads):
+    """nn.MultiheadAttention's core without a mask (cell_retrieval.py:101-103, language_encoder.py:143-145) in fp32: the
+    row-per-warp kernel (short sequences) and the sequence-per-warp kernel (64-wide heads, S > 16) against torch in fp64."""
+    g = torch.Generator(device="cuda").manual_seed(n_seq * 3 + S)
+    qkv = torch.randn(n_seq * S, 3 * d, device="cuda", generator=g)
+    got = eng.debug_mha(qkv, n_seq, S, heads)
+    q, k, v = (t.reshape(n_seq, S, heads, d // heads).permute(0, 2, 1, 3).double() for t in qkv.split(d, dim=1))
+    att = torch.softmax(q @ k.transpose(-1, -2) / (d // heads) ** 0.5, dim=-1)
+    want = (att @ v).permute(0, 2, 1, 3).reshape(n_seq * S, d)
+    err = (got.double() - want).abs().max().item()
+    print(f"\n[mha {n_seq}x{S}x{d}/{heads}] |out-fp64|={err:.3e}")
+    assert err < 5e-6
+
+
+def test_intra_cell_attention_without_duplicate_padding_rows(eng):
+    """The reference zero-pads every cell to 28 object slots and attends without a mask (cell_retrieval.py:81-103): the
+    28 - n padded slots of a cell are identical rows.  The engine carries one of them, weighted by its count as a key.
+    Against torch on the full padded [B, 28, 3d] tensor (padded slots = copies of the representative row)."""
+    slots, d, heads = 28, 256, 4
+    counts = [8, 1, 28, 30, 27, 16, 2, 8, 8, 40, 5] * 20
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rows = [min(n, slots) + (1 if n < slots else 0) for n in counts]
+    row_ptr = torch.tensor([0] + list(np.cumsum(rows)), dtype=torch.int32)
+    cell_ptr = torch.tensor([0] + list(np.cumsum(counts)), dtype=torch.int32)
+    qkv = torch.randn(int(row_ptr[-1]), 3 * d, device="cuda", generator=g)
+    got = eng.debug_mha_cells(qkv, row_ptr, cell_ptr, slots, heads)
+    worst = 0.0
+    for b, n in enumerate(counts):
+        r0, r = int(row_ptr[b]), rows[b]
+        idx = list(range(r0, r0 + r)) + [r0 + r - 1] * (slots - r)  # expand the representative into the padded slots
+        full = qkv[idx].double()
+        q, k, v = (t.reshape(slots, heads, d // heads).permute(1, 0, 2) for t in full.split(d, dim=1))
+        att = torch.softmax(q @ k.transpose(-1, -2) / (d // heads) ** 0.5, dim=-1)
+        want = (att @ v).permute(1, 0, 2).reshape(slots, d)[:r]
+        worst = max(worst, (got[r0:r0 + r].double() - want).abs().max().item())
+    print(f"\n[intra-cell attention, ragged] |out-fp64|={worst:.3e}")
+    assert worst < 5e-6
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (4224 * 4, 64, 32), (2112 * 3, 128, 128), (1056, 256, 256), (64, 1024, 512)])
 def test_umma_segmax_epilogue(eng, M, N, K):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)

@@ -50,6 +50,8 @@ SIGNATURES = {
     "t2l_launch_count": (c_int64, [_P]),
     "t2l_debug_linear": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "t2l_debug_linear_f16": (c_int, [_P, _P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
+    "t2l_debug_mha": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "t2l_debug_mha_cells": (c_int, [_P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P]),
     "t2l_debug_linear_f16_residual": (c_int, [_P, _P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
 }
 

@@ -515,6 +515,29 @@ static int encoder_layer(t2l_engine* e, const std::string& pfx, bool fast, const
   return 0;
 }
 
+// One intra-cell layer (cell_retrieval.py:101-103: nn.TransformerEncoderLayer(256, 4 heads, ffn 512), no mask over the 28
+// zero-padded slots) on the packed rows of a chunk: `rows` = sum over cells of min(n_b, 28) + [n_b < 28] (the padded slots
+// of a cell are identical rows; one representative stands for them, weighted as a key by their count).  Three-pass tf32
+// projections like encoder_layer's precise branch.
+static int cell_attention_layer(t2l_engine* e, const std::string& pfx, const float* X, float* Xout, int rows, int n_cells,
+                                const int32_t* row_ptr_dev, const int32_t* cell_ptr_dev, cudaStream_t st) {
+  constexpr int d = T2L_EMBED_DIM, ffn = 512;
+  Arena& a = e->arena;
+  float* qkv = a.get<float>(static_cast<size_t>(rows) * 3 * d);
+  float* att = a.get<float>(static_cast<size_t>(rows) * d);
+  float* y = a.get<float>(static_cast<size_t>(rows) * d);
+  float* x1 = a.get<float>(static_cast<size_t>(rows) * d);
+  float* h = a.get<float>(static_cast<size_t>(rows) * ffn);
+  CU(lin3(e, X, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st));
+  CU(mha_cells64(qkv, att, n_cells, row_ptr_dev, cell_ptr_dev, kObjectSlots, d, 4, st, &e->lc));
+  CU(lin3(e, att, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, X, d));
+  CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc));
+  CU(lin3(e, x1, d, rows, pfx + ".l1_w", pfx + ".l1_b", h, ffn, 1, st));
+  CU(lin3(e, h, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x1, d));
+  CU(layer_norm_rows(y, Xout, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, rows, d, st, &e->lc));
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // encode_cells
 // ---------------------------------------------------------------------------------------------
@@ -541,7 +564,7 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
   const float* p = pts + static_cast<size_t>(o0) * kPoints * 6;
 
   // self-loop source of each object (PyG add_self_loops on per-cell indices) + local cell_ptr
-  const size_t host_n = 2 * static_cast<size_t>(n) + B + 1;
+  const size_t host_n = 2 * static_cast<size_t>(n) + 2 * (static_cast<size_t>(B) + 1);
   auto& hs = e->stage[e->stage_next++ % 4];
   if (hs.used) CU(cudaEventSynchronize(hs.ev));  // the copy that last read this buffer has finished
   if (hs.cap < host_n) {
@@ -559,6 +582,14 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
       host[n + (o - o0)] = b & 1;
     }
   for (int c = c0; c <= c1; ++c) host[2 * static_cast<size_t>(n) + (c - c0)] = cell_ptr[c] - o0;
+  // rows of the intra-cell attention layers: min(n_b, 28) objects + ONE row for all 28 - n_b zero-padded slots (mha_seq64_kernel)
+  int32_t* rp_host = host + 2 * static_cast<size_t>(n) + B + 1;
+  rp_host[0] = 0;
+  for (int c = c0; c < c1; ++c) {
+    const int nb = cell_ptr[c + 1] - cell_ptr[c];
+    rp_host[c - c0 + 1] = rp_host[c - c0] + (nb < kObjectSlots ? nb + 1 : kObjectSlots);
+  }
+  const int attn_rows = rp_host[B];
   int32_t* d_host = a.get<int32_t>(host_n);
   CU(cudaMemcpyAsync(d_host, host, host_n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   CU(cudaEventRecord(hs.ev, st));
@@ -566,6 +597,7 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
   const int32_t* loop_src = d_host;
   const int32_t* loop_half = d_host + n;
   const int32_t* cell_ptr_dev = d_host + 2 * static_cast<size_t>(n);
+  const int32_t* row_ptr_dev = cell_ptr_dev + B + 1;
 
   Geometry g;
   const size_t N = n;
@@ -664,15 +696,15 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
 
   // intra-cell attention (cell_retrieval.py:85-108); fp32 throughout: these two layers amplify
   // operand rounding the most (precision table)
-  float* X = a.get<float>(static_cast<size_t>(B) * 28 * 256);
-  float* Xb = a.get<float>(static_cast<size_t>(B) * 28 * 256);
+  float* X = a.get<float>(static_cast<size_t>(attn_rows) * 256);
+  float* Xb = a.get<float>(static_cast<size_t>(attn_rows) * 256);
   float* pooled = a.get<float>(static_cast<size_t>(B) * 256);
-  CU(scatter_objects(emb, cell_ptr_dev, B, X, st, &e->lc));
+  CU(scatter_objects_ragged(emb, cell_ptr_dev, row_ptr_dev, B, X, st, &e->lc));
   const size_t mark = a.off;
-  if (encoder_layer(e, "obj_attn0", false, X, Xb, B, 28, 256, 512, st)) return 1;
+  if (cell_attention_layer(e, "obj_attn0", X, Xb, attn_rows, B, row_ptr_dev, cell_ptr_dev, st)) return 1;
   a.off = mark;
-  if (encoder_layer(e, "obj_attn1", false, Xb, X, B, 28, 256, 512, st)) return 1;
-  CU(max_over_rows(X, pooled, B, 28, 256, st, &e->lc));
+  if (cell_attention_layer(e, "obj_attn1", Xb, X, attn_rows, B, row_ptr_dev, cell_ptr_dev, st)) return 1;
+  CU(max_over_rows_ragged(X, row_ptr_dev, pooled, B, st, &e->lc));
   CU(l2_normalize_rows(pooled, 256, out + static_cast<size_t>(c0) * 256, 256, B, 256, st, &e->lc));
   if (a.overflow) return fail(e, "internal: workspace arena too small for %d objects / %d cells", n, B);
   return 0;
@@ -1180,5 +1212,22 @@ extern "C" int t2l_debug_linear_f16_residual(t2l_engine* e, const void* A, int l
   l.C = static_cast<float*>(C); l.ldc = ldc; l.M = M; l.N = N; l.K = K; l.half_ops = 1; l.out_half = 1;
   l.residual = static_cast<const float*>(R); l.ldr = ldr; l.residual_half = 1; l.reg_epilogue = reg_epilogue;
   CU(linear_umma(l, static_cast<cudaStream_t>(stream), &e->lc));
+  return 0;
+}
+
+extern "C" int t2l_debug_mha(t2l_engine* e, const float* qkv, float* out, int n_seq, int S, int d, int n_heads, void* stream) {
+  if (!e) return 1;
+  if (!qkv || !out || n_seq < 0 || S < 1 || S > 32 || n_heads < 1 || d % n_heads) return fail(e, "debug_mha: bad argument");
+  ENTER_STREAM(e, stream);
+  CU(mha_small(qkv, out, n_seq, S, d, n_heads, static_cast<cudaStream_t>(stream), &e->lc));
+  return 0;
+}
+
+extern "C" int t2l_debug_mha_cells(t2l_engine* e, const float* qkv, float* out, int n_cells, const int32_t* row_ptr_dev,
+                                   const int32_t* cell_ptr_dev, int slots, int d, int n_heads, void* stream) {
+  if (!e) return 1;
+  if (!qkv || !out || !row_ptr_dev || !cell_ptr_dev || n_cells < 0) return fail(e, "debug_mha_cells: bad argument");
+  ENTER_STREAM(e, stream);
+  CU(mha_cells64(qkv, out, n_cells, row_ptr_dev, cell_ptr_dev, slots, d, n_heads, static_cast<cudaStream_t>(stream), &e->lc));
   return 0;
 }

@@ -111,6 +111,13 @@ cudaError_t layer_norm_max_half_rows(const __half* x, float* y, const float* w, 
                                      Launches* lc);
 // y[g, :] = max over the S rows of group g
 cudaError_t max_over_rows(const float* x, float* y, int groups, int S, int d, cudaStream_t st, Launches* lc);
+// Intra-cell attention without the duplicate padding rows (rowops.cu::mha_seq64_kernel): cell b owns packed rows
+// row_ptr[b] .. row_ptr[b+1]) = its min(n_b, slots) objects + one row for all slots - n_b zero-padded slots
+cudaError_t mha_cells64(const float* qkv, float* out, int n_cells, const int32_t* row_ptr_dev, const int32_t* cell_ptr_dev, int slots, int d,
+                        int n_heads, cudaStream_t st, Launches* lc);
+cudaError_t scatter_objects_ragged(const float* emb, const int32_t* cell_ptr_dev, const int32_t* row_ptr_dev, int n_cells, float* X, cudaStream_t st,
+                                   Launches* lc);
+cudaError_t max_over_rows_ragged(const float* x, const int32_t* row_ptr_dev, float* y, int n_cells, cudaStream_t st, Launches* lc);
 // X[b, s, :] = normalize(emb[cell_ptr[b]+s]) for s < min(n_b, 28), else 0   (cell_retrieval.py:85-98)
 cudaError_t scatter_objects(const float* emb, const int32_t* cell_ptr_dev, int n_cells, float* X, cudaStream_t st, Launches* lc);
 // meta[:, 6] -> (cnt - mean) / std  (object_encoder.py:141-143)

@@ -14,47 +14,58 @@
 namespace t2l {
 
 // SA1's per-point half of the first Linear for sa_obj2.cu: Qx[i, :] = fp16(W1x . rgb_i + b1 + W1p . (pos_i - o)), o = the
-// object's point 0, clamped to +-32752 so that Qx - v stays finite in fp16.  One thread per (point, 8 channels).
+// object's point 0, clamped to +-32752 so that Qx - v stays finite in fp16.  One thread per point, all 32 channels: the
+// weights sit in shared memory and every lane of a warp reads the same address (broadcast).  (One thread per (point, 8
+// channels) with the weights through __ldg made each weight load touch four 128-byte lines per warp: 132 us per 1M points
+// against a 15 us HBM floor, bound by L1 tag lookups -- profiles/r02.)
 __global__ void __launch_bounds__(256) qx1_kernel(const float* __restrict__ pts, long n_pts, const float* __restrict__ w1x /*[32, ld 4]*/,
                                                   const float* __restrict__ w1p /*[32, ld 4]*/, const float* __restrict__ b1,
                                                   __half* __restrict__ qx16) {
-  const long idx = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long i = idx >> 2;
-  const int q = static_cast<int>(idx & 3);
-  if (i >= n_pts) return;
-  const float* pi = pts + i * 6;
-  const float* po = pts + (i / kPoints) * kPoints * 6;  // the object's point 0
-  const float r = pi[3], g = pi[4], b = pi[5];
-  const float dx = pi[0] - po[0], dy = pi[1] - po[1], dz = pi[2] - po[2];
-  uint32_t out[4];
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    float v[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int c = q * 8 + p * 2 + e;
-      const float4 w = __ldg(reinterpret_cast<const float4*>(w1x + c * 4));
-      const float4 wp = __ldg(reinterpret_cast<const float4*>(w1p + c * 4));
-      float acc = fmaf(r, w.x, 0.f);
-      acc = fmaf(g, w.y, acc);
-      acc = fmaf(b, w.z, acc);
-      acc += __ldg(b1 + c);
-      acc = fmaf(wp.x, dx, acc);
-      acc = fmaf(wp.y, dy, acc);
-      acc = fmaf(wp.z, dz, acc);
-      v[e] = fminf(fmaxf(acc, -kQxMax), kQxMax);
-    }
-    const __half2 h = __floats2half2_rn(v[0], v[1]);
-    out[p] = *reinterpret_cast<const uint32_t*>(&h);
+  __shared__ __align__(16) float wsm[32 * 8];  // per channel: rgb weights (3) | bias | position weights (3) | 0
+  for (int t = threadIdx.x; t < 32 * 8; t += blockDim.x) {
+    const int c = t >> 3, k = t & 7;
+    wsm[t] = k < 3 ? w1x[c * 4 + k] : (k == 3 ? b1[c] : (k < 7 ? w1p[c * 4 + k - 4] : 0.f));
   }
-  *reinterpret_cast<uint4*>(qx16 + i * 32 + q * 8) = make_uint4(out[0], out[1], out[2], out[3]);
+  __syncthreads();
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_pts) return;
+  const float2* pi = reinterpret_cast<const float2*>(pts + i * 6);               // 24-byte rows: 8-byte aligned
+  const float2* po = reinterpret_cast<const float2*>(pts + (i / kPoints) * kPoints * 6);  // the object's point 0
+  const float2 a0 = pi[0], a1 = pi[1], a2 = pi[2], o0 = __ldg(po), o1 = __ldg(po + 1);
+  const float dx = a0.x - o0.x, dy = a0.y - o0.y, dz = a1.x - o1.x;
+  const float r = a1.y, g = a2.x, b = a2.y;
+  uint4* dst = reinterpret_cast<uint4*>(qx16 + i * 32);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t out[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = q * 8 + p * 2 + e;
+        const float4 w = *reinterpret_cast<const float4*>(wsm + c * 8), wp = *reinterpret_cast<const float4*>(wsm + c * 8 + 4);
+        float acc = fmaf(r, w.x, 0.f);  // same order of operations as before: bit-identical Qx
+        acc = fmaf(g, w.y, acc);
+        acc = fmaf(b, w.z, acc);
+        acc += w.w;
+        acc = fmaf(wp.x, dx, acc);
+        acc = fmaf(wp.y, dy, acc);
+        acc = fmaf(wp.z, dz, acc);
+        v[e] = fminf(fmaxf(acc, -kQxMax), kQxMax);
+      }
+      const __half2 h = __floats2half2_rn(v[0], v[1]);
+      out[p] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    dst[q] = make_uint4(out[0], out[1], out[2], out[3]);
+  }
 }
 
 cudaError_t sa1_qx16(const float* pts, int n_obj, const float* w1x, const float* w1p, const float* b1, __half* qx16, cudaStream_t st, Launches* lc) {
   const long n = static_cast<long>(n_obj) * kPoints;
   if (n <= 0) return cudaSuccess;
   if (lc) lc->n++;
-  qx1_kernel<<<static_cast<unsigned>((n * 4 + 255) / 256), 256, 0, st>>>(pts, n, w1x, w1p, b1, qx16);
+  qx1_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(pts, n, w1x, w1p, b1, qx16);
   return cudaGetLastError();
 }
 

@@ -248,6 +248,109 @@ __global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict_
   for (int r = 0; r < R; ++r) o[r * 32 + lane] = round_out ? round_tf32(acc[r]) : acc[r];
 }
 
+// Self attention with head_dim 64 and 16 < S <= 32 (the intra-cell layers: 28 object slots, cell_retrieval.py:101-103): ONE warp
+// per (sequence, head), lane i = query row i.  K, V and Q of the head are staged in shared memory once (coalesced 256-byte
+// rows); a lane then walks the keys with its q row in registers and K / V rows arriving as warp-wide broadcasts, 64 independent
+// FMAs per key.  The row-per-warp kernel above reads every K and V row S times and spends a 5-step shuffle reduction per
+// (row, key): ~4x the instructions (0.28 ms per layer and 2048 cells, 6 % of a database encode -- profiles/r02).
+constexpr int kSeq64Warps = 4;
+constexpr int kSeq64WarpFloats = 2 * 32 * 64 + 32 * 68;  // K | V | Q rows (pitch 68: conflict-free row-per-lane reads), reused for scores and O
+//
+// Ragged form (seq_ptr != nullptr) for the intra-cell layers: the reference zero-pads every cell to 28 object slots and
+// attends WITHOUT a mask (cell_retrieval.py:81-103), so the 28 - n padded slots of a cell carry identical rows through both
+// layers.  The engine keeps ONE representative of them: cell b owns rows seq_ptr[b] .. seq_ptr[b+1]) = its min(n, slots)
+// objects followed, if n < slots, by the padding row, which counts `slots - n` times as a KEY (its softmax weight is
+// multiplied by that count) and once as a query.  Same mathematics, 9 rows instead of 28 at 8 objects per cell.
+__global__ void __launch_bounds__(kSeq64Warps * 32, 2) mha_seq64_kernel(const float* __restrict__ qkv, float* __restrict__ out, int n_units, int S_fixed, int d,
+                                                                     int n_heads, float scale, int round_out, const int32_t* __restrict__ seq_ptr,
+                                                                     const int32_t* __restrict__ cell_ptr, int slots) {
+  extern __shared__ __align__(16) float seq64_smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* Ks = seq64_smem + w * kSeq64WarpFloats;
+  float* Vs = Ks + 32 * 64;
+  float* Qs = Vs + 32 * 64;
+  const long ld = 3L * d;
+  const int rr = lane >> 4, c4 = (lane & 15) * 4;
+  for (int unit = blockIdx.x * kSeq64Warps + w; unit < n_units; unit += gridDim.x * kSeq64Warps) {
+    const int h = unit % n_heads;
+    const int seq = unit / n_heads;
+    long row0 = static_cast<long>(seq) * S_fixed;
+    int S = S_fixed;
+    float last_weight = 1.f;  // multiplicity of the last key
+    if (seq_ptr) {
+      row0 = seq_ptr[seq];
+      S = seq_ptr[seq + 1] - seq_ptr[seq];
+      const int n_obj = cell_ptr[seq + 1] - cell_ptr[seq];
+      if (n_obj < slots) last_weight = static_cast<float>(slots - n_obj);
+    }
+    const float* base = qkv + row0 * ld + h * 64 + c4;
+    for (int j = rr; j < S; j += 2) {  // two rows per instruction, 16 lanes x 16 bytes each
+      const float4 q4 = *reinterpret_cast<const float4*>(base + j * ld);
+      const float4 k4 = *reinterpret_cast<const float4*>(base + j * ld + d);
+      const float4 v4 = *reinterpret_cast<const float4*>(base + j * ld + 2 * d);
+      *reinterpret_cast<float4*>(Qs + j * 68 + c4) = q4;
+      *reinterpret_cast<float4*>(Ks + j * 64 + c4) = k4;
+      *reinterpret_cast<float4*>(Vs + j * 64 + c4) = v4;
+    }
+    __syncwarp();
+    const int i = lane < S ? lane : S - 1;  // idle lanes shadow the last row (no divergence); they store nothing
+    float q[64];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 t = *reinterpret_cast<const float4*>(Qs + i * 68 + c * 4);
+      q[4 * c] = t.x; q[4 * c + 1] = t.y; q[4 * c + 2] = t.z; q[4 * c + 3] = t.w;
+    }
+    __syncwarp();  // every lane holds its q row: Qs becomes the score buffer [key][lane]
+    float mx = -INFINITY;
+#pragma unroll 2
+    for (int j = 0; j < S; ++j) {
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float4 k4 = *reinterpret_cast<const float4*>(Ks + j * 64 + c * 4);  // same address in every lane: broadcast
+        p0 = fmaf(q[4 * c], k4.x, p0); p1 = fmaf(q[4 * c + 1], k4.y, p1); p2 = fmaf(q[4 * c + 2], k4.z, p2); p3 = fmaf(q[4 * c + 3], k4.w, p3);
+      }
+      const float sc = ((p0 + p1) + (p2 + p3)) * scale;
+      Qs[j * 32 + lane] = sc;
+      mx = fmaxf(mx, sc);
+    }
+    float sum = 0.f;
+    for (int j = 0; j < S; ++j) {
+      float e = expf(Qs[j * 32 + lane] - mx);
+      if (j == S - 1) e *= last_weight;
+      Qs[j * 32 + lane] = e;
+      sum += e;
+    }
+    const float inv = 1.f / sum;
+    float acc[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < S; ++j) {
+      const float pj = Qs[j * 32 + lane] * inv;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const float4 v4 = *reinterpret_cast<const float4*>(Vs + j * 64 + c * 4);
+        acc[4 * c] = fmaf(pj, v4.x, acc[4 * c]); acc[4 * c + 1] = fmaf(pj, v4.y, acc[4 * c + 1]);
+        acc[4 * c + 2] = fmaf(pj, v4.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(pj, v4.w, acc[4 * c + 3]);
+      }
+    }
+    __syncwarp();  // scores are dead: Qs becomes the output staging [row][68]
+    if (lane < S) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float4 o = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+        if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        *reinterpret_cast<float4*>(Qs + lane * 68 + c * 4) = o;
+      }
+    }
+    __syncwarp();
+    float* obase = out + row0 * d + h * 64 + c4;
+    for (int j = rr; j < S; j += 2) *reinterpret_cast<float4*>(obase + static_cast<long>(j) * d) = *reinterpret_cast<const float4*>(Qs + j * 68 + c4);
+    __syncwarp();  // before the next unit's staging overwrites the buffers
+  }
+}
+
 cudaError_t mha_cross_small(const float* q, long ldq, const float* k, const float* v, long ldkv, float* out, int n_seq, int Sq, int Sk, int d,
                             int n_heads, cudaStream_t st, Launches* lc, int round_out) {
   if (n_seq <= 0) return cudaSuccess;
@@ -265,7 +368,34 @@ cudaError_t mha_cross_small(const float* q, long ldq, const float* k, const floa
   return cudaGetLastError();
 }
 
+static cudaError_t launch_seq64(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, int round_out, const int32_t* seq_ptr,
+                                const int32_t* cell_ptr, int slots, cudaStream_t st, Launches* lc) {
+  static bool configured_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  constexpr int smem = kSeq64Warps * kSeq64WarpFloats * 4;
+  if (!configured_dev[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(mha_seq64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    configured_dev[dev & 63] = true;
+  }
+  if (lc) lc->n++;
+  const int n_units = n_seq * n_heads;
+  const int blocks = (n_units + kSeq64Warps - 1) / kSeq64Warps;
+  mha_seq64_kernel<<<blocks, kSeq64Warps * 32, smem, st>>>(qkv, out, n_units, S, d, n_heads, 1.f / sqrtf(64.f), round_out, seq_ptr, cell_ptr, slots);
+  return cudaGetLastError();
+}
+
+cudaError_t mha_cells64(const float* qkv, float* out, int n_cells, const int32_t* row_ptr_dev, const int32_t* cell_ptr_dev, int slots, int d,
+                        int n_heads, cudaStream_t st, Launches* lc) {
+  if (n_cells <= 0) return cudaSuccess;
+  if (d != 64 * n_heads || slots < 1 || slots > 32 || static_cast<long>(n_cells) * n_heads >= (1L << 31)) return cudaErrorInvalidValue;
+  return launch_seq64(qkv, out, n_cells, 0, d, n_heads, 0, row_ptr_dev, cell_ptr_dev, slots, st, lc);
+}
+
 cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out) {
+  if (n_seq > 0 && d == 64 * n_heads && S > 16 && S <= 32 && static_cast<long>(n_seq) * n_heads < (1L << 31))
+    return launch_seq64(qkv, out, n_seq, S, d, n_heads, round_out, nullptr, nullptr, 0, st, lc);  // long sequences, 64-wide heads
   return mha_cross_small(qkv, 3L * d, qkv + d, qkv + 2 * d, 3L * d, out, n_seq, S, S, d, n_heads, st, lc, round_out);
 }
 
@@ -631,6 +761,65 @@ cudaError_t scatter_objects(const float* emb, const int32_t* cell_ptr_dev, int n
   if (lc) lc->n++;
   const long slots = static_cast<long>(n_cells) * kObjectSlots;
   scatter_objects_kernel<<<static_cast<unsigned>((slots + 7) / 8), 256, 0, st>>>(emb, cell_ptr_dev, n_cells, X);
+  return cudaGetLastError();
+}
+
+// ---- the same without the duplicate padding rows: cell b -> rows row_ptr[b] ..: its min(n, 28) normalised objects, then ONE
+// zero row standing for all 28 - n padded slots (see mha_seq64_kernel).  One warp per cell.
+__global__ void scatter_objects_ragged_kernel(const float* __restrict__ emb, const int32_t* __restrict__ cell_ptr, const int32_t* __restrict__ row_ptr,
+                                              int n_cells, float* __restrict__ X) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= n_cells) return;
+  const int lane = threadIdx.x & 31;
+  const int n = cell_ptr[b + 1] - cell_ptr[b];
+  const int rows = row_ptr[b + 1] - row_ptr[b];
+  for (int s = 0; s < rows; ++s) {
+    float4* dst = reinterpret_cast<float4*>(X + static_cast<long>(row_ptr[b] + s) * kEmbed);
+    if (s >= n) {
+      dst[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      dst[lane + 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const float4* src = reinterpret_cast<const float4*>(emb + static_cast<long>(cell_ptr[b] + s) * kEmbed);
+    const float4 a = src[lane], c = src[lane + 32];
+    float ss = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w) + (c.x * c.x + c.y * c.y) + (c.z * c.z + c.w * c.w);
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    dst[lane] = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+    dst[lane + 32] = make_float4(c.x * inv, c.y * inv, c.z * inv, c.w * inv);
+  }
+}
+
+cudaError_t scatter_objects_ragged(const float* emb, const int32_t* cell_ptr_dev, const int32_t* row_ptr_dev, int n_cells, float* X, cudaStream_t st,
+                                   Launches* lc) {
+  if (n_cells <= 0) return cudaSuccess;
+  if (lc) lc->n++;
+  scatter_objects_ragged_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(emb, cell_ptr_dev, row_ptr_dev, n_cells, X);
+  return cudaGetLastError();
+}
+
+// y[b, :] = max over the rows row_ptr[b] .. row_ptr[b+1]) of x (d = 256); one warp per cell
+__global__ void max_over_rows_ragged_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_ptr, float* __restrict__ y, int n_cells) {
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= n_cells) return;
+  const int lane = threadIdx.x & 31;
+  const int r0 = row_ptr[b], r1 = row_ptr[b + 1];
+  float4 m0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), m1 = m0;
+  for (int r = r0; r < r1; ++r) {
+    const float4* src = reinterpret_cast<const float4*>(x + static_cast<long>(r) * kEmbed);
+    const float4 a = src[lane], c = src[lane + 32];
+    m0.x = fmaxf(m0.x, a.x); m0.y = fmaxf(m0.y, a.y); m0.z = fmaxf(m0.z, a.z); m0.w = fmaxf(m0.w, a.w);
+    m1.x = fmaxf(m1.x, c.x); m1.y = fmaxf(m1.y, c.y); m1.z = fmaxf(m1.z, c.z); m1.w = fmaxf(m1.w, c.w);
+  }
+  float4* dst = reinterpret_cast<float4*>(y + static_cast<long>(b) * kEmbed);
+  dst[lane] = m0;
+  dst[lane + 32] = m1;
+}
+
+cudaError_t max_over_rows_ragged(const float* x, const int32_t* row_ptr_dev, float* y, int n_cells, cudaStream_t st, Launches* lc) {
+  if (n_cells <= 0) return cudaSuccess;
+  if (lc) lc->n++;
+  max_over_rows_ragged_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(x, row_ptr_dev, y, n_cells);
   return cudaGetLastError();
 }
 

@@ -371,9 +371,17 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
     const int ch0 = (PAIR ? (sub & 3) : sub) * 8;         // my 8 channels inside a 64-channel slice of a Qx row
     const ulonglong2* tab2 = reinterpret_cast<const ulonglong2*>(table);
     // -v for my 8 channels: W1p . (o' - pos_i), fp32, rounded once to fp16 (saturating)
+    // paired tiles (SA1) have ONE 64-channel slice: the thread's 24 W1p values never change and stay in registers (the six
+    // 16-byte table reads were a quarter of the gather's shared-memory wavefronts per item)
+    ulonglong2 tabr[6];
+    if (PAIR) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) tabr[k] = tab2[(sub & 3) + 8 * k];
+    }
     auto neg_v8 = [&](int slice, float ex, float ey, float ez, uint32_t (&nv)[4]) {
       const ulonglong2* tb = tab2 + slice * 48 + (PAIR ? (sub & 3) : sub);  // 48 = 3 coordinates x 2 halves x 8 groups
-      const ulonglong2 wx01 = tb[0], wx23 = tb[8], wy01 = tb[16], wy23 = tb[24], wz01 = tb[32], wz23 = tb[40];
+      const ulonglong2 wx01 = PAIR ? tabr[0] : tb[0], wx23 = PAIR ? tabr[1] : tb[8], wy01 = PAIR ? tabr[2] : tb[16],
+                       wy23 = PAIR ? tabr[3] : tb[24], wz01 = PAIR ? tabr[4] : tb[32], wz23 = PAIR ? tabr[5] : tb[40];
       const uint64_t wx[4] = {wx01.x, wx01.y, wx23.x, wx23.y}, wy[4] = {wy01.x, wy01.y, wy23.x, wy23.y},
                      wz[4] = {wz01.x, wz01.y, wz23.x, wz23.y};
 #pragma unroll
@@ -434,11 +442,17 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
           const int cen = (PAIR ? (2 * (tt - 1) + set) * 4 : (tt - 1) * 4) + cq;
           const int cnt = cnt_s[cen];
           int src_off[8];
+          {
+            // the centroid's whole 32-byte list as two broadcast 16-byte reads; my slot (rb & 3) + 4 i is byte rb & 3 of word i
+            const uint4 l0 = *reinterpret_cast<const uint4*>(nbr_s + cen * 32), l1 = *reinterpret_cast<const uint4*>(nbr_s + cen * 32 + 16);
+            const uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+            const int sh = (rb & 3) * 8;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int sl = (rb & 3) + 4 * i;
-            const int j = nbr_s[cen * 32 + (sl < cnt ? sl : 0)];  // empty slots replicate slot 0: the max is unchanged
-            src_off[i] = j * (C1 * 2) + ch0 * 2;
+            for (int i = 0; i < 8; ++i) {
+              const int sl = (rb & 3) + 4 * i;
+              const int j = sl < cnt ? ((lw[i] >> sh) & 0xff) : (lw[0] & 0xff);  // empty slots replicate slot 0: the max is unchanged
+              src_off[i] = j * (C1 * 2) + ch0 * 2;
+            }
           }
           const float ex = cpos_s[0] - cpos_s[cen * 3 + 0], ey = cpos_s[1] - cpos_s[cen * 3 + 1], ez = cpos_s[2] - cpos_s[cen * 3 + 2];  // o - pos_i
 #pragma unroll 1

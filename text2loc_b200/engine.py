@@ -350,6 +350,24 @@ class Engine:
             raise RuntimeError("debug_linear_f16_residual: rows beyond M were written")
         return buf[:M]
 
+    def debug_mha(self, qkv, n_seq: int, S: int, n_heads: int):
+        """Small-sequence attention core on packed rows [n_seq*S, 3d] -> [n_seq*S, d]."""
+        qkv = self._dev(qkv, torch.float32)
+        d = qkv.shape[1] // 3
+        out = torch.empty((n_seq * S, d), dtype=torch.float32, device=self.device)
+        self._check(self._lib.t2l_debug_mha(self._h, _ptr(qkv), _ptr(out), n_seq, S, d, n_heads, self._stream()))
+        return out
+
+    def debug_mha_cells(self, qkv, row_ptr, cell_ptr, slots: int, n_heads: int):
+        """Intra-cell attention core on packed rows with one representative padding row per cell."""
+        qkv = self._dev(qkv, torch.float32)
+        row_ptr, cell_ptr = self._dev(row_ptr, torch.int32), self._dev(cell_ptr, torch.int32)
+        d = qkv.shape[1] // 3
+        out = torch.empty((qkv.shape[0], d), dtype=torch.float32, device=self.device)
+        self._check(self._lib.t2l_debug_mha_cells(self._h, _ptr(qkv), _ptr(out), row_ptr.numel() - 1, _ptr(row_ptr), _ptr(cell_ptr), slots, d,
+                                                  n_heads, self._stream()))
+        return out
+
     def debug_linear(self, A, W, bias=None, act=0, segmax=False, path=1):
         rowmajor = lambda t: t if (t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1) else self._dev(t, torch.float32)
         A, W = rowmajor(A), rowmajor(W)  # row-padded views (stride(0) > K) are passed through as lda / ldw
