@@ -207,6 +207,10 @@ int t2l_debug_mha(t2l_engine* e, const float* qkv, float* out, int n_seq, int S,
 int t2l_debug_mha_cells(t2l_engine* e, const float* qkv, float* out, int n_cells, const int32_t* row_ptr_dev,
                         const int32_t* cell_ptr_dev, int slots, int d, int n_heads, void* stream);
 
+/* Timing bisect of the fused set-abstraction kernel (profiling only; embeddings are INVALID while mode != 0):
+ * 1 = the epilogue releases the accumulators without reading them, 2 = the MMA issuer skips the MMAs, 3 = both, 0 = normal. */
+int t2l_debug_sa_bisect(t2l_engine* e, int mode);
+
 #ifdef __cplusplus
 }
 #endif

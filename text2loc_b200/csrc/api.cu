@@ -72,6 +72,7 @@ struct t2l_engine {
                              // operand bytes); T2L_TEXT_TF32=1 selects the tf32 path for A/B checks
   bool text_stream16 = true; // token layer's residual stream (x + attn, LayerNorm1, x1 + ffn) carried as fp16 rows between the GEMMs and
                              // the LayerNorms; T2L_TEXT_STREAM32=1 keeps it in fp32 (round 1's layout)
+  int sa_bisect = 0;         // t2l_debug_sa_bisect: timing bisect of the fused set-abstraction kernel (results invalid when != 0)
   bool text_reg_epilogue = false;  // T2L_TEXT_REG_EPI=1: register-staged residual epilogue instead of the TMA one (A/B)
   float* pooled = nullptr;   // [pooled_cap, 1024] max-over-tokens sentence features between the two text stages
   size_t pooled_cap = 0;
@@ -639,7 +640,7 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
     SaObj2 so;
     so.Qx16 = L.Qx; so.C1 = L.C1; so.C2 = L.C2; so.cpos = L.cpos; so.nbr = L.nbr; so.cnt = L.cnt; so.loop_src_obj = loop_src;
     so.loop_half = loop_half; so.Wp = W(e, nm + ".w1p").dev; so.W2h = W(e, nm + ".w2").dev16; so.b2 = W(e, nm + ".b2").dev;
-    so.out = L.xout; so.ldo = L.ldo; so.n_obj = n; so.P = L.P; so.M = L.M;
+    so.out = L.xout; so.ldo = L.ldo; so.n_obj = n; so.P = L.P; so.M = L.M; so.bisect = e->sa_bisect;
     if (!so.W2h) return fail(e, "internal: no fp16 copy of %s.w2", L.name);
     CU(sa_obj2(so, st, &e->lc));
   }
@@ -913,7 +914,7 @@ extern "C" int t2l_fine_encode_hints(t2l_engine* e, const float* t5, int n_sente
 static int fine_match_impl(t2l_engine* e, const float* obj_emb, const int32_t* pair_cell, const float* hints, const int32_t* pair_query, int n_pairs,
                            int n_obj, int n_hints, float* offsets, cudaStream_t st) {
   const int d = T2L_FINE_DIM;
-  const int chunk = 4096;  // pairs per pass (~300 KB of scratch each)
+  const int chunk = 16384;  // pairs per pass (~300 KB of scratch each; 4 096 -> 16 384: a quarter of the ~100 small launches per pass)
   for (int p0 = 0; p0 < n_pairs; p0 += chunk) {
     const int np = n_pairs - p0 < chunk ? n_pairs - p0 : chunk;
     if (ensure_arena(e, static_cast<size_t>(np) * (static_cast<size_t>(n_obj) + n_hints) * d * 4 * 40 + (size_t(1) << 22))) return 1;
@@ -1229,5 +1230,12 @@ extern "C" int t2l_debug_mha_cells(t2l_engine* e, const float* qkv, float* out, 
   if (!qkv || !out || !row_ptr_dev || !cell_ptr_dev || n_cells < 0) return fail(e, "debug_mha_cells: bad argument");
   ENTER_STREAM(e, stream);
   CU(mha_cells64(qkv, out, n_cells, row_ptr_dev, cell_ptr_dev, slots, d, n_heads, static_cast<cudaStream_t>(stream), &e->lc));
+  return 0;
+}
+
+extern "C" int t2l_debug_sa_bisect(t2l_engine* e, int mode) {
+  if (!e) return 1;
+  if (mode < 0 || mode > 3) return fail(e, "debug_sa_bisect: mode must be 0..3");
+  e->sa_bisect = mode;
   return 0;
 }

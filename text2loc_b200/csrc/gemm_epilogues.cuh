@@ -313,16 +313,18 @@ struct SegMaxEpi {
     int M, N;           // M % 32 == 0
     int round_out;
   };
-  static constexpr int kSmemBytes = kEpiBiasSmem;
+  // Two epilogue warp sets (even / odd 32-column chunks): the 31-shuffle butterfly per chunk made the single set the limiter
+  // of GA's second layer (K = 512: 0.52 ms per 16 384 objects = 1 057 TFLOP/s, profiles/r02).
+  static constexpr int kSets = 2;
+  static constexpr int kSmemBytes = kSets * kEpiBiasSmem;  // one 256-float bias slice per epilogue warp
   static constexpr bool kCompactLoop = false;
-  static constexpr int kSets = 1;
   const Params& p;
   float* s_bias;
   int ew, lane, block_n;
   float side_v[8];  // this lane's side value for each 32-column chunk of the tile
   int bias_col0 = -1;
-  __device__ SegMaxEpi(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_, int)
-      : p(p_), s_bias(reinterpret_cast<float*>(smem) + ew_ * 256), ew(ew_), lane(lane_), block_n(block_n_) {}
+  __device__ SegMaxEpi(const Params& p_, uint8_t* smem, int ew_, int lane_, int block_n_, int set_)
+      : p(p_), s_bias(reinterpret_cast<float*>(smem) + (set_ * 4 + ew_) * 256), ew(ew_), lane(lane_), block_n(block_n_) {}
   __device__ void prefetch_unit(int, int) {}
   __device__ void begin_unit(int, int) {}
   __device__ void end_unit(int, int) {}

@@ -77,6 +77,7 @@ struct SaObj2 {
   const __half* W2h; const float* b2;    // [C2, C1] fp16, [C2]
   float* out; int ldo;                   // [n*M, ldo], ldo >= C2
   int n_obj, P, M;
+  int bisect = 0;                        // timing bisect (t2l_debug_sa_bisect): 1 = skip the accumulator drain, 2 = skip the MMAs; results invalid
 };
 cudaError_t sa_obj2(const SaObj2& a, cudaStream_t st, Launches* lc);
 // GA input as fp16 rows of 264 halfs: A16[n*32, 264] = [x3 (256) | cpos3 (3) | 0 x 5] (K padded to a 16-byte multiple)

@@ -30,8 +30,9 @@
 //     epilogue warps.  Its tiles are now PAIRED: one item carries the 32 channels of two different edge groups side by side
 //     (K = 64) and W2 sits in tensor memory as a block-diagonal [[W2, 0], [0, W2]], so lanes 0..63 of the accumulator
 //     are group A's channels and lanes 64..127 group B's: half as many tiles, barriers and fences per object.
-//   * For SA3 the two 128-channel halves of a tile go to two accumulators one after the other (half outer, K inner): the
-//     epilogue of half 0 overlaps the MMAs of half 1; the edge items stay in the ring until half 1 has read them.
+//   * For SA3 the two 128-channel halves of a tile go to two accumulators; half 0 consumes every item as it arrives, half 1
+//     follows two items behind and releases the ring slot, so its tail overlaps the drain of half 0 and no item waits in the
+//     ring for a whole tile (the first form -- half outer, K inner -- held all four items until half 1 had read them).
 //
 // Warp roles (512 threads): 0 = bulk-copy producer (one block of six copies per object), 1 = MMA issuer, 2 = TMEM
 // allocator, 4..7 = W2 upload, then epilogue (one TMEM lane quadrant each), 8..15 = gather (two groups of four warps).
@@ -55,6 +56,7 @@ struct SaObj2Params {
   float* out;                 // [n*M, ldo]
   int ldo;                    // row pitch of out (>= C2: the next level appends position columns)
   int n_obj;
+  int bisect;                 // timing bisect (t2l_debug_sa_bisect; results are INVALID when != 0): 1 = no accumulator drain, 2 = no MMAs
 };
 
 template <int C1_, int C2_, int P_, int M_, bool PAIR_>
@@ -95,7 +97,7 @@ struct Sa2Cfg {
                 "bulk copies move multiples of 16 bytes");
   static_assert(W_COLS <= ACC_COL0, "W2 and the accumulators share the 512 tensor-memory columns");
   static_assert((2 * STAGES + 2 * NACC + 2 * NOBJ) * 8 + 4 <= BAR_BYTES, "barrier block too small");
-  static_assert(STAGES >= KB + 1 || MH == 1, "half-outer MMA order keeps a whole tile in the ring");
+  static_assert(STAGES >= 4 || MH == 1, "half 1 of a tile lags two items behind half 0: three items live plus one being built");
   static_assert(STAGES >= 3, "ring too shallow");
   static_assert(PAIR ? (C1 == 32 && C2 == 64) : (C1 % 64 == 0 && C2 % 128 == 0), "shape not covered");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
@@ -263,30 +265,63 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    long u0 = 0;  // first ring item of the current tile
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const long n_tiles = static_cast<long>(o1 - o0) * kTilesPerObj;
-    for (long tile = 0; tile < n_tiles; ++tile, u0 += Cfg::KB) {
-#pragma unroll 1
-      for (int h = 0; h < Cfg::MH; ++h) {
+    // (32-bit item counters: `u % STAGES` on a 64-bit counter was a 25-instruction sequence per item in every gather thread)
+    const uint32_t n_tiles = static_cast<uint32_t>(o1 - o0) * kTilesPerObj;
+    if constexpr (Cfg::MH == 2) {
+      // Two 128-channel halves per tile, one accumulator each (NACC == 2).  Half 0 consumes an item as soon as it is built;
+      // half 1 follows kLag items behind and releases the ring slot.  (Round-2 first form: half outer, K inner -- all four items
+      // of a tile stayed in the five-slot ring until half 1 had read them, and the gather warps spent a third of their time
+      // waiting for slots: ncu source view, 16 % of all samples on that one wait.)  Half 1's tail overlaps the drain of half 0.
+      constexpr uint32_t kLag = 2;
+      const uint32_t n_items = n_tiles * Cfg::KB;
+      auto issue = [&](uint32_t g, int h) {
+        const uint32_t tile = g / Cfg::KB, kb = g % Cfg::KB;
+        const int stage = static_cast<int>(g % Cfg::STAGES);
+        if (kb == 0) {  // first MMA of this tile into accumulator h: the epilogue has drained the previous tile's
+          mbar_wait(&tmem_empty[h], (tile & 1) ^ 1);
+          tc_fence_after();
+        }
+        if (h == 0) {
+          mbar_wait(&full_bar[stage], (g / Cfg::STAGES) & 1);
+          tc_fence_after();
+        }
+        if (elect_one()) {
+          const uint64_t edesc = umma_desc_sw128(stage_base + stage * Cfg::A_BYTES);
+          const uint32_t d_addr = tmem_base + Cfg::ACC_COL0 + h * 128;
+          const uint32_t w_addr = tmem_base + h * (Cfg::KC / 2) + kb * 32;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (!(p.bisect & 2)) umma_f16_ts(d_addr, w_addr + 8 * k, edesc + 2 * k, Cfg::IDESC, (kb | k) != 0);
+          if (h == 1) tc_commit(&empty_bar[stage]);
+          if (kb == Cfg::KB - 1) tc_commit(&tmem_full[h]);
+        }
+        __syncwarp();
+      };
+      for (uint32_t g = 0; g < n_items + kLag; ++g) {
+        if (g >= kLag) issue(g - kLag, 1);
+        if (g < n_items) issue(g, 0);
+      }
+    } else {
+      uint32_t u0 = 0;  // first ring item of the current tile
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (uint32_t tile = 0; tile < n_tiles; ++tile, u0 += Cfg::KB) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_addr = tmem_base + Cfg::ACC_COL0 + acc * 128;
 #pragma unroll 1
         for (int kb = 0; kb < Cfg::KB; ++kb) {
-          const long u = u0 + kb;
+          const uint32_t u = u0 + kb;
           const int stage = static_cast<int>(u % Cfg::STAGES);
-          if (h == 0) {  // the items stay resident for the later halves
-            mbar_wait(&full_bar[stage], static_cast<uint32_t>(u / Cfg::STAGES) & 1);
-            tc_fence_after();
-          }
+          mbar_wait(&full_bar[stage], (u / Cfg::STAGES) & 1);
+          tc_fence_after();
           if (elect_one()) {  // see umma_gemm.cuh: keeps UTCHMMA/UTCBAR straight-line
             const uint64_t edesc = umma_desc_sw128(stage_base + stage * Cfg::A_BYTES);  // edge tile: the N-side operand
-            const uint32_t w_addr = tmem_base + h * (Cfg::KC / 2) + kb * 32;            // 64 K elements = 32 columns per item
+            const uint32_t w_addr = tmem_base + kb * 32;                                // 64 K elements = 32 columns per item
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16_ts(d_addr, w_addr + 8 * k, edesc + 2 * k, Cfg::IDESC, (kb | k) != 0);
-            if (h == Cfg::MH - 1) tc_commit(&empty_bar[stage]);
+            for (int k = 0; k < 4; ++k)
+              if (!(p.bisect & 2)) umma_f16_ts(d_addr, w_addr + 8 * k, edesc + 2 * k, Cfg::IDESC, (kb | k) != 0);
+            tc_commit(&empty_bar[stage]);
             if (kb == Cfg::KB - 1) tc_commit(&tmem_full[acc]);
           }
           __syncwarp();
@@ -315,6 +350,13 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
           tc_fence_after();
           const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + Cfg::ACC_COL0 + acc * 128;
           float v[2][32];
+          if (p.bisect & 1) {  // timing bisect: release the accumulator without reading it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1; }
+            continue;
+          }
           tmem_ld_32x32(t_addr, v[0]);
           if (t == 0) {
             // self-loop tile: column e = one centroid's self-loop edge; park relu(. + b2) until that centroid's neighbour tile is reduced
@@ -392,8 +434,8 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
         nv[q] = s2_pack_half2(lo, hi);
       }
     };
-    long u = 0;     // ring item counter of this CTA
-    long tile = 0;  // tile counter of this CTA (self-loop tiles included)
+    uint32_t u = 0;     // ring item counter of this CTA
+    uint32_t tile = 0;  // tile counter of this CTA (self-loop tiles included)
     for (int o = o0, n = 0; o < o1; ++o, ++n) {
       const int buf = n % Cfg::NOBJ;
       const uint8_t* ob = obj_base + buf * Cfg::OBJ_BYTES;
@@ -406,8 +448,8 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
       mbar_wait(&obj_full[buf], (n / Cfg::NOBJ) & 1);
 #pragma unroll 1
       for (int tt = 0; tt < kTilesPerObj; ++tt, ++tile) {
-        if (kTileMode && (tile & 1) != group) { u += Cfg::KB; continue; }
-        const long u_tile = u;
+        if (kTileMode && static_cast<int>(tile & 1) != group) { u += Cfg::KB; continue; }
+        const uint32_t u_tile = u;
         if (tt == 0) {
           // ---- self-loop tile: row e = the self-loop edge of centroid e (source row e of the other object's half block);
           // every row has its own centroid, so -v is formed per row.  Only the tile's live rows are built.
@@ -415,9 +457,9 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
           const float ox = sorg_s[0], oy = sorg_s[1], oz = sorg_s[2];  // origin of the SOURCE object: its Qx rows are relative to it
 #pragma unroll 1
           for (int kb = 0; kb < Cfg::KB; ++kb, ++u) {
-            if (!kTileMode && (u & 1) != group) continue;
+            if (!kTileMode && static_cast<int>(u & 1) != group) continue;
             const int stage = static_cast<int>(u % Cfg::STAGES);
-            mbar_wait(&empty_bar[stage], (static_cast<uint32_t>(u / Cfg::STAGES) & 1) ^ 1);
+            mbar_wait(&empty_bar[stage], ((u / Cfg::STAGES) & 1) ^ 1);
             uint8_t* abase = stage_base + stage * Cfg::A_BYTES;
             if (live) {
 #pragma unroll 2
@@ -457,14 +499,14 @@ __global__ void __launch_bounds__(kSa2Threads, 1) sa_obj2_kernel(const SaObj2Par
           const float ex = cpos_s[0] - cpos_s[cen * 3 + 0], ey = cpos_s[1] - cpos_s[cen * 3 + 1], ez = cpos_s[2] - cpos_s[cen * 3 + 2];  // o - pos_i
 #pragma unroll 1
           for (int kb = 0; kb < Cfg::KB; ++kb, ++u) {
-            if (!kTileMode && (u & 1) != group) continue;
+            if (!kTileMode && static_cast<int>(u & 1) != group) continue;
             const int stage = static_cast<int>(u % Cfg::STAGES);
             uint4 raw[8];  // all Qx reads of the item in flight before anything waits
 #pragma unroll
             for (int i = 0; i < 8; ++i) raw[i] = *reinterpret_cast<const uint4*>(px_s + src_off[i] + (PAIR ? 0 : kb * 128));
             uint32_t nv[4];
             neg_v8(PAIR ? 0 : kb, ex, ey, ez, nv);
-            mbar_wait(&empty_bar[stage], (static_cast<uint32_t>(u / Cfg::STAGES) & 1) ^ 1);
+            mbar_wait(&empty_bar[stage], ((u / Cfg::STAGES) & 1) ^ 1);
             uint8_t* abase = stage_base + stage * Cfg::A_BYTES;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -512,7 +554,7 @@ static cudaError_t launch_sa_obj2(const SaObj2& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  SaObj2Params p{a.Qx16, a.cpos, a.nbr, a.cnt, a.loop_src_obj, a.loop_half, a.Wp, a.W2h, a.b2, a.out, a.ldo, a.n_obj};
+  SaObj2Params p{a.Qx16, a.cpos, a.nbr, a.cnt, a.loop_src_obj, a.loop_half, a.Wp, a.W2h, a.b2, a.out, a.ldo, a.n_obj, a.bisect};
   const int grid = a.n_obj < tma_api().num_sms ? a.n_obj : tma_api().num_sms;
   sa_obj2_kernel<Cfg><<<grid, kSa2Threads, Cfg::SMEM, st>>>(p);
   return cudaGetLastError();

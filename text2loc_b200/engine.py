@@ -6,6 +6,7 @@ libtext2loc_b200.so.  Work is enqueued on torch's current CUDA stream.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 import numpy as np
@@ -115,7 +116,8 @@ class Engine:
             *[_ptr(r[k]) for k in ("features2", "fps1", "fps2", "fps3", "nbr1", "nbr2", "nbr3", "cnt1", "cnt2", "cnt3")], self._stream()))
         return r
 
-    TOKENS_PER_CHUNK = 32768  # the engine's internal text chunk (api.cu: tok_chunk)
+    # tokens per H2D staging chunk of a HOST input (the copy of chunk i+1 hides behind the compute of chunk i)
+    TOKENS_PER_CHUNK = int(os.environ.get("T2L_HOST_TOK_CHUNK", "16384"))
 
     def encode_text(self, t5, n_sent: int) -> torch.Tensor:
         """t5 [nq*n_sent, n_tok, 1024] (T5 last_hidden_state, float32 or float16) -> unit rows [nq,256] on device.
