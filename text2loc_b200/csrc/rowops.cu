@@ -248,66 +248,78 @@ __global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict_
   for (int r = 0; r < R; ++r) o[r * 32 + lane] = round_out ? round_tf32(acc[r]) : acc[r];
 }
 
-// Self attention with head_dim 64 and 16 < S <= 32 (the intra-cell layers: 28 object slots, cell_retrieval.py:101-103): ONE warp
-// per (sequence, head), lane i = query row i.  K, V and Q of the head are staged in shared memory once (coalesced 256-byte
-// rows); a lane then walks the keys with its q row in registers and K / V rows arriving as warp-wide broadcasts, 64 independent
-// FMAs per key.  The row-per-warp kernel above reads every K and V row S times and spends a 5-step shuffle reduction per
-// (row, key): ~4x the instructions (0.28 ms per layer and 2048 cells, 6 % of a database encode -- profiles/r02).
-constexpr int kSeq64Warps = 4;
-constexpr int kSeq64WarpFloats = 2 * 32 * 64 + 32 * 68;  // K | V | Q rows (pitch 68: conflict-free row-per-lane reads), reused for scores and O
+// Sequence-per-warp attention core (head_dim 64 or 32; at most 32 queries and 32 keys per sequence): ONE warp per
+// (sequence, head), lane i = query row i.  K, V and Q of the head are staged in shared memory once (coalesced rows); a lane
+// then walks the keys with its q row in registers and K / V rows arriving as warp-wide broadcasts, HD independent FMAs per
+// key.  The row-per-warp kernel above reads every K and V row S times and spends a 5-step shuffle reduction per (row, key):
+// ~4x the instructions (intra-cell layers: 0.28 ms per layer and 2 048 cells; fine-stage decoder layers with 32-wide heads:
+// 42 % of the match stage -- profiles/r02).  Self attention (q, k, v slices of one packed buffer) and cross attention
+// (queries from one buffer, keys / values from the memory buffer; nn.TransformerDecoderLayer.multihead_attn).
 //
-// Ragged form (seq_ptr != nullptr) for the intra-cell layers: the reference zero-pads every cell to 28 object slots and
-// attends WITHOUT a mask (cell_retrieval.py:81-103), so the 28 - n padded slots of a cell carry identical rows through both
-// layers.  The engine keeps ONE representative of them: cell b owns rows seq_ptr[b] .. seq_ptr[b+1]) = its min(n, slots)
-// objects followed, if n < slots, by the padding row, which counts `slots - n` times as a KEY (its softmax weight is
-// multiplied by that count) and once as a query.  Same mathematics, 9 rows instead of 28 at 8 objects per cell.
-__global__ void __launch_bounds__(kSeq64Warps * 32, 2) mha_seq64_kernel(const float* __restrict__ qkv, float* __restrict__ out, int n_units, int S_fixed, int d,
-                                                                     int n_heads, float scale, int round_out, const int32_t* __restrict__ seq_ptr,
-                                                                     const int32_t* __restrict__ cell_ptr, int slots) {
-  extern __shared__ __align__(16) float seq64_smem[];
+// Ragged form (seq_ptr != nullptr, self attention) for the intra-cell layers: the reference zero-pads every cell to 28 object
+// slots and attends WITHOUT a mask (cell_retrieval.py:81-103), so the 28 - n padded slots of a cell carry identical rows
+// through both layers.  The engine keeps ONE representative of them: cell b owns rows seq_ptr[b] .. seq_ptr[b+1]) = its
+// min(n, slots) objects followed, if n < slots, by the padding row, which counts `slots - n` times as a KEY (its softmax
+// weight is multiplied by that count) and once as a query.  Same mathematics, 9 rows instead of 28 at 8 objects per cell.
+constexpr int kSeqWarps = 4;
+template <int HD>
+struct SeqAttn {
+  static constexpr int QP = HD + 4;                            // Q / O row pitch: conflict-free row-per-lane 16-byte reads
+  static constexpr int kWarpFloats = 2 * 32 * HD + 32 * QP;    // K | V | Q rows; the Q block is reused for scores [key][lane] and O
+  static constexpr int kSmemBytes = kSeqWarps * kWarpFloats * 4;
+  static constexpr int LPR = HD / 4;                           // lanes per staged row (16 bytes each)
+  static constexpr int RPI = 32 / LPR;                         // rows per staging instruction
+  static_assert(32 * 32 <= 32 * QP, "score buffer fits the Q block");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(kSeqWarps * 32, 2) mha_seq_kernel(const float* __restrict__ qp, long ldq, const float* __restrict__ kp,
+                                                                    const float* __restrict__ vp, long ldkv, float* __restrict__ out, long ldo,
+                                                                    int n_units, int Sq_fixed, int Sk_fixed, int n_heads, float scale, int round_out,
+                                                                    const int32_t* __restrict__ seq_ptr, const int32_t* __restrict__ cell_ptr, int slots) {
+  using A = SeqAttn<HD>;
+  extern __shared__ __align__(16) float seq_smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* Ks = seq64_smem + w * kSeq64WarpFloats;
-  float* Vs = Ks + 32 * 64;
-  float* Qs = Vs + 32 * 64;
-  const long ld = 3L * d;
-  const int rr = lane >> 4, c4 = (lane & 15) * 4;
-  for (int unit = blockIdx.x * kSeq64Warps + w; unit < n_units; unit += gridDim.x * kSeq64Warps) {
+  float* Ks = seq_smem + w * A::kWarpFloats;
+  float* Vs = Ks + 32 * HD;
+  float* Qs = Vs + 32 * HD;
+  const int rr = lane / A::LPR, c4 = (lane % A::LPR) * 4;
+  for (int unit = blockIdx.x * kSeqWarps + w; unit < n_units; unit += gridDim.x * kSeqWarps) {
     const int h = unit % n_heads;
     const int seq = unit / n_heads;
-    long row0 = static_cast<long>(seq) * S_fixed;
-    int S = S_fixed;
+    long qrow0 = static_cast<long>(seq) * Sq_fixed, krow0 = static_cast<long>(seq) * Sk_fixed;
+    int Sq = Sq_fixed, Sk = Sk_fixed;
     float last_weight = 1.f;  // multiplicity of the last key
     if (seq_ptr) {
-      row0 = seq_ptr[seq];
-      S = seq_ptr[seq + 1] - seq_ptr[seq];
+      qrow0 = krow0 = seq_ptr[seq];
+      Sq = Sk = seq_ptr[seq + 1] - seq_ptr[seq];
       const int n_obj = cell_ptr[seq + 1] - cell_ptr[seq];
       if (n_obj < slots) last_weight = static_cast<float>(slots - n_obj);
     }
-    const float* base = qkv + row0 * ld + h * 64 + c4;
-    for (int j = rr; j < S; j += 2) {  // two rows per instruction, 16 lanes x 16 bytes each
-      const float4 q4 = *reinterpret_cast<const float4*>(base + j * ld);
-      const float4 k4 = *reinterpret_cast<const float4*>(base + j * ld + d);
-      const float4 v4 = *reinterpret_cast<const float4*>(base + j * ld + 2 * d);
-      *reinterpret_cast<float4*>(Qs + j * 68 + c4) = q4;
-      *reinterpret_cast<float4*>(Ks + j * 64 + c4) = k4;
-      *reinterpret_cast<float4*>(Vs + j * 64 + c4) = v4;
+    const float* qb = qp + qrow0 * ldq + h * HD + c4;
+    const float* kb = kp + krow0 * ldkv + h * HD + c4;
+    const float* vb = vp + krow0 * ldkv + h * HD + c4;
+    for (int j = rr; j < Sq; j += A::RPI) *reinterpret_cast<float4*>(Qs + j * A::QP + c4) = *reinterpret_cast<const float4*>(qb + j * ldq);
+    for (int j = rr; j < Sk; j += A::RPI) {
+      *reinterpret_cast<float4*>(Ks + j * HD + c4) = *reinterpret_cast<const float4*>(kb + j * ldkv);
+      *reinterpret_cast<float4*>(Vs + j * HD + c4) = *reinterpret_cast<const float4*>(vb + j * ldkv);
     }
     __syncwarp();
-    const int i = lane < S ? lane : S - 1;  // idle lanes shadow the last row (no divergence); they store nothing
-    float q[64];
+    const int i = lane < Sq ? lane : Sq - 1;  // idle lanes shadow the last row (no divergence); they store nothing
+    float q[HD];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const float4 t = *reinterpret_cast<const float4*>(Qs + i * 68 + c * 4);
+    for (int c = 0; c < HD / 4; ++c) {
+      const float4 t = *reinterpret_cast<const float4*>(Qs + i * A::QP + c * 4);
       q[4 * c] = t.x; q[4 * c + 1] = t.y; q[4 * c + 2] = t.z; q[4 * c + 3] = t.w;
     }
     __syncwarp();  // every lane holds its q row: Qs becomes the score buffer [key][lane]
     float mx = -INFINITY;
 #pragma unroll 2
-    for (int j = 0; j < S; ++j) {
+    for (int j = 0; j < Sk; ++j) {
       float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float4 k4 = *reinterpret_cast<const float4*>(Ks + j * 64 + c * 4);  // same address in every lane: broadcast
+      for (int c = 0; c < HD / 4; ++c) {
+        const float4 k4 = *reinterpret_cast<const float4*>(Ks + j * HD + c * 4);  // same address in every lane: broadcast
         p0 = fmaf(q[4 * c], k4.x, p0); p1 = fmaf(q[4 * c + 1], k4.y, p1); p2 = fmaf(q[4 * c + 2], k4.z, p2); p3 = fmaf(q[4 * c + 3], k4.w, p3);
       }
       const float sc = ((p0 + p1) + (p2 + p3)) * scale;
@@ -315,50 +327,83 @@ __global__ void __launch_bounds__(kSeq64Warps * 32, 2) mha_seq64_kernel(const fl
       mx = fmaxf(mx, sc);
     }
     float sum = 0.f;
-    for (int j = 0; j < S; ++j) {
+    for (int j = 0; j < Sk; ++j) {
       float e = expf(Qs[j * 32 + lane] - mx);
-      if (j == S - 1) e *= last_weight;
+      if (j == Sk - 1) e *= last_weight;
       Qs[j * 32 + lane] = e;
       sum += e;
     }
     const float inv = 1.f / sum;
-    float acc[64];
+    float acc[HD];
 #pragma unroll
-    for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+    for (int c = 0; c < HD; ++c) acc[c] = 0.f;
 #pragma unroll 2
-    for (int j = 0; j < S; ++j) {
+    for (int j = 0; j < Sk; ++j) {
       const float pj = Qs[j * 32 + lane] * inv;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const float4 v4 = *reinterpret_cast<const float4*>(Vs + j * 64 + c * 4);
+      for (int c = 0; c < HD / 4; ++c) {
+        const float4 v4 = *reinterpret_cast<const float4*>(Vs + j * HD + c * 4);
         acc[4 * c] = fmaf(pj, v4.x, acc[4 * c]); acc[4 * c + 1] = fmaf(pj, v4.y, acc[4 * c + 1]);
         acc[4 * c + 2] = fmaf(pj, v4.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(pj, v4.w, acc[4 * c + 3]);
       }
     }
-    __syncwarp();  // scores are dead: Qs becomes the output staging [row][68]
-    if (lane < S) {
+    __syncwarp();  // scores are dead: Qs becomes the output staging [row][QP]
+    if (lane < Sq) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
+      for (int c = 0; c < HD / 4; ++c) {
         float4 o = make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
         if (round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-        *reinterpret_cast<float4*>(Qs + lane * 68 + c * 4) = o;
+        *reinterpret_cast<float4*>(Qs + lane * A::QP + c * 4) = o;
       }
     }
     __syncwarp();
-    float* obase = out + row0 * d + h * 64 + c4;
-    for (int j = rr; j < S; j += 2) *reinterpret_cast<float4*>(obase + static_cast<long>(j) * d) = *reinterpret_cast<const float4*>(Qs + j * 68 + c4);
+    float* obase = out + qrow0 * ldo + h * HD + c4;
+    for (int j = rr; j < Sq; j += A::RPI) *reinterpret_cast<float4*>(obase + static_cast<long>(j) * ldo) = *reinterpret_cast<const float4*>(Qs + j * A::QP + c4);
     __syncwarp();  // before the next unit's staging overwrites the buffers
   }
+}
+
+template <int HD>
+static cudaError_t launch_seq(const float* q, long ldq, const float* k, const float* v, long ldkv, float* out, int n_seq, int Sq, int Sk, int d,
+                              int n_heads, int round_out, const int32_t* seq_ptr, const int32_t* cell_ptr, int slots, cudaStream_t st, Launches* lc) {
+  static bool configured_dev[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured_dev[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(mha_seq_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SeqAttn<HD>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured_dev[dev & 63] = true;
+  }
+  if (lc) lc->n++;
+  const int n_units = n_seq * n_heads;
+  const int blocks = (n_units + kSeqWarps - 1) / kSeqWarps;
+  mha_seq_kernel<HD><<<blocks, kSeqWarps * 32, SeqAttn<HD>::kSmemBytes, st>>>(q, ldq, k, v, ldkv, out, d, n_units, Sq, Sk, n_heads,
+                                                                               1.f / sqrtf(static_cast<float>(HD)), round_out, seq_ptr, cell_ptr, slots);
+  return cudaGetLastError();
+}
+
+cudaError_t mha_cells64(const float* qkv, float* out, int n_cells, const int32_t* row_ptr_dev, const int32_t* cell_ptr_dev, int slots, int d,
+                        int n_heads, cudaStream_t st, Launches* lc) {
+  if (n_cells <= 0) return cudaSuccess;
+  if (d != 64 * n_heads || slots < 1 || slots > 32 || static_cast<long>(n_cells) * n_heads >= (1L << 31)) return cudaErrorInvalidValue;
+  return launch_seq<64>(qkv, 3L * d, qkv + d, qkv + 2 * d, 3L * d, out, n_cells, 0, 0, d, n_heads, 0, row_ptr_dev, cell_ptr_dev, slots, st, lc);
 }
 
 cudaError_t mha_cross_small(const float* q, long ldq, const float* k, const float* v, long ldkv, float* out, int n_seq, int Sq, int Sk, int d,
                             int n_heads, cudaStream_t st, Launches* lc, int round_out) {
   if (n_seq <= 0) return cudaSuccess;
   if (Sk > 32 || Sk < 1 || Sq < 1) return cudaErrorInvalidValue;
-  if (lc) lc->n++;
   const long rows = static_cast<long>(n_seq) * Sq;
   const int hd = d / n_heads;
   if (rows * n_heads >= (1L << 31)) return cudaErrorInvalidValue;
+  // sequence-per-warp core: 32-wide heads (fine-stage decoder layers) always, 64-wide heads for the longer sequences
+  const bool aligned = !(ldq % 4) && !(ldkv % 4) && !(d % 4) &&
+                       !((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15);
+  if (aligned && Sq <= 32 && hd * n_heads == d) {
+    if (hd == 32) return launch_seq<32>(q, ldq, k, v, ldkv, out, n_seq, Sq, Sk, d, n_heads, round_out, nullptr, nullptr, 0, st, lc);
+    if (hd == 64 && Sq > 16) return launch_seq<64>(q, ldq, k, v, ldkv, out, n_seq, Sq, Sk, d, n_heads, round_out, nullptr, nullptr, 0, st, lc);
+  }
+  if (lc) lc->n++;
   const unsigned grid = static_cast<unsigned>((rows * n_heads + 7) / 8);
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
   if (hd == 64) mha_small_kernel<64><<<grid, 256, 0, st>>>(q, ldq, k, v, ldkv, out, rows, Sq, Sk, d, n_heads, scale, round_out);
@@ -368,34 +413,7 @@ cudaError_t mha_cross_small(const float* q, long ldq, const float* k, const floa
   return cudaGetLastError();
 }
 
-static cudaError_t launch_seq64(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, int round_out, const int32_t* seq_ptr,
-                                const int32_t* cell_ptr, int slots, cudaStream_t st, Launches* lc) {
-  static bool configured_dev[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  constexpr int smem = kSeq64Warps * kSeq64WarpFloats * 4;
-  if (!configured_dev[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(mha_seq64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    configured_dev[dev & 63] = true;
-  }
-  if (lc) lc->n++;
-  const int n_units = n_seq * n_heads;
-  const int blocks = (n_units + kSeq64Warps - 1) / kSeq64Warps;
-  mha_seq64_kernel<<<blocks, kSeq64Warps * 32, smem, st>>>(qkv, out, n_units, S, d, n_heads, 1.f / sqrtf(64.f), round_out, seq_ptr, cell_ptr, slots);
-  return cudaGetLastError();
-}
-
-cudaError_t mha_cells64(const float* qkv, float* out, int n_cells, const int32_t* row_ptr_dev, const int32_t* cell_ptr_dev, int slots, int d,
-                        int n_heads, cudaStream_t st, Launches* lc) {
-  if (n_cells <= 0) return cudaSuccess;
-  if (d != 64 * n_heads || slots < 1 || slots > 32 || static_cast<long>(n_cells) * n_heads >= (1L << 31)) return cudaErrorInvalidValue;
-  return launch_seq64(qkv, out, n_cells, 0, d, n_heads, 0, row_ptr_dev, cell_ptr_dev, slots, st, lc);
-}
-
 cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out) {
-  if (n_seq > 0 && d == 64 * n_heads && S > 16 && S <= 32 && static_cast<long>(n_seq) * n_heads < (1L << 31))
-    return launch_seq64(qkv, out, n_seq, S, d, n_heads, round_out, nullptr, nullptr, 0, st, lc);  // long sequences, 64-wide heads
   return mha_cross_small(qkv, 3L * d, qkv + d, qkv + 2 * d, 3L * d, out, n_seq, S, S, d, n_heads, st, lc, round_out);
 }
 
