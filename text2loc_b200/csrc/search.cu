@@ -280,8 +280,38 @@ __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const float* 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * kRerankWarps + w;
   if (q >= nq) return;
-  const int C = n_splits * kList;
+  int C = n_splits * kList;
   const float* qr = Q + static_cast<long>(q) * kEmbed;
+  const float qn = q_norm[q] * 1.000001f, dn = max_norm[0] * 1.000001f;  // fp32 norms may be rounded down
+  const double eps = static_cast<double>(eps_cand) * qn * dn;            // error bound of the candidate pass that ran
+  const double unscale = q_scale ? static_cast<double>(q_scale[q]) * static_cast<double>(db_scale[0]) : 1.0;  // exact powers of two
+  const int32_t* ci = cand_idx + static_cast<long>(q) * C;
+  // Pre-filter (<= 32 candidates, one per lane): with t the k-th largest APPROXIMATE score, k candidates have an exact score
+  // >= t - eps, so a candidate whose approximate score is below t - 2 eps has an exact score strictly below all of them and
+  // cannot enter (or tie into) the top-k.  About half of the 24 candidates of a query go: half the row gathers and fp64 dots.
+  __shared__ int32_t s_keep[kRerankWarps][32];
+  if (C <= 32) {
+    const int my_idx = lane < C ? ci[lane] : -1;
+    const double my_a = lane < C && my_idx >= 0 ? static_cast<double>(cand_score[static_cast<long>(q) * C + lane]) * unscale : 0.0;
+    int rank = 0;
+    for (int j = 0; j < C; ++j) {
+      const double oa = __shfl_sync(0xffffffffu, my_a, j);
+      const int oi = __shfl_sync(0xffffffffu, my_idx, j);
+      if (oi >= 0 && (oa > my_a || (oa == my_a && j < lane))) ++rank;
+    }
+    const unsigned valid = __ballot_sync(0xffffffffu, my_idx >= 0);
+    bool keep = my_idx >= 0;
+    if (__popc(valid) > k) {
+      const unsigned at_k = __ballot_sync(0xffffffffu, my_idx >= 0 && rank == k - 1);  // exactly one lane: the ranks of valid lanes are distinct
+      const double t = __shfl_sync(0xffffffffu, my_a, __ffs(at_k) - 1);
+      keep = keep && !(my_a < t - 2.000001 * eps);
+    }
+    const unsigned kept = __ballot_sync(0xffffffffu, keep);
+    if (keep) s_keep[w][__popc(kept & ((1u << lane) - 1u))] = my_idx;
+    __syncwarp();
+    C = __popc(kept);
+    ci = s_keep[w];
+  }
   // The query's elements stay in registers, and four candidates are in flight at a time (their row reads and fp64 chains are
   // independent): one candidate after the other, each dot waited for its own loads and eight dependent fp64 FMAs -- 0.21 ms per
   // 32 768 queries x 24 candidates, as much as the candidate GEMM itself at 12 500 rows.  Same operations in the same
@@ -289,7 +319,6 @@ __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const float* 
   double qd[kEmbed / 32];
 #pragma unroll
   for (int i = 0; i < kEmbed / 32; ++i) qd[i] = static_cast<double>(qr[i * 32 + lane]);
-  const int32_t* ci = cand_idx + static_cast<long>(q) * C;
   for (int c0 = 0; c0 < C; c0 += 4) {
     int idx[4];
     double acc[4];
@@ -323,9 +352,6 @@ __global__ void __launch_bounds__(kRerankWarps * 32) rerank_kernel(const float* 
   // proof: every dropped row has approx <= thr_s, hence exact <= thr_s + eps; it cannot enter
   // (or tie into) the top-k if thr_s + eps < k-th exact score.
   const double kth = s_osc[w][k - 1];
-  const float qn = q_norm[q] * 1.000001f, dn = max_norm[0] * 1.000001f;  // fp32 norms may be rounded down
-  const double eps = static_cast<double>(eps_cand) * qn * dn;            // error bound of the candidate pass that ran
-  const double unscale = q_scale ? static_cast<double>(q_scale[q]) * static_cast<double>(db_scale[0]) : 1.0;  // exact powers of two
   bool fail = false;
   for (int s = lane; s < n_splits; s += 32) {
     const float thr = cand_thr[static_cast<long>(q) * n_splits + s];

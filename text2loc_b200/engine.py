@@ -159,10 +159,22 @@ class Engine:
             self._copy_stream.wait_stream(cur)
             self._stage_done = [None, None]
         pooled = torch.empty((nq * n_sent, T5_DIM), dtype=torch.float32, device=self.device)
-        for i, q0 in enumerate(range(0, nq, cq)):
-            q1 = min(nq, q0 + cq)
+        # Chunk schedule: the copy of chunk i+1 runs under the compute of chunk i, so what stays exposed is the FIRST copy and
+        # the LAST chunk's compute -- both start and end with quarter and half chunks.  The sentence stage runs per group of
+        # ~4 chunks instead of once at the end (it would otherwise sit, whole, behind the last copy).
+        sizes = []
+        if nq >= 6 * cq and cq >= 4:
+            head = [cq // 4, cq // 2]
+            body = nq - 2 * sum(head)
+            sizes = head + [cq] * (body // cq) + ([body % cq] if body % cq else []) + head[::-1]
+        else:
+            sizes = [cq] * (nq // cq) + ([nq % cq] if nq % cq else [])
+        group_q = 4 * cq
+        q0 = g0 = 0
+        for i, n_q in enumerate(sizes):
+            q1 = q0 + n_q
             b = i % 2
-            n_rows = (q1 - q0) * n_sent
+            n_rows = n_q * n_sent
             with torch.cuda.stream(self._copy_stream):
                 if self._stage_done[b] is not None:
                     self._copy_stream.wait_event(self._stage_done[b])  # the engine is done reading this buffer
@@ -170,11 +182,15 @@ class Engine:
                 copied = torch.cuda.Event()
                 copied.record(self._copy_stream)
             cur.wait_event(copied)
-            self._check(tokens(  # token stage of this chunk; sentence stage once at the end
+            self._check(tokens(  # token stage of this chunk
                 self._h, _ptr(self._stage[b]), n_rows, n_tok, _ptr(pooled[q0 * n_sent:q1 * n_sent]), self._stream()))
             self._stage_done[b] = torch.cuda.Event()
             self._stage_done[b].record(cur)
-        self._check(self._lib.t2l_encode_text_sentences(self._h, _ptr(pooled), nq, n_sent, _ptr(out), self._stream()))
+            if q1 - g0 >= group_q or q1 == nq:  # sentence stage of the queries whose tokens are done
+                self._check(self._lib.t2l_encode_text_sentences(self._h, _ptr(pooled[g0 * n_sent:q1 * n_sent]), q1 - g0, n_sent,
+                                                                _ptr(out[g0:q1]), self._stream()))
+                g0 = q1
+            q0 = q1
         return out
 
     def _encode_text_dev(self, t5: torch.Tensor, n_sent: int, out: torch.Tensor):
