@@ -417,14 +417,21 @@ static cudaError_t lin(t2l_engine* e, bool umma, const float* A, long lda, int M
 // fp32-accurate layer on the tensor cores: split A into [hi | lo] tf32 planes, three-pass GEMM
 // against the weight's planes (hi*hi + lo*hi + hi*lo).  Error ~2^-21 per product, i.e. fp32 level.
 static cudaError_t lin3(t2l_engine* e, const float* A, long lda, int M, const std::string& wname, const std::string& bname, float* C,
-                        long ldc, int act, cudaStream_t st, const float* residual = nullptr, long ldr = 0) {
+                        long ldc, int act, cudaStream_t st, const float* residual = nullptr, long ldr = 0, const float* A_planes = nullptr,
+                        int split_out = 0) {
+  // A_planes: the producer of A already wrote its [hi | lo] planes ([M, 2K]; LayerNorm, the attention cores and the split_out
+  // epilogue do): no split kernel.  split_out: C receives the planes of the result ([M, ldc >= 2N]) for the next such layer.
   const Weight& w = W(e, wname);
-  float* planes = e->arena.get<float>(static_cast<size_t>(M) * 2 * w.cols);
-  cudaError_t err = split_tf32_planes(A, lda, planes, M, w.cols, st, &e->lc);
-  if (err != cudaSuccess) return err;
+  if (!A_planes) {
+    float* planes = e->arena.get<float>(static_cast<size_t>(M) * 2 * w.cols);
+    cudaError_t err = split_tf32_planes(A, lda, planes, M, w.cols, st, &e->lc);
+    if (err != cudaSuccess) return err;
+    A_planes = planes;
+  }
   Linear l;
-  l.A = planes; l.lda = 2L * w.cols; l.W = w.dev; l.ldw = w.ld; l.bias = bname.empty() ? nullptr : W(e, bname).dev;
+  l.A = A_planes; l.lda = 2L * w.cols; l.W = w.dev; l.ldw = w.ld; l.bias = bname.empty() ? nullptr : W(e, bname).dev;
   l.C = C; l.ldc = ldc; l.M = M; l.N = w.rows; l.K = w.cols; l.act = act; l.residual = residual; l.ldr = ldr; l.passes = 3;
+  l.split_out = split_out;
   return linear_umma(l, st, &e->lc);
 }
 
@@ -501,12 +508,17 @@ static int encoder_layer(t2l_engine* e, const std::string& pfx, bool fast, const
     CU(lin(e, true, x1, d, rows, pfx + ".l1_w", pfx + ".l1_b", h, ffn, 1, st, nullptr, 0, 1));
     CU(lin(e, true, h, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x1, d));
   } else {
+    // the operand planes of the three-pass GEMMs come straight from their producers (attention core, LayerNorm1, the ReLU
+    // epilogue of linear1): one split kernel (the layer's input) instead of four
+    float* attp = a.get<float>(static_cast<size_t>(rows) * 2 * d);
+    float* x1p = a.get<float>(static_cast<size_t>(rows) * 2 * d);
+    float* hp = a.get<float>(static_cast<size_t>(rows) * 2 * ffn);
     CU(lin3(e, X, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st));
-    CU(mha_small(qkv, att, n_seq, S, d, 4, st, &e->lc));
-    CU(lin3(e, att, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, X, d));
-    CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc));
-    CU(lin3(e, x1, d, rows, pfx + ".l1_w", pfx + ".l1_b", h, ffn, 1, st));
-    CU(lin3(e, h, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x1, d));
+    CU(mha_small(qkv, nullptr, n_seq, S, d, 4, st, &e->lc, 0, attp));
+    CU(lin3(e, nullptr, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, X, d, attp));
+    CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc, nullptr, x1p));
+    CU(lin3(e, nullptr, d, rows, pfx + ".l1_w", pfx + ".l1_b", hp, 2L * ffn, 1, st, nullptr, 0, x1p, /*split_out=*/1));
+    CU(lin3(e, nullptr, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x1, d, hp));
   }
   if (pooled_out && d == 1024) CU(layer_norm_max_rows(y, pooled_out, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, n_seq, S, d, st, &e->lc));
   else {
@@ -520,22 +532,24 @@ static int encoder_layer(t2l_engine* e, const std::string& pfx, bool fast, const
 // zero-padded slots) on the packed rows of a chunk: `rows` = sum over cells of min(n_b, 28) + [n_b < 28] (the padded slots
 // of a cell are identical rows; one representative stands for them, weighted as a key by their count).  Three-pass tf32
 // projections like encoder_layer's precise branch.
-static int cell_attention_layer(t2l_engine* e, const std::string& pfx, const float* X, float* Xout, int rows, int n_cells,
-                                const int32_t* row_ptr_dev, const int32_t* cell_ptr_dev, cudaStream_t st) {
+static int cell_attention_layer(t2l_engine* e, const std::string& pfx, const float* X, const float* Xp, float* Xout, float* Xoutp, int rows,
+                                int n_cells, const int32_t* row_ptr_dev, const int32_t* cell_ptr_dev, cudaStream_t st) {
+  // Xp / Xoutp: tf32 hi | lo planes of the layer's input (from the previous layer's LayerNorm2 or one split kernel) / output
   constexpr int d = T2L_EMBED_DIM, ffn = 512;
   Arena& a = e->arena;
   float* qkv = a.get<float>(static_cast<size_t>(rows) * 3 * d);
-  float* att = a.get<float>(static_cast<size_t>(rows) * d);
+  float* attp = a.get<float>(static_cast<size_t>(rows) * 2 * d);
   float* y = a.get<float>(static_cast<size_t>(rows) * d);
   float* x1 = a.get<float>(static_cast<size_t>(rows) * d);
-  float* h = a.get<float>(static_cast<size_t>(rows) * ffn);
-  CU(lin3(e, X, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st));
-  CU(mha_cells64(qkv, att, n_cells, row_ptr_dev, cell_ptr_dev, kObjectSlots, d, 4, st, &e->lc));
-  CU(lin3(e, att, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, X, d));
-  CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc));
-  CU(lin3(e, x1, d, rows, pfx + ".l1_w", pfx + ".l1_b", h, ffn, 1, st));
-  CU(lin3(e, h, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x1, d));
-  CU(layer_norm_rows(y, Xout, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, rows, d, st, &e->lc));
+  float* x1p = a.get<float>(static_cast<size_t>(rows) * 2 * d);
+  float* hp = a.get<float>(static_cast<size_t>(rows) * 2 * ffn);
+  CU(lin3(e, X, d, rows, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st, nullptr, 0, Xp));
+  CU(mha_cells64(qkv, nullptr, n_cells, row_ptr_dev, cell_ptr_dev, kObjectSlots, d, 4, st, &e->lc, attp));
+  CU(lin3(e, nullptr, d, rows, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, X, d, attp));
+  CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rows, d, st, &e->lc, nullptr, x1p));
+  CU(lin3(e, nullptr, d, rows, pfx + ".l1_w", pfx + ".l1_b", hp, 2L * ffn, 1, st, nullptr, 0, x1p, /*split_out=*/1));
+  CU(lin3(e, nullptr, ffn, rows, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x1, d, hp));
+  CU(layer_norm_rows(y, Xout, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, rows, d, st, &e->lc, nullptr, Xoutp));
   return 0;
 }
 
@@ -699,12 +713,13 @@ static int encode_chunk(t2l_engine* e, const float* pts, const float* meta, cons
   // operand rounding the most (precision table)
   float* X = a.get<float>(static_cast<size_t>(attn_rows) * 256);
   float* Xb = a.get<float>(static_cast<size_t>(attn_rows) * 256);
+  float* Xbp = a.get<float>(static_cast<size_t>(attn_rows) * 512);  // hi | lo planes of the first layer's output
   float* pooled = a.get<float>(static_cast<size_t>(B) * 256);
   CU(scatter_objects_ragged(emb, cell_ptr_dev, row_ptr_dev, B, X, st, &e->lc));
   const size_t mark = a.off;
-  if (cell_attention_layer(e, "obj_attn0", X, Xb, attn_rows, B, row_ptr_dev, cell_ptr_dev, st)) return 1;
+  if (cell_attention_layer(e, "obj_attn0", X, nullptr, Xb, Xbp, attn_rows, B, row_ptr_dev, cell_ptr_dev, st)) return 1;
   a.off = mark;
-  if (cell_attention_layer(e, "obj_attn1", Xb, X, attn_rows, B, row_ptr_dev, cell_ptr_dev, st)) return 1;
+  if (cell_attention_layer(e, "obj_attn1", Xb, Xbp, X, nullptr, attn_rows, B, row_ptr_dev, cell_ptr_dev, st)) return 1;
   CU(max_over_rows_ragged(X, row_ptr_dev, pooled, B, st, &e->lc));
   CU(l2_normalize_rows(pooled, 256, out + static_cast<size_t>(c0) * 256, 256, B, 256, st, &e->lc));
   if (a.overflow) return fail(e, "internal: workspace arena too small for %d objects / %d cells", n, B);
@@ -844,32 +859,36 @@ extern "C" int t2l_encode_text(t2l_engine* e, const float* t5, int nq, int S, in
 // One post-norm nn.TransformerDecoderLayer (ReLU, eps 1e-5, eval, no masks; cross_matcher.py:66-72) on packed rows:
 //   x = LN1(t + SelfAttn(t));  x = LN2(x + CrossAttn(x, mem));  x = LN3(x + FFN(x))
 // T [n_seq * St, d], Mem [n_seq * Sm, d] -> Tout [n_seq * St, d].  All projections are three-pass split products (fp32 accuracy).
-static int decoder_layer(t2l_engine* e, const std::string& pfx, const float* T, int St, const float* Mem, int Sm, float* Tout, int n_seq, int d,
-                         cudaStream_t st) {
+static int decoder_layer(t2l_engine* e, const std::string& pfx, const float* T, const float* Tp, int St, const float* Mem, const float* Memp, int Sm,
+                         float* Tout, float* Toutp, int n_seq, int d, cudaStream_t st) {
+  // Tp / Memp / Toutp: tf32 hi | lo planes ([rows, 2d]) of the target, the memory and the output.  Every three-pass GEMM of the
+  // layer reads planes its producer wrote (LayerNorms, attention cores, the ReLU epilogue): no split kernels inside the layer.
   const int rt = n_seq * St, rm = n_seq * Sm;
   Arena& a = e->arena;
   const size_t mark = a.off;
   float* qkv = a.get<float>(static_cast<size_t>(rt) * 3 * d);
-  float* att = a.get<float>(static_cast<size_t>(rt) * d);
+  float* attp = a.get<float>(static_cast<size_t>(rt) * 2 * d);
   float* y = a.get<float>(static_cast<size_t>(rt) * d);
   float* x1 = a.get<float>(static_cast<size_t>(rt) * d);
+  float* x1p = a.get<float>(static_cast<size_t>(rt) * 2 * d);
   float* q2 = a.get<float>(static_cast<size_t>(rt) * d);
   float* kv2 = a.get<float>(static_cast<size_t>(rm) * 2 * d);
   float* x2 = a.get<float>(static_cast<size_t>(rt) * d);
-  float* h = a.get<float>(static_cast<size_t>(rt) * 4 * d);
-  CU(lin3(e, T, d, rt, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st));
-  CU(mha_small(qkv, att, n_seq, St, d, 4, st, &e->lc));
-  CU(lin3(e, att, d, rt, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, T, d));
-  CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rt, d, st, &e->lc));
-  CU(lin3(e, x1, d, rt, pfx + ".ca_q_w", pfx + ".ca_q_b", q2, d, 0, st));
-  CU(lin3(e, Mem, d, rm, pfx + ".ca_kv_w", pfx + ".ca_kv_b", kv2, 2L * d, 0, st));
-  CU(mha_cross_small(q2, d, kv2, kv2 + d, 2L * d, att, n_seq, St, Sm, d, 4, st, &e->lc));
-  CU(lin3(e, att, d, rt, pfx + ".ca_out_w", pfx + ".ca_out_b", y, d, 0, st, x1, d));
-  CU(layer_norm_rows(y, x2, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, rt, d, st, &e->lc));
-  CU(lin3(e, x2, d, rt, pfx + ".l1_w", pfx + ".l1_b", h, 4L * d, 1, st));
-  CU(lin3(e, h, 4 * d, rt, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x2, d));
-  CU(layer_norm_rows(y, Tout, W(e, pfx + ".n3_w").dev, W(e, pfx + ".n3_b").dev, rt, d, st, &e->lc));
-  a.off = mark;  // Tout lives outside the scratch of this layer
+  float* x2p = a.get<float>(static_cast<size_t>(rt) * 2 * d);
+  float* hp = a.get<float>(static_cast<size_t>(rt) * 8 * d);
+  CU(lin3(e, T, d, rt, pfx + ".in_w", pfx + ".in_b", qkv, 3L * d, 0, st, nullptr, 0, Tp));
+  CU(mha_small(qkv, nullptr, n_seq, St, d, 4, st, &e->lc, 0, attp));
+  CU(lin3(e, nullptr, d, rt, pfx + ".out_w", pfx + ".out_b", y, d, 0, st, T, d, attp));
+  CU(layer_norm_rows(y, x1, W(e, pfx + ".n1_w").dev, W(e, pfx + ".n1_b").dev, rt, d, st, &e->lc, nullptr, x1p));
+  CU(lin3(e, nullptr, d, rt, pfx + ".ca_q_w", pfx + ".ca_q_b", q2, d, 0, st, nullptr, 0, x1p));
+  CU(lin3(e, Mem, d, rm, pfx + ".ca_kv_w", pfx + ".ca_kv_b", kv2, 2L * d, 0, st, nullptr, 0, Memp));
+  CU(mha_cross_small(q2, d, kv2, kv2 + d, 2L * d, nullptr, n_seq, St, Sm, d, 4, st, &e->lc, 0, attp));
+  CU(lin3(e, nullptr, d, rt, pfx + ".ca_out_w", pfx + ".ca_out_b", y, d, 0, st, x1, d, attp));
+  CU(layer_norm_rows(y, x2, W(e, pfx + ".n2_w").dev, W(e, pfx + ".n2_b").dev, rt, d, st, &e->lc, nullptr, x2p));
+  CU(lin3(e, nullptr, d, rt, pfx + ".l1_w", pfx + ".l1_b", hp, 8L * d, 1, st, nullptr, 0, x2p, /*split_out=*/1));
+  CU(lin3(e, nullptr, 4 * d, rt, pfx + ".l2_w", pfx + ".l2_b", y, d, 0, st, x2, d, hp));
+  CU(layer_norm_rows(y, Tout, W(e, pfx + ".n3_w").dev, W(e, pfx + ".n3_b").dev, rt, d, st, &e->lc, nullptr, Toutp));
+  a.off = mark;  // Tout / Toutp live outside the scratch of this layer
   return 0;
 }
 
@@ -923,18 +942,28 @@ static int fine_match_impl(t2l_engine* e, const float* obj_emb, const int32_t* p
     float* d0b = a.get<float>(static_cast<size_t>(np) * n_obj * d);
     float* d1 = a.get<float>(static_cast<size_t>(np) * n_hints * d);
     float* d1b = a.get<float>(static_cast<size_t>(np) * n_hints * d);
+    // tf32 hi | lo planes of the four row sets (operands of the decoder layers' three-pass GEMMs)
+    float* d0p = a.get<float>(static_cast<size_t>(np) * n_obj * 2 * d);
+    float* d0bp = a.get<float>(static_cast<size_t>(np) * n_obj * 2 * d);
+    float* d1p = a.get<float>(static_cast<size_t>(np) * n_hints * 2 * d);
+    float* d1bp = a.get<float>(static_cast<size_t>(np) * n_hints * 2 * d);
     float* hmax = a.get<float>(static_cast<size_t>(np) * d);
     float* h64 = a.get<float>(static_cast<size_t>(np) * (d / 2));
     // desc0 / desc1 of every pair: rows of the cell's (already normalised) objects, rows of the query's hints (:105-111)
     CU(gather_row_groups(obj_emb, pair_cell ? pair_cell + p0 : nullptr, p0, np, n_obj, d, d0, st, &e->lc));
     CU(gather_row_groups(hints, pair_query ? pair_query + p0 : nullptr, p0, np, n_hints, d, d1, st, &e->lc));
     // cascaded cross-attention (:113-115): objects attend to hints, then hints to the updated objects, twice
+    CU(split_tf32_planes(d0, d, d0p, np * n_obj, d, st, &e->lc));
+    CU(split_tf32_planes(d1, d, d1p, np * n_hints, d, st, &e->lc));
     float *o_in = d0, *o_out = d0b, *h_in = d1, *h_out = d1b;
+    float *o_inp = d0p, *o_outp = d0bp, *h_inp = d1p, *h_outp = d1bp;
     for (int i = 0; i < 2; ++i) {
-      if (decoder_layer(e, "cross_objects" + std::to_string(i), o_in, n_obj, h_in, n_hints, o_out, np, d, st)) return 1;
-      if (decoder_layer(e, "cross_hints" + std::to_string(i), h_in, n_hints, o_out, n_obj, h_out, np, d, st)) return 1;
+      if (decoder_layer(e, "cross_objects" + std::to_string(i), o_in, o_inp, n_obj, h_in, h_inp, n_hints, o_out, o_outp, np, d, st)) return 1;
+      if (decoder_layer(e, "cross_hints" + std::to_string(i), h_in, h_inp, n_hints, o_out, o_outp, n_obj, h_out, h_outp, np, d, st)) return 1;
       std::swap(o_in, o_out);
       std::swap(h_in, h_out);
+      std::swap(o_inp, o_outp);
+      std::swap(h_inp, h_outp);
     }
     CU(max_over_rows(h_in, hmax, np, n_hints, d, st, &e->lc));  // desc1.max(dim=0) (:126)
     // mlp_offsets = Linear(d, d/2) + ReLU + Linear(d/2, 2) (:17-36, :127), exact fp32

@@ -46,6 +46,7 @@ struct StoreParams {
   int out_half;  // C is __half [M, ldc]: the consumer is an fp16 tensor-core GEMM (same 11-bit significand as tf32)
   float half_max = kHalfMax;  // fp16 stores saturate at +-half_max
   int res_half = 0;           // residual points at __half data [M, ldr] (the token layer fed with fp16 T5 states)
+  int split_out = 0;          // (fp32, no residual) store the tf32 hi | lo planes of the result: hi at column c, lo at column N + c
 };
 
 template <bool kHalfOut, bool kResidual>
@@ -174,6 +175,15 @@ struct StoreEpiT {
         if (row0 + r < p.M)
           *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.C) + (row0 + r) * p.ldc + col0 + ch * 4) =
               make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        continue;
+      }
+      if (!kResidual && p.split_out) {  // the consumer is a three-pass split-product GEMM: emit its operand planes here
+        const float4 hi = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+        const float4 lo = make_float4(round_tf32(o.x - hi.x), round_tf32(o.y - hi.y), round_tf32(o.z - hi.z), round_tf32(o.w - hi.w));
+        if (row0 + r < p.M) {
+          *reinterpret_cast<float4*>(p.C + (row0 + r) * p.ldc + col0 + ch * 4) = hi;
+          *reinterpret_cast<float4*>(p.C + (row0 + r) * p.ldc + p.N + col0 + ch * 4) = lo;
+        }
         continue;
       }
       if (p.round_out) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }

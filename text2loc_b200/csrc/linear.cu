@@ -66,7 +66,8 @@ cudaError_t linear_umma(const Linear& l, cudaStream_t st, Launches* lc) {
     return wide ? run_umma<256, 1, SegMaxEpi>(l, ep, st) : run_umma<128, 1, SegMaxEpi>(l, ep, st);
   }
   if (l.out_half && l.residual && !l.half_ops) return cudaErrorInvalidValue;
-  StoreParams ep{l.C, l.ldc, l.bias, l.residual, l.ldr, l.M, l.N, l.act, l.round_out, l.out_half, l.half_max, l.residual_half};
+  if (l.split_out && (l.residual || l.out_half || l.ldc < 2L * l.N)) return cudaErrorInvalidValue;
+  StoreParams ep{l.C, l.ldc, l.bias, l.residual, l.ldr, l.M, l.N, l.act, l.round_out, l.out_half, l.half_max, l.residual_half, l.split_out};
   if (l.half_ops) {  // fp16 operands (A, W are __half), kind::f16: twice the tf32 rate at the same 11-bit significand
     if (l.out_half && l.residual) {  // fp16 residual stream
       if (pair && l.residual_half && !l.reg_epilogue && !(l.ldr % 8) && !(l.ldc % 8)) return run_residual_tma(l, st);

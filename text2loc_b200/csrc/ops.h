@@ -35,6 +35,8 @@ struct Linear {
   int out_half = 0;           // C points at __half data (ldc in elements); values saturate at +-half_max
   float half_max = 65504.f;
   int reg_epilogue = 0;       // out_half + residual: force the register-staged epilogue instead of the TMA one (A/B switch)
+  int split_out = 0;          // fp32 store mode without residual: C is [M, ldc >= 2N] and receives the tf32 [hi | lo] planes of the result
+                              // (hi at column c, lo at column N + c): the A operand of a following passes=3 GEMM, no split kernel
 };
 // tf32 tensor-core path: needs K-major operands with 16-byte aligned rows (lda, ldw % 4 == 0),
 // N % 32 == 0.  K tails are zero-filled by TMA.
@@ -88,18 +90,21 @@ cudaError_t ga_concat_half(const float* x3, const float* cpos3, int n_obj, __hal
 cudaError_t l2_normalize_rows(const float* x, long ldx, float* y, long ldy, int rows, int d, cudaStream_t st, Launches* lc);
 // y = LayerNorm(x) * w + b, eps 1e-5, one warp per row
 // (optional y_half: an fp16 copy of the output, the A operand of a following fp16 tensor-core GEMM)
+// (optional y_planes [rows, 2d]: the tf32 hi | lo planes of the output, as split_tf32_planes would produce them)
 cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const float* b, int rows, int d, cudaStream_t st, Launches* lc,
-                            __half* y_half = nullptr);
+                            __half* y_half = nullptr, float* y_planes = nullptr);
 // the same on fp16 rows in and out (d = 1024): the token layer's fp16 residual stream
 cudaError_t layer_norm_half_rows(const __half* x, __half* y, const float* w, const float* b, int rows, int d, cudaStream_t st, Launches* lc);
 // y = fp16(x), saturating at +-65504; n % 4 == 0
 cudaError_t to_half_rows(const float* x, __half* y, long n, cudaStream_t st, Launches* lc);
 // Unmasked multi-head self attention on packed QKV rows [n_seq*S, 3d] (q | k | v), head h uses
 // columns [h*hd, (h+1)*hd); out [n_seq*S, d].  softmax(q k^T / sqrt(hd)) v, fp32.
-cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out = 0);
+// out_planes (optional, [rows, 2d]): tf32 hi | lo planes of the output for a following passes=3 GEMM; `out` may then be nullptr
+cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out = 0,
+                      float* out_planes = nullptr);
 // Cross attention with the same core: q [n_seq*Sq, ldq], k / v [n_seq*Sk, ldkv] -> out [n_seq*Sq, d]; Sk <= 32, head dim 32 / 64 / 256
 cudaError_t mha_cross_small(const float* q, long ldq, const float* k, const float* v, long ldkv, float* out, int n_seq, int Sq, int Sk, int d,
-                            int n_heads, cudaStream_t st, Launches* lc, int round_out = 0);
+                            int n_heads, cudaStream_t st, Launches* lc, int round_out = 0, float* out_planes = nullptr);
 // Same contract for d = 1024, 4 heads of 256 (the token layer): warp-level mma.sync tf32 tiles.
 // round_out: 0 fp32, 1 fp32 rounded to tf32, 2 `out` is __half [rows, 1024].
 // half_in: qkv is __half [rows, 3072].
@@ -115,7 +120,7 @@ cudaError_t max_over_rows(const float* x, float* y, int groups, int S, int d, cu
 // Intra-cell attention without the duplicate padding rows (rowops.cu::mha_seq64_kernel): cell b owns packed rows
 // row_ptr[b] .. row_ptr[b+1]) = its min(n_b, slots) objects + one row for all slots - n_b zero-padded slots
 cudaError_t mha_cells64(const float* qkv, float* out, int n_cells, const int32_t* row_ptr_dev, const int32_t* cell_ptr_dev, int slots, int d,
-                        int n_heads, cudaStream_t st, Launches* lc);
+                        int n_heads, cudaStream_t st, Launches* lc, float* out_planes = nullptr);
 cudaError_t scatter_objects_ragged(const float* emb, const int32_t* cell_ptr_dev, const int32_t* row_ptr_dev, int n_cells, float* X, cudaStream_t st,
                                    Launches* lc);
 cudaError_t max_over_rows_ragged(const float* x, const int32_t* row_ptr_dev, float* y, int n_cells, cudaStream_t st, Launches* lc);

@@ -55,7 +55,7 @@ cudaError_t to_half_rows(const float* x, __half* y, long n, cudaStream_t st, Lau
 // ---- LayerNorm (eps 1e-5, biased variance), one warp per row, d <= 1024 ----------------------
 template <int D>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ w,
-                                                         const float* __restrict__ b, int rows, __half* __restrict__ yh) {
+                                                         const float* __restrict__ b, int rows, __half* __restrict__ yh, float* __restrict__ yp) {
   constexpr int R = D / 128;  // float4 per lane
   const long r = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -87,6 +87,12 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
     o.z = (v[i].z - mean) * rstd * ww.z + bv.z;
     o.w = (v[i].w - mean) * rstd * ww.w + bv.w;
     yr[i * 32 + lane] = o;
+    if (yp) {  // tf32 hi | lo planes for a following three-pass GEMM (what split_tf32_kernel would write)
+      const float4 hi = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+      float4* pr = reinterpret_cast<float4*>(yp + r * 2 * D);
+      pr[i * 32 + lane] = hi;
+      pr[D / 4 + i * 32 + lane] = make_float4(round_tf32(o.x - hi.x), round_tf32(o.y - hi.y), round_tf32(o.z - hi.z), round_tf32(o.w - hi.w));
+    }
     if (yh) {  // fp16 copy for the next tensor-core GEMM's A operand
       const __half2 h0 = __floats2half2_rn(sat_half(o.x), sat_half(o.y)), h1 = __floats2half2_rn(sat_half(o.z), sat_half(o.w));
       uint2 u;
@@ -98,13 +104,13 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
 }
 
 cudaError_t layer_norm_rows(const float* x, float* y, const float* w, const float* b, int rows, int d, cudaStream_t st, Launches* lc,
-                            __half* y_half) {
+                            __half* y_half, float* y_planes) {
   if (rows <= 0) return cudaSuccess;
   if (lc) lc->n++;
   const unsigned grid = (rows + 7) / 8;
-  if (d == 256) layer_norm_kernel<256><<<grid, 256, 0, st>>>(x, y, w, b, rows, y_half);
-  else if (d == 128) layer_norm_kernel<128><<<grid, 256, 0, st>>>(x, y, w, b, rows, y_half);
-  else if (d == 1024) layer_norm_kernel<1024><<<grid, 256, 0, st>>>(x, y, w, b, rows, y_half);
+  if (d == 256) layer_norm_kernel<256><<<grid, 256, 0, st>>>(x, y, w, b, rows, y_half, y_planes);
+  else if (d == 128) layer_norm_kernel<128><<<grid, 256, 0, st>>>(x, y, w, b, rows, y_half, y_planes);
+  else if (d == 1024) layer_norm_kernel<1024><<<grid, 256, 0, st>>>(x, y, w, b, rows, y_half, y_planes);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
@@ -187,7 +193,7 @@ cudaError_t layer_norm_half_rows(const __half* x, __half* y, const float* w, con
 template <int HD>
 __global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict__ qp, long ldq, const float* __restrict__ kp, const float* __restrict__ vp,
                                                         long ldkv, float* __restrict__ out, long n_rows_total, int Sq, int S, int d, int n_heads,
-                                                        float scale, int round_out) {
+                                                        float scale, int round_out, float* __restrict__ out_planes) {
   constexpr int R = HD / 32;
   constexpr int U = 4;
   // 32-bit index math: the 64-bit runtime divisions this replaced cost more instructions than the attention itself
@@ -243,9 +249,20 @@ __global__ void __launch_bounds__(256) mha_small_kernel(const float* __restrict_
       for (int r = 0; r < R; ++r) acc[r] = fmaf(pj, vv[u][r], acc[r]);
     }
   }
-  float* o = out + row * d + h * HD;
+  if (out) {
+    float* o = out + row * d + h * HD;
 #pragma unroll
-  for (int r = 0; r < R; ++r) o[r * 32 + lane] = round_out ? round_tf32(acc[r]) : acc[r];
+    for (int r = 0; r < R; ++r) o[r * 32 + lane] = round_out ? round_tf32(acc[r]) : acc[r];
+  }
+  if (out_planes) {  // tf32 hi | lo planes [rows, 2d] for a following three-pass GEMM
+    float* o = out_planes + row * 2 * d + h * HD;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float hi = round_tf32(acc[r]);
+      o[r * 32 + lane] = hi;
+      o[d + r * 32 + lane] = round_tf32(acc[r] - hi);
+    }
+  }
 }
 
 // Sequence-per-warp attention core (head_dim 64 or 32; at most 32 queries and 32 keys per sequence): ONE warp per
@@ -276,7 +293,8 @@ template <int HD>
 __global__ void __launch_bounds__(kSeqWarps * 32, 2) mha_seq_kernel(const float* __restrict__ qp, long ldq, const float* __restrict__ kp,
                                                                     const float* __restrict__ vp, long ldkv, float* __restrict__ out, long ldo,
                                                                     int n_units, int Sq_fixed, int Sk_fixed, int n_heads, float scale, int round_out,
-                                                                    const int32_t* __restrict__ seq_ptr, const int32_t* __restrict__ cell_ptr, int slots) {
+                                                                    const int32_t* __restrict__ seq_ptr, const int32_t* __restrict__ cell_ptr, int slots,
+                                                                    float* __restrict__ out_planes) {
   using A = SeqAttn<HD>;
   extern __shared__ __align__(16) float seq_smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -357,15 +375,28 @@ __global__ void __launch_bounds__(kSeqWarps * 32, 2) mha_seq_kernel(const float*
       }
     }
     __syncwarp();
-    float* obase = out + qrow0 * ldo + h * HD + c4;
-    for (int j = rr; j < Sq; j += A::RPI) *reinterpret_cast<float4*>(obase + static_cast<long>(j) * ldo) = *reinterpret_cast<const float4*>(Qs + j * A::QP + c4);
+    if (out) {
+      float* obase = out + qrow0 * ldo + h * HD + c4;
+      for (int j = rr; j < Sq; j += A::RPI) *reinterpret_cast<float4*>(obase + static_cast<long>(j) * ldo) = *reinterpret_cast<const float4*>(Qs + j * A::QP + c4);
+    }
+    if (out_planes) {  // tf32 hi | lo planes [rows, 2 ldo] for a following three-pass GEMM
+      float* pbase = out_planes + qrow0 * 2 * ldo + h * HD + c4;
+      for (int j = rr; j < Sq; j += A::RPI) {
+        const float4 o = *reinterpret_cast<const float4*>(Qs + j * A::QP + c4);
+        const float4 hi = make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+        *reinterpret_cast<float4*>(pbase + static_cast<long>(j) * 2 * ldo) = hi;
+        *reinterpret_cast<float4*>(pbase + static_cast<long>(j) * 2 * ldo + ldo) =
+            make_float4(round_tf32(o.x - hi.x), round_tf32(o.y - hi.y), round_tf32(o.z - hi.z), round_tf32(o.w - hi.w));
+      }
+    }
     __syncwarp();  // before the next unit's staging overwrites the buffers
   }
 }
 
 template <int HD>
 static cudaError_t launch_seq(const float* q, long ldq, const float* k, const float* v, long ldkv, float* out, int n_seq, int Sq, int Sk, int d,
-                              int n_heads, int round_out, const int32_t* seq_ptr, const int32_t* cell_ptr, int slots, cudaStream_t st, Launches* lc) {
+                              int n_heads, int round_out, const int32_t* seq_ptr, const int32_t* cell_ptr, int slots, cudaStream_t st, Launches* lc,
+                              float* out_planes = nullptr) {
   static bool configured_dev[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -378,19 +409,20 @@ static cudaError_t launch_seq(const float* q, long ldq, const float* k, const fl
   const int n_units = n_seq * n_heads;
   const int blocks = (n_units + kSeqWarps - 1) / kSeqWarps;
   mha_seq_kernel<HD><<<blocks, kSeqWarps * 32, SeqAttn<HD>::kSmemBytes, st>>>(q, ldq, k, v, ldkv, out, d, n_units, Sq, Sk, n_heads,
-                                                                               1.f / sqrtf(static_cast<float>(HD)), round_out, seq_ptr, cell_ptr, slots);
+                                                                               1.f / sqrtf(static_cast<float>(HD)), round_out, seq_ptr, cell_ptr, slots,
+                                                                               out_planes);
   return cudaGetLastError();
 }
 
 cudaError_t mha_cells64(const float* qkv, float* out, int n_cells, const int32_t* row_ptr_dev, const int32_t* cell_ptr_dev, int slots, int d,
-                        int n_heads, cudaStream_t st, Launches* lc) {
+                        int n_heads, cudaStream_t st, Launches* lc, float* out_planes) {
   if (n_cells <= 0) return cudaSuccess;
   if (d != 64 * n_heads || slots < 1 || slots > 32 || static_cast<long>(n_cells) * n_heads >= (1L << 31)) return cudaErrorInvalidValue;
-  return launch_seq<64>(qkv, 3L * d, qkv + d, qkv + 2 * d, 3L * d, out, n_cells, 0, 0, d, n_heads, 0, row_ptr_dev, cell_ptr_dev, slots, st, lc);
+  return launch_seq<64>(qkv, 3L * d, qkv + d, qkv + 2 * d, 3L * d, out, n_cells, 0, 0, d, n_heads, 0, row_ptr_dev, cell_ptr_dev, slots, st, lc, out_planes);
 }
 
 cudaError_t mha_cross_small(const float* q, long ldq, const float* k, const float* v, long ldkv, float* out, int n_seq, int Sq, int Sk, int d,
-                            int n_heads, cudaStream_t st, Launches* lc, int round_out) {
+                            int n_heads, cudaStream_t st, Launches* lc, int round_out, float* out_planes) {
   if (n_seq <= 0) return cudaSuccess;
   if (Sk > 32 || Sk < 1 || Sq < 1) return cudaErrorInvalidValue;
   const long rows = static_cast<long>(n_seq) * Sq;
@@ -398,23 +430,24 @@ cudaError_t mha_cross_small(const float* q, long ldq, const float* k, const floa
   if (rows * n_heads >= (1L << 31)) return cudaErrorInvalidValue;
   // sequence-per-warp core: 32-wide heads (fine-stage decoder layers) always, 64-wide heads for the longer sequences
   const bool aligned = !(ldq % 4) && !(ldkv % 4) && !(d % 4) &&
-                       !((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15);
+                       !((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(out_planes)) & 15);
   if (aligned && Sq <= 32 && hd * n_heads == d) {
-    if (hd == 32) return launch_seq<32>(q, ldq, k, v, ldkv, out, n_seq, Sq, Sk, d, n_heads, round_out, nullptr, nullptr, 0, st, lc);
-    if (hd == 64 && Sq > 16) return launch_seq<64>(q, ldq, k, v, ldkv, out, n_seq, Sq, Sk, d, n_heads, round_out, nullptr, nullptr, 0, st, lc);
+    if (hd == 32) return launch_seq<32>(q, ldq, k, v, ldkv, out, n_seq, Sq, Sk, d, n_heads, round_out, nullptr, nullptr, 0, st, lc, out_planes);
+    if (hd == 64 && Sq > 16) return launch_seq<64>(q, ldq, k, v, ldkv, out, n_seq, Sq, Sk, d, n_heads, round_out, nullptr, nullptr, 0, st, lc, out_planes);
   }
   if (lc) lc->n++;
   const unsigned grid = static_cast<unsigned>((rows * n_heads + 7) / 8);
   const float scale = 1.f / sqrtf(static_cast<float>(hd));
-  if (hd == 64) mha_small_kernel<64><<<grid, 256, 0, st>>>(q, ldq, k, v, ldkv, out, rows, Sq, Sk, d, n_heads, scale, round_out);
-  else if (hd == 32) mha_small_kernel<32><<<grid, 256, 0, st>>>(q, ldq, k, v, ldkv, out, rows, Sq, Sk, d, n_heads, scale, round_out);
-  else if (hd == 256) mha_small_kernel<256><<<grid, 256, 0, st>>>(q, ldq, k, v, ldkv, out, rows, Sq, Sk, d, n_heads, scale, round_out);
+  if (hd == 64) mha_small_kernel<64><<<grid, 256, 0, st>>>(q, ldq, k, v, ldkv, out, rows, Sq, Sk, d, n_heads, scale, round_out, out_planes);
+  else if (hd == 32) mha_small_kernel<32><<<grid, 256, 0, st>>>(q, ldq, k, v, ldkv, out, rows, Sq, Sk, d, n_heads, scale, round_out, out_planes);
+  else if (hd == 256) mha_small_kernel<256><<<grid, 256, 0, st>>>(q, ldq, k, v, ldkv, out, rows, Sq, Sk, d, n_heads, scale, round_out, out_planes);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 
-cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out) {
-  return mha_cross_small(qkv, 3L * d, qkv + d, qkv + 2 * d, 3L * d, out, n_seq, S, S, d, n_heads, st, lc, round_out);
+cudaError_t mha_small(const float* qkv, float* out, int n_seq, int S, int d, int n_heads, cudaStream_t st, Launches* lc, int round_out,
+                      float* out_planes) {
+  return mha_cross_small(qkv, 3L * d, qkv + d, qkv + 2 * d, 3L * d, out, n_seq, S, S, d, n_heads, st, lc, round_out, out_planes);
 }
 
 // ---- tensor-core attention core for the token layer (head_dim 256) ---------------------------------
