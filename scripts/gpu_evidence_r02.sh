@@ -29,7 +29,7 @@ timeout 900 ncu --profile-from-start off --set full --clock-control none -f \
     -k regex:umma_gemm_kernel -s 0 -c 4 -o /tmp/prof_text python scripts/profile_step.py --skip-cells --cells 64 --queries 455 > $O/prof_text.log 2>&1; echo "ncu text rc=$?"
 ncu -i /tmp/prof_text.ncu-rep --page raw --csv > $O/ncu_full_text_gemms_raw.csv 2>/dev/null
 timeout 900 ncu --profile-from-start off --set full --clock-control none -f \
-    -k regex:mha_seq64 -c 1 -o /tmp/prof_mha python scripts/profile_step.py --cells 2048 --queries 8 > $O/prof_mha.log 2>&1; echo "ncu mha rc=$?"
+    -k regex:mha_seq_kernel -c 1 -o /tmp/prof_mha python scripts/profile_step.py --cells 2048 --queries 8 > $O/prof_mha.log 2>&1; echo "ncu mha rc=$?"
 ncu -i /tmp/prof_mha.ncu-rep --page raw --csv > $O/ncu_full_mha_seq64_raw.csv 2>/dev/null
 python scripts/launch_summary.py $O/launches_cells.csv > $O/launches_cells_summary.txt 2>&1
 python scripts/launch_summary.py $O/launches_text.csv > $O/launches_text_summary.txt 2>&1
