@@ -189,3 +189,16 @@ def test_pack_cell_database_vectorised_matches_per_object_packing():
     ns = dataio.pack_cell_database(cells, normalize_scale=True, rng=np.random.default_rng(0))
     p = ns.pts[:, :, 0:3].numpy()
     assert np.abs(p.mean(axis=1)).max() < 1e-5 and abs(np.abs(p).max(axis=(1, 2)).max() - 0.999999) < 1e-5
+
+
+def test_host_chunk_schedule_covers_every_query_once():
+    """engine.host_chunk_schedule: the H2D staging chunks of a host-streamed encode_text partition the batch, never exceed the
+    staging buffer, and start / end with short chunks when the batch is long."""
+    from text2loc_b200.engine import host_chunk_schedule
+
+    for nq in (0, 1, 5, 37, 221, 222, 223, 4096, 32768):
+        for cq in (1, 3, 4, 37, 227, 5000):
+            sizes = host_chunk_schedule(nq, cq)
+            assert sum(sizes) == nq and all(0 < n <= cq for n in sizes), (nq, cq, sizes)
+            if nq >= 6 * cq and cq >= 4:
+                assert sizes[0] == cq // 4 and sizes[-1] == cq // 4 and sizes[1] == cq // 2 and sizes[-2] == cq // 2

@@ -385,3 +385,52 @@ def test_precision_plan_per_point_first_linear(state_dict, monkeypatch):
     print("\nfirst-Linear formulation, cell embedding error:", {k: f"{v:.2e}" for k, v in errs.items()})
     assert errs["per point + per centroid"] < 3e-4
     assert errs["per point + per centroid"] < 2 * errs["per edge (round 1)"] + 5e-5
+
+
+def test_padded_slots_are_identical_rows_and_one_weighted_row_stands_for_them(state_dict):
+    """The engine's intra-cell layers carry min(n, 28) object rows + ONE padding row per cell instead of the reference's 28
+    zero-padded slots (cell_retrieval.py:81-103: zero padding, no mask).  CPU proof on the oracle: (1) after each of the two
+    layers the padded slots of a cell are identical rows; (2) a layer evaluated on the reduced rows, with the padding row's
+    softmax weight multiplied by its multiplicity as a KEY, equals the full layer; (3) the cell embeddings agree."""
+    import math
+
+    import torch.nn.functional as F_
+
+    from oracle.restate import _t
+
+    slots, d, heads = 28, 256, 4
+    g = torch.Generator().manual_seed(3)
+    counts = [8, 1, 27, 28, 16]
+    full = torch.zeros(len(counts), slots, d)
+    for c, n in enumerate(counts):
+        full[c, :n] = F_.normalize(torch.randn(n, d, generator=g), dim=-1)
+
+    def reduced_layer(prefix, x, mult):  # x [rows, d] of ONE cell; mult = weight of the last row as a key
+        hd = d // heads
+        qkv = F_.linear(x, _t(state_dict, prefix + ".self_attn.in_proj_weight"), _t(state_dict, prefix + ".self_attn.in_proj_bias"))
+        q, k, v = (t.reshape(-1, heads, hd).permute(1, 0, 2) for t in qkv.split(d, dim=-1))
+        sc = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+        e = torch.exp(sc - sc.max(dim=-1, keepdim=True)[0])
+        e[..., -1] *= mult
+        o = ((e / e.sum(dim=-1, keepdim=True)) @ v).permute(1, 0, 2).reshape(-1, d)
+        o = F_.linear(o, _t(state_dict, prefix + ".self_attn.out_proj.weight"), _t(state_dict, prefix + ".self_attn.out_proj.bias"))
+        x = F_.layer_norm(x + o, (d,), _t(state_dict, prefix + ".norm1.weight"), _t(state_dict, prefix + ".norm1.bias"), 1e-5)
+        f = F_.linear(F_.relu(F_.linear(x, _t(state_dict, prefix + ".linear1.weight"), _t(state_dict, prefix + ".linear1.bias"))),
+                      _t(state_dict, prefix + ".linear2.weight"), _t(state_dict, prefix + ".linear2.bias"))
+        return F_.layer_norm(x + f, (d,), _t(state_dict, prefix + ".norm2.weight"), _t(state_dict, prefix + ".norm2.bias"), 1e-5)
+
+    with torch.no_grad():
+        x = full.permute(1, 0, 2).contiguous()
+        for i in range(2):
+            x = restate.encoder_layer(state_dict, f"obj_inter_module.{i}", x, heads)
+            for c, n in enumerate(counts):
+                if n < slots - 1:
+                    assert (x[n:, c] - x[n, c]).abs().max() < 1e-6, "padded slots of a cell must stay identical rows"
+        want = F_.normalize(x.max(dim=0)[0])
+        for c, n in enumerate(counts):
+            r = full[c, :n + 1] if n < slots else full[c]
+            mult = float(slots - n) if n < slots else 1.0
+            for i in range(2):
+                r = reduced_layer(f"obj_inter_module.{i}", r, mult)
+            got = F_.normalize(r.max(dim=0)[0], dim=0)
+            assert (got - want[c]).abs().max() < 2e-6, f"cell {c} ({n} objects): reduced rows differ from the padded tensor"

@@ -28,6 +28,19 @@ def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+def host_chunk_schedule(nq: int, cq: int):
+    """Queries per H2D staging chunk of a host-streamed encode_text: full chunks of `cq` queries, with a quarter and a half
+    chunk at both ends when the batch is long enough (the first copy and the last chunk's compute are what stays exposed).
+    Every entry is in 1..cq and the entries sum to nq."""
+    if nq <= 0:
+        return []
+    if nq >= 6 * cq and cq >= 4:
+        head = [cq // 4, cq // 2]
+        body = nq - 2 * sum(head)
+        return head + [cq] * (body // cq) + ([body % cq] if body % cq else []) + head[::-1]
+    return [cq] * (nq // cq) + ([nq % cq] if nq % cq else [])
+
+
 class Engine:
     """One engine per CUDA device (t2l_create / t2l_destroy)."""
 
@@ -162,13 +175,7 @@ class Engine:
         # Chunk schedule: the copy of chunk i+1 runs under the compute of chunk i, so what stays exposed is the FIRST copy and
         # the LAST chunk's compute -- both start and end with quarter and half chunks.  The sentence stage runs per group of
         # ~4 chunks instead of once at the end (it would otherwise sit, whole, behind the last copy).
-        sizes = []
-        if nq >= 6 * cq and cq >= 4:
-            head = [cq // 4, cq // 2]
-            body = nq - 2 * sum(head)
-            sizes = head + [cq] * (body // cq) + ([body % cq] if body % cq else []) + head[::-1]
-        else:
-            sizes = [cq] * (nq // cq) + ([nq % cq] if nq % cq else [])
+        sizes = host_chunk_schedule(nq, cq)
         group_q = 4 * cq
         q0 = g0 = 0
         for i, n_q in enumerate(sizes):
