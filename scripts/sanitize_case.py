@@ -26,3 +26,12 @@ if which in ("all", "search"):
     eng.search_topk_accumulate(Qn, 10, *run)
     torch.cuda.synchronize()
     print("search ok", int(nfb), bool((run[0] == idx).all()))
+if which in ("all", "fine"):
+    # fine stage (CrossMatch): object encoder at d = 128, hint encoder, decoder layers (sequence-per-warp self / cross attention,
+    # operand planes written by LayerNorm / attention / the ReLU epilogue), offset MLP
+    fe = Engine("cuda:0"); fe.load_state_dict(synth.make_fine_state_dict(0))
+    pts, meta, ptr = fe.synth_cells(3, 0, 12, 16)
+    t5 = torch.from_numpy(synth.make_t5_features(4, 12, 6, 12)).cuda()
+    off = fe.fine_offsets(pts, meta, ptr, t5, 6)
+    torch.cuda.synchronize()
+    print("fine ok", bool(torch.isfinite(off).all()))
