@@ -201,6 +201,11 @@ int t2l_debug_linear_f16_residual(t2l_engine* e, const void* A, int lda, const v
  * (q | k | v), head h = columns [h*d/n_heads, ...), no mask; out device f32 [n_seq*S, d] = softmax(q k^T / sqrt(hd)) v. */
 int t2l_debug_mha(t2l_engine* e, const float* qkv, float* out, int n_seq, int S, int d, int n_heads, void* stream);
 
+/* Test hook for cross attention with the same cores (nn.TransformerDecoderLayer.multihead_attn, models/cross_matcher.py:113-115):
+ * q device f32 [n_seq*Sq, d], kv device f32 [n_seq*Sk, 2d] packed (k | v), out device f32 [n_seq*Sq, d]; Sk <= 32. */
+int t2l_debug_mha_cross(t2l_engine* e, const float* q, const float* kv, float* out, int n_seq, int Sq, int Sk, int d, int n_heads,
+                        void* stream);
+
 /* Test hook for the intra-cell attention core on packed rows without duplicate padding rows: cell b owns rows
  * row_ptr[b] .. row_ptr[b+1]) = its min(n_b, slots) objects + (if n_b < slots) one row standing for the slots - n_b
  * zero-padded slots of the reference's [B, slots, d] tensor; n_b = cell_ptr[b+1] - cell_ptr[b].  All pointers device. */

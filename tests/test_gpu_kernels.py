@@ -95,7 +95,8 @@ def test_umma_gemm_f16_residual_stream(eng, M, N, K):
 
 
 @pytest.mark.parametrize("n_seq,S,d,heads", [(2048, 28, 256, 4), (37, 17, 256, 4), (5, 32, 256, 4), (300, 16, 256, 4), (1000, 6, 256, 4),
-                                             (64, 9, 128, 4), (1, 28, 256, 4)])
+                                             (64, 9, 128, 4), (1, 28, 256, 4), (500, 6, 128, 4), (333, 16, 128, 4), (7, 3, 128, 4), (1, 1, 128, 4),
+                                             (40, 28, 128, 4)])
 def test_small_attention_core(eng, n_seq, S, d, heads):
     """nn.MultiheadAttention's core without a mask (cell_retrieval.py:101-103, language_encoder.py:143-145) in fp32: the
     row-per-warp kernel (short sequences) and the sequence-per-warp kernel (64-wide heads, S > 16) against torch in fp64."""
@@ -107,6 +108,25 @@ def test_small_attention_core(eng, n_seq, S, d, heads):
     want = (att @ v).permute(0, 2, 1, 3).reshape(n_seq * S, d)
     err = (got.double() - want).abs().max().item()
     print(f"\n[mha {n_seq}x{S}x{d}/{heads}] |out-fp64|={err:.3e}")
+    assert err < 5e-6
+
+
+@pytest.mark.parametrize("n_seq,Sq,Sk,d,heads", [(900, 16, 6, 128, 4), (900, 6, 16, 128, 4), (5, 3, 32, 128, 4), (77, 28, 9, 256, 4), (33, 16, 16, 128, 4),
+                                                 (3, 40, 7, 128, 4)])
+def test_small_cross_attention_core(eng, n_seq, Sq, Sk, d, heads):
+    """nn.TransformerDecoderLayer's multihead_attn core (models/cross_matcher.py:113-115): queries from the target rows, keys /
+    values from the memory rows, no mask; the packed short-sequence kernel (32-wide heads), the sequence-per-warp kernel and the
+    row-per-warp kernel against torch in fp64."""
+    g = torch.Generator(device="cuda").manual_seed(n_seq * 5 + Sq * 3 + Sk)
+    q = torch.randn(n_seq * Sq, d, device="cuda", generator=g)
+    kv = torch.randn(n_seq * Sk, 2 * d, device="cuda", generator=g)
+    got = eng.debug_mha_cross(q, kv, n_seq, Sq, Sk, heads)
+    hd = d // heads
+    qq = q.reshape(n_seq, Sq, heads, hd).permute(0, 2, 1, 3).double()
+    kk, vv = (t.reshape(n_seq, Sk, heads, hd).permute(0, 2, 1, 3).double() for t in kv.split(d, dim=1))
+    want = (torch.softmax(qq @ kk.transpose(-1, -2) / hd ** 0.5, dim=-1) @ vv).permute(0, 2, 1, 3).reshape(n_seq * Sq, d)
+    err = (got.double() - want).abs().max().item()
+    print(f"\n[cross mha {n_seq}x{Sq}x{Sk}x{d}/{heads}] |out-fp64|={err:.3e}")
     assert err < 5e-6
 
 

@@ -52,6 +52,7 @@ SIGNATURES = {
     "t2l_debug_linear_f16": (c_int, [_P, _P, c_int, _P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     "t2l_debug_mha": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "t2l_debug_sa_bisect": (c_int, [_P, c_int]),
+    "t2l_debug_mha_cross": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "t2l_debug_mha_cells": (c_int, [_P, _P, _P, c_int, _P, _P, c_int, c_int, c_int, _P]),
     "t2l_debug_linear_f16_residual": (c_int, [_P, _P, c_int, _P, c_int, _P, _P, c_int, _P, c_int, c_int, c_int, c_int, c_int, _P]),
 }

@@ -1268,3 +1268,12 @@ extern "C" int t2l_debug_sa_bisect(t2l_engine* e, int mode) {
   e->sa_bisect = mode;
   return 0;
 }
+
+extern "C" int t2l_debug_mha_cross(t2l_engine* e, const float* q, const float* kv, float* out, int n_seq, int Sq, int Sk, int d, int n_heads,
+                                   void* stream) {
+  if (!e) return 1;
+  if (!q || !kv || !out || n_seq < 0 || Sq < 1 || Sk < 1 || Sk > 32 || n_heads < 1 || d % n_heads) return fail(e, "debug_mha_cross: bad argument");
+  ENTER_STREAM(e, stream);
+  CU(mha_cross_small(q, d, kv, kv + d, 2L * d, out, n_seq, Sq, Sk, d, n_heads, static_cast<cudaStream_t>(stream), &e->lc));
+  return 0;
+}

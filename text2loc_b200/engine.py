@@ -383,6 +383,14 @@ class Engine:
         self._check(self._lib.t2l_debug_mha(self._h, _ptr(qkv), _ptr(out), n_seq, S, d, n_heads, self._stream()))
         return out
 
+    def debug_mha_cross(self, q, kv, n_seq: int, Sq: int, Sk: int, n_heads: int):
+        """Cross attention core: q [n_seq*Sq, d], kv [n_seq*Sk, 2d] (k | v) -> [n_seq*Sq, d]."""
+        q, kv = self._dev(q, torch.float32), self._dev(kv, torch.float32)
+        d = q.shape[1]
+        out = torch.empty((n_seq * Sq, d), dtype=torch.float32, device=self.device)
+        self._check(self._lib.t2l_debug_mha_cross(self._h, _ptr(q), _ptr(kv), _ptr(out), n_seq, Sq, Sk, d, n_heads, self._stream()))
+        return out
+
     def debug_mha_cells(self, qkv, row_ptr, cell_ptr, slots: int, n_heads: int):
         """Intra-cell attention core on packed rows with one representative padding row per cell."""
         qkv = self._dev(qkv, torch.float32)
