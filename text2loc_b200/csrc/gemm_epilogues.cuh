@@ -57,7 +57,7 @@ struct StoreEpiT {
   // (4 KB) per warp -- not by the MMAs (out-proj: 105 us against a 52 us HBM floor, profiles/r01).  They run TWO epilogue warp
   // sets (even / odd 32-column chunks), which doubles the loads in flight; their bias then comes straight from L1 (__ldg, a
   // broadcast) instead of a per-warp shared-memory slice, which keeps the second set's transpose tiles inside the 227 KB.
-  static constexpr int kSets = kResidual ? 2 : 1;
+  static constexpr int kSets = (kResidual || kHalfOut) ? 2 : 1;  // (the fp16-output variant too: see DESIGN.md section 4, QKV / FFN1)
   static constexpr bool kSmemBias = kSets == 1;
   static constexpr int kSmemBytes = (kSmemBias ? kEpiBiasSmem : 0) + 4 * kSets * kStageBytes;
   static constexpr bool kCompactLoop = kSets == 2;  // two inlined chunk() copies keep the 384-thread variant inside its 168 registers
