@@ -124,10 +124,6 @@ cudaError_t mha_cells64(const float* qkv, float* out, int n_cells, const int32_t
 cudaError_t scatter_objects_ragged(const float* emb, const int32_t* cell_ptr_dev, const int32_t* row_ptr_dev, int n_cells, float* X, cudaStream_t st,
                                    Launches* lc);
 cudaError_t max_over_rows_ragged(const float* x, const int32_t* row_ptr_dev, float* y, int n_cells, cudaStream_t st, Launches* lc);
-// X[b, s, :] = normalize(emb[cell_ptr[b]+s]) for s < min(n_b, 28), else 0   (cell_retrieval.py:85-98)
-cudaError_t scatter_objects(const float* emb, const int32_t* cell_ptr_dev, int n_cells, float* X, cudaStream_t st, Launches* lc);
-// meta[:, 6] -> (cnt - mean) / std  (object_encoder.py:141-143)
-cudaError_t num_feature(const float* meta, int n_obj, float* out, cudaStream_t st, Launches* lc);
 // cat[:, d:4d] = [normalize(color_enc(mean rgb)) | normalize(pos_enc(centre)) | normalize(num_enc((count-mean)/std))], d = 256 or 128
 // from meta [n, 7]; w1[i] [64, ld 4], b1[i] [64], w2[i] [256, 64], b2[i] [256] for i = colour, position, count
 // (models/object_encoder.py:122-145)

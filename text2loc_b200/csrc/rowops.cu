@@ -787,37 +787,9 @@ cudaError_t max_over_rows(const float* x, float* y, int groups, int S, int d, cu
   return cudaGetLastError();
 }
 
-// ---- objects -> zero-padded [B, 28, 256], each row normalised ---------------------------------------
-__global__ void scatter_objects_kernel(const float* __restrict__ emb, const int32_t* __restrict__ cell_ptr, int n_cells, float* __restrict__ X) {
-  const long slot = static_cast<long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (slot >= static_cast<long>(n_cells) * kObjectSlots) return;
-  const int lane = threadIdx.x & 31;
-  const int b = static_cast<int>(slot / kObjectSlots), s = static_cast<int>(slot % kObjectSlots);
-  const int n = cell_ptr[b + 1] - cell_ptr[b];
-  float4* dst = reinterpret_cast<float4*>(X + slot * kEmbed);
-  if (s >= n) {  // padding slot (objects beyond 28 are dropped by construction of the loop bound)
-    dst[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-    dst[lane + 32] = make_float4(0.f, 0.f, 0.f, 0.f);
-    return;
-  }
-  const float4* src = reinterpret_cast<const float4*>(emb + static_cast<long>(cell_ptr[b] + s) * kEmbed);
-  const float4 a = src[lane], c = src[lane + 32];
-  float ss = (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w) + (c.x * c.x + c.y * c.y) + (c.z * c.z + c.w * c.w);
-  ss = warp_sum(ss);
-  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-  dst[lane] = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
-  dst[lane + 32] = make_float4(c.x * inv, c.y * inv, c.z * inv, c.w * inv);
-}
-
-cudaError_t scatter_objects(const float* emb, const int32_t* cell_ptr_dev, int n_cells, float* X, cudaStream_t st, Launches* lc) {
-  if (n_cells <= 0) return cudaSuccess;
-  if (lc) lc->n++;
-  const long slots = static_cast<long>(n_cells) * kObjectSlots;
-  scatter_objects_kernel<<<static_cast<unsigned>((slots + 7) / 8), 256, 0, st>>>(emb, cell_ptr_dev, n_cells, X);
-  return cudaGetLastError();
-}
-
-// ---- the same without the duplicate padding rows: cell b -> rows row_ptr[b] ..: its min(n, 28) normalised objects, then ONE
+// ---- objects -> packed attention rows of the intra-cell layers ---------------------------------------
+// (the reference builds a zero-padded [B, 28, 256] tensor, cell_retrieval.py:85-98)
+// Cell b -> rows row_ptr[b] ..: its min(n, 28) normalised objects, then ONE
 // zero row standing for all 28 - n padded slots (see mha_seq64_kernel).  One warp per cell.
 __global__ void scatter_objects_ragged_kernel(const float* __restrict__ emb, const int32_t* __restrict__ cell_ptr, const int32_t* __restrict__ row_ptr,
                                               int n_cells, float* __restrict__ X) {
@@ -873,21 +845,6 @@ cudaError_t max_over_rows_ragged(const float* x, const int32_t* row_ptr_dev, flo
   if (n_cells <= 0) return cudaSuccess;
   if (lc) lc->n++;
   max_over_rows_ragged_kernel<<<(n_cells + 7) / 8, 256, 0, st>>>(x, row_ptr_dev, y, n_cells);
-  return cudaGetLastError();
-}
-
-// ---- (count - mean) / std  (models/object_encoder.py:44-45,141-143; fp32 like the reference) ---------
-__global__ void num_feature_kernel(const float* __restrict__ meta, int n, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float mean = static_cast<float>(1826.6844940968194), std_ = static_cast<float>(2516.8905096993817);
-  out[i] = __fdiv_rn(__fsub_rn(meta[static_cast<long>(i) * 7 + 6], mean), std_);
-}
-
-cudaError_t num_feature(const float* meta, int n_obj, float* out, cudaStream_t st, Launches* lc) {
-  if (n_obj <= 0) return cudaSuccess;
-  if (lc) lc->n++;
-  num_feature_kernel<<<(n_obj + 255) / 256, 256, 0, st>>>(meta, n_obj, out);
   return cudaGetLastError();
 }
 
