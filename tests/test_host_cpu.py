@@ -31,6 +31,42 @@ def test_library_exports_every_header_symbol(lib):
     assert lib.t2l_version() == 1
 
 
+def test_built_library_is_blackwell_native(lib):
+    """The hot kernels of the built .so carry the sm_100a tensor-core / TMA instructions in their SASS (cuobjdump):
+    UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / .st (tensor memory), UTMALDG / UTMASTG = TMA tensor load / store,
+    UBLKCP = cp.async.bulk.  Guards against a build that silently fell back to SIMT code paths."""
+    import shutil
+    import subprocess
+    from collections import Counter, defaultdict
+
+    from text2loc_b200 import _lib
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    per_kernel = defaultdict(Counter)
+    cur = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            continue
+        for op in ("UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP"):
+            if op in line:
+                per_kernel[cur][op] += 1
+    gemms = {k: v for k, v in per_kernel.items() if "umma_gemm_kernel" in k}
+    sa = {k: v for k, v in per_kernel.items() if "sa_obj2_kernel" in k}
+    assert len(gemms) >= 20 and len(sa) == 3
+    for name, ops in gemms.items():  # TMA-fed tcgen05 tiles, accumulators read back from tensor memory
+        assert ops["UTCHMMA"] and ops["LDTM"] and ops["UTMALDG"], (name, dict(ops))
+    for name, ops in sa.items():  # bulk-copied object blocks, W2 parked in tensor memory (tcgen05.st), TS-mode MMAs
+        assert ops["UTCHMMA"] and ops["LDTM"] and ops["STTM"] and ops["UBLKCP"], (name, dict(ops))
+    assert any("TopKEpi" in k for k in gemms), "the fused top-k search epilogue is missing"
+    assert any("ResidualTmaEpi" in k and v["UTMASTG"] for k, v in gemms.items()), "the TMA-store residual epilogue is missing"
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_engine_fails_loudly_without_cuda(lib):
     from text2loc_b200.engine import Engine, EngineError

@@ -63,7 +63,7 @@ struct t2l_engine {
   SearchWork sw{};
   size_t sw_planes_rows = 0;
   int obj_chunk = 16384;     // objects per encode chunk (cell-aligned); 2048 -> 4096 -> 8192 -> 16384 is +9 % / +5 % / +4 % cells/s (fuller
-                             // grids for the small kernels), ~48 GB of workspace (T2L_OBJ_CHUNK to change)
+                             // grids for the small kernels), ~6.5 GB of workspace reserved (T2L_OBJ_CHUNK to change)
   bool dist_fma = false;     // FPS / ball-query distances with FMA contraction (T2L_DIST_FMA=1; oracle: pyg_ops.DIST_FMA)
   int tok_chunk = 75776;     // tokens per text chunk (sentence-aligned): 296 row tiles of 256 = whole waves of 74 CTA pairs for all four
                              // token GEMMs; 32768 -> 75776 is ~5 % on the text head (fewer launch tails), larger gains nothing
