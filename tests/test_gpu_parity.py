@@ -556,6 +556,48 @@ def make_model(state_dict, fake_seed=0):
     return model.eval(), args
 
 
+def test_sentence_row_cache_equals_uncached_encode_text(state_dict, fine_sd):
+    """With a sentence-caching front end the drop-in models run the token stage once per distinct (sentence, n_tok) and
+    assemble batches from cached rows (text_frontend.SentenceRowCache).  Same embeddings as
+    pushing every batch through the text head whole -- rows of the token stage do not depend on their neighbours."""
+    from oracle import fake_t5, reference_run
+    from oracle.stubs import sent_tokenize
+    from text2loc_b200 import CellRetrievalNetwork, CrossMatch
+    from text2loc_b200.text_frontend import SentenceCacheFrontend
+
+    def frontend():
+        return SentenceCacheFrontend(fake_t5.FakeTokenizer(), fake_t5.FakeT5Encoder(0).eval().cuda(), "cuda:0", cap=16, split=sent_tokenize)
+
+    dirs, cols, labs = ["north", "east", "on-top", "west"], ["gray", "red", "dark-green"], ["building", "pole", "traffic light", "vending machine"]
+    rng = np.random.default_rng(5)
+    texts = [" ".join(f"The pose is {dirs[rng.integers(4)]} of a {cols[rng.integers(3)]} {labs[rng.integers(4)]}." for _ in range(6))
+             for _ in range(300)]
+    model, _ = make_model(state_dict)
+    model._frontend = frontend()
+    plain, _ = make_model(state_dict)
+    plain._frontend = frontend()
+    plain.cache_sentence_rows = False
+    worst = 0.0
+    for batch in (texts[:64], texts[64:70], texts[:300]):
+        got, want = model.encode_text(batch), plain.encode_text(batch)
+        assert got.shape == want.shape == (len(batch), 256)
+        worst = max(worst, float((got - want).abs().max()))
+    n_distinct = len({s for t in texts for s in sent_tokenize(t)})
+    print(f"\nsentence row cache: {model._sentence_rows.computed} token-stage rows for {300 * 6 + 70 * 6} sentences "
+          f"({n_distinct} distinct), max |cached - uncached| = {worst:.1e}")
+    assert worst <= 1e-5  # bit-equal in practice; 1 % of the 1e-3 tolerance is the bound asserted
+    assert model._sentence_rows.computed <= 3 * n_distinct  # at most one row per distinct sentence and padding length
+
+    args = reference_run.fine_args(top_k=[1, 3], threshs=[5, 10, 15])
+    fine = CrossMatch([], [], args, text_frontend=frontend())
+    fine.load_state_dict({k: torch.as_tensor(np.asarray(v)) for k, v in fine_sd.items()}, strict=False)
+    got, nh = fine.encode_hints(texts[:40])
+    fine.cache_sentence_rows = False
+    want, nh2 = fine.encode_hints(texts[:40])
+    assert nh == nh2 == 6 and got.shape == want.shape == (240, 128)
+    assert float((got - want).abs().max()) <= 1e-5
+
+
 def test_dropin_eval_epoch_and_run_coarse_golden(state_dict, golden):
     """The reference's own eval_epoch / run_coarse outputs on the same seeded dataset."""
     from oracle.make_golden import e2e_dataset

@@ -204,6 +204,57 @@ def test_sentence_cache_frontend_reproduces_the_uncached_front_end():
     assert cached.encoder_calls == 2 and len(cached.cache) == 4  # the third batch was served from the cache alone
 
 
+def test_sentence_row_cache_computes_each_distinct_sentence_once():
+    """SentenceRowCache (token stage of the text head per distinct (sentence, n_tok)): a batch assembled from the cache equals
+    the row-by-row computation, repeated sentences are computed once, another padding length is another key, and the table
+    is bounded."""
+    from text2loc_b200.text_frontend import SentenceRowCache
+
+    calls = []
+
+    def row_of(s, n_tok):
+        return torch.full((4,), float(len(s) * 100 + n_tok))
+
+    def compute_for(n_tok):
+        def compute(new):
+            calls.append(list(new))
+            assert len(set(new)) == len(new)
+            return torch.stack([row_of(s, n_tok) for s in new])
+        return compute
+
+    cache = SentenceRowCache(max_rows=6)
+    batch = ["a", "bb", "a", "ccc", "bb", "a"]
+    got = cache.rows(batch, 9, compute_for(9))
+    assert torch.equal(got, torch.stack([row_of(s, 9) for s in batch]))
+    assert calls == [["a", "bb", "ccc"]] and cache.computed == 3
+    got = cache.rows(["ccc", "a"], 9, compute_for(9))  # served from the table alone
+    assert torch.equal(got, torch.stack([row_of("ccc", 9), row_of("a", 9)])) and len(calls) == 1
+    got = cache.rows(["a", "dddd"], 11, compute_for(11))  # same sentence, longer padding: a different row
+    assert torch.equal(got, torch.stack([row_of("a", 11), row_of("dddd", 11)])) and calls[-1] == ["a", "dddd"]
+    assert len(cache.index) == 5
+    got = cache.rows(["e", "ff", "a"], 9, compute_for(9))  # 5 + 2 new > max_rows: the cache starts over with this batch
+    assert torch.equal(got, torch.stack([row_of(s, 9) for s in ("e", "ff", "a")]))
+    assert calls[-1] == ["e", "ff", "a"] and len(cache.index) == 3 and cache.table.shape == (3, 4)
+
+
+def test_sentence_cache_frontend_prepare_and_states():
+    """prepare() / states() are the two halves of the cached front end's call (the drop-in models use them to run the
+    token stage per distinct sentence)."""
+    from oracle import fake_t5
+    from oracle.stubs import sent_tokenize
+    from text2loc_b200.text_frontend import SentenceCacheFrontend
+
+    fe = SentenceCacheFrontend(fake_t5.FakeTokenizer(), fake_t5.FakeT5Encoder(0).eval(), "cpu", cap=16, split=sent_tokenize)
+    batch = ["The pose is north of a gray building. The pose is east of a red pole.",
+             "The pose is east of a red pole. The pose is on-top of a dark-green traffic light."]
+    sentences, n_sent, n_tok = fe.prepare(batch)
+    assert n_sent == 2 and len(sentences) == 4 and sentences[1] == sentences[2]
+    full, ns = fe(batch)
+    assert ns == 2 and full.shape == (4, n_tok, 1024)
+    assert torch.equal(fe.states(sentences, n_tok), full)
+    assert torch.equal(fe.states([sentences[3]], n_tok)[0], full[3])
+
+
 def test_pack_cell_database_vectorised_matches_per_object_packing():
     """meta is the per-object reductions of pack_cells; every sampled point is one of the object's raw points; the
     NormalizeScale variant centres each sample and scales it into (-1, 1)."""

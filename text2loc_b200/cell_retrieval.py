@@ -50,6 +50,12 @@ class CellRetrievalNetwork:
         self.training = False
         # opt-in: eval_epoch packs the cell database once (vectorised) and re-uses it across evaluations (evaluation.py)
         self.cache_packed_cells = False
+        # with a front end that caches T5 states per sentence (text_frontend.SentenceCacheFrontend) the token stage of the
+        # text head is cached per distinct sentence as well; set False to push every batch through it whole
+        self.cache_sentence_rows = True
+        from .text_frontend import SentenceRowCache
+
+        self._sentence_rows = SentenceRowCache()
 
     # ---- nn.Module surface the eval drivers touch -----------------------------------------
     def eval(self):
@@ -93,7 +99,14 @@ class CellRetrievalNetwork:
             from .text_frontend import HFT5Frontend
 
             self._frontend = HFT5Frontend(self.args.hungging_model, self.device)
-        feats, n_sent = self._frontend(descriptions)
+        fe = self._frontend
+        if self.cache_sentence_rows and hasattr(fe, "prepare") and hasattr(fe, "states"):
+            # a caching front end knows the batch's sentences: the token stage runs once per distinct (sentence, n_tok)
+            # and the batch is assembled from the cached rows (text_frontend.SentenceRowCache)
+            sentences, n_sent, n_tok = fe.prepare(descriptions)
+            pooled = self._sentence_rows.rows(sentences, n_tok, lambda new: self._engine.encode_text_tokens(fe.states(new, n_tok)))
+            return self._engine.encode_text_sentences(pooled, n_sent)
+        feats, n_sent = fe(descriptions)
         return self._engine.encode_text(feats, n_sent)
 
     @torch.no_grad()

@@ -34,6 +34,11 @@ class CrossMatch:
         self._engine = Engine(device)
         self._frontend = text_frontend
         self.training = False
+        # run_fine: with a sentence-caching front end the hint encodings are cached per distinct (sentence, n_tok) too
+        self.cache_sentence_rows = True
+        from .text_frontend import SentenceRowCache
+
+        self._sentence_rows = SentenceRowCache()
 
     def eval(self):
         self.training = False
@@ -71,6 +76,18 @@ class CrossMatch:
 
             self._frontend = HFT5Frontend(self.args.hungging_model, self.device)
         return self._frontend
+
+    @torch.no_grad()
+    def encode_hints(self, descriptions: List[str]):
+        """-> (hint encodings [len(descriptions) * n_hints, 128] on device, n_hints): LanguageEncoder(is_fine) behind the
+        frozen T5 (models/language_encoder.py:108-140), one row per hint sentence.  Every row depends on its own sentence
+        only, so a sentence-caching front end lets each distinct (sentence, n_tok) be encoded once."""
+        fe = self.frontend()
+        if self.cache_sentence_rows and hasattr(fe, "prepare") and hasattr(fe, "states"):
+            sentences, n_hints, n_tok = fe.prepare(descriptions)
+            return self._sentence_rows.rows(sentences, n_tok, lambda new: self._engine.fine_encode_hints(fe.states(new, n_tok))), n_hints
+        feats, n_hints = fe(descriptions)
+        return self._engine.fine_encode_hints(feats), n_hints
 
     @torch.no_grad()
     def forward(self, objects, hints: List[str], object_points) -> torch.Tensor:

@@ -200,6 +200,29 @@ class Engine:
             q0 = q1
         return out
 
+    def encode_text_tokens(self, t5) -> torch.Tensor:
+        """Token stage alone (t2l_encode_text_tokens / _f16): device t5 [n_sentences, n_tok, 1024] float32 or float16 ->
+        [n_sentences, 1024] = intra_module + max over tokens (models/language_encoder.py:130-133).  Rows are independent."""
+        t5 = torch.as_tensor(t5)
+        if t5.dim() != 3 or t5.shape[2] != T5_DIM or t5.dtype not in (torch.float32, torch.float16):
+            raise EngineError(f"encode_text_tokens: need float32 / float16 [n_sentences, n_tok, 1024], got {t5.dtype} {tuple(t5.shape)}")
+        t5 = self._dev(t5, t5.dtype)
+        tokens = self._lib.t2l_encode_text_tokens_f16 if t5.dtype == torch.float16 else self._lib.t2l_encode_text_tokens
+        pooled = torch.empty((t5.shape[0], T5_DIM), dtype=torch.float32, device=self.device)
+        self._check(tokens(self._h, _ptr(t5), t5.shape[0], t5.shape[1], _ptr(pooled), self._stream()))
+        return pooled
+
+    def encode_text_sentences(self, pooled, n_sent: int) -> torch.Tensor:
+        """Sentence stage alone (t2l_encode_text_sentences): pooled [nq*n_sent, 1024] -> unit rows [nq, 256]
+        (inter_mlp, inter_module with `x += layer(x)`, max over sentences, normalise; language_encoder.py:137-148)."""
+        pooled = self._dev(pooled, torch.float32)
+        if pooled.dim() != 2 or pooled.shape[1] != T5_DIM or pooled.shape[0] % n_sent:
+            raise EngineError(f"encode_text_sentences: need [nq*{n_sent}, 1024], got {tuple(pooled.shape)}")
+        nq = pooled.shape[0] // n_sent
+        out = torch.empty((nq, EMBED_DIM), dtype=torch.float32, device=self.device)
+        self._check(self._lib.t2l_encode_text_sentences(self._h, _ptr(pooled), nq, n_sent, _ptr(out), self._stream()))
+        return out
+
     def _encode_text_dev(self, t5: torch.Tensor, n_sent: int, out: torch.Tensor):
         nq = t5.shape[0] // n_sent
         self._check(self._lib.t2l_encode_text(self._h, _ptr(t5), nq, n_sent, t5.shape[1], _ptr(out), self._stream()))

@@ -222,14 +222,13 @@ def run_fine(model, retrievals, dataloader, args, transform_fine, return_offsets
         obj_emb[b0 * pad:(b0 + len(cells)) * pad] = engine.fine_encode_objects(pts, meta, cell_ptr)
 
     # ---- textual branch, once per query
-    frontend = model.frontend()
     hints, n_hints = [], None
     qb = 256
     for q0 in range(0, n_q, qb):
-        feats, nh = frontend([_hint_text(p) for p in poses[q0:q0 + qb]])
+        rows, nh = model.encode_hints([_hint_text(p) for p in poses[q0:q0 + qb]])
         assert n_hints in (None, nh), "every description must have the same number of hints (language_encoder.py:114)"
         n_hints = nh
-        hints.append(engine.fine_encode_hints(feats))
+        hints.append(rows)
     hints = torch.cat(hints)
 
     # ---- all query x retrieved-cell pairs

@@ -79,7 +79,9 @@ class SentenceCacheFrontend:
             self.cache[s] = (int(n), h.contiguous())
 
     @torch.no_grad()
-    def __call__(self, descriptions: List[str]) -> Tuple[torch.Tensor, int]:
+    def prepare(self, descriptions: List[str]) -> Tuple[List[str], int, int]:
+        """-> (the batch's sentences in order, sentences per description, the batch's longest token count); every
+        sentence is in the cache afterwards."""
         sentences: List[str] = []
         for d in descriptions:
             sentences.extend(self.split(d))
@@ -87,8 +89,51 @@ class SentenceCacheFrontend:
         new = [s for s in dict.fromkeys(sentences) if s not in self.cache]
         if new:
             self._encode_new(new)
-        L = max(self.cache[s][0] for s in sentences)  # padding="longest" over THIS batch
-        return torch.stack([self.cache[s][1][:L] for s in sentences]).contiguous(), n_sent
+        return sentences, n_sent, max(self.cache[s][0] for s in sentences)  # padding="longest" over THIS batch
+
+    def states(self, sentences: List[str], n_tok: int) -> torch.Tensor:
+        """Cached states of `sentences`, each cut to n_tok positions -> [len(sentences), n_tok, 1024]."""
+        return torch.stack([self.cache[s][1][:n_tok] for s in sentences]).contiguous()
+
+    @torch.no_grad()
+    def __call__(self, descriptions: List[str]) -> Tuple[torch.Tensor, int]:
+        sentences, n_sent, n_tok = self.prepare(descriptions)
+        return self.states(sentences, n_tok), n_sent
+
+
+class SentenceRowCache:
+    """Per-sentence rows of the text head behind a SentenceCacheFrontend, computed once per distinct (sentence, n_tok).
+
+    Everything the language encoder does BEFORE its sentence-level module is a function of one sentence's token states
+    alone: intra_module over the sentence's tokens and the max over them (models/language_encoder.py:130-133; for the fine
+    model also inter_mlp, :137-140).  That token stage is 99 % of the text head's arithmetic (906 of
+    914 MMAC per query), and with the templated hint vocabulary a batch of B x 6 sentences holds only a few hundred distinct
+    ones.  The cache keeps one row per (sentence, n_tok) -- n_tok is part of the key because the reference feeds pad
+    positions UNMASKED into intra_module, so the row depends on how far the batch was padded -- in one device table and
+    assembles a batch with a single index_select.  The engine's token stage is row-independent bit for bit
+    (tests/test_gpu_parity.py::test_encode_text_host_streaming_equals_device), so the result equals the uncached call."""
+
+    def __init__(self, max_rows: int = 1 << 16):
+        self.max_rows = max_rows
+        self.index = {}    # (sentence, n_tok) -> row of the table
+        self.table = None  # [rows, width] on the engine's device
+        self.computed = 0  # rows ever computed (tests / diagnostics)
+
+    def rows(self, sentences: List[str], n_tok: int, compute) -> torch.Tensor:
+        """compute(list of distinct missing sentences) -> tensor [len, width]; returns [len(sentences), width]."""
+        keys = [(s, n_tok) for s in sentences]
+        missing = [k for k in dict.fromkeys(keys) if k not in self.index]
+        if missing and len(self.index) + len(missing) > self.max_rows:  # bounded: start over rather than grow without limit
+            self.index, self.table = {}, None
+            missing = list(dict.fromkeys(keys))
+        if missing:
+            new = compute([s for s, _ in missing])
+            base = 0 if self.table is None else self.table.shape[0]
+            self.table = new.clone() if self.table is None else torch.cat([self.table, new])
+            self.index.update({k: base + i for i, k in enumerate(missing)})
+            self.computed += len(missing)
+        sel = torch.tensor([self.index[k] for k in keys], dtype=torch.long, device=self.table.device)
+        return self.table.index_select(0, sel)
 
 
 class HFT5Frontend:
