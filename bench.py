@@ -493,9 +493,21 @@ def run_engine_arm(args):
         if os.path.isfile(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("ffn1_f16_bytes_per_launch")
+        # DRAM bytes of the whole text head of one step and of one encode chunk, from the committed ncu pass over the same
+        # kernels (profiles/r02/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum, 4 096 queries / 16 384 objects)
+        traffic_r02 = {}
+        tpath = os.path.join(ROOT, "profiles", "r02", "traffic.json")
+        if os.path.isfile(tpath):
+            with open(tpath) as f:
+                traffic_r02 = json.load(f)
+        step_traffic = traffic_r02.get("text_head_step_bytes")
+        if step_traffic is not None:
+            step_traffic = int(step_traffic * nq_local / 4096)  # linear in the queries of a step (per GPU)
         roof = {"bound": "tensor", "kernel": "umma_gemm_kernel<GemmCfg<256,f16,cta_group::2>,StoreEpiT<...>> x4 per chunk (token layer QKV / out-proj / "
                                              "FFN1 / FFN2) + attention core + LayerNorms = the text head of one step",
-                "achieved": alg_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": alg_tf / pk["bf16_sustained"], "traffic": None,
+                "achieved": alg_tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": alg_tf / pk["bf16_sustained"], "traffic": step_traffic,
+                "traffic_source": "profiles/r02/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over every launch of the text head of one "
+                                  "step, per GPU; algorithmic I/O of the step: %d bytes)" % (nq_local * (N_SENT * N_TOK * 1024 * 4 + 256 * 4)),
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['source']}); kind::f16 issues at the bf16 rate",
                 "ms": ms_text, "algorithmic_flop": nq_local * 1.83e9, "frac_of_burst_peak": alg_tf / pk["bf16"],
                 "step_share_text_head": ms_text / ms_step}
@@ -540,6 +552,9 @@ def run_engine_arm(args):
                               "frac_of_f16_sustained_peak": obj_per_s * flop_per_obj / 1e12 / pk.get("bf16_sustained", pk["bf16"]),
                               "hbm_algorithmic_gbs": obj_per_s * 7196 / 1e9, "hbm_frac": obj_per_s * 7196 / 1e9 / pk["hbm_gbs"],
                               "cells_per_s": n_cells_local / (enc_warm * 1e-3),
+                              "traffic_bytes_per_object": traffic_r02.get("encode_chunk_bytes_per_object"),
+                              "hbm_measured_traffic_gbs": (obj_per_s * traffic_r02["encode_chunk_bytes_per_object"] / 1e9
+                                                           if "encode_chunk_bytes_per_object" in traffic_r02 else None),
                               "note": "algorithmic FLOPs of the whole encode / wall time of encode_cells (FPS, ball query, gathers, attention and all small "
                                       "layers included) against the measured bf16/f16 burst peak"}
         # (b) search at the per-GPU shape of configs[2] (32 768 queries x 12 500 rows) and at 100k rows
