@@ -164,6 +164,48 @@ def test_restatement_matches_reference_modules_other_seed():
     assert (got - want).abs().max() < 2e-6
 
 
+@pytest.mark.skipif(not reference_run.available(), reason="reference tree not present (GPU box)")
+def test_restatement_text_head_matches_reference_other_shapes():
+    """The reference's own CellRetrievalNetwork.encode_text (sentence split, fake tokenizer / T5, LanguageEncoder) on
+    descriptions with 1, 3 and 6 sentences of different lengths (so n_sent and the padded token count vary), another
+    weight seed: the restatement on the same T5 states agrees to fp32 rounding."""
+    from oracle import fake_t5
+
+    sd = synth.make_state_dict(7)
+    model = reference_run.build_model(sd)
+    rng = np.random.default_rng(12)
+    for n_sent in (1, 3, 6):
+        texts = [" ".join(f"The pose is {synth.DIRECTIONS[rng.integers(5)]} of a {synth.COLOR_WORDS[rng.integers(8)]} "
+                          f"{synth.CLASS_WORDS[rng.integers(22)]}." for _ in range(n_sent)) for _ in range(5)]
+        with torch.no_grad():
+            want = model.encode_text(texts)
+        feats, ns = fake_t5.FakeFrontend(0)(texts)
+        assert ns == n_sent and want.shape == (5, 256)
+        got = restate.encode_text(sd, feats, ns)
+        assert (got - want).abs().max() < 2e-6, n_sent
+
+
+@pytest.mark.skipif(not reference_run.available(), reason="reference tree not present (GPU box)")
+def test_restatement_fine_stage_matches_reference_other_seed():
+    """The reference's own CrossMatch.forward with another weight seed, 3 cells padded to 16 objects, 6 hints each."""
+    from oracle import fake_t5
+
+    sd = synth.make_fine_state_dict(5)
+    model = reference_run.build_fine_model(sd)
+    cells = synth.make_cell_objects(41, 3, [16] * 3, max_raw=300)
+    np.random.seed(3)
+    batches = [dataio.batch_object_points(o, dataio.FixedPoints(256)) for o in cells]
+    rng = np.random.default_rng(8)
+    texts = [" ".join(f"The pose is {synth.DIRECTIONS[rng.integers(5)]} of a {synth.COLOR_WORDS[rng.integers(8)]} "
+                      f"{synth.CLASS_WORDS[rng.integers(22)]}." for _ in range(6)) for _ in range(3)]
+    with torch.no_grad():
+        want = model(cells, texts, batches)
+    pts, meta, ptr = dataio.pack_cells(cells, batches)
+    feats, n_hints = fake_t5.FakeFrontend(0)(texts)
+    got = restate.fine_offsets(sd, pts, meta, ptr, feats, n_hints)
+    assert want.shape == (3, 2) and (got - want).abs().max() < 5e-6
+
+
 # ---- precision plan (DESIGN.md section 2): operand rounding emulated on the CPU -----------------------------
 
 def _emulated_text_error(state_dict, rounder, monkeypatch):
