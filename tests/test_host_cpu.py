@@ -278,6 +278,60 @@ def test_pack_cell_database_vectorised_matches_per_object_packing():
     assert np.abs(p.mean(axis=1)).max() < 1e-5 and abs(np.abs(p).max(axis=(1, 2)).max() - 0.999999) < 1e-5
 
 
+def test_run_fine_vectorised_packing_feeds_the_engine_the_same_layout(monkeypatch):
+    """run_fine's opt-in vectorised packing (model.vectorised_packing) against the per-object path, with the engine replaced
+    by a recorder: same shapes and cell_ptr, identical per-object meta rows (mean colour, centre, raw count, padding objects
+    included), every sampled point one of its object's raw points."""
+    import types
+
+    import synth
+    from oracle import fake_t5, reference_run
+    from text2loc_b200 import dataio, evaluation
+
+    class Recorder:
+        FINE_DIM, device = 128, torch.device("cpu")
+
+        def __init__(self):
+            self.calls = []
+
+        def fine_encode_objects(self, pts, meta, cell_ptr):
+            self.calls.append((pts.clone(), meta.clone(), np.asarray(cell_ptr).copy()))
+            return torch.zeros((pts.shape[0], 128))
+
+        def fine_encode_hints(self, feats):
+            return torch.zeros((feats.shape[0], 128))
+
+        def fine_match(self, obj_emb, pair_cell, hints, pair_query, n_obj, n_hints):
+            return torch.full((len(pair_cell), 2), 0.5)
+
+    args = reference_run.fine_args(top_k=[1, 3], threshs=[5, 10])
+    ds = synth.SynthCoarseDataset(seed=4, n_cells=6, n_poses=4, n_obj=[3, 16, 20, 1, 8, 5], max_raw=200)
+    loader = torch.utils.data.DataLoader(ds, batch_size=2, collate_fn=dataio.collate_fn, shuffle=False)
+    ids = np.array([c.id for c in ds.all_cells])
+    retrievals = np.stack([ids[[0, 2, 4]], ids[[1, 2, 3]], ids[[5, 0, 1]], ids[[2, 4, 5]]])
+    monkeypatch.setattr(evaluation, "localisation_accuracies", lambda *a, **k: {1: {5: 0.0, 10: 0.0}, 3: {5: 0.0, 10: 0.0}})
+    seen = {}
+    for mode in (False, True):
+        rec = Recorder()
+        frontend = fake_t5.FakeFrontend(0)
+        model = types.SimpleNamespace(engine=rec, vectorised_packing=mode, eval=lambda: None,
+                                      encode_hints=lambda d, rec=rec, fe=frontend: (rec.fine_encode_hints(fe(d)[0]), fe(d)[1]))
+        np.random.seed(11)
+        acc, offsets = evaluation.run_fine(model, retrievals, loader, args, dataio.Compose([dataio.FixedPoints(256), dataio.NormalizeScale()]),
+                                           return_offsets=True)
+        assert offsets.shape == (4, 3, 2) and len(rec.calls) == 1
+        seen[mode] = rec.calls[0]
+    (pts_a, meta_a, ptr_a), (pts_b, meta_b, ptr_b) = seen[False], seen[True]
+    assert pts_a.shape == pts_b.shape == (6 * 16, 256, 6) and (ptr_a == ptr_b).all() and (ptr_a == np.arange(7) * 16).all()
+    assert torch.equal(meta_a, meta_b)  # padding objects are drawn before any sampling in both modes
+    for pts in (pts_a, pts_b):  # NormalizeScale: centred, inside (-1, 1), the largest coordinate at 0.999999
+        assert float(pts[:, :, :3].mean(dim=1).abs().max()) < 1e-4
+        assert np.allclose(pts[:, :, :3].abs().amax(dim=(1, 2)).numpy(), 0.999999, atol=1e-6)
+    with pytest.raises(ValueError):
+        model.vectorised_packing = True
+        evaluation.run_fine(model, retrievals, loader, args, lambda d: d)
+
+
 def test_host_chunk_schedule_covers_every_query_once():
     """engine.host_chunk_schedule: the H2D staging chunks of a host-streamed encode_text partition the batch, never exceed the
     staging buffer, and start / end with short chunks when the batch is long."""

@@ -34,6 +34,8 @@ class CrossMatch:
         self._engine = Engine(device)
         self._frontend = text_frontend
         self.training = False
+        # opt-in: run_fine packs the retrieved cells' padded objects with the vectorised packer (dataio.pack_cell_database)
+        self.vectorised_packing = False
         # run_fine: with a sentence-caching front end the hint encodings are cached per distinct (sentence, n_tok) too
         self.cache_sentence_rows = True
         from .text_frontend import SentenceRowCache

@@ -46,12 +46,19 @@ def _cached_database(model, cells_dataset):
     cache = model.__dict__.setdefault("_packed_cells", {})
     key = (id(cells_dataset.cells), len(cells_dataset.cells))
     if key not in cache:
-        names = [type(t).__name__ for t in getattr(cells_dataset.transform, "transforms", [cells_dataset.transform])]
-        if not names or names[0] != "FixedPoints" or any(n not in ("FixedPoints", "NormalizeScale") for n in names):
-            raise ValueError(f"cache_packed_cells supports FixedPoints [+ NormalizeScale] transforms, got {names}")
-        num = getattr(getattr(cells_dataset.transform, "transforms", [cells_dataset.transform])[0], "num", dataio.NUM_POINTS)
-        cache[key] = dataio.pack_cell_database(cells_dataset.cells, num, normalize_scale="NormalizeScale" in names)
+        num, normalize_scale = _transform_spec(cells_dataset.transform)
+        cache[key] = dataio.pack_cell_database(cells_dataset.cells, num, normalize_scale=normalize_scale)
     return cache[key]
+
+
+def _transform_spec(transform):
+    """(points per object, NormalizeScale?) of a point transform the vectorised packer can stand in for: the two the
+    reference's eval scripts build (evaluation/coarse.py:95-98, evaluation/pipeline.py:216-224)."""
+    stages = list(getattr(transform, "transforms", [transform]))
+    names = [type(t).__name__ for t in stages]
+    if not names or names[0] != "FixedPoints" or any(n not in ("FixedPoints", "NormalizeScale") for n in names):
+        raise ValueError(f"vectorised packing supports FixedPoints [+ NormalizeScale] transforms, got {names}")
+    return getattr(stages[0], "num", dataio.NUM_POINTS), "NormalizeScale" in names
 
 
 @torch.no_grad()
@@ -188,6 +195,13 @@ def _padded_objects(cell, pad_size: int):
     return objects
 
 
+class _CellView:
+    """A padded object list seen as a cell by dataio.pack_cell_database."""
+
+    def __init__(self, objects, cell_id=None):
+        self.objects, self.id = objects, cell_id
+
+
 @torch.no_grad()
 def run_fine(model, retrievals, dataloader, args, transform_fine, return_offsets: bool = False):
     """evaluation/pipeline.py:91-204: offsets of every query against each of its max(top_k) retrieved cells, then the
@@ -217,8 +231,15 @@ def run_fine(model, retrievals, dataloader, args, transform_fine, return_offsets
     for b0 in range(0, len(used), batch):
         cells = [all_cells[int(r)] for r in used[b0:b0 + batch]]
         objects = [_padded_objects(c, pad) for c in cells]
-        points = [dataio.batch_object_points(o, transform_fine) for o in objects]
-        pts, meta, cell_ptr = dataio.pack_cells(objects, points)
+        if getattr(model, "vectorised_packing", False):
+            # opt-in: all objects of the batch sampled and reduced in one vectorised pass instead of
+            # one T.FixedPoints call + three numpy reductions per object (the draw differs from the per-object sequence)
+            num, normalize_scale = _transform_spec(transform_fine)
+            packed = dataio.pack_cell_database([_CellView(o) for o in objects], num, normalize_scale=normalize_scale)
+            pts, meta, cell_ptr = packed.pts, packed.meta, packed.cell_ptr
+        else:
+            points = [dataio.batch_object_points(o, transform_fine) for o in objects]
+            pts, meta, cell_ptr = dataio.pack_cells(objects, points)
         obj_emb[b0 * pad:(b0 + len(cells)) * pad] = engine.fine_encode_objects(pts, meta, cell_ptr)
 
     # ---- textual branch, once per query
