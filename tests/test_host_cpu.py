@@ -235,6 +235,10 @@ def test_sentence_row_cache_computes_each_distinct_sentence_once():
     got = cache.rows(["e", "ff", "a"], 9, compute_for(9))  # 5 + 2 new > max_rows: the cache starts over with this batch
     assert torch.equal(got, torch.stack([row_of(s, 9) for s in ("e", "ff", "a")]))
     assert calls[-1] == ["e", "ff", "a"] and len(cache.index) == 3 and cache.table.shape == (3, 4)
+    cache.clear()  # what load_state_dict does: rows of the previous weights must not survive
+    assert cache.index == {} and cache.table is None
+    got = cache.rows(["a"], 9, compute_for(9))
+    assert torch.equal(got, row_of("a", 9)[None]) and calls[-1] == ["a"]
 
 
 def test_sentence_cache_frontend_prepare_and_states():

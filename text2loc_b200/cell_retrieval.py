@@ -78,6 +78,7 @@ class CellRetrievalNetwork:
         """Reference key names; llm_model.* keys are ignored as the reference
         checkpoints omit them (training/coarse.py:329-331)."""
         self._engine.load_state_dict({k: v for k, v in state_dict.items() if "llm_model" not in k})
+        self._sentence_rows.clear()  # cached rows were computed with the previous weights
         return self
 
     @property

@@ -59,6 +59,7 @@ class CrossMatch:
     def load_state_dict(self, state_dict, strict: bool = False):
         """CrossMatch.state_dict() key names; llm_model.* keys are ignored (training/fine.py:274-279 never saves them)."""
         self._engine.load_state_dict({k: v for k, v in state_dict.items() if "llm_model" not in k})
+        self._sentence_rows.clear()  # cached rows were computed with the previous weights
         return self
 
     @property

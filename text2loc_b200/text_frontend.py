@@ -119,12 +119,16 @@ class SentenceRowCache:
         self.table = None  # [rows, width] on the engine's device
         self.computed = 0  # rows ever computed (tests / diagnostics)
 
+    def clear(self):
+        """Forget every row (the weights behind `compute` changed)."""
+        self.index, self.table = {}, None
+
     def rows(self, sentences: List[str], n_tok: int, compute) -> torch.Tensor:
         """compute(list of distinct missing sentences) -> tensor [len, width]; returns [len(sentences), width]."""
         keys = [(s, n_tok) for s in sentences]
         missing = [k for k in dict.fromkeys(keys) if k not in self.index]
         if missing and len(self.index) + len(missing) > self.max_rows:  # bounded: start over rather than grow without limit
-            self.index, self.table = {}, None
+            self.clear()
             missing = list(dict.fromkeys(keys))
         if missing:
             new = compute([s for s, _ in missing])
